@@ -1,0 +1,350 @@
+"""ctypes mirror of ``include/jpp_b200.h`` plus numpy-backed holders for the
+model description, staged lattice batches and results.
+
+The structures here are byte-for-byte the C ABI; nothing in this module
+computes scores.  ``StagedBatch`` / ``ModelSpec`` can be built from the JPPB
+files that the reference-side stager writes (``oracle/ref_harness.cc``) or
+from arrays produced by any other host-side lattice builder.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+ABI_VERSION = 1
+
+# jpp_b200_status
+OK, INVALID_PARAMETER, INVALID_STATE, NOT_IMPLEMENTED, CUDA_ERROR = range(5)
+
+# jpp_b200_prim_kind
+PRIM_COPY, PRIM_SHIFT_MASK, PRIM_PROVIDED, PRIM_BYTE_LENGTH, PRIM_CODEPOINT_SIZE = 1, 2, 3, 4, 5
+PRIM_SURFACE_CODEPOINT_SIZE, PRIM_CODEPOINT_TYPE, PRIM_CODEPOINT = 6, 7, 8
+
+
+class Primitive(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("a", C.c_int32), ("b", C.c_int32), ("c", C.c_int32)]
+
+
+class Computation(C.Structure):
+    _fields_ = [("primitive", C.c_int32), ("true_off", C.c_uint32), ("true_len", C.c_uint32),
+                ("false_off", C.c_uint32), ("false_len", C.c_uint32)]
+
+
+class Pattern(C.Structure):
+    _fields_ = [("index", C.c_uint32), ("ref_off", C.c_uint32), ("ref_len", C.c_uint32)]
+
+
+class Ngram(C.Structure):
+    _fields_ = [("order", C.c_uint32), ("index", C.c_uint32), ("refs", C.c_uint32 * 3)]
+
+
+class RnnModel(C.Structure):
+    _fields_ = [("layer_size", C.c_uint32), ("maxent_order", C.c_uint32), ("maxent_size", C.c_uint64),
+                ("vocab_size", C.c_uint64), ("nce_constant", C.c_float), ("unk_id", C.c_int32),
+                ("unk_constant", C.c_float), ("unk_length_penalty", C.c_float),
+                ("matrix", C.c_void_p), ("embeddings", C.c_void_p), ("nce_embeddings", C.c_void_p),
+                ("maxent", C.c_void_p)]
+
+
+class Model(C.Structure):
+    _fields_ = [("abi_version", C.c_uint32), ("weights", C.c_void_p), ("log2_weights", C.c_uint32),
+                ("weight_seed", C.c_uint64), ("weight_scale", C.c_float),
+                ("entry_size", C.c_uint32), ("num_placeholders", C.c_uint32),
+                ("num_primitives", C.c_uint32), ("primitives", C.POINTER(Primitive)),
+                ("num_computations", C.c_uint32), ("computations", C.POINTER(Computation)),
+                ("branch_pool_size", C.c_uint32), ("branch_pool", C.c_void_p),
+                ("num_patterns", C.c_uint32), ("num_stored_patterns", C.c_uint32),
+                ("patterns", C.POINTER(Pattern)),
+                ("pattern_ref_pool_size", C.c_uint32), ("pattern_ref_pool", C.c_void_p),
+                ("num_ngrams", C.c_uint32), ("ngrams", C.POINTER(Ngram)),
+                ("num_scorers", C.c_uint32), ("score_weights", C.c_float * 2),
+                ("rnn", C.POINTER(RnnModel))]
+
+
+class Config(C.Structure):
+    _fields_ = [("beam_size", C.c_int32), ("global_beam_size", C.c_int32),
+                ("right_gbeam_check", C.c_int32), ("right_gbeam_size", C.c_int32)]
+
+
+class Batch(C.Structure):
+    _fields_ = [("num_sentences", C.c_uint32),
+                ("sent_boundary_off", C.c_void_p), ("sent_codepoint_off", C.c_void_p),
+                ("boundary_node_off", C.c_void_p), ("boundary_end_off", C.c_void_p),
+                ("node_info", C.c_void_p), ("node_entry", C.c_void_p), ("node_placeholders", C.c_void_p),
+                ("node_rnn_id", C.c_void_p), ("ends", C.c_void_p), ("codepoints", C.c_void_p)]
+
+
+class Result(C.Structure):
+    _fields_ = [("node_beam", C.c_void_p), ("node_beam_scores", C.c_void_p),
+                ("node_patterns", C.c_void_p), ("node_t0_score", C.c_void_p)]
+
+
+class Counters(C.Structure):
+    _fields_ = [("sentences", C.c_uint64), ("boundaries", C.c_uint64), ("nodes", C.c_uint64),
+                ("gathers", C.c_uint64), ("algorithmic_bytes", C.c_uint64),
+                ("rnn_nodes", C.c_uint64), ("rnn_scores", C.c_uint64), ("kernel_ms", C.c_float * 8)]
+
+
+NODE_INFO_DT = np.dtype([("entry_ptr", "<i4"), ("start", "<u2"), ("end", "<u2")])
+NODE_PTR_DT = np.dtype([("boundary", "<u2"), ("position", "<u2")])
+CODEPOINT_DT = np.dtype([("codepoint", "<u4"), ("char_class", "<u4")])
+BEAM_EL_DT = np.dtype([("left", "<u2"), ("prev_beam", "<u2"), ("total_score", "<f4")])
+
+
+def _ptr(a: np.ndarray | None) -> int | None:
+    return None if a is None else a.ctypes.data
+
+
+@dataclass
+class RnnSpec:
+    layer_size: int
+    maxent_order: int
+    maxent_size: int
+    vocab_size: int
+    nce_constant: float
+    unk_id: int
+    unk_constant: float
+    unk_length_penalty: float
+    matrix: np.ndarray
+    embeddings: np.ndarray
+    nce_embeddings: np.ndarray
+    maxent: np.ndarray
+
+    @staticmethod
+    def from_files(prefix: str, icfg: np.ndarray, fcfg: np.ndarray) -> "RnnSpec":
+        """Read the four float blocks of a ``.nnet`` v6 file
+        (reference src/rnn/mikolov_rnn.cc:29-76 header, :196-209 blocks)."""
+        h, order, msize, vocab, unk_id = (int(x) for x in icfg[:5])
+        raw = np.fromfile(prefix + ".nnet", dtype=np.uint8)
+        off = 8 + 8 + 4 + 1 + 4 + 1 + 64 + 4 + 4
+        f = raw[off:].view(np.float32) if (len(raw) - off) % 4 == 0 else np.frombuffer(raw[off:].tobytes(), np.float32)
+        emb = f[: vocab * h]
+        nce = f[vocab * h: 2 * vocab * h]
+        mat = f[2 * vocab * h: 2 * vocab * h + h * h]
+        me = f[2 * vocab * h + h * h: 2 * vocab * h + h * h + msize]
+        assert me.size == msize, "truncated .nnet"
+        return RnnSpec(h, order, msize, vocab, float(fcfg[0]), unk_id, float(fcfg[1]), float(fcfg[2]),
+                       np.ascontiguousarray(mat), np.ascontiguousarray(emb), np.ascontiguousarray(nce),
+                       np.ascontiguousarray(me))
+
+
+@dataclass
+class ModelSpec:
+    """Compiled feature program + scorer constants (jpp_b200_model)."""
+    log2_weights: int
+    weight_seed: int
+    weight_scale: float
+    entry_size: int
+    num_placeholders: int
+    prims: np.ndarray          # [n][4] i32
+    comps: np.ndarray          # [n][5] i32
+    branch_pool: np.ndarray    # i32
+    patterns: np.ndarray       # [n][3] i32
+    pattern_ref_pool: np.ndarray
+    ngrams: np.ndarray         # [n][5] i32: order, index, refs[3]
+    num_stored_patterns: int
+    score_weights: tuple[float, float] = (1.0, 0.0)
+    num_scorers: int = 1
+    weights: np.ndarray | None = None   # explicit table, else synthesised from the seed
+    rnn: RnnSpec | None = None
+    _keep: list = field(default_factory=list, repr=False)
+
+    @staticmethod
+    def from_jppb(d: dict[str, np.ndarray], rnn_prefix: str | None = None) -> "ModelSpec":
+        cfg, fcfg, cnt = d["cfg"], d["fcfg"], d["spec_counts"]
+        ms = ModelSpec(
+            log2_weights=int(cfg[5]), weight_seed=int(cfg[6]), weight_scale=float(fcfg[0]),
+            entry_size=int(cnt[5]), num_placeholders=int(cnt[6]),
+            prims=np.ascontiguousarray(d["spec_prims"], np.int32),
+            comps=np.ascontiguousarray(d["spec_comps"], np.int32),
+            branch_pool=np.ascontiguousarray(d["spec_branch_pool"], np.int32),
+            patterns=np.ascontiguousarray(d["spec_patterns"], np.int32),
+            pattern_ref_pool=np.ascontiguousarray(d["spec_pattern_ref_pool"], np.int32),
+            ngrams=np.ascontiguousarray(d["spec_ngrams"], np.int32),
+            num_stored_patterns=int(cnt[3]),
+            score_weights=(float(fcfg[1]), float(fcfg[2])), num_scorers=int(cfg[4]))
+        if ms.num_scorers == 2:
+            if rnn_prefix is None:
+                raise ValueError("model has an RNN scorer: pass rnn_prefix")
+            ms.rnn = RnnSpec.from_files(rnn_prefix, d["rnn_icfg"], d["rnn_fcfg"])
+        return ms
+
+    def as_struct(self) -> Model:
+        m = Model()
+        m.abi_version = ABI_VERSION
+        m.weights = _ptr(self.weights)
+        m.log2_weights = self.log2_weights
+        m.weight_seed = self.weight_seed
+        m.weight_scale = self.weight_scale
+        m.entry_size = self.entry_size
+        m.num_placeholders = self.num_placeholders
+        prims = np.ascontiguousarray(self.prims, np.int32)
+        comps = np.ascontiguousarray(self.comps, np.int32).astype(np.int32)
+        pats = np.ascontiguousarray(self.patterns, np.int32)
+        ngr = np.ascontiguousarray(self.ngrams, np.int32)
+        self._keep = [prims, comps, pats, ngr]
+        m.num_primitives = len(prims)
+        m.primitives = C.cast(prims.ctypes.data, C.POINTER(Primitive))
+        m.num_computations = len(comps)
+        m.computations = C.cast(comps.ctypes.data, C.POINTER(Computation))
+        m.branch_pool_size = len(self.branch_pool)
+        m.branch_pool = _ptr(self.branch_pool)
+        m.num_patterns = len(pats)
+        m.num_stored_patterns = self.num_stored_patterns
+        m.patterns = C.cast(pats.ctypes.data, C.POINTER(Pattern))
+        m.pattern_ref_pool_size = len(self.pattern_ref_pool)
+        m.pattern_ref_pool = _ptr(self.pattern_ref_pool)
+        m.num_ngrams = len(ngr)
+        m.ngrams = C.cast(ngr.ctypes.data, C.POINTER(Ngram))
+        m.num_scorers = self.num_scorers
+        m.score_weights[0] = self.score_weights[0]
+        m.score_weights[1] = self.score_weights[1]
+        if self.rnn is not None:
+            r = RnnModel()
+            r.layer_size, r.maxent_order = self.rnn.layer_size, self.rnn.maxent_order
+            r.maxent_size, r.vocab_size = self.rnn.maxent_size, self.rnn.vocab_size
+            r.nce_constant, r.unk_id = self.rnn.nce_constant, self.rnn.unk_id
+            r.unk_constant, r.unk_length_penalty = self.rnn.unk_constant, self.rnn.unk_length_penalty
+            r.matrix, r.embeddings = _ptr(self.rnn.matrix), _ptr(self.rnn.embeddings)
+            r.nce_embeddings, r.maxent = _ptr(self.rnn.nce_embeddings), _ptr(self.rnn.maxent)
+            self._keep.append(r)
+            m.rnn = C.pointer(r)
+        return m
+
+
+@dataclass
+class ScoringConfig:
+    beam_size: int = 5
+    global_beam_size: int = 6
+    right_gbeam_check: int = 1
+    right_gbeam_size: int = 5
+
+    @staticmethod
+    def from_jppb(d: dict[str, np.ndarray]) -> "ScoringConfig":
+        c = d["cfg"]
+        return ScoringConfig(int(c[0]), int(c[1]), int(c[2]), int(c[3]))
+
+    def as_struct(self) -> Config:
+        return Config(self.beam_size, self.global_beam_size, self.right_gbeam_check, self.right_gbeam_size)
+
+
+@dataclass
+class StagedBatch:
+    """N built lattices in CSR form (jpp_b200_batch)."""
+    sent_boundary_off: np.ndarray
+    sent_codepoint_off: np.ndarray
+    boundary_node_off: np.ndarray
+    boundary_end_off: np.ndarray
+    node_info: np.ndarray        # NODE_INFO_DT
+    node_entry: np.ndarray       # [nodes][entry_size] i32
+    node_placeholders: np.ndarray | None
+    node_rnn_id: np.ndarray | None
+    ends: np.ndarray             # NODE_PTR_DT
+    codepoints: np.ndarray       # CODEPOINT_DT
+
+    @property
+    def num_sentences(self) -> int:
+        return len(self.sent_boundary_off) - 1
+
+    @property
+    def num_nodes(self) -> int:
+        return int(self.boundary_node_off[-1])
+
+    @property
+    def num_boundaries(self) -> int:
+        return len(self.boundary_node_off) - 1
+
+    @staticmethod
+    def from_jppb(d: dict[str, np.ndarray]) -> "StagedBatch":
+        n = len(d["node_entry_ptr"])
+        ni = np.empty(n, NODE_INFO_DT)
+        ni["entry_ptr"] = d["node_entry_ptr"]
+        ni["start"] = d["node_start_end"][:, 0]
+        ni["end"] = d["node_start_end"][:, 1]
+        ends = np.ascontiguousarray(d["ends"], np.uint16).view(NODE_PTR_DT).reshape(-1)
+        cps = np.ascontiguousarray(d["codepoints"], np.uint32).view(CODEPOINT_DT).reshape(-1)
+        return StagedBatch(
+            np.ascontiguousarray(d["sent_boundary_off"], np.uint32),
+            np.ascontiguousarray(d["sent_codepoint_off"], np.uint32),
+            np.ascontiguousarray(d["boundary_node_off"], np.uint32),
+            np.ascontiguousarray(d["boundary_end_off"], np.uint32),
+            ni, np.ascontiguousarray(d["node_entry"], np.int32),
+            np.ascontiguousarray(d["node_placeholders"], np.int32) if "node_placeholders" in d else None,
+            np.ascontiguousarray(d["node_rnn_id"], np.int32) if "node_rnn_id" in d else None,
+            ends, cps)
+
+    def as_struct(self) -> Batch:
+        b = Batch()
+        b.num_sentences = self.num_sentences
+        b.sent_boundary_off = _ptr(self.sent_boundary_off)
+        b.sent_codepoint_off = _ptr(self.sent_codepoint_off)
+        b.boundary_node_off = _ptr(self.boundary_node_off)
+        b.boundary_end_off = _ptr(self.boundary_end_off)
+        b.node_info = _ptr(self.node_info)
+        b.node_entry = _ptr(self.node_entry)
+        b.node_placeholders = _ptr(self.node_placeholders)
+        b.node_rnn_id = _ptr(self.node_rnn_id)
+        b.ends = _ptr(self.ends)
+        b.codepoints = _ptr(self.codepoints)
+        return b
+
+    def select(self, lo: int, hi: int) -> "StagedBatch":
+        """Sentences [lo, hi) as an independent batch (offsets rebased)."""
+        b0, b1 = int(self.sent_boundary_off[lo]), int(self.sent_boundary_off[hi])
+        n0, n1 = int(self.boundary_node_off[b0]), int(self.boundary_node_off[b1])
+        e0, e1 = int(self.boundary_end_off[b0]), int(self.boundary_end_off[b1])
+        c0, c1 = int(self.sent_codepoint_off[lo]), int(self.sent_codepoint_off[hi])
+        return StagedBatch(
+            (self.sent_boundary_off[lo:hi + 1] - b0).astype(np.uint32),
+            (self.sent_codepoint_off[lo:hi + 1] - c0).astype(np.uint32),
+            (self.boundary_node_off[b0:b1 + 1] - n0).astype(np.uint32),
+            (self.boundary_end_off[b0:b1 + 1] - e0).astype(np.uint32),
+            np.ascontiguousarray(self.node_info[n0:n1]), np.ascontiguousarray(self.node_entry[n0:n1]),
+            None if self.node_placeholders is None else np.ascontiguousarray(self.node_placeholders[n0:n1]),
+            None if self.node_rnn_id is None else np.ascontiguousarray(self.node_rnn_id[n0:n1]),
+            np.ascontiguousarray(self.ends[e0:e1]), np.ascontiguousarray(self.codepoints[c0:c1]))
+
+
+@dataclass
+class ScoreResult:
+    """Post-state of computeScores (jpp_b200_result)."""
+    node_beam: np.ndarray          # [nodes][beam] BEAM_EL_DT
+    node_beam_scores: np.ndarray   # [nodes][beam][S] f32
+    node_patterns: np.ndarray      # [nodes][stored] u64
+    node_t0_score: np.ndarray      # [nodes] f32
+
+    @staticmethod
+    def allocate(num_nodes: int, beam: int, num_scorers: int, stored: int) -> "ScoreResult":
+        return ScoreResult(np.zeros((num_nodes, beam), BEAM_EL_DT),
+                           np.zeros((num_nodes, beam, num_scorers), np.float32),
+                           np.zeros((num_nodes, stored), np.uint64), np.zeros(num_nodes, np.float32))
+
+    def as_struct(self) -> Result:
+        return Result(_ptr(self.node_beam), _ptr(self.node_beam_scores), _ptr(self.node_patterns),
+                      _ptr(self.node_t0_score))
+
+
+def best_paths(batch: StagedBatch, res: ScoreResult) -> list[list[tuple[int, int]]]:
+    """1-best path of every sentence as [(boundary, position), ...] from BOS to
+    EOS: what AnalysisPath::fillIn walks (reference analysis_result.cc:25-76)."""
+    out = []
+    sbo, bno, beo = batch.sent_boundary_off, batch.boundary_node_off, batch.boundary_end_off
+    for s in range(batch.num_sentences):
+        b0 = int(sbo[s])
+        nb = int(sbo[s + 1]) - b0
+        path: list[tuple[int, int]] = []
+        bnd, pos, slot = nb - 1, 0, 0
+        while bnd >= 2:
+            node = int(bno[b0 + bnd]) + pos
+            el = res.node_beam[node, slot]
+            if el["left"] == 0xFFFF:
+                path = []
+                break
+            path.append((bnd, pos))
+            ptr = batch.ends[int(beo[b0 + bnd]) + int(el["left"])]
+            slot = int(el["prev_beam"])
+            bnd, pos = int(ptr["boundary"]), int(ptr["position"])
+        out.append(path[::-1])
+    return out
