@@ -165,6 +165,8 @@ class ModelSpec:
             ngrams=np.ascontiguousarray(d["spec_ngrams"], np.int32),
             num_stored_patterns=int(cnt[3]),
             score_weights=(float(fcfg[1]), float(fcfg[2])), num_scorers=int(cfg[4]))
+        if "weights" in d:
+            ms.weights = np.ascontiguousarray(d["weights"], np.float32)
         if ms.num_scorers == 2:
             if rnn_prefix is None:
                 raise ValueError("model has an RNN scorer: pass rnn_prefix")

@@ -1,0 +1,666 @@
+// jpp_b200.cu -- C ABI (include/jpp_b200.h) + CUDA kernels of the B200 lattice
+// scorer.  Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false
+// (see jumanpp_b200/build.py).  There is no CPU path in this library: every
+// entry point that scores needs a CUDA device.
+#include <cuda_runtime.h>
+#include <cub/device/device_scan.cuh>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "jpp_b200.h"
+#include "jpp_b200_host.h"
+#include "jpp_b200_kernels.h"
+#include "jpp_b200_rnn.h"
+
+using namespace jppb200;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+// ------------------------------------------------------------- kernels ------
+__global__ void k_fill_weights(float* w, u64 n, u64 seed, float scale) {
+  const float f = (float)((double)scale * 1.7320508075688772);
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+    u64 x = i + (seed << 40);
+    x += 0x9E3779B97F4A7C15ULL;
+    u64 z = x;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    z = z ^ (z >> 31);
+    const u32 s = (u32)(z & 0xFFFF) + (u32)((z >> 16) & 0xFFFF) + (u32)((z >> 32) & 0xFFFF) + (u32)((z >> 48) & 0xFFFF);
+    const float v = __fsub_rn(__fmul_rn((float)s, 1.0f / 65536.0f), 2.0f);
+    w[i] = __fmul_rn(v, f);
+  }
+}
+
+// derived index arrays of a batch
+__global__ void k_boundary_index(BatchView bv) {
+  const u32 s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= bv.numSentences) return;
+  for (u32 b = bv.sentBndOff[s]; b < bv.sentBndOff[s + 1]; ++b) bv.bndSent[b] = s;
+}
+
+__global__ void k_node_index(BatchView bv) {
+  const u32 b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= bv.totalBoundaries) return;
+  for (u32 n = bv.bndNodeOff[b]; n < bv.bndNodeOff[b + 1]; ++n) bv.nodeBnd[n] = b;
+  const u32 s = bv.bndSent[b];
+  const u32 b0 = bv.sentBndOff[s];
+  for (u32 e = bv.bndEndOff[b]; e < bv.bndEndOff[b + 1]; ++e) {
+    const jpp_b200_node_ptr p = bv.ends[e];
+    bv.endNode[e] = bv.bndNodeOff[b0 + p.boundary] + p.position;
+  }
+}
+
+__global__ void __launch_bounds__(128) k_t0(const FeatTables* __restrict__ ftg, BatchView bv, const float* __restrict__ w) {
+  __shared__ FeatTables ft;
+  {
+    const u32* src = reinterpret_cast<const u32*>(ftg);
+    u32* dst = reinterpret_cast<u32*>(&ft);
+    for (u32 i = threadIdx.x; i < sizeof(FeatTables) / 4; i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+  const u32 node = blockIdx.x * blockDim.x + threadIdx.x;
+  if (node < bv.totalNodes) t0_node(ft, bv, w, node);
+}
+
+// persistent warps pull sentences (longest first) from a global counter
+__global__ void __launch_bounds__(128) k_walk(const FeatTables* __restrict__ ftg, BatchView bv, ScoreCfg cfg,
+                                             const float* __restrict__ w, u32* workCounter, u32 warpSmemBytes) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  FeatTables* ft = reinterpret_cast<FeatTables*>(smem);
+  {
+    const u32* src = reinterpret_cast<const u32*>(ftg);
+    u32* dst = reinterpret_cast<u32*>(ft);
+    for (u32 i = threadIdx.x; i < sizeof(FeatTables) / 4; i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+  const u32 warp = threadIdx.x >> 5;
+  unsigned char* base = smem + ((sizeof(FeatTables) + 15) & ~(size_t)15) + (size_t)warp * warpSmemBytes;
+  WarpSmem sm = carve_warp_smem(base, (u32)cfg.gbeam, ft->nStored);
+  for (;;) {
+    u32 item = 0;
+    if ((threadIdx.x & 31u) == 0) item = atomicAdd(workCounter, 1u);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= bv.numSentences) break;
+    const u32 sent = bv.sentOrder ? bv.sentOrder[item] : item;
+    walk_sentence(*ft, bv, cfg, w, sm, sent);
+    __syncwarp();
+  }
+}
+
+__global__ void k_fill_i32(i32* p, size_t n, i32 v) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+__global__ void k_rnn_tree(BatchView bv, ScoreCfg cfg, RnnWork rw) {
+  const u32 s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < bv.numSentences) rnn_build_tree(bv, cfg, rw, s);
+}
+
+// level histogram / lists; ctxSlot[rnode] = compact context row
+__global__ void k_rnn_level_count(BatchView bv, RnnWork rw, const u32* ctxOff) {
+  const u32 s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= bv.numSentences) return;
+  const u32 base0 = rw.rnOff[s];
+  const u32 n = rw.rnCount[s];
+  const u32 nb = bv.sentBndOff[s + 1] - bv.sentBndOff[s];
+  for (u32 i = 2; i < n; ++i) {
+    const u32 q = base0 + i;
+    if ((u32)rw.bnd[q] + 1 < nb) atomicAdd(rw.levelCount + rw.depth[q], 1u);
+  }
+  (void)ctxOff;
+}
+
+__global__ void k_rnn_level_fill(BatchView bv, RnnWork rw, u32* cursor) {
+  const u32 s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= bv.numSentences) return;
+  const u32 base0 = rw.rnOff[s];
+  const u32 n = rw.rnCount[s];
+  const u32 nb = bv.sentBndOff[s + 1] - bv.sentBndOff[s];
+  for (u32 i = 2; i < n; ++i) {
+    const u32 q = base0 + i;
+    if ((u32)rw.bnd[q] + 1 < nb) {
+      const u32 d = (u32)rw.depth[q];
+      const u32 pos = atomicAdd(cursor + d, 1u);
+      rw.levelList[rw.levelOff[d] + pos] = q;
+    }
+  }
+}
+
+// context row of an rnode: sentence-compact
+__device__ __forceinline__ size_t ctx_row(const RnnWork& rw, const u32* ctxOff, const u32* rnSent, u32 q) {
+  const u32 s = rnSent[q];
+  return (size_t)ctxOff[s] + (q - rw.rnOff[s]);
+}
+
+__global__ void k_rnn_mark_sentence(BatchView bv, RnnWork rw, u32* rnSent) {
+  const u32 s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= bv.numSentences) return;
+  const u32 base0 = rw.rnOff[s];
+  const u32 n = rw.rnCount[s];
+  for (u32 i = 0; i < n; ++i) rnSent[base0 + i] = s;
+}
+
+// BOS context of every sentence: sigmoid(W^T 0 + emb[0]) (rnn_scorer_gbeam.cc:37-46);
+// dot32 of a zero vector is +0, so the state is sigmoid(0 + emb[0][i])
+__global__ void k_rnn_bos(BatchView bv, RnnWork rw, RnnTables rt, const u32* ctxOff) {
+  const u32 s = blockIdx.x;
+  if (rw.rnCount[s] < 2) return;
+  float* out = rw.ctx + ((size_t)ctxOff[s] + 1) * rt.H;
+  for (u32 i = threadIdx.x; i < rt.H; i += blockDim.x) {
+    float v = __fadd_rn(0.0f, rt.emb[i]);
+    out[i] = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-v)));
+  }
+  (void)bv;
+}
+
+// one warp per tree node of the level: ctx' = sigmoid(W^T ctx + emb[id])
+__global__ void __launch_bounds__(256) k_rnn_level(RnnWork rw, RnnTables rt, const u32* ctxOff, const u32* rnSent, u32 level) {
+  const u32 cnt = rw.levelCount[level];
+  const u32 off = rw.levelOff[level];
+  const int lane = threadIdx.x & 31;
+  const u32 warpsPerBlock = blockDim.x >> 5;
+  const u32 H = rt.H;
+  for (u32 item = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); item < cnt; item += gridDim.x * warpsPerBlock) {
+    const u32 q = rw.levelList[off + item];
+    const u32 p = (u32)rw.prev[q];
+    const float* cin = rw.ctx + ctx_row(rw, ctxOff, rnSent, p) * H;
+    float* cout = rw.ctx + ctx_row(rw, ctxOff, rnSent, q) * H;
+    i32 id = rw.id[q];
+    if (id == -1) id = 0;  // rnn_scorer_gbeam.cc:126-129
+    const float* emb = rt.emb + (size_t)id * H;
+    for (u32 i = 0; i < H; ++i) {
+      float v = warp_dot32(rt.matrix + (size_t)i * H, cin, H, lane);
+      if (lane == 0) {
+        v = __fadd_rn(v, emb[i]);
+        cout[i] = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-v)));
+      }
+    }
+  }
+}
+
+// one warp per score entry
+__global__ void __launch_bounds__(256) k_rnn_scores(BatchView bv, ScoreCfg cfg, RnnWork rw, RnnTables rt, const u32* ctxOff,
+                                                  const u32* rnSent) {
+  const int lane = threadIdx.x & 31;
+  const u32 warpsPerBlock = blockDim.x >> 5;
+  const u32 H = rt.H;
+  // sentences are few relative to warps: iterate (sentence, entry) with a flat loop per sentence
+  for (u32 s = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); s < bv.numSentences; s += gridDim.x * warpsPerBlock) {
+    const u32 base0 = rw.rnOff[s];
+    const u32 n = rw.rsCount[s];
+    for (u32 i = 0; i < n; ++i) {
+      const u32 si = base0 + i;
+      const i32 q = rw.rsRnode[si];
+      const i32 id = rw.id[q];
+      float sc;
+      if (id == rt.unkId) {
+        sc = __fadd_rn(rt.unkConstant, __fmul_rn(rt.unkLengthPenalty, (float)rw.length[q]));  // rnn_scorer_gbeam.cc:236-240
+      } else {
+        const i32 p = rw.prev[q];
+        const i32 eid = id == -1 ? 0 : id;
+        const float d = warp_dot32(rt.nce + (size_t)eid * H, rw.ctx + ctx_row(rw, ctxOff, rnSent, (u32)p) * H, H, lane);
+        sc = rnn_finish_score(rt, d, rw.id[p], id);
+      }
+      if (lane == 0) {
+        const u16 g = rw.rsEosG[si];
+        if (g != 0xFFFFu) bv.eosRnn[(size_t)s * cfg.gbeam + g] = sc;
+        else bv.beamScores[((size_t)rw.rsNode[si] * cfg.beam + rw.rsSlot[si]) * cfg.S + 1] = sc;
+      }
+    }
+  }
+}
+
+__global__ void k_rerank(BatchView bv, ScoreCfg cfg, float w0, float w1) {
+  const u32 s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < bv.numSentences) rerank_sentence(bv, cfg, w0, w1, s);
+}
+
+// ------------------------------------------------------------- helpers ------
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T>
+  T* as() const { return static_cast<T*>(p); }
+};
+
+}  // namespace
+
+struct jpp_b200_handle {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string error;
+  HostModel hm;
+  ScoreCfg cfg{};
+  jpp_b200_config pubCfg{};
+  FeatTables* dFt = nullptr;
+  float* dWeights = nullptr;
+  RnnTables rt{};
+  bool hasRnn = false;
+  float* dRnnBlocks[4] = {nullptr, nullptr, nullptr, nullptr};
+  float scoreW[2] = {1.0f, 0.0f};
+  int smCount = 148;
+  // batch buffers
+  enum { B_SBO, B_SCO, B_BNO, B_BEO, B_INFO, B_ENTRY, B_PH, B_RNNID, B_ENDS, B_CPS, B_NODEBND, B_BNDSENT, B_ENDNODE,
+         B_ORDER, B_BEAM, B_BSCORES, B_PATS, B_T0, B_PRE, B_CUT, B_CUTIDX, B_SELK, B_GBNODE, B_GBSLOT, B_GBLBND, B_GBCNT,
+         B_EOSG, B_EOSLOC, B_EOSRNN, B_COUNTERS, B_WORK,
+         R_OFF, R_ID, R_PREV, R_NEXT, R_BND, R_LEN, R_DEPTH, R_HASH, R_RNCNT, R_RSNODE, R_RSSLOT, R_RSEOSG, R_RSRNODE,
+         R_RSCNT, R_CONN, R_BNDHEAD, R_CTX, R_LVLCNT, R_LVLOFF, R_LVLLIST, R_CTXOFF, R_RNSENT, R_CURSOR, R_CUBTMP,
+         NUM_BUFS };
+  DevBuf buf[NUM_BUFS];
+  BatchView bv{};
+  RnnWork rw{};
+  bool resident = false;
+  u32 maxNb = 0;
+  size_t rnTotal = 0;
+  jpp_b200_counters counters{};
+  cudaEvent_t ev[10] = {};
+};
+
+namespace {
+
+jpp_b200_status fail(jpp_b200_handle* h, jpp_b200_status st, const std::string& msg) {
+  if (h) h->error = msg; else g_create_error = msg;
+  return st;
+}
+
+#define CU_CHECK(h, expr)                                                                         \
+  do {                                                                                            \
+    cudaError_t e_ = (expr);                                                                      \
+    if (e_ != cudaSuccess)                                                                        \
+      return fail(h, JPP_B200_CUDA_ERROR, std::string(#expr) + ": " + cudaGetErrorString(e_));    \
+  } while (0)
+
+jpp_b200_status check_config(jpp_b200_handle* h, const jpp_b200_config* c, u32 numScorers) {
+  if (c->beam_size <= 0) return fail(h, JPP_B200_INVALID_PARAMETER, "beam size can not be zero for scoring");  // analyzer_impl.cc:53-56
+  if (c->right_gbeam_check > 0 && c->right_gbeam_size <= 0)
+    return fail(h, JPP_B200_INVALID_PARAMETER, "right global beam size should not be zero if you enable it");  // :58-61
+  if (numScorers > 1 && c->global_beam_size <= 0)
+    return fail(h, JPP_B200_INVALID_STATE, "additional scorers are supported only with global beam enabled");  // :83-88
+  if (c->global_beam_size <= 0)
+    return fail(h, JPP_B200_NOT_IMPLEMENTED, "full-beam scoring (global_beam_size <= 0, computeScoresFull) is not on the GPU path yet");
+  if (c->beam_size > MAX_BEAM || c->global_beam_size > MAX_BEAM || c->right_gbeam_size > MAX_BEAM || c->right_gbeam_check > MAX_BEAM)
+    return fail(h, JPP_B200_NOT_IMPLEMENTED, "beam sizes above 32 are not supported by the GPU path");
+  return JPP_B200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+uint32_t jpp_b200_abi_version(void) { return JPP_B200_ABI_VERSION; }
+
+const char* jpp_b200_build_info(void) {
+  return "jpp_b200 sm_100a cuda-runtime " JPP_STR(CUDART_VERSION) " fmad=off";
+}
+
+const char* jpp_b200_last_error(const jpp_b200_handle* h) { return h ? h->error.c_str() : g_create_error.c_str(); }
+
+jpp_b200_status jpp_b200_create(const jpp_b200_model* model, const jpp_b200_config* config, int device,
+                                jpp_b200_handle** out) {
+  if (!model || !config || !out) return fail(nullptr, JPP_B200_INVALID_PARAMETER, "null argument");
+  *out = nullptr;
+  HostModel hm;
+  std::string err;
+  jpp_b200_status st = compile_host_model(model, &hm, &err);
+  if (st != JPP_B200_OK) return fail(nullptr, st, err);
+  st = check_config(nullptr, config, model->num_scorers);
+  if (st != JPP_B200_OK) return st;
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0)
+    return fail(nullptr, JPP_B200_CUDA_ERROR,
+                std::string("no CUDA device available (this library has no CPU path): ") + cudaGetErrorString(ce));
+  if (device < 0 || device >= ndev) return fail(nullptr, JPP_B200_INVALID_PARAMETER, "device index out of range");
+  jpp_b200_handle* h = new (std::nothrow) jpp_b200_handle();
+  if (!h) return fail(nullptr, JPP_B200_INVALID_STATE, "out of host memory");
+  h->device = device;
+  h->hm = hm;
+  h->pubCfg = *config;
+  h->cfg = ScoreCfg{config->beam_size, config->global_beam_size, config->right_gbeam_check, config->right_gbeam_size,
+                    model->num_scorers};
+  h->scoreW[0] = model->score_weights[0];
+  h->scoreW[1] = model->score_weights[1];
+#define CREATE_CHECK(expr)                                                                      \
+  do {                                                                                          \
+    cudaError_t e_ = (expr);                                                                    \
+    if (e_ != cudaSuccess) {                                                                    \
+      g_create_error = std::string(#expr) + ": " + cudaGetErrorString(e_);                     \
+      jpp_b200_destroy(h);                                                                      \
+      return JPP_B200_CUDA_ERROR;                                                               \
+    }                                                                                           \
+  } while (0)
+  CREATE_CHECK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CREATE_CHECK(cudaGetDeviceProperties(&prop, device));
+  h->smCount = prop.multiProcessorCount;
+  CREATE_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  for (auto& e : h->ev) CREATE_CHECK(cudaEventCreate(&e));
+  CREATE_CHECK(cudaMalloc(&h->dFt, sizeof(FeatTables)));
+  CREATE_CHECK(cudaMemcpyAsync(h->dFt, &h->hm.ft, sizeof(FeatTables), cudaMemcpyHostToDevice, h->stream));
+  const size_t nw = size_t{1} << model->log2_weights;
+  CREATE_CHECK(cudaMalloc(&h->dWeights, nw * sizeof(float)));
+  if (model->weights) {
+    CREATE_CHECK(cudaMemcpyAsync(h->dWeights, model->weights, nw * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  } else {
+    k_fill_weights<<<h->smCount * 8, 256, 0, h->stream>>>(h->dWeights, nw, model->weight_seed, model->weight_scale);
+    CREATE_CHECK(cudaGetLastError());
+  }
+  if (model->num_scorers == 2) {
+    const jpp_b200_rnn_model* r = model->rnn;
+    h->hasRnn = true;
+    const size_t sizes[4] = {(size_t)r->layer_size * r->layer_size, (size_t)r->vocab_size * r->layer_size,
+                             (size_t)r->vocab_size * r->layer_size, (size_t)r->maxent_size};
+    const float* src[4] = {r->matrix, r->embeddings, r->nce_embeddings, r->maxent};
+    for (int i = 0; i < 4; ++i) {
+      CREATE_CHECK(cudaMalloc(&h->dRnnBlocks[i], sizes[i] * sizeof(float)));
+      CREATE_CHECK(cudaMemcpyAsync(h->dRnnBlocks[i], src[i], sizes[i] * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    }
+    h->rt = RnnTables{r->layer_size, r->maxent_order, r->maxent_size, r->vocab_size, r->nce_constant, r->unk_constant,
+                      r->unk_length_penalty, r->unk_id, h->dRnnBlocks[0], h->dRnnBlocks[1], h->dRnnBlocks[2],
+                      h->dRnnBlocks[3]};
+  }
+  CREATE_CHECK(cudaStreamSynchronize(h->stream));
+#undef CREATE_CHECK
+  *out = h;
+  return JPP_B200_OK;
+}
+
+jpp_b200_status jpp_b200_set_config(jpp_b200_handle* h, const jpp_b200_config* config) {
+  if (!h || !config) return JPP_B200_INVALID_PARAMETER;
+  jpp_b200_status st = check_config(h, config, h->cfg.S);
+  if (st != JPP_B200_OK) return st;
+  h->pubCfg = *config;
+  h->cfg.beam = config->beam_size;
+  h->cfg.gbeam = config->global_beam_size;
+  h->cfg.rcheck = config->right_gbeam_check;
+  h->cfg.rbeam = config->right_gbeam_size;
+  h->resident = false;  // result / scratch shapes depend on the configuration
+  return JPP_B200_OK;
+}
+
+void jpp_b200_destroy(jpp_b200_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  for (auto& b : h->buf) b.release();
+  if (h->dFt) cudaFree(h->dFt);
+  if (h->dWeights) cudaFree(h->dWeights);
+  for (auto& p : h->dRnnBlocks) if (p) cudaFree(p);
+  for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+jpp_b200_status jpp_b200_upload_batch(jpp_b200_handle* h, const jpp_b200_batch* b) {
+  if (!h || !b) return JPP_B200_INVALID_PARAMETER;
+  h->resident = false;
+  CU_CHECK(h, cudaSetDevice(h->device));
+  if (b->num_sentences == 0) return fail(h, JPP_B200_INVALID_PARAMETER, "empty batch");
+  if (!b->sent_boundary_off || !b->sent_codepoint_off || !b->boundary_node_off || !b->boundary_end_off || !b->node_info ||
+      !b->node_entry || !b->ends || (!b->codepoints && b->sent_codepoint_off[b->num_sentences] > 0))
+    return fail(h, JPP_B200_INVALID_PARAMETER, "batch has null arrays");
+  if (h->hm.ft.nPlaceholders > 0 && !b->node_placeholders)
+    return fail(h, JPP_B200_INVALID_PARAMETER, "model has placeholders but batch.node_placeholders is null");
+  if (h->hasRnn && !b->node_rnn_id) return fail(h, JPP_B200_INVALID_PARAMETER, "model has an RNN but batch.node_rnn_id is null");
+  const u32 NS = b->num_sentences;
+  const u32 NB = b->sent_boundary_off[NS];
+  const u32 NN = b->boundary_node_off[NB];
+  const u32 NE = b->boundary_end_off[NB];
+  const u32 NC = b->sent_codepoint_off[NS];
+  const u32 B = (u32)h->cfg.beam, G = (u32)h->cfg.gbeam, S = h->cfg.S, SP = h->hm.ft.nStored;
+  const u32 RC = h->cfg.rcheck > 0 ? (u32)h->cfg.rcheck : 1u;
+  // work order: longest sentence first; validate shapes on the way
+  std::vector<u32> order(NS);
+  u32 maxNb = 0;
+  size_t rnTotal = 0;
+  std::vector<u32> rnOff(NS + 1);
+  for (u32 s = 0; s < NS; ++s) {
+    order[s] = s;
+    const u32 nb = b->sent_boundary_off[s + 1] - b->sent_boundary_off[s];
+    if (nb < 3 || nb > 65535u) return fail(h, JPP_B200_INVALID_PARAMETER, "sentence with fewer than 3 or more than 65535 boundaries");
+    maxNb = std::max(maxNb, nb);
+    rnOff[s] = (u32)rnTotal;
+    rnTotal += (size_t)G * (nb + 1) + 4;
+  }
+  rnOff[NS] = (u32)rnTotal;
+  if (rnTotal > 0xFFFFFFF0ull) return fail(h, JPP_B200_INVALID_PARAMETER, "batch too large for the RNN workspace; split it");
+  std::stable_sort(order.begin(), order.end(), [&](u32 a, u32 c) {
+    return (b->sent_boundary_off[a + 1] - b->sent_boundary_off[a]) > (b->sent_boundary_off[c + 1] - b->sent_boundary_off[c]);
+  });
+  h->maxNb = maxNb;
+  h->rnTotal = rnTotal;
+  auto& bf = h->buf;
+#define ENSURE(idx, bytes) CU_CHECK(h, bf[jpp_b200_handle::idx].ensure(bytes))
+  ENSURE(B_SBO, (size_t)(NS + 1) * 4); ENSURE(B_SCO, (size_t)(NS + 1) * 4);
+  ENSURE(B_BNO, (size_t)(NB + 1) * 4); ENSURE(B_BEO, (size_t)(NB + 1) * 4);
+  ENSURE(B_INFO, (size_t)NN * sizeof(jpp_b200_node_info));
+  ENSURE(B_ENTRY, (size_t)NN * h->hm.ft.entrySize * 4);
+  ENSURE(B_PH, (size_t)NN * std::max(1u, h->hm.ft.nPlaceholders) * 4);
+  ENSURE(B_RNNID, (size_t)NN * 4);
+  ENSURE(B_ENDS, (size_t)NE * sizeof(jpp_b200_node_ptr));
+  ENSURE(B_CPS, (size_t)std::max(1u, NC) * sizeof(jpp_b200_codepoint));
+  ENSURE(B_NODEBND, (size_t)NN * 4); ENSURE(B_BNDSENT, (size_t)NB * 4); ENSURE(B_ENDNODE, (size_t)NE * 4);
+  ENSURE(B_ORDER, (size_t)NS * 4);
+  ENSURE(B_BEAM, (size_t)NN * B * sizeof(jpp_b200_beam_element));
+  ENSURE(B_BSCORES, (size_t)NN * B * S * 4);
+  ENSURE(B_PATS, (size_t)NN * SP * 8);
+  ENSURE(B_T0, (size_t)NN * 4);
+  ENSURE(B_PRE, (size_t)NN * RC * 4);
+  ENSURE(B_CUT, (size_t)NN * 4); ENSURE(B_CUTIDX, (size_t)NN * 4); ENSURE(B_SELK, (size_t)NN * 2);
+  ENSURE(B_GBNODE, (size_t)NB * G * 4); ENSURE(B_GBSLOT, (size_t)NB * G * 2); ENSURE(B_GBLBND, (size_t)NB * G * 2);
+  ENSURE(B_GBCNT, (size_t)NB);
+  ENSURE(B_EOSG, (size_t)NS * G * 8); ENSURE(B_EOSLOC, (size_t)NS * G * 4); ENSURE(B_EOSRNN, (size_t)NS * G * 4);
+  ENSURE(B_COUNTERS, 64); ENSURE(B_WORK, 16);
+  cudaStream_t st = h->stream;
+#define H2D(idx, src, bytes) CU_CHECK(h, cudaMemcpyAsync(bf[jpp_b200_handle::idx].p, src, bytes, cudaMemcpyHostToDevice, st))
+  CU_CHECK(h, cudaEventRecord(h->ev[0], st));
+  H2D(B_SBO, b->sent_boundary_off, (size_t)(NS + 1) * 4);
+  H2D(B_SCO, b->sent_codepoint_off, (size_t)(NS + 1) * 4);
+  H2D(B_BNO, b->boundary_node_off, (size_t)(NB + 1) * 4);
+  H2D(B_BEO, b->boundary_end_off, (size_t)(NB + 1) * 4);
+  H2D(B_INFO, b->node_info, (size_t)NN * sizeof(jpp_b200_node_info));
+  H2D(B_ENTRY, b->node_entry, (size_t)NN * h->hm.ft.entrySize * 4);
+  if (h->hm.ft.nPlaceholders) H2D(B_PH, b->node_placeholders, (size_t)NN * h->hm.ft.nPlaceholders * 4);
+  if (h->hasRnn) H2D(B_RNNID, b->node_rnn_id, (size_t)NN * 4);
+  H2D(B_ENDS, b->ends, (size_t)NE * sizeof(jpp_b200_node_ptr));
+  if (NC) H2D(B_CPS, b->codepoints, (size_t)NC * sizeof(jpp_b200_codepoint));
+  H2D(B_ORDER, order.data(), (size_t)NS * 4);
+  BatchView& bv = h->bv;
+  bv = BatchView{};
+  bv.numSentences = NS; bv.totalBoundaries = NB; bv.totalNodes = NN; bv.totalEnds = NE;
+#define P(idx, T) bf[jpp_b200_handle::idx].as<T>()
+  bv.sentBndOff = P(B_SBO, u32); bv.sentCpOff = P(B_SCO, u32); bv.bndNodeOff = P(B_BNO, u32); bv.bndEndOff = P(B_BEO, u32);
+  bv.nodeInfo = P(B_INFO, jpp_b200_node_info); bv.nodeEntry = P(B_ENTRY, i32);
+  bv.nodePlaceholders = h->hm.ft.nPlaceholders ? P(B_PH, i32) : nullptr;
+  bv.nodeRnnId = h->hasRnn ? P(B_RNNID, i32) : nullptr;
+  bv.ends = P(B_ENDS, jpp_b200_node_ptr); bv.cps = P(B_CPS, jpp_b200_codepoint);
+  bv.nodeBnd = P(B_NODEBND, u32); bv.bndSent = P(B_BNDSENT, u32); bv.endNode = P(B_ENDNODE, u32); bv.sentOrder = P(B_ORDER, u32);
+  bv.beam = P(B_BEAM, jpp_b200_beam_element); bv.beamScores = P(B_BSCORES, float); bv.patterns = P(B_PATS, u64);
+  bv.t0 = P(B_T0, float); bv.pre = P(B_PRE, float); bv.cut = P(B_CUT, float); bv.cutIdx = P(B_CUTIDX, u32);
+  bv.selK = P(B_SELK, u16); bv.gbNode = P(B_GBNODE, u32); bv.gbSlot = P(B_GBSLOT, u16); bv.gbLeftBnd = P(B_GBLBND, u16);
+  bv.gbCount = P(B_GBCNT, u8); bv.eosGbeam = P(B_EOSG, u64); bv.eosLocal = P(B_EOSLOC, float); bv.eosRnn = P(B_EOSRNN, float);
+  bv.counters = P(B_COUNTERS, unsigned long long);
+  k_boundary_index<<<(NS + 127) / 128, 128, 0, st>>>(bv);
+  k_node_index<<<(NB + 127) / 128, 128, 0, st>>>(bv);
+  CU_CHECK(h, cudaGetLastError());
+  if (h->hasRnn) {
+    ENSURE(R_OFF, (size_t)(NS + 1) * 4);
+    H2D(R_OFF, rnOff.data(), (size_t)(NS + 1) * 4);
+    ENSURE(R_ID, rnTotal * 4); ENSURE(R_PREV, rnTotal * 4); ENSURE(R_NEXT, rnTotal * 4); ENSURE(R_BND, rnTotal * 4);
+    ENSURE(R_LEN, rnTotal * 4); ENSURE(R_DEPTH, rnTotal * 4); ENSURE(R_HASH, rnTotal * 8); ENSURE(R_RNCNT, (size_t)NS * 4);
+    ENSURE(R_RSNODE, rnTotal * 4); ENSURE(R_RSSLOT, rnTotal * 2); ENSURE(R_RSEOSG, rnTotal * 2); ENSURE(R_RSRNODE, rnTotal * 4);
+    ENSURE(R_RSCNT, (size_t)NS * 4); ENSURE(R_CONN, (size_t)NN * B * 4); ENSURE(R_BNDHEAD, (size_t)NB * 4);
+    ENSURE(R_LVLCNT, (size_t)(maxNb + 4) * 4); ENSURE(R_LVLOFF, (size_t)(maxNb + 4) * 4); ENSURE(R_CURSOR, (size_t)(maxNb + 4) * 4);
+    ENSURE(R_LVLLIST, rnTotal * 4); ENSURE(R_CTXOFF, (size_t)(NS + 1) * 4); ENSURE(R_RNSENT, rnTotal * 4);
+    RnnWork& rw = h->rw;
+    rw = RnnWork{};
+    rw.rnOff = P(R_OFF, u32); rw.id = P(R_ID, i32); rw.prev = P(R_PREV, i32); rw.next = P(R_NEXT, i32); rw.bnd = P(R_BND, i32);
+    rw.length = P(R_LEN, i32); rw.depth = P(R_DEPTH, i32); rw.hash = P(R_HASH, u64); rw.rnCount = P(R_RNCNT, u32);
+    rw.rsNode = P(R_RSNODE, u32); rw.rsSlot = P(R_RSSLOT, u16); rw.rsEosG = P(R_RSEOSG, u16); rw.rsRnode = P(R_RSRNODE, i32);
+    rw.rsCount = P(R_RSCNT, u32); rw.connNode = P(R_CONN, i32); rw.bndHead = P(R_BNDHEAD, i32);
+    rw.levelCount = P(R_LVLCNT, u32); rw.levelOff = P(R_LVLOFF, u32); rw.levelList = P(R_LVLLIST, u32);
+    rw.maxDepth = maxNb + 1;
+  }
+  CU_CHECK(h, cudaEventRecord(h->ev[1], st));
+  CU_CHECK(h, cudaStreamSynchronize(st));
+  h->resident = true;
+  return JPP_B200_OK;
+#undef H2D
+#undef ENSURE
+}
+
+jpp_b200_status jpp_b200_score_resident(jpp_b200_handle* h) {
+  if (!h) return JPP_B200_INVALID_PARAMETER;
+  if (!h->resident) return fail(h, JPP_B200_INVALID_STATE, "no batch resident: call jpp_b200_upload_batch first");
+  CU_CHECK(h, cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  BatchView& bv = h->bv;
+  auto& bf = h->buf;
+  const u32 NS = bv.numSentences, NN = bv.totalNodes, NB = bv.totalBoundaries;
+  CU_CHECK(h, cudaMemsetAsync(bf[jpp_b200_handle::B_COUNTERS].p, 0, 64, st));
+  CU_CHECK(h, cudaMemsetAsync(bf[jpp_b200_handle::B_WORK].p, 0, 16, st));
+  CU_CHECK(h, cudaEventRecord(h->ev[2], st));
+  k_t0<<<(NN + 127) / 128, 128, 0, st>>>(h->dFt, bv, h->dWeights);
+  CU_CHECK(h, cudaGetLastError());
+  CU_CHECK(h, cudaEventRecord(h->ev[3], st));
+  {
+    const u32 warpBytes = (u32)warp_smem_bytes((u32)h->cfg.gbeam, h->hm.ft.nStored);
+    const u32 warpsPerBlock = 4;
+    const size_t smem = ((sizeof(FeatTables) + 15) & ~(size_t)15) + (size_t)warpsPerBlock * warpBytes;
+    if (smem > 200 * 1024) return fail(h, JPP_B200_NOT_IMPLEMENTED, "configuration needs more shared memory than one CTA has");
+    CU_CHECK(h, cudaFuncSetAttribute(k_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int perSm = 0;
+    CU_CHECK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_walk, 128, smem));
+    if (perSm < 1) perSm = 1;
+    const u32 grid = std::min<u32>((u32)h->smCount * (u32)perSm, (NS + warpsPerBlock - 1) / warpsPerBlock);
+    k_walk<<<std::max(1u, grid), 128, smem, st>>>(h->dFt, bv, h->cfg, h->dWeights, bf[jpp_b200_handle::B_WORK].as<u32>(), warpBytes);
+    CU_CHECK(h, cudaGetLastError());
+  }
+  CU_CHECK(h, cudaEventRecord(h->ev[4], st));
+  if (h->hasRnn) {
+    RnnWork& rw = h->rw;
+    const u32 B = (u32)h->cfg.beam;
+    k_fill_i32<<<h->smCount * 4, 256, 0, st>>>(rw.connNode, (size_t)NN * B, -1);
+    k_fill_i32<<<h->smCount, 256, 0, st>>>(rw.bndHead, (size_t)NB, -1);
+    CU_CHECK(h, cudaMemsetAsync(rw.levelCount, 0, (size_t)(h->maxNb + 4) * 4, st));
+    CU_CHECK(h, cudaMemsetAsync(bf[jpp_b200_handle::R_CURSOR].p, 0, (size_t)(h->maxNb + 4) * 4, st));
+    k_rnn_tree<<<(NS + 63) / 64, 64, 0, st>>>(bv, h->cfg, rw);
+    CU_CHECK(h, cudaGetLastError());
+    // compact context rows: exclusive scan of the per-sentence node counts
+    u32* ctxOff = bf[jpp_b200_handle::R_CTXOFF].as<u32>();
+    size_t tmpBytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, rw.rnCount, ctxOff, (int)NS, st);
+    CU_CHECK(h, bf[jpp_b200_handle::R_CUBTMP].ensure(tmpBytes + 16));
+    cub::DeviceScan::ExclusiveSum(bf[jpp_b200_handle::R_CUBTMP].p, tmpBytes, rw.rnCount, ctxOff, (int)NS, st);
+    // worst case rows = rnTotal, but allocate from the actual sum: needs one small sync
+    u32 lastOff = 0, lastCnt = 0;
+    CU_CHECK(h, cudaMemcpyAsync(&lastOff, ctxOff + (NS - 1), 4, cudaMemcpyDeviceToHost, st));
+    CU_CHECK(h, cudaMemcpyAsync(&lastCnt, rw.rnCount + (NS - 1), 4, cudaMemcpyDeviceToHost, st));
+    CU_CHECK(h, cudaStreamSynchronize(st));
+    const size_t rows = (size_t)lastOff + lastCnt;
+    CU_CHECK(h, bf[jpp_b200_handle::R_CTX].ensure(std::max<size_t>(1, rows) * h->rt.H * 4));
+    rw.ctx = bf[jpp_b200_handle::R_CTX].as<float>();
+    u32* rnSent = bf[jpp_b200_handle::R_RNSENT].as<u32>();
+    k_rnn_mark_sentence<<<(NS + 127) / 128, 128, 0, st>>>(bv, rw, rnSent);
+    k_rnn_level_count<<<(NS + 127) / 128, 128, 0, st>>>(bv, rw, ctxOff);
+    cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, rw.levelCount, rw.levelOff, (int)(h->maxNb + 2), st);
+    CU_CHECK(h, bf[jpp_b200_handle::R_CUBTMP].ensure(tmpBytes + 16));
+    cub::DeviceScan::ExclusiveSum(bf[jpp_b200_handle::R_CUBTMP].p, tmpBytes, rw.levelCount, rw.levelOff, (int)(h->maxNb + 2), st);
+    k_rnn_level_fill<<<(NS + 127) / 128, 128, 0, st>>>(bv, rw, bf[jpp_b200_handle::R_CURSOR].as<u32>());
+    k_rnn_bos<<<NS, 64, 0, st>>>(bv, rw, h->rt, ctxOff);
+    CU_CHECK(h, cudaGetLastError());
+    CU_CHECK(h, cudaEventRecord(h->ev[5], st));
+    for (u32 level = 1; level <= h->maxNb; ++level) {
+      k_rnn_level<<<h->smCount * 2, 256, 0, st>>>(rw, h->rt, ctxOff, rnSent, level);
+    }
+    CU_CHECK(h, cudaGetLastError());
+    CU_CHECK(h, cudaEventRecord(h->ev[6], st));
+    k_rnn_scores<<<h->smCount * 2, 256, 0, st>>>(bv, h->cfg, rw, h->rt, ctxOff, rnSent);
+    CU_CHECK(h, cudaGetLastError());
+    CU_CHECK(h, cudaEventRecord(h->ev[7], st));
+    k_rerank<<<(NS + 63) / 64, 64, 0, st>>>(bv, h->cfg, h->scoreW[0], h->scoreW[1]);
+    CU_CHECK(h, cudaGetLastError());
+    // counters: tree nodes and scores
+    h->counters.rnn_nodes = rows;
+  }
+  CU_CHECK(h, cudaEventRecord(h->ev[8], st));
+  CU_CHECK(h, cudaStreamSynchronize(st));
+  // counters
+  unsigned long long dc[8] = {0};
+  CU_CHECK(h, cudaMemcpy(dc, bf[jpp_b200_handle::B_COUNTERS].p, 64, cudaMemcpyDeviceToHost));
+  jpp_b200_counters& c = h->counters;
+  c.sentences = NS; c.boundaries = NB; c.nodes = NN;
+  c.gathers = dc[0] + (unsigned long long)NN * h->hm.ft.nUni;
+  // BASELINE.md roofline accounting: 4 B per gather + streaming terms
+  const u32 B = (u32)h->cfg.beam, SP = h->hm.ft.nStored;
+  c.algorithmic_bytes = 4ull * c.gathers + (unsigned long long)NN * (h->hm.ft.entrySize * 4 + 8 + 4 * h->hm.ft.nPlaceholders) +
+                        8ull * SP * NN * 2 + 8ull * B * NN + 4ull * bv.totalEnds;
+  float ms = 0;
+  for (int i = 0; i < 8; ++i) c.kernel_ms[i] = 0;
+  cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]); c.kernel_ms[0] = ms;  // T0
+  cudaEventElapsedTime(&ms, h->ev[3], h->ev[4]); c.kernel_ms[1] = ms;  // beam walk
+  if (h->hasRnn) {
+    cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]); c.kernel_ms[2] = ms;  // rnn tree + lists
+    cudaEventElapsedTime(&ms, h->ev[5], h->ev[6]); c.kernel_ms[3] = ms;  // rnn contexts
+    cudaEventElapsedTime(&ms, h->ev[6], h->ev[7]); c.kernel_ms[4] = ms;  // rnn scores
+    cudaEventElapsedTime(&ms, h->ev[7], h->ev[8]); c.kernel_ms[5] = ms;  // re-rank
+  }
+  cudaEventElapsedTime(&ms, h->ev[2], h->ev[8]); c.kernel_ms[7] = ms;    // whole scoring
+  cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); c.kernel_ms[6] = ms;    // upload (H2D + index kernels)
+  return JPP_B200_OK;
+}
+
+jpp_b200_status jpp_b200_download_result(jpp_b200_handle* h, jpp_b200_result* r) {
+  if (!h || !r) return JPP_B200_INVALID_PARAMETER;
+  if (!h->resident) return fail(h, JPP_B200_INVALID_STATE, "no batch resident");
+  CU_CHECK(h, cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  const BatchView& bv = h->bv;
+  const size_t NN = bv.totalNodes, B = (size_t)h->cfg.beam, S = h->cfg.S, SP = h->hm.ft.nStored;
+  if (r->node_beam) CU_CHECK(h, cudaMemcpyAsync(r->node_beam, bv.beam, NN * B * sizeof(jpp_b200_beam_element), cudaMemcpyDeviceToHost, st));
+  if (r->node_beam_scores) CU_CHECK(h, cudaMemcpyAsync(r->node_beam_scores, bv.beamScores, NN * B * S * 4, cudaMemcpyDeviceToHost, st));
+  if (r->node_patterns) CU_CHECK(h, cudaMemcpyAsync(r->node_patterns, bv.patterns, NN * SP * 8, cudaMemcpyDeviceToHost, st));
+  if (r->node_t0_score) CU_CHECK(h, cudaMemcpyAsync(r->node_t0_score, bv.t0, NN * 4, cudaMemcpyDeviceToHost, st));
+  CU_CHECK(h, cudaStreamSynchronize(st));
+  return JPP_B200_OK;
+}
+
+jpp_b200_status jpp_b200_score_batch(jpp_b200_handle* h, const jpp_b200_batch* batch, jpp_b200_result* result) {
+  if (!h || !batch || !result) return JPP_B200_INVALID_PARAMETER;
+  jpp_b200_status st = jpp_b200_upload_batch(h, batch);
+  if (st != JPP_B200_OK) return st;
+  st = jpp_b200_score_resident(h);
+  if (st != JPP_B200_OK) return st;
+  return jpp_b200_download_result(h, result);
+}
+
+jpp_b200_status jpp_b200_get_counters(const jpp_b200_handle* h, jpp_b200_counters* out) {
+  if (!h || !out) return JPP_B200_INVALID_PARAMETER;
+  *out = h->counters;
+  return JPP_B200_OK;
+}
+
+}  // extern "C"

@@ -35,13 +35,10 @@
  *                      oracle/eigen_shim/eigen3/Eigen/Core)
  *   re-rank            score_processor.cc:521-576
  *
- * Tie-breaking: the reference sorts per-node beams with std::sort on float
- * keys (score_processor.cc:432-438); for <= 16 candidates libstdc++ runs an
- * insertion sort, i.e. equal scores keep global-beam order.  This file uses a
- * stable insertion sort for every size (documented deviation for > 16 equal
- * keys only).  makeT0cutoffBeam uses std::nth_element; only the selected SET
- * matters and it is unique unless two cutoff scores are exactly equal, in
- * which case this file keeps the lower node index.
+ * Tie-breaking: equal float keys are common (homograph entries with identical
+ * feature fields), so the sorts the reference links against are emulated
+ * exactly: libstdc++ std::sort / std::nth_element and jumanpp's own
+ * util::partition (see the "Exact emulation" block below).
  */
 #include <math.h>
 #include <pthread.h>
@@ -321,17 +318,253 @@ static void node_patterns(const CModel* cm, const i32* entry, const i32* ph, con
   }
 }
 
-/* stable descending insertion sort of indices by score (makeT0Beam, :426-438) */
-static void sort_idx_desc(u32* idx, int n, const float* score) {
-  for (int i = 1; i < n; ++i) {
-    u32 v = idx[i];
-    int j = i - 1;
-    while (j >= 0 && score[v] > score[idx[j]]) {
-      idx[j + 1] = idx[j];
-      --j;
+/* ---------------------------------------------------------------------------
+ * Exact emulation of the sorting the reference links against, so that EQUAL
+ * float keys land where they land in the reference:
+ *   - libstdc++ std::sort      (introsort: median-of-3 + unguarded partition
+ *     down to 16-element runs, then insertion sort; heap sort when the depth
+ *     limit 2*floor(log2 n) is exhausted)          used by makeT0Beam
+ *   - libstdc++ std::nth_element (introselect)      used by makeT0cutoffBeam
+ *   - jumanpp util::partition / part_step (reference src/util/stl_util.h:50-135)
+ * All operate on u32 index arrays with comp(a, b) := score[a] > score[b].
+ * tests/test_sort_emulation.py checks these against the real std:: functions.
+ * ------------------------------------------------------------------------- */
+#define CMP(a, b) (score[(a)] > score[(b)])
+#define SWAPU(x, y) do { u32 t_ = (x); (x) = (y); (y) = t_; } while (0)
+
+static void em_insertion_sort(u32* first, u32* last, const float* score) {
+  if (first == last) return;
+  for (u32* i = first + 1; i != last; ++i) {
+    u32 val = *i;
+    if (CMP(val, *first)) {
+      memmove(first + 1, first, (size_t)(i - first) * sizeof(u32));
+      *first = val;
+    } else {
+      u32* l = i;
+      u32* next = i - 1;
+      while (CMP(val, *next)) { *l = *next; l = next; --next; }
+      *l = val;
     }
-    idx[j + 1] = v;
   }
+}
+
+static void em_unguarded_insertion_sort(u32* first, u32* last, const float* score) {
+  for (u32* i = first; i != last; ++i) {
+    u32 val = *i;
+    u32* l = i;
+    u32* next = i - 1;
+    while (CMP(val, *next)) { *l = *next; l = next; --next; }
+    *l = val;
+  }
+}
+
+static void em_move_median_to_first(u32* result, u32* a, u32* b, u32* c, const float* score) {
+  if (CMP(*a, *b)) {
+    if (CMP(*b, *c)) SWAPU(*result, *b);
+    else if (CMP(*a, *c)) SWAPU(*result, *c);
+    else SWAPU(*result, *a);
+  } else if (CMP(*a, *c)) SWAPU(*result, *a);
+  else if (CMP(*b, *c)) SWAPU(*result, *c);
+  else SWAPU(*result, *b);
+}
+
+static u32* em_unguarded_partition(u32* first, u32* last, u32* pivot, const float* score) {
+  for (;;) {
+    while (CMP(*first, *pivot)) ++first;
+    --last;
+    while (CMP(*pivot, *last)) --last;
+    if (!(first < last)) return first;
+    SWAPU(*first, *last);
+    ++first;
+  }
+}
+
+static u32* em_partition_pivot(u32* first, u32* last, const float* score) {
+  u32* mid = first + (last - first) / 2;
+  em_move_median_to_first(first, first + 1, mid, last - 1, score);
+  return em_unguarded_partition(first + 1, last, first, score);
+}
+
+static void em_push_heap(u32* first, long hole, long top, u32 value, const float* score) {
+  long parent = (hole - 1) / 2;
+  while (hole > top && CMP(first[parent], value)) {
+    first[hole] = first[parent];
+    hole = parent;
+    parent = (hole - 1) / 2;
+  }
+  first[hole] = value;
+}
+
+static void em_adjust_heap(u32* first, long hole, long len, u32 value, const float* score) {
+  const long top = hole;
+  long child = hole;
+  while (child < (len - 1) / 2) {
+    child = 2 * (child + 1);
+    if (CMP(first[child], first[child - 1])) child--;
+    first[hole] = first[child];
+    hole = child;
+  }
+  if ((len & 1) == 0 && child == (len - 2) / 2) {
+    child = 2 * (child + 1);
+    first[hole] = first[child - 1];
+    hole = child - 1;
+  }
+  em_push_heap(first, hole, top, value, score);
+}
+
+static void em_make_heap(u32* first, u32* last, const float* score) {
+  long len = last - first;
+  if (len < 2) return;
+  long parent = (len - 2) / 2;
+  for (;;) {
+    u32 value = first[parent];
+    em_adjust_heap(first, parent, len, value, score);
+    if (parent == 0) return;
+    parent--;
+  }
+}
+
+static void em_pop_heap(u32* first, u32* last, u32* result, const float* score) {
+  u32 value = *result;
+  *result = *first;
+  em_adjust_heap(first, 0, last - first, value, score);
+}
+
+static void em_heap_select(u32* first, u32* middle, u32* last, const float* score) {
+  em_make_heap(first, middle, score);
+  for (u32* i = middle; i < last; ++i)
+    if (CMP(*i, *first)) em_pop_heap(first, middle, i, score);
+}
+
+static void em_sort_heap(u32* first, u32* last, const float* score) {
+  while (last - first > 1) {
+    --last;
+    em_pop_heap(first, last, last, score);
+  }
+}
+
+static int em_lg(long n) {
+  int k = 0;
+  while (n > 1) { n >>= 1; ++k; }
+  return k;
+}
+
+static void em_introsort_loop(u32* first, u32* last, long depth, const float* score) {
+  while (last - first > 16) {
+    if (depth == 0) {
+      em_heap_select(first, last, last, score);
+      em_sort_heap(first, last, score);
+      return;
+    }
+    --depth;
+    u32* cut = em_partition_pivot(first, last, score);
+    em_introsort_loop(cut, last, depth, score);
+    last = cut;
+  }
+}
+
+/* std::sort(first, last, comp) */
+void jpp_oracle_std_sort(u32* first, long n, const float* score) {
+  if (n <= 0) return;
+  u32* last = first + n;
+  em_introsort_loop(first, last, 2L * em_lg(n), score);
+  if (n > 16) {
+    em_insertion_sort(first, first + 16, score);
+    em_unguarded_insertion_sort(first + 16, last, score);
+  } else {
+    em_insertion_sort(first, last, score);
+  }
+}
+
+/* std::nth_element(first, first + nth, last, comp) */
+void jpp_oracle_std_nth_element(u32* first, long nth, long n, const float* score) {
+  u32* last = first + n;
+  u32* nthp = first + nth;
+  if (n <= 0 || nthp == last) return;
+  long depth = 2L * em_lg(n);
+  while (last - first > 3) {
+    if (depth == 0) {
+      em_heap_select(first, nthp + 1, last, score);
+      SWAPU(*first, *nthp);
+      return;
+    }
+    --depth;
+    u32* cut = em_partition_pivot(first, last, score);
+    if (cut <= nthp) first = cut; else last = cut;
+  }
+  em_insertion_sort(first, last, score);
+}
+
+/* jumanpp util::part_step (stl_util.h:50-104) */
+static u32* em_part_step(u32* start, u32* end, const float* score) {
+  long sz = end - start;
+  if (sz == 1) return end;
+  if (sz == 2) {
+    u32* n = start + 1;
+    if (CMP(*n, *start)) SWAPU(*n, *start);
+    return n;
+  }
+  if (sz == 3) {
+    u32 *n0 = start, *n1 = start + 1, *n2 = start + 2;
+    if (CMP(*n1, *n0)) SWAPU(*n1, *n0);
+    if (CMP(*n2, *n1)) SWAPU(*n2, *n1);
+    if (CMP(*n1, *n0)) SWAPU(*n1, *n0);
+    return n1;
+  }
+  u32* pivot = start + sz / 2;
+  --end;
+  SWAPU(*pivot, *end);
+  pivot = end;
+  --end;
+  while (start != end) {
+    if (CMP(*start, *pivot)) {
+      ++start;
+    } else {
+      SWAPU(*start, *end);
+      --end;
+    }
+  }
+  if (CMP(*pivot, *end)) {
+    SWAPU(*pivot, *end);
+  } else {
+    ++end;
+    SWAPU(*pivot, *end);
+  }
+  return end;
+}
+
+/* jumanpp util::partition (stl_util.h:106-135); returns the new length */
+long jpp_oracle_ref_partition(u32* first, long n, const float* score, long minSize, long maxSize) {
+  u32* start = first;
+  u32* end = first + n;
+  for (;;) {
+    u32* mid = em_part_step(start, end, score);
+    long sz = mid - start;
+    if (minSize <= sz && sz <= maxSize) return mid - first;
+    if (sz > maxSize) {
+      end = mid;
+      continue;
+    }
+    sz += 1;
+    start = mid;
+    ++start;
+    minSize -= sz;
+    maxSize -= sz;
+    if (minSize == 0) return start - first;
+  }
+}
+#undef CMP
+#undef SWAPU
+
+/* makeT0Beam ordering (score_processor.cc:426-438): iota, optional
+ * util::partition when more than maxBeam*4/3 candidates, then std::sort */
+static int sort_for_beam(u32* idx, int n, const float* score, int maxBeam) {
+  for (int i = 0; i < n; ++i) idx[i] = (u32)i;
+  long len = n;
+  long boundary = (long)maxBeam * 4 / 3;
+  if (n > boundary) len = jpp_oracle_ref_partition(idx, n, score, maxBeam, boundary);
+  jpp_oracle_std_sort(idx, len, score);
+  return (int)len;
 }
 
 typedef struct {
@@ -355,10 +588,9 @@ static u32 prev_node_of(const Ctx* c, const SentView* sv, u32 node, u32 nodeBoun
 static void make_beam(const Ctx* c, Scratch* s, jpp_b200_beam_element* beamRow, float* scoreRow /* [beam][S] or NULL */,
                       const u64* gbeam, int n, const float* totals, const float* local) {
   int maxBeam = (int)c->beam;
-  for (int i = 0; i < n; ++i) s->idxbuf[i] = (u32)i;
-  sort_idx_desc(s->idxbuf, n, totals);
+  int len = sort_for_beam(s->idxbuf, n, totals, maxBeam);
   int k = 0;
-  for (; k < n && k < maxBeam; ++k) {
+  for (; k < len && k < maxBeam; ++k) {
     u32 g = s->idxbuf[k];
     beamRow[k].left = (u16)(gbeam[g] >> 16);
     beamRow[k].prev_beam = (u16)gbeam[g];
@@ -644,7 +876,7 @@ static int score_sentence(const Ctx* c, Scratch* s, u32 sent) {
           for (u32 j = 0; j < full; ++j) v += s->pre[(size_t)j * s->maxR + r];
           s->cutoff[r] = v;
         }
-        sort_idx_desc(s->cutIdx, (int)R, s->cutoff); /* top-toKeep SET == nth_element's */
+        jpp_oracle_std_nth_element(s->cutIdx, (long)toKeep, (long)R, s->cutoff);
       }
       for (u32 pos = 0; pos < R; ++pos) {
         u32 t0i = s->cutIdx[pos];
@@ -755,63 +987,134 @@ static int score_sentence(const Ctx* c, Scratch* s, u32 sent) {
     const u32 eosBnd = nb - 1;
     const u32 eosNode = B->boundary_node_off[sv.boundary0 + eosBnd];
     const u32 eosE0 = B->boundary_end_off[sv.boundary0 + eosBnd];
-    /* memo of contexts keyed by (node, slot): linear list, paths are short */
-    u32 cap = 0;
-    for (u32 i = 0; i < eosG; ++i) cap += nb;
-    ElemRef* keys = (ElemRef*)malloc(sizeof(ElemRef) * (cap + 2));
-    float* ctxs = (float*)malloc(sizeof(float) * (size_t)(cap + 2) * H);
-    i32* ids = (i32*)malloc(sizeof(i32) * (cap + 2));
-    u32 nctx = 0;
-    /* BOS state (rnn_scorer_gbeam.cc:37-46): ctx = sigmoid(W^T * 0 + emb[0]) */
-    float* zeros = (float*)calloc(H, sizeof(float));
-    u32 bos1 = B->boundary_node_off[sv.boundary0 + 1];
-    keys[0].node = bos1; keys[0].slot = 0; ids[0] = 0;
-    rnn_new_context(rm, zeros, 0, ctxs);
-    nctx = 1;
+    /* ---- RnnIdResolver::resolveIdsAtGbeam + RnnIdContainer (rnn_id_resolver.cc:173-276) ----
+     * The prefix tree is restated literally, INCLUDING its collapse quirk: when
+     * a connection's (id,length)-history hash matches some published node of
+     * the same coordinate chain, the connection is attached to crdCache_'s
+     * entry `it->second` (the NEWEST published node with that coordinate,
+     * :224-231), not to the node whose hash matched. */
+    typedef struct { i32 id, idx, boundary, length, prev, nextInBnd; u64 hash; } RNode;
+    typedef struct { u32 node; u16 slot; u16 isEos; u32 g; i32 rnode; } RScore;
+    const u32 sentNode0 = B->boundary_node_off[sv.boundary0];
+    const u32 sentNodes = B->boundary_node_off[sv.boundary0 + nb] - sentNode0;
+    u32 rcap = eosG * (nb + 1) + 4;
+    RNode* rn = (RNode*)malloc(sizeof(RNode) * rcap);
+    RScore* rs = (RScore*)malloc(sizeof(RScore) * rcap);
+    i32* bndHead = (i32*)malloc(sizeof(i32) * nb);
+    i32* bndCnt = (i32*)calloc(nb, sizeof(i32));
+    i32* connNode = (i32*)malloc(sizeof(i32) * (size_t)sentNodes * c->beam); /* ptrCache_ */
+    i32 eosConn[64];
+    u32 nrn = 0, nrs = 0;
+    for (u32 i = 0; i < nb; ++i) bndHead[i] = -1;
+    for (size_t i = 0; i < (size_t)sentNodes * c->beam; ++i) connNode[i] = -1;
+    /* addBos (:311-329) */
+    rn[0] = (RNode){0, 0, 0, 0, -1, -1, 0};
+    rn[1] = (RNode){0, 0, 1, 0, 0, -1, 0xdeadbeef0000ULL};
+    nrn = 2;
+    bndHead[1] = 1; bndCnt[1] = 1;
+    const u32 bos1 = B->boundary_node_off[sv.boundary0 + 1];
+    connNode[(size_t)(bos1 - sentNode0) * c->beam + 0] = 1; /* ptrCache_[&bosBeam.ptr] = bos1 */
     ElemRef* chainp = (ElemRef*)malloc(sizeof(ElemRef) * (nb + 2));
+    u16* chainBnd = (u16*)malloc(sizeof(u16) * (nb + 2));
     for (u32 g = 0; g < eosG; ++g) {
-      /* walk back from the EOS connection's previous element to BOS */
+      /* addPrevChain: walk back until a connection already in ptrCache_ */
       u32 len = 0;
       u32 curNode = node_of(c, &sv, B->ends[eosE0 + (u16)(eosGbeam[g] >> 16)]);
       u32 curBnd = B->ends[eosE0 + (u16)(eosGbeam[g] >> 16)].boundary;
       u16 curSlot = (u16)eosGbeam[g];
-      while (curBnd >= 2) {
-        chainp[len].node = curNode; chainp[len].slot = curSlot; ++len;
+      i32 base;
+      for (;;) {
+        i32 known = connNode[(size_t)(curNode - sentNode0) * c->beam + curSlot];
+        if (known != -1) { base = known; break; }
+        chainp[len].node = curNode; chainp[len].slot = curSlot; chainBnd[len] = (u16)curBnd; ++len;
         const jpp_b200_beam_element* el = &beams[(size_t)curNode * c->beam + curSlot];
         jpp_b200_node_ptr pp = B->ends[B->boundary_end_off[sv.boundary0 + curBnd] + el->left];
         curSlot = el->prev_beam;
         curBnd = pp.boundary;
         curNode = node_of(c, &sv, pp);
       }
-      /* forward: contexts and scores */
-      u32 prevCtx = 0; /* BOS */
-      for (i32 k = (i32)len - 1; k >= 0; --k) {
-        ElemRef e = chainp[k];
-        u32 found = 0xFFFFFFFFu;
-        for (u32 q = 1; q < nctx; ++q) if (keys[q].node == e.node && keys[q].slot == e.slot) { found = q; break; }
-        i32 id = B->node_rnn_id[e.node];
-        if (found == 0xFFFFFFFFu) {
-          float sc;
-          if (id == rm->unk_id) {
-            i32 length = (i32)B->node_info[e.node].end - (i32)B->node_info[e.node].start;
-            sc = rm->unk_constant + rm->unk_length_penalty * (float)length; /* rnn_scorer_gbeam.cc:236-240 */
-          } else {
-            sc = rnn_score(rm, ctxs + (size_t)prevCtx * H, ids[prevCtx], id);
-          }
-          bscores[((size_t)e.node * c->beam + e.slot) * c->S + 1] = sc;
-          rnn_new_context(rm, ctxs + (size_t)prevCtx * H, id, ctxs + (size_t)nctx * H);
-          keys[nctx] = e; ids[nctx] = id;
-          found = nctx++;
-          if (c->stats) { __sync_fetch_and_add(&c->stats->rnn_nodes, 1); __sync_fetch_and_add(&c->stats->rnn_scores, 1); }
+      /* unwind from the deepest new connection to the EOS fake connection (k == -1) */
+      i32 first = base, prev = base;
+      i32 newTip = -1;      /* first of the not yet published new nodes (deepest) */
+      for (i32 k = (i32)len - 1; k >= -1; --k) {
+        i32 id, length; u32 cb;
+        if (k >= 0) {
+          id = B->node_rnn_id[chainp[k].node];
+          length = (i32)B->node_info[chainp[k].node].end - (i32)B->node_info[chainp[k].node].start;
+          cb = chainBnd[k];
+        } else {
+          id = 0; length = 0; cb = eosBnd; /* nodeCache_[{eos,0}] = {eos,0,0}, :306-308 */
         }
-        prevCtx = found;
+        u64 data = (u64)(u32)id | ((u64)(u16)length << 32);
+        u64 hv = (rn[prev].hash ^ data) * SEA_MULT;
+        hv = hv ^ (hv >> 32); /* FastHash1::mix, util/fast_hash.h:46-51 */
+        /* crdCache_.find(coord): newest published node of (boundary,length,id) */
+        i32 it = -1;
+        for (i32 q = bndHead[cb]; q != -1; q = rn[q].nextInBnd)
+          if (rn[q].length == length && rn[q].id == id) { it = q; break; }
+        int collapsed = 0;
+        if (it != -1) {
+          for (i32 q = it; q != -1; q = rn[q].nextInBnd) {
+            if (rn[q].hash == hv) { collapsed = 1; break; }
+          }
+        }
+        i32 mine;
+        if (collapsed) {
+          mine = it;
+          rs[nrs++] = (RScore){k >= 0 ? chainp[k].node : 0, k >= 0 ? chainp[k].slot : 0, (u16)(k < 0), g, mine};
+          first = mine;
+          newTip = -1;
+        } else {
+          mine = (i32)nrn;
+          rn[nrn++] = (RNode){id, -1, (i32)cb, length, prev, -1, hv};
+          if (newTip == -1) newTip = mine;
+        }
+        if (k >= 0) connNode[(size_t)(chainp[k].node - sentNode0) * c->beam + chainp[k].slot] = mine; else eosConn[g] = mine;
+        prev = mine;
       }
-      /* EOS connection score (id 0 = </s>); stored per gbeam element g */
-      s->sortScore[g] = rnn_score(rm, ctxs + (size_t)prevCtx * H, ids[prevCtx], 0);
+      /* addPath publish loop (:247-266): from the tip back to `first` */
+      {
+        i32 last = prev;
+        i32 k = -1;
+        while (last != first) {
+          u32 cb = (u32)rn[last].boundary;
+          rn[last].idx = bndCnt[cb];
+          rn[last].nextInBnd = bndHead[cb];
+          bndHead[cb] = last;
+          bndCnt[cb] += 1;
+          rs[nrs++] = (RScore){k >= 0 ? chainp[k].node : 0, k >= 0 ? chainp[k].slot : 0, (u16)(k < 0), g, last};
+          last = rn[last].prev;
+          ++k;
+        }
+      }
+    }
+    /* contexts in boundary order (rnn_scorer_gbeam.cc:142-156), BOS state (:37-46) */
+    float* ctxs = (float*)malloc(sizeof(float) * (size_t)nrn * H);
+    {
+      float* zeros = (float*)calloc(H, sizeof(float));
+      rnn_new_context(rm, zeros, 0, ctxs + (size_t)1 * H);
+      free(zeros);
+    }
+    for (u32 bb = 2; bb < eosBnd; ++bb) {
+      for (i32 q = bndHead[bb]; q != -1; q = rn[q].nextInBnd) {
+        rnn_new_context(rm, ctxs + (size_t)rn[q].prev * H, rn[q].id, ctxs + (size_t)q * H);
+        if (c->stats) __sync_fetch_and_add(&c->stats->rnn_nodes, 1);
+      }
+    }
+    /* scores (scoreBoundary + copyScoresToLattice, :226-267) */
+    for (u32 i = 0; i < nrs; ++i) {
+      const RNode* node = &rn[rs[i].rnode];
+      float sc;
+      if (node->id == rm->unk_id) {
+        sc = rm->unk_constant + rm->unk_length_penalty * (float)node->length;
+      } else {
+        sc = rnn_score(rm, ctxs + (size_t)node->prev * H, rn[node->prev].id, node->id);
+      }
+      if (rs[i].isEos) s->sortScore[rs[i].g] = sc;
+      else bscores[((size_t)rs[i].node * c->beam + rs[i].slot) * c->S + 1] = sc;
       if (c->stats) __sync_fetch_and_add(&c->stats->rnn_scores, 1);
     }
-    free(chainp);
-    free(keys); free(ctxs); free(ids); free(zeros);
+    free(chainp); free(chainBnd); free(rn); free(rs); free(bndHead); free(bndCnt); free(connNode); free(ctxs);
 
     /* adjustBeamScores (score_processor.cc:521-549) in boundary order */
     const float w0 = m->score_weights[0], w1 = m->score_weights[1];
@@ -852,12 +1155,11 @@ static int score_sentence(const Ctx* c, Scratch* s, u32 sent) {
     /* keep rnn scores aligned with the new order */
     float rnnS[64];
     for (u32 g = 0; g < eosG; ++g) rnnS[g] = s->sortScore[g];
-    for (u32 i = 0; i < eosG; ++i) s->idxbuf[i] = i;
-    sort_idx_desc(s->idxbuf, (int)eosG, full);
+    int elen = sort_for_beam(s->idxbuf, (int)eosG, full, maxBeam);
     jpp_b200_beam_element* row = &beams[(size_t)eosNode * c->beam];
     float* srow = &bscores[(size_t)eosNode * c->beam * c->S];
     int k = 0;
-    for (; k < (int)eosG && k < maxBeam; ++k) {
+    for (; k < elen && k < maxBeam; ++k) {
       u32 g = s->idxbuf[k];
       row[k].left = (u16)(gb2[g] >> 16);
       row[k].prev_beam = (u16)gb2[g];

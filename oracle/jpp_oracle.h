@@ -22,6 +22,12 @@ typedef struct jpp_oracle_stats {
 int jpp_oracle_score_batch(const jpp_b200_model* model, const jpp_b200_config* cfg, const jpp_b200_batch* batch,
                            jpp_b200_result* result, const float* weights, int num_threads, jpp_oracle_stats* stats);
 
+/* exact emulations of libstdc++ std::sort / std::nth_element and of jumanpp's
+ * util::partition over u32 index arrays, comp(a,b) := score[a] > score[b] */
+void jpp_oracle_std_sort(uint32_t* first, long n, const float* score);
+void jpp_oracle_std_nth_element(uint32_t* first, long nth, long n, const float* score);
+long jpp_oracle_ref_partition(uint32_t* first, long n, const float* score, long min_size, long max_size);
+
 float jpp_oracle_synth_weight(uint64_t seed, uint64_t i, float scale);
 void jpp_oracle_fill_weights(float* out, uint32_t log2_size, uint64_t seed, float scale);
 

@@ -168,6 +168,7 @@ struct RefEnv {
   util::FullyMappedFile dicFile;
   float* weights = nullptr;
   size_t numWeights = 0;
+  bool explicitWeights = false;
   std::unique_ptr<HashedFeaturePerceptron> perceptron;
   RnnScorerGbeamFactory rnnFactory;
   bool hasRnn = false;
@@ -213,15 +214,24 @@ struct RefEnv {
     uint64_t wseed = (uint64_t)a.num("wseed", 1);
     float wscale = (float)a.real("wscale", 0.5);
     numWeights = size_t{1} << log2w;
-    weights = static_cast<float*>(aligned_alloc(64, numWeights * sizeof(float)));
-    unsigned nt = std::max(1u, std::thread::hardware_concurrency());
-    std::vector<std::thread> ts;
-    for (unsigned t = 0; t < nt; ++t) {
-      ts.emplace_back([=] {
-        for (size_t i = t; i < numWeights; i += nt) weights[i] = synth_weight(wseed, i, wscale);
-      });
+    weights = static_cast<float*>(aligned_alloc(64, std::max<size_t>(64, numWeights * sizeof(float))));
+    if (a.has("weights_file")) {
+      // explicit table (raw little-endian float32, exactly 2^log2w values)
+      std::ifstream wf(a.str("weights_file"), std::ios::binary);
+      if (!wf) die("cannot open weights_file");
+      wf.read(reinterpret_cast<char*>(weights), numWeights * sizeof(float));
+      if ((size_t)wf.gcount() != numWeights * sizeof(float)) die("weights_file too short");
+      explicitWeights = true;
+    } else {
+      unsigned nt = std::max(1u, std::thread::hardware_concurrency());
+      std::vector<std::thread> ts;
+      for (unsigned t = 0; t < nt; ++t) {
+        ts.emplace_back([=] {
+          for (size_t i = t; i < numWeights; i += nt) weights[i] = synth_weight(wseed, i, wscale);
+        });
+      }
+      for (auto& t : ts) t.join();
     }
-    for (auto& t : ts) t.join();
     perceptron.reset(new HashedFeaturePerceptron{util::ArraySlice<float>{weights, numWeights}});
     sdef.feature = perceptron.get();
     sdef.scoreWeights.push_back((float)a.real("perc_weight", 1.0));
@@ -483,6 +493,11 @@ int cmdStage(const Args& a) {
                                 env.sdef.scoreWeights.size() > 1 ? env.sdef.scoreWeights[1] : 0.0f};
         w.add("cfg", I32, cfg);
         w.add("fcfg", F32, fcfg);
+        std::vector<float> wcopy;
+        if (env.explicitWeights) {
+          wcopy.assign(env.weights, env.weights + env.numWeights);
+          w.add("weights", F32, wcopy);
+        }
         sa.addTo(w);
         std::vector<float> rnnf;
         std::vector<int32_t> rnni;
