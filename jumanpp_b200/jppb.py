@@ -22,7 +22,19 @@ MAGIC = b"JPPB0001"
 
 def load(path: str | Path, mmap: bool = False) -> dict[str, np.ndarray]:
     path = str(path)
+    if path.endswith(".gz"):
+        import gzip
+        with gzip.open(path, "rb") as f:
+            return loads(f.read())
     raw = np.memmap(path, dtype=np.uint8, mode="r") if mmap else np.fromfile(path, dtype=np.uint8)
+    return _parse(raw, path)
+
+
+def loads(data: bytes) -> dict[str, np.ndarray]:
+    return _parse(np.frombuffer(data, dtype=np.uint8).copy(), "<bytes>")
+
+
+def _parse(raw: np.ndarray, path: str) -> dict[str, np.ndarray]:
     if bytes(raw[:8]) != MAGIC:
         raise ValueError(f"{path}: not a JPPB0001 file")
     pos = 8

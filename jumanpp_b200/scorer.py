@@ -158,7 +158,6 @@ def pinned_copy(a: np.ndarray) -> np.ndarray:
             t = torch.empty(a.nbytes, dtype=torch.uint8, pin_memory=True)
             out = t.numpy().view(a.dtype).reshape(a.shape)
             out[...] = a
-            out._pin_keep = t  # type: ignore[attr-defined]
             return out
     except Exception:
         pass

@@ -1,0 +1,57 @@
+"""The device code of jumanpp_b200/csrc (the source the GPU runs) compiled as
+plain C++ with the lanes of a warp run one after another (tests/emul, test
+only) must reproduce the reference's golden vectors bit for bit.  This checks
+kernel LOGIC without a GPU; the CUDA build itself is checked by the gpu tests."""
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import pytest
+
+import oracle_lib
+import parity
+from conftest import LINEAR_GBEAM, RNN, load_golden
+from jumanpp_b200 import abi
+
+ROOT = Path(__file__).resolve().parent.parent
+EMUL = ROOT / "tests" / "emul"
+
+
+@pytest.fixture(scope="module")
+def emul():
+    src = EMUL / "jpp_b200_emul.cpp"
+    lib = EMUL / "libjpp_b200_emul.so"
+    deps = [src] + list((ROOT / "jumanpp_b200" / "csrc").glob("*.h")) + [ROOT / "include" / "jpp_b200.h"]
+    if not lib.exists() or lib.stat().st_mtime < max(p.stat().st_mtime for p in deps):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-march=x86-64-v2", "-fPIC", "-shared", "-w",
+                        f"-I{ROOT / 'include'}", f"-I{ROOT / 'jumanpp_b200' / 'csrc'}", str(src), "-o", str(lib)],
+                       check=True)
+    return C.CDLL(str(lib))
+
+
+def run_emul(emul, model, cfg, batch):
+    res = abi.ScoreResult.allocate(batch.num_nodes, cfg.beam_size, model.num_scorers, model.num_stored_patterns)
+    w = oracle_lib.weights_for(model)
+    ms, cs, bs, rs = model.as_struct(), cfg.as_struct(), batch.as_struct(), res.as_struct()
+    err = C.create_string_buffer(512)
+    rc = emul.jpp_b200_emul_score_batch(C.byref(ms), C.byref(cs), C.byref(bs), C.byref(rs), C.c_void_p(w.ctypes.data),
+                                        err, 512)
+    assert rc == 0, err.value
+    return res
+
+
+@pytest.mark.parametrize("name", LINEAR_GBEAM)
+def test_linear_kernels(emul, name):
+    d, model, cfg, batch = load_golden(name)
+    res = run_emul(emul, model, cfg, batch)
+    rep = parity.compare_with_expected(d, batch, res, rnn=False)
+    assert rep == {"patterns": 0, "beam_links": 0, "beam_totals": 0, "conn_scores": 0}, rep
+
+
+@pytest.mark.parametrize("name", RNN)
+def test_rnn_kernels(emul, name, rnn_dir):
+    d, model, cfg, batch = load_golden(name, rnn_dir)
+    res = run_emul(emul, model, cfg, batch)
+    rep = parity.compare_with_expected(d, batch, res, rnn=True)
+    rep.pop("final_path_elements")
+    assert all(v == 0 for v in rep.values()), rep
