@@ -1,0 +1,391 @@
+#!/usr/bin/env python3
+"""bench.py -- sentences/sec of the Juman++ lattice-scoring hot path.
+
+    python bench.py --gpus N --steps K --warmup W            (product arm, CUDA)
+    python bench.py --impl reference --gpus N --steps K ...   (reference CPU arm)
+
+A *step* is one pass of the hot path (AnalyzerImpl::computeScores for every
+sentence: T0 features, global-beam scoring, beams, RNN rescoring, re-rank) over
+the whole synthetic workload.  The workload is BASELINE.json configs[1]:
+Jumandic spec, beam=5 (global beam 6, right check 1, right beam 5), RNN on,
+100 000 synthetic sentences of 8-128 codepoints; per rank under torchrun (weak
+scaling: every rank scores its own 100 000 sentences).
+
+Untimed preparation (cached under --cache): the synthetic dictionary / corpus /
+RNN model are generated from seeds, and the lattices are BUILT ON THE HOST by
+the reference's own lattice builder (oracle/_ref/jpp_ref_harness stage
+expected=0 -- resetForInput/prepareNodeSeeds/buildLattice only; host lattice
+construction is out of scope and stays the reference's job, SURVEY.md section 2
+rows 12-13).  No scoring of the product arm goes through oracle/: the harness
+is used again only in the cpu_baseline leg (timing the reference's
+computeScores on a bounded sample, and as the 1-best checker).
+
+Printed JSON (rank 0): see README "bench contract".  `value` = device-resident
+throughput, `e2e` = the same work through jpp_b200_score_batch with pinned host
+buffers (H2D of the staged lattices + D2H of the beams inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+from jumanpp_b200 import abi, jppb, synth  # noqa: E402
+
+HARNESS = ROOT / "oracle" / "_ref" / "jpp_ref_harness"
+
+WORKLOADS = {
+    # name: scoring flags, rnn layer size, RNN on
+    "jumandic_beam5": dict(beam=5, gbeam=6, rcheck=1, rbeam=5, rnn=True, H=128,
+                           desc="BASELINE configs[1]: Jumandic beam=5 (gbeam 6, right-check 1, right-beam 5) + RNN H=128"),
+    "jumandic_beam20": dict(beam=20, gbeam=20, rcheck=1, rbeam=5, rnn=True, H=256,
+                            desc="BASELINE configs[2]: Jumandic beam=20 gbeam=20 wide beam + RNN H=256"),
+    "jumandic_beam5_linear": dict(beam=5, gbeam=6, rcheck=1, rbeam=5, rnn=False, H=0,
+                                  desc="BASELINE configs[3]: Jumandic beam=5, RNN disabled (linear features only)"),
+}
+
+
+def log(*a):
+    print("[bench]", *a, file=sys.stderr, flush=True)
+
+
+# ------------------------------------------------------------------ workload --
+def prepare_workload(args, rank: int) -> dict:
+    wl = WORKLOADS[args.workload]
+    cache = Path(args.cache)
+    tag = f"{args.workload}_d{args.dict_rows}_n{args.sentences}_l{args.min_len}-{args.max_len}_s{args.seed + rank}_w{args.log2w}"
+    d = cache / tag
+    d.mkdir(parents=True, exist_ok=True)
+    dic, corpus, rnn = d / "dict.csv", d / "corpus.txt", d / "rnn"
+    done = d / "staged.done"
+    info = dict(dir=d, dict=dic, corpus=corpus, rnn=rnn if wl["rnn"] else None, wl=wl)
+    if done.exists():
+        return info
+    if not HARNESS.exists():
+        raise SystemExit(f"{HARNESS} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` where "
+                         "/root/reference is mounted (the host lattice builder is the reference's)")
+    t0 = time.time()
+    surfaces = synth.write_dictionary(dic, args.dict_rows, 20260923)
+    synth.write_corpus(corpus, args.sentences, args.min_len, args.max_len, args.seed + rank, surfaces)
+    if wl["rnn"]:
+        words = synth.rnn_vocabulary(dic, 50000)
+        synth.write_rnn_model(rnn, words, wl["H"], 3, 1 << 22, 9.0, 2)
+    log(f"rank {rank}: synthetic dictionary/corpus/rnn in {time.time() - t0:.1f}s")
+    t0 = time.time()
+    cmd = [str(HARNESS), "stage", f"dict={dic}", f"corpus={corpus}", f"out={d / 'staged.jppb'}", "expected=0",
+           f"chunk={args.stage_chunk}", f"threads={max(1, (os.cpu_count() or 8) // max(1, args.gpus))}",
+           f"log2w=10", *harness_model_args(args, wl, rnn, log2w=10)]
+    subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    log(f"rank {rank}: lattices built by the reference host pipeline in {time.time() - t0:.1f}s")
+    done.write_text("ok")
+    return info
+
+
+def harness_model_args(args, wl, rnn, log2w=None) -> list[str]:
+    a = [f"beam={wl['beam']}", f"gbeam={wl['gbeam']}", f"rcheck={wl['rcheck']}", f"rbeam={wl['rbeam']}",
+         f"wseed={args.wseed}", "wscale=0.5"]
+    if log2w is None:
+        a.append(f"log2w={args.log2w}")
+    if wl["rnn"]:
+        a.append(f"rnn={rnn}")
+    return a
+
+
+def load_staged(info, args, pin) -> tuple[abi.ModelSpec, abi.ScoringConfig, abi.StagedBatch]:
+    files = sorted(info["dir"].glob("staged.jppb*"))
+    files = [f for f in files if not f.name.endswith(".done")]
+    parts, first = [], None
+    for f in files:
+        dd = jppb.load(f)
+        first = first or dd
+        parts.append(abi.StagedBatch.from_jppb(dd))
+    model = abi.ModelSpec.from_jppb(first, str(info["rnn"]) if info["rnn"] else None)
+    model.log2_weights, model.weight_seed, model.weight_scale = args.log2w, args.wseed, 0.5
+    cfg = abi.ScoringConfig.from_jppb(first)
+    batch = abi.StagedBatch.concat(parts, pin=pin)
+    return model, cfg, batch
+
+
+# -------------------------------------------------------------------- clocks --
+class ClockSampler:
+    def __init__(self, device: int):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for i, n in enumerate(names):
+                if len(r) > 3 + i and r[3 + i].lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------- reference arm --
+def run_harness_bench(info, args, sample: int, threads: int, steps: int = 1, warmup: int = 0) -> dict:
+    cmd = [str(HARNESS), "bench", f"dict={info['dict']}", f"corpus={info['corpus']}", f"max_sent={sample}",
+           f"threads={threads}", f"steps={steps}", f"warmup={warmup}", *harness_model_args(args, info["wl"], info["rnn"])]
+    r = subprocess.run(cmd, check=True, capture_output=True, text=True)
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
+def reference_arm(args, rank: int, world: int) -> None:
+    if rank != 0:
+        return
+    info = prepare_workload(args, 0)
+    cores = os.cpu_count() or 1
+    sample = min(args.sentences, args.cpu_sample_per_core * cores)
+    # one process: model loaded once, W untimed + K timed passes over the sample
+    o = run_harness_bench(info, args, sample, cores, steps=args.steps, warmup=args.warmup)
+    outs, times = [o], [o["score_path_s_max_thread"]]
+    n = o["sentences"]
+    value = o["score_path_sentences_per_s"]
+    line = {
+        "impl": "reference", "metric": "sentences/sec Jumandic beam=5 (lattice-scoring path)", "value": value,
+        "unit": "sentences/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1000.0 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64 hash / f32 sums", "data": "synthetic",
+        "config": workload_config(args, info["wl"]),
+        "cpu_baseline": {"value": value, "unit": "sentences/s", "cores": cores, "kind": "reference",
+                         "sample": f"first {n} sentences of the corpus per step, {cores} threads each owning an "
+                                   "AnalyzerImpl; timed region = AnalyzerImpl::computeScores only (lattice build excluded); "
+                                   f"whole Analyzer::analyze runs at {outs[-1]['analyze_sentences_per_s']:.0f} sentences/s"},
+        "e2e": {"value": value, "unit": "sentences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, wl) -> dict:
+    return {"workload": wl["desc"], "sentences_per_gpu": args.sentences, "length_codepoints": [args.min_len, args.max_len],
+            "dictionary_rows": args.dict_rows, "weights": f"float[2^{args.log2w}] counter-based synthetic",
+            "beam": wl["beam"], "global_beam": wl["gbeam"], "right_check": wl["rcheck"], "right_beam": wl["rbeam"],
+            "rnn_layer": wl["H"], "l2_policy": "inputs of one step (several GB of staged lattices + 256 MiB table) exceed the 126 MB L2"}
+
+
+# --------------------------------------------------------------- product arm --
+def product_arm(args, rank: int, world: int, local_rank: int) -> None:
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the scored path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from jumanpp_b200.scorer import LatticeScorer, pinned_copy
+
+    info = prepare_workload(args, rank)
+    t0 = time.time()
+    model, cfg, batch = load_staged(info, args, pin=pinned_copy)
+    log(f"rank {rank}: staged batch in pinned memory: {batch.num_sentences} sentences, {batch.num_nodes} nodes, "
+        f"{batch.num_boundaries} boundaries ({time.time() - t0:.1f}s)")
+    scorer = LatticeScorer(model, cfg, device=local_rank)
+    res = scorer.allocate_result(batch)
+    res.node_beam = pinned_copy(res.node_beam)
+    h2d = sum(a.nbytes for a in (batch.sent_boundary_off, batch.sent_codepoint_off, batch.boundary_node_off,
+                                 batch.boundary_end_off, batch.node_info, batch.node_entry, batch.ends, batch.codepoints)
+              ) + sum(a.nbytes for a in (batch.node_placeholders, batch.node_rnn_id) if a is not None)
+    d2h = res.node_beam.nbytes
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput (`value`)
+    scorer.upload(batch)
+    for _ in range(args.warmup):
+        scorer.score_resident()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    t0 = time.perf_counter()
+    kms = []
+    for _ in range(args.steps):
+        scorer.score_resident()          # synchronises its own stream (CUDA events inside)
+        kms.append(scorer.counters()["kernel_ms"])
+    torch.cuda.synchronize()
+    dt_res = time.perf_counter() - t0
+    clocks = sampler.stop()
+    cnt = scorer.counters()
+    # device-side time of the step = events around all kernels of score_resident
+    dev_ms = [k["score_total"] for k in kms]
+    t_res = torch.tensor([sum(dev_ms) / 1000.0, dt_res], dtype=torch.float64, device="cuda")
+    # ---- end to end through the C ABI with host buffers (`e2e`)
+    for _ in range(min(2, args.warmup)):
+        scorer.upload(batch); scorer.score_resident(); scorer.download(res, beams_only=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        scorer.upload(batch)
+        scorer.score_resident()
+        scorer.download(res, beams_only=True)
+    torch.cuda.synchronize()
+    dt_e2e = time.perf_counter() - t0
+    t_e2e = torch.tensor([dt_e2e], dtype=torch.float64, device="cuda")
+    counts = torch.tensor([batch.num_sentences, cnt["gathers"], cnt["nodes"]], dtype=torch.float64, device="cuda")
+    if dist:
+        dist.all_reduce(t_res, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM)   # NCCL: gather the per-rank counters
+    total_sent = float(counts[0].item())
+    dev_s, wall_s, e2e_s = float(t_res[0].item()), float(t_res[1].item()), float(t_e2e[0].item())
+    value = total_sent * args.steps / dev_s
+    e2e_value = total_sent * args.steps / e2e_s
+
+    if rank == 0:
+        walk_ms = statistics.mean(k["beam_walk"] for k in kms)
+        peaks = {}
+        try:
+            peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        achieved = cnt["walk_bytes"] / (walk_ms / 1000.0) / 1e9
+        traffic = None
+        tf = ROOT / "profiles" / "r1_walk_traffic.json"
+        if tf.exists():
+            try:
+                t = json.loads(tf.read_text())
+                if t.get("workload") == args.workload and t.get("sentences") == args.sentences:
+                    traffic = t["dram_bytes_per_launch"]
+            except Exception:
+                pass
+        line = {
+            "metric": "sentences/sec Jumandic beam=5 (lattice-scoring path)", "value": value, "unit": "sentences/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dev_s / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 hash / f32 sums",
+            "data": "synthetic", "config": workload_config(args, info["wl"]),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "sentences/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": 1000.0 * e2e_s / args.steps},
+            "gpu_launches": int(cnt["launches"]) * args.steps,
+            "wall_ms_per_step_resident": 1000.0 * wall_s / args.steps,
+            "stage_ms": {k: statistics.mean(x[k] for x in kms) for k in kms[0]},
+            "roofline": {"bound": "hbm", "kernel": "k_walk (beam walk: n-gram hash + weight gather + beams)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
+                         "algorithmic_bytes_per_launch": int(cnt["walk_bytes"]), "kernel_ms": walk_ms,
+                         "gathers_per_launch": int(cnt["walk_gathers"]), "traffic": traffic},
+            "work": {"sentences": int(total_sent), "nodes": int(counts[2].item()), "gathers": int(counts[1].item()),
+                     "rnn_nodes": int(cnt["rnn_nodes"])},
+        }
+        if not args.no_cpu_baseline:
+            line.update(cpu_baseline_leg(args, info, model, cfg, batch, scorer, res))
+        print(json.dumps(line), flush=True)
+    scorer.close()
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_baseline_leg(args, info, model, cfg, batch, scorer, res) -> dict:
+    """Rank 0 only: (1) time the reference's computeScores on the host cores over a
+    bounded sample; (2) check the GPU beams of a bounded sample against the
+    reference's own post-state (1-best + every beam element)."""
+    out = {}
+    cores = os.cpu_count() or 1
+    sample = min(args.sentences, args.cpu_sample_per_core * cores)
+    try:
+        o = run_harness_bench(info, args, sample, cores)
+        out["cpu_baseline"] = {
+            "value": o["score_path_sentences_per_s"], "unit": "sentences/s", "cores": cores, "kind": "reference",
+            "sample": f"first {o['sentences']} sentences, {cores} threads x AnalyzerImpl over one CoreHolder, "
+                      f"computeScores only ({o['score_path_s_max_thread']:.2f}s); Analyzer::analyze incl. lattice build: "
+                      f"{o['analyze_sentences_per_s']:.0f} sentences/s"}
+        o1 = run_harness_bench(info, args, min(sample, args.cpu_sample_per_core), 1)
+        out["cpu_baseline"]["single_thread_value"] = o1["score_path_sentences_per_s"]
+    except Exception as e:  # pragma: no cover
+        out["cpu_baseline"] = {"error": repr(e)}
+    # parity sample: reference post-state for the first sentences of the same corpus
+    try:
+        n = min(args.parity_sample, batch.num_sentences)
+        exp_file = info["dir"] / f"parity_{n}.jppb"
+        if not exp_file.exists():
+            cmd = [str(HARNESS), "stage", f"dict={info['dict']}", f"corpus={info['corpus']}", f"out={exp_file}",
+                   "expected=1", f"max_sent={n}", *harness_model_args(args, info["wl"], info["rnn"])]
+            subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        d = jppb.load(exp_file)
+        sub = batch.select(0, n)
+        got = scorer.compute_scores(sub)
+        exp_beam = np.zeros(got.node_beam.shape, abi.BEAM_EL_DT)
+        exp_beam["left"], exp_beam["prev_beam"] = d["exp_beam_lp"][:, :, 0], d["exp_beam_lp"][:, :, 1]
+        exp_beam["total_score"] = d["exp_beam_total"]
+        exp_res = abi.ScoreResult(exp_beam, d["exp_beam_scores"], d["exp_patterns"], got.node_t0_score)
+        pg, pe = abi.best_paths(sub, got), abi.best_paths(sub, exp_res)
+        mism = sum(1 for a, b in zip(pg, pe) if a != b)
+        links = int(((exp_beam["left"] != got.node_beam["left"]) | (exp_beam["prev_beam"] != got.node_beam["prev_beam"])).sum())
+        out["parity"] = {"checked_sentences": n, "onebest_mismatches": mism, "beam_link_mismatches": links,
+                         "pattern_mismatches": int((d["exp_patterns"] != got.node_patterns).sum()),
+                         "checker": "reference post-state (oracle/_ref) on the same lattices"}
+    except Exception as e:  # pragma: no cover
+        out["parity"] = {"error": repr(e)}
+    return out
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="jumandic_beam5", choices=sorted(WORKLOADS))
+    ap.add_argument("--sentences", type=int, default=100_000)
+    ap.add_argument("--min-len", type=int, default=8)
+    ap.add_argument("--max-len", type=int, default=128)
+    ap.add_argument("--dict-rows", type=int, default=200_000)
+    ap.add_argument("--log2w", type=int, default=26)
+    ap.add_argument("--wseed", type=int, default=1)
+    ap.add_argument("--seed", type=int, default=2)
+    ap.add_argument("--stage-chunk", type=int, default=2048)
+    ap.add_argument("--cache", default=os.environ.get("JPP_B200_CACHE", "/tmp/jpp_b200_cache"))
+    ap.add_argument("--cpu-sample-per-core", type=int, default=1500)
+    ap.add_argument("--parity-sample", type=int, default=2000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.warmup < 3 and args.impl == "b200":
+        log("warning: fewer than 3 warm-up steps")
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+    else:
+        product_arm(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

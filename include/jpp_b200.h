@@ -250,7 +250,12 @@ typedef struct jpp_b200_counters {
   uint64_t algorithmic_bytes; /* A of BASELINE.md "Roofline accounting"           */
   uint64_t rnn_nodes;      /* prefix-tree contexts computed (2*H*H flop each)   */
   uint64_t rnn_scores;
-  float kernel_ms[8];      /* per stage, CUDA events on the scoring stream       */
+  uint64_t walk_gathers;   /* table reads of the beam-walk kernel alone         */
+  uint64_t walk_bytes;     /* algorithmic bytes of the beam-walk kernel alone   */
+  uint64_t launches;       /* kernels launched by the last score call           */
+  float kernel_ms[8];      /* per stage, CUDA events on the scoring stream:
+                              0 T0, 1 beam walk, 2 rnn tree, 3 rnn contexts, 4 rnn
+                              scores, 5 re-rank, 6 upload (H2D + index), 7 all scoring */
 } jpp_b200_counters;
 
 typedef struct jpp_b200_handle jpp_b200_handle;

@@ -84,7 +84,8 @@ class Result(C.Structure):
 class Counters(C.Structure):
     _fields_ = [("sentences", C.c_uint64), ("boundaries", C.c_uint64), ("nodes", C.c_uint64),
                 ("gathers", C.c_uint64), ("algorithmic_bytes", C.c_uint64),
-                ("rnn_nodes", C.c_uint64), ("rnn_scores", C.c_uint64), ("kernel_ms", C.c_float * 8)]
+                ("rnn_nodes", C.c_uint64), ("rnn_scores", C.c_uint64), ("walk_gathers", C.c_uint64),
+                ("walk_bytes", C.c_uint64), ("launches", C.c_uint64), ("kernel_ms", C.c_float * 8)]
 
 
 NODE_INFO_DT = np.dtype([("entry_ptr", "<i4"), ("start", "<u2"), ("end", "<u2")])
@@ -291,6 +292,30 @@ class StagedBatch:
         b.ends = _ptr(self.ends)
         b.codepoints = _ptr(self.codepoints)
         return b
+
+    @staticmethod
+    def concat(parts: list["StagedBatch"], pin=None) -> "StagedBatch":
+        """Concatenate batches (offsets rebased). `pin(array)` may copy into pinned memory."""
+        pin = pin or (lambda a: a)
+
+        def offs(get, base_of):
+            out = [np.zeros(1, np.uint32)]
+            base = 0
+            for p in parts:
+                o = get(p)
+                out.append((o[1:].astype(np.uint64) + base).astype(np.uint32))
+                base += int(o[-1])
+            return np.concatenate(out)
+
+        def cat(get):
+            arrs = [get(p) for p in parts]
+            return None if arrs[0] is None else pin(np.concatenate(arrs))
+
+        return StagedBatch(
+            pin(offs(lambda p: p.sent_boundary_off, None)), pin(offs(lambda p: p.sent_codepoint_off, None)),
+            pin(offs(lambda p: p.boundary_node_off, None)), pin(offs(lambda p: p.boundary_end_off, None)),
+            cat(lambda p: p.node_info), cat(lambda p: p.node_entry), cat(lambda p: p.node_placeholders),
+            cat(lambda p: p.node_rnn_id), cat(lambda p: p.ends), cat(lambda p: p.codepoints))
 
     def select(self, lo: int, hi: int) -> "StagedBatch":
         """Sentences [lo, hi) as an independent batch (offsets rebased)."""

@@ -613,11 +613,18 @@ jpp_b200_status jpp_b200_score_resident(jpp_b200_handle* h) {
   CU_CHECK(h, cudaMemcpy(dc, bf[jpp_b200_handle::B_COUNTERS].p, 64, cudaMemcpyDeviceToHost));
   jpp_b200_counters& c = h->counters;
   c.sentences = NS; c.boundaries = NB; c.nodes = NN;
-  c.gathers = dc[0] + (unsigned long long)NN * h->hm.ft.nUni;
+  // T0 runs on every node except the two BOS nodes of each sentence
+  const unsigned long long t0Nodes = (unsigned long long)NN - 2ull * NS;
+  c.gathers = dc[0] + t0Nodes * h->hm.ft.nUni;
+  c.walk_gathers = dc[0];
+  c.walk_bytes = 4ull * dc[0] + dc[1];
+  c.launches = 2 + (h->hasRnn ? (12ull + h->maxNb) : 0ull);
   // BASELINE.md roofline accounting: 4 B per gather + streaming terms
   const u32 B = (u32)h->cfg.beam, SP = h->hm.ft.nStored;
-  c.algorithmic_bytes = 4ull * c.gathers + (unsigned long long)NN * (h->hm.ft.entrySize * 4 + 8 + 4 * h->hm.ft.nPlaceholders) +
-                        8ull * SP * NN * 2 + 8ull * B * NN + 4ull * bv.totalEnds;
+  // T0 kernel: entry + NodeInfo + placeholders in, pattern row + score out; walk kernel: see walk_sentence
+  c.algorithmic_bytes = c.walk_bytes + 4ull * t0Nodes * h->hm.ft.nUni +
+                        (unsigned long long)NN * (h->hm.ft.entrySize * 4 + 8 + 4 * h->hm.ft.nPlaceholders + 8ull * SP + 4);
+  (void)B;
   float ms = 0;
   for (int i = 0; i < 8; ++i) c.kernel_ms[i] = 0;
   cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]); c.kernel_ms[0] = ms;  // T0

@@ -690,7 +690,7 @@ JPP_HD void walk_sentence(const FeatTables& ft, const BatchView& bv, const Score
   const u32 SP = ft.nStored;
   const u32 nB = ft.nBi, nT = ft.nTri, mask = ft.mask;
   const u32 GMAX = (u32)cfg.gbeam;
-  unsigned long long gathers = 0;
+  unsigned long long gathers = 0, streamBytes = 0;
 
   // BOS beams (analyzer_impl.cc:185-192)
   JPP_LANES
@@ -788,6 +788,10 @@ JPP_HD void walk_sentence(const FeatTables& ft, const BatchView& bv, const Score
     }
     JPP_SYNC();
     U = sm.misc[1];
+    // algorithmic streaming bytes of this boundary (DESIGN.md "roofline accounting"):
+    // left beams read, pattern rows of right / unique-t1 / t2 nodes, ends, beams + scores written
+    streamBytes += 8ull * L * B + 8ull * SP * ((unsigned long long)R + U + G) + 4ull * L +
+                   (8ull + 4ull * cfg.S) * R * B;
     JPP_LANES
     for (u32 i = (u32)lane; i < U * SP; i += 32) sm.t1pat[i] = bv.patterns[(size_t)sm.t1node[i / SP] * SP + i % SP];
     for (u32 i = (u32)lane; i < G * SP; i += 32) sm.t2pat[i] = bv.patterns[(size_t)sm.gbT2node[i / SP] * SP + i % SP];
@@ -984,8 +988,10 @@ JPP_HD void walk_sentence(const FeatTables& ft, const BatchView& bv, const Score
   if (JPP_LANE0 && bv.counters) {
 #if defined(__CUDA_ARCH__)
     atomicAdd(bv.counters + 0, gathers);
+    atomicAdd(bv.counters + 1, streamBytes);
 #else
     bv.counters[0] += gathers;
+    bv.counters[1] += streamBytes;
 #endif
   }
 }

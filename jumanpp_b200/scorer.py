@@ -134,6 +134,7 @@ class LatticeScorer:
         names = ["t0", "beam_walk", "rnn_tree", "rnn_contexts", "rnn_scores", "rerank", "upload", "score_total"]
         return {"sentences": c.sentences, "boundaries": c.boundaries, "nodes": c.nodes, "gathers": c.gathers,
                 "algorithmic_bytes": c.algorithmic_bytes, "rnn_nodes": c.rnn_nodes,
+                "walk_gathers": c.walk_gathers, "walk_bytes": c.walk_bytes, "launches": c.launches,
                 "kernel_ms": {n: float(c.kernel_ms[i]) for i, n in enumerate(names)}}
 
     def close(self) -> None:

@@ -556,18 +556,23 @@ int cmdBench(const Args& a) {
   env.init(a);
   auto lines = readLines(a.str("corpus"), a.num("max_sent", 0));
   unsigned nt = (unsigned)std::max<long>(1, a.num("threads", 1));
-  int repeat = (int)a.num("repeat", 1);
-  std::vector<double> scoreSec(nt, 0), totalSec(nt, 0);
-  std::vector<long> done(nt, 0);
-  std::vector<double> checksum(nt, 0);
+  int warmup = (int)a.num("warmup", 0);
+  int steps = (int)std::max<long>(1, a.num("steps", a.num("repeat", 1)));
   using clk = std::chrono::steady_clock;
-  auto wall0 = clk::now();
-  std::vector<std::thread> ts;
-  for (unsigned t = 0; t < nt; ++t) {
-    ts.emplace_back([&, t] {
-      auto ana = env.makeAnalyzer();
-      size_t lo = lines.size() * t / nt, hi = lines.size() * (t + 1) / nt;
-      for (int r = 0; r < repeat; ++r) {
+  std::vector<std::unique_ptr<AnalyzerImpl>> anas;
+  for (unsigned t = 0; t < nt; ++t) anas.push_back(env.makeAnalyzer());
+  std::vector<double> stepScore, stepTotal, stepWall;
+  long n = 0;
+  double cs = 0;
+  for (int pass = 0; pass < warmup + steps; ++pass) {
+    std::vector<double> scoreSec(nt, 0), totalSec(nt, 0), checksum(nt, 0);
+    std::vector<long> done(nt, 0);
+    auto wall0 = clk::now();
+    std::vector<std::thread> ts;
+    for (unsigned t = 0; t < nt; ++t) {
+      ts.emplace_back([&, t] {
+        auto* ana = anas[t].get();
+        size_t lo = lines.size() * t / nt, hi = lines.size() * (t + 1) / nt;
         for (size_t i = lo; i < hi; ++i) {
           auto t0 = clk::now();
           Status s = ana->resetForInput(lines[i]);
@@ -585,24 +590,33 @@ int cmdBench(const Args& a) {
           auto& top = lat->boundary(lat->createdBoundaryCount() - 1)->starts()->beamData().row(0).at(0);
           checksum[t] += top.totalScore;
         }
-      }
-    });
+      });
+    }
+    for (auto& t : ts) t.join();
+    double wall = std::chrono::duration<double>(clk::now() - wall0).count();
+    if (pass < warmup) continue;
+    double maxScore = 0, maxTotal = 0;
+    n = 0;
+    cs = 0;
+    for (unsigned t = 0; t < nt; ++t) {
+      n += done[t];
+      maxScore = std::max(maxScore, scoreSec[t]);
+      maxTotal = std::max(maxTotal, totalSec[t]);
+      cs += checksum[t];
+    }
+    stepScore.push_back(maxScore);
+    stepTotal.push_back(maxTotal);
+    stepWall.push_back(wall);
   }
-  for (auto& t : ts) t.join();
-  double wall = std::chrono::duration<double>(clk::now() - wall0).count();
-  long n = 0;
-  double maxScore = 0, maxTotal = 0, cs = 0;
-  for (unsigned t = 0; t < nt; ++t) {
-    n += done[t];
-    maxScore = std::max(maxScore, scoreSec[t]);
-    maxTotal = std::max(maxTotal, totalSec[t]);
-    cs += checksum[t];
-  }
+  double sumScore = 0, sumTotal = 0, sumWall = 0;
+  for (size_t i = 0; i < stepScore.size(); ++i) { sumScore += stepScore[i]; sumTotal += stepTotal[i]; sumWall += stepWall[i]; }
+  double k = (double)stepScore.size();
   std::printf(
-      "{\"sentences\": %ld, \"threads\": %u, \"wall_s\": %.6f, \"score_path_s_max_thread\": %.6f, "
+      "{\"sentences\": %ld, \"threads\": %u, \"steps\": %d, \"wall_s\": %.6f, \"score_path_s_max_thread\": %.6f, "
       "\"analyze_s_max_thread\": %.6f, \"score_path_sentences_per_s\": %.3f, "
       "\"analyze_sentences_per_s\": %.3f, \"checksum\": %.6f}\n",
-      n, nt, wall, maxScore, maxTotal, maxScore > 0 ? n / maxScore : 0.0, maxTotal > 0 ? n / maxTotal : 0.0, cs);
+      n, nt, (int)k, sumWall / k, sumScore / k, sumTotal / k, sumScore > 0 ? n * k / sumScore : 0.0,
+      sumTotal > 0 ? n * k / sumTotal : 0.0, cs);
   return 0;
 }
 
