@@ -72,8 +72,8 @@ __global__ void __launch_bounds__(128) k_t0(const FeatTables* __restrict__ ftg, 
 }
 
 // persistent warps pull sentences (longest first) from a global counter
-__global__ void __launch_bounds__(128) k_walk(const FeatTables* __restrict__ ftg, BatchView bv, ScoreCfg cfg,
-                                             const float* __restrict__ w, u32* workCounter, u32 warpSmemBytes) {
+__global__ void __launch_bounds__(128, 4) k_walk(const FeatTables* __restrict__ ftg, BatchView bv, ScoreCfg cfg,
+                                             const float* __restrict__ w, u32* workCounter, u32 warpSmemBytes, u32 wcap) {
   extern __shared__ __align__(16) unsigned char smem[];
   FeatTables* ft = reinterpret_cast<FeatTables*>(smem);
   {
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(128) k_walk(const FeatTables* __restrict__ ftg
   __syncthreads();
   const u32 warp = threadIdx.x >> 5;
   unsigned char* base = smem + ((sizeof(FeatTables) + 15) & ~(size_t)15) + (size_t)warp * warpSmemBytes;
-  WarpSmem sm = carve_warp_smem(base, (u32)cfg.gbeam, ft->nStored);
+  WarpSmem sm = carve_warp_smem(base, (u32)cfg.gbeam, ft->nStored, wcap);
   for (;;) {
     u32 item = 0;
     if ((threadIdx.x & 31u) == 0) item = atomicAdd(workCounter, 1u);
@@ -162,14 +162,24 @@ __global__ void k_rnn_bos(BatchView bv, RnnWork rw, RnnTables rt, const u32* ctx
   (void)bv;
 }
 
-// one warp per tree node of the level: ctx' = sigmoid(W^T ctx + emb[id])
-__global__ void __launch_bounds__(256) k_rnn_level(RnnWork rw, RnnTables rt, const u32* ctxOff, const u32* rnSent, u32 level) {
+// One warp per tree node of the level: ctx' = sigmoid(W^T ctx + emb[id])
+// (mikolov_rnn_impl.h:202-214).  Lane l owns output i = i0 + l and keeps the 32
+// interleaved partial sums of the eigen_shim order in registers (partial j
+// accumulates k = j, j+32, ...), then folds them with the 16/8/4/2/1 tree --
+// the same additions, in the same order, as the shuffle formulation, without
+// cross-lane traffic.  Wt is the transposed recurrent matrix, so the 32 lanes
+// read 128 contiguous bytes per k; the input context is staged in shared memory.
+__global__ void __launch_bounds__(256) k_rnn_level(RnnWork rw, RnnTables rt, const float* __restrict__ Wt,
+                                                 const u32* ctxOff, const u32* rnSent, u32 level) {
+  extern __shared__ float sctx[];
   const u32 cnt = rw.levelCount[level];
   const u32 off = rw.levelOff[level];
   const int lane = threadIdx.x & 31;
+  const u32 warp = threadIdx.x >> 5;
   const u32 warpsPerBlock = blockDim.x >> 5;
   const u32 H = rt.H;
-  for (u32 item = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); item < cnt; item += gridDim.x * warpsPerBlock) {
+  float* cinS = sctx + (size_t)warp * H;
+  for (u32 item = blockIdx.x * warpsPerBlock + warp; item < cnt; item += gridDim.x * warpsPerBlock) {
     const u32 q = rw.levelList[off + item];
     const u32 p = (u32)rw.prev[q];
     const float* cin = rw.ctx + ctx_row(rw, ctxOff, rnSent, p) * H;
@@ -177,10 +187,28 @@ __global__ void __launch_bounds__(256) k_rnn_level(RnnWork rw, RnnTables rt, con
     i32 id = rw.id[q];
     if (id == -1) id = 0;  // rnn_scorer_gbeam.cc:126-129
     const float* emb = rt.emb + (size_t)id * H;
-    for (u32 i = 0; i < H; ++i) {
-      float v = warp_dot32(rt.matrix + (size_t)i * H, cin, H, lane);
-      if (lane == 0) {
-        v = __fadd_rn(v, emb[i]);
+    __syncwarp();
+    for (u32 k = (u32)lane; k < H; k += 32) cinS[k] = cin[k];
+    __syncwarp();
+    for (u32 i0 = 0; i0 < H; i0 += 32) {
+      const u32 i = i0 + (u32)lane;
+      float part[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) part[j] = 0.0f;
+      if (i < H) {
+        for (u32 k0 = 0; k0 < H; k0 += 32) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const u32 k = k0 + (u32)j;
+            if (k < H) part[j] = __fadd_rn(part[j], __fmul_rn(Wt[(size_t)k * H + i], cinS[k]));
+          }
+        }
+#pragma unroll
+        for (int stride = 16; stride >= 1; stride >>= 1) {
+#pragma unroll
+          for (int l = 0; l < stride; ++l) part[l] = __fadd_rn(part[l], part[l + stride]);
+        }
+        const float v = __fadd_rn(part[0], emb[i]);
         cout[i] = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-v)));
       }
     }
@@ -261,6 +289,7 @@ struct jpp_b200_handle {
   RnnTables rt{};
   bool hasRnn = false;
   float* dRnnBlocks[4] = {nullptr, nullptr, nullptr, nullptr};
+  float* dRnnWt = nullptr;  // transposed recurrent matrix
   float scoreW[2] = {1.0f, 0.0f};
   int smCount = 148;
   // batch buffers
@@ -379,6 +408,16 @@ jpp_b200_status jpp_b200_create(const jpp_b200_model* model, const jpp_b200_conf
       CREATE_CHECK(cudaMalloc(&h->dRnnBlocks[i], sizes[i] * sizeof(float)));
       CREATE_CHECK(cudaMemcpyAsync(h->dRnnBlocks[i], src[i], sizes[i] * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     }
+    {
+      const u32 H = r->layer_size;
+      std::vector<float> wt((size_t)H * H);
+      for (u32 i = 0; i < H; ++i)
+        for (u32 k = 0; k < H; ++k) wt[(size_t)k * H + i] = r->matrix[(size_t)i * H + k];
+      CREATE_CHECK(cudaMalloc(&h->dRnnWt, wt.size() * sizeof(float)));
+      CREATE_CHECK(cudaMemcpy(h->dRnnWt, wt.data(), wt.size() * sizeof(float), cudaMemcpyHostToDevice));
+      if (8 * H * sizeof(float) > 48 * 1024)
+        CREATE_CHECK(cudaFuncSetAttribute(k_rnn_level, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * H * sizeof(float))));
+    }
     h->rt = RnnTables{r->layer_size, r->maxent_order, r->maxent_size, r->vocab_size, r->nce_constant, r->unk_constant,
                       r->unk_length_penalty, r->unk_id, h->dRnnBlocks[0], h->dRnnBlocks[1], h->dRnnBlocks[2],
                       h->dRnnBlocks[3]};
@@ -409,6 +448,7 @@ void jpp_b200_destroy(jpp_b200_handle* h) {
   if (h->dFt) cudaFree(h->dFt);
   if (h->dWeights) cudaFree(h->dWeights);
   for (auto& p : h->dRnnBlocks) if (p) cudaFree(p);
+  if (h->dRnnWt) cudaFree(h->dRnnWt);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -547,7 +587,8 @@ jpp_b200_status jpp_b200_score_resident(jpp_b200_handle* h) {
   CU_CHECK(h, cudaGetLastError());
   CU_CHECK(h, cudaEventRecord(h->ev[3], st));
   {
-    const u32 warpBytes = (u32)warp_smem_bytes((u32)h->cfg.gbeam, h->hm.ft.nStored);
+    const u32 wcap = warp_wcap((u32)h->cfg.gbeam, (u32)std::max(0, h->cfg.rbeam), h->hm.ft.nBi + h->hm.ft.nTri);
+    const u32 warpBytes = (u32)warp_smem_bytes((u32)h->cfg.gbeam, h->hm.ft.nStored, wcap);
     const u32 warpsPerBlock = 4;
     const size_t smem = ((sizeof(FeatTables) + 15) & ~(size_t)15) + (size_t)warpsPerBlock * warpBytes;
     if (smem > 200 * 1024) return fail(h, JPP_B200_NOT_IMPLEMENTED, "configuration needs more shared memory than one CTA has");
@@ -556,7 +597,7 @@ jpp_b200_status jpp_b200_score_resident(jpp_b200_handle* h) {
     CU_CHECK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_walk, 128, smem));
     if (perSm < 1) perSm = 1;
     const u32 grid = std::min<u32>((u32)h->smCount * (u32)perSm, (NS + warpsPerBlock - 1) / warpsPerBlock);
-    k_walk<<<std::max(1u, grid), 128, smem, st>>>(h->dFt, bv, h->cfg, h->dWeights, bf[jpp_b200_handle::B_WORK].as<u32>(), warpBytes);
+    k_walk<<<std::max(1u, grid), 128, smem, st>>>(h->dFt, bv, h->cfg, h->dWeights, bf[jpp_b200_handle::B_WORK].as<u32>(), warpBytes, wcap);
     CU_CHECK(h, cudaGetLastError());
   }
   CU_CHECK(h, cudaEventRecord(h->ev[4], st));
@@ -594,7 +635,7 @@ jpp_b200_status jpp_b200_score_resident(jpp_b200_handle* h) {
     CU_CHECK(h, cudaGetLastError());
     CU_CHECK(h, cudaEventRecord(h->ev[5], st));
     for (u32 level = 1; level <= h->maxNb; ++level) {
-      k_rnn_level<<<h->smCount * 2, 256, 0, st>>>(rw, h->rt, ctxOff, rnSent, level);
+      k_rnn_level<<<h->smCount * 2, 256, 8 * h->rt.H * sizeof(float), st>>>(rw, h->rt, h->dRnnWt, ctxOff, rnSent, level);
     }
     CU_CHECK(h, cudaGetLastError());
     CU_CHECK(h, cudaEventRecord(h->ev[6], st));

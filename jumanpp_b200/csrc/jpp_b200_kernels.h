@@ -298,65 +298,6 @@ JPP_HD void t0_node(const FeatTables& ft, const BatchView& bv, const float* __re
   bv.t0[node] = s;
 }
 
-// ------------------------------------------------ ordered weight sums -------
-// 8/4/2/1 interleaved accumulators "f_j = 0; f_j += w" then f_0 + f_1 + ...
-// (partial_ngram_feature_codegen.cc:44-66, :115-137); `nv` <= 8.
-template <typename IdxFn>
-JPP_HD float sum_vars(const float* __restrict__ w, u32 n, u32 nv, IdxFn idxOf) {
-  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (u32 f0 = 0; f0 < n; f0 += 8) {
-    float wv[8];
-#pragma unroll
-    for (u32 j = 0; j < 8; ++j)
-      if (f0 + j < n) wv[j] = JPP_LDG(w + idxOf(f0 + j));
-#pragma unroll
-    for (u32 j = 0; j < 8; ++j)
-      if (f0 + j < n) {
-        // (f0 + j) % nv with nv in {1,2,4,8} and f0 % 8 == 0
-        acc[j & (nv - 1)] += wv[j];
-      }
-  }
-  float s = acc[0];
-  for (u32 v = 1; v < nv; ++v) s = s + acc[v];
-  return s;
-}
-
-// computeUnrolled4RawPerceptron (perceptron.h:46-72): r1..r4, returns r1+r2+r3+r4
-template <typename IdxFn>
-JPP_HD float sum_unrolled4(const float* __restrict__ w, u32 n, IdxFn idxOf) {
-  float r[4] = {0, 0, 0, 0};
-  for (u32 f0 = 0; f0 < n; f0 += 8) {
-    float wv[8];
-#pragma unroll
-    for (u32 j = 0; j < 8; ++j)
-      if (f0 + j < n) wv[j] = JPP_LDG(w + idxOf(f0 + j));
-#pragma unroll
-    for (u32 j = 0; j < 8; ++j)
-      if (f0 + j < n) r[j & 3] += wv[j];
-  }
-  return r[0] + r[1] + r[2] + r[3];
-}
-
-// two accumulators of applyBiTriFullKernel (feature_impl_ngram_partial_kernels.h:35-61):
-// even features -> r1, odd -> r2 (an odd tail lands in r1)
-template <typename IdxFn>
-JPP_HD void sum_two(const float* __restrict__ w, u32 n, IdxFn idxOf, float* r1o, float* r2o) {
-  float r1 = 0, r2 = 0;
-  for (u32 f0 = 0; f0 < n; f0 += 8) {
-    float wv[8];
-#pragma unroll
-    for (u32 j = 0; j < 8; ++j)
-      if (f0 + j < n) wv[j] = JPP_LDG(w + idxOf(f0 + j));
-#pragma unroll
-    for (u32 j = 0; j < 8; ++j)
-      if (f0 + j < n) {
-        if (j & 1) r2 += wv[j]; else r1 += wv[j];
-      }
-  }
-  *r1o = r1;
-  *r2o = r2;
-}
-
 // ------------------------------------------------- exact sort emulation -----
 // Equal float keys are common (homograph entries with identical feature
 // fields), so the order the reference produces for them matters.  These follow
@@ -617,32 +558,48 @@ struct WarpSmem {
   u32* t1idx;      // [G]
   u64* t1pat;      // [G][SP]
   u64* t2pat;      // [G][SP]
+  u64* t0pat;      // [KCHUNK][SP]  pattern rows of the right nodes being scored
   u32* selNode;    // [KCHUNK] right-node offsets (in boundary) of the current chunk
   float* scbuf;    // [KCHUNK][G]  bigram score per (selected node, unique t1)
   float* tot;      // [KCHUNK][G]
   float* loc;      // [KCHUNK][G]
-  u32* misc;       // [8] uniform scalars: [0]=G, [1]=U, [2]=flag
+  float* wbuf;     // [wcap] gathered weights, summed in reference order afterwards
+  u32* misc;       // [8] uniform scalars
+  u32 wcap;
 };
 
-JPP_HD size_t warp_smem_bytes(u32 G, u32 SP) {
+// gathered-weight staging capacity (floats) for a configuration
+JPP_HD u32 warp_wcap(u32 G, u32 rbeam, u32 NF) {
+  u32 k = rbeam ? rbeam : 8u;
+  if (k > 8u) k = 8u;
+  u32 a = 16u * NF, b = k * G * NF;
+  u32 c = a > b ? a : b;
+  if (c < G * NF) c = G * NF;
+  return c;
+}
+
+JPP_HD size_t warp_smem_bytes(u32 G, u32 SP, u32 wcap) {
   size_t b = 0;
   b += 32 * 8;                 // red
   b += (size_t)G * 8;          // gbeam
-  b += (size_t)G * 4 * 4;      // gbLnode, gbT2node, t1node, t1idx
   b += (size_t)G * SP * 8 * 2; // t1pat, t2pat
+  b += (size_t)KCHUNK * SP * 8;// t0pat
+  b += (size_t)G * 4 * 4;      // gbLnode, gbT2node, t1node, t1idx
   b += KCHUNK * 4;             // selNode
   b += (size_t)KCHUNK * G * 4 * 3;
+  b += (size_t)wcap * 4;
   b += 8 * 4;
   return (b + 15) & ~(size_t)15;
 }
 
-JPP_HD WarpSmem carve_warp_smem(unsigned char* base, u32 G, u32 SP) {
+JPP_HD WarpSmem carve_warp_smem(unsigned char* base, u32 G, u32 SP, u32 wcap) {
   WarpSmem s;
   unsigned char* p = base;
   s.red = (u64*)p; p += 32 * 8;
   s.gbeam = (u64*)p; p += (size_t)G * 8;
   s.t1pat = (u64*)p; p += (size_t)G * SP * 8;
   s.t2pat = (u64*)p; p += (size_t)G * SP * 8;
+  s.t0pat = (u64*)p; p += (size_t)KCHUNK * SP * 8;
   s.gbLnode = (u32*)p; p += (size_t)G * 4;
   s.gbT2node = (u32*)p; p += (size_t)G * 4;
   s.t1node = (u32*)p; p += (size_t)G * 4;
@@ -651,16 +608,85 @@ JPP_HD WarpSmem carve_warp_smem(unsigned char* base, u32 G, u32 SP) {
   s.scbuf = (float*)p; p += (size_t)KCHUNK * G * 4;
   s.tot = (float*)p; p += (size_t)KCHUNK * G * 4;
   s.loc = (float*)p; p += (size_t)KCHUNK * G * 4;
+  s.wbuf = (float*)p; p += (size_t)wcap * 4;
   s.misc = (u32*)p;
+  s.wcap = wcap;
   return s;
 }
 
+// Ordered sums over gathered weights x[0..n): NV interleaved accumulators
+// started at 0 ("f_j = 0; f_j += w", partial_ngram_feature_codegen.cc:44-66;
+// NV = 4 is also computeUnrolled4RawPerceptron, perceptron.h:46-72; NV = 2 is
+// the r1/r2 pair of applyBiTriFullKernel, feature_impl_ngram_partial_kernels.h:35-61).
+template <int NV>
+JPP_HD void osum(const float* x, u32 n, float* acc) {
+#pragma unroll
+  for (int j = 0; j < NV; ++j) acc[j] = 0.0f;
+  u32 f = 0;
+  for (; f + NV <= n; f += NV) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) acc[j] += x[f + j];
+  }
+#pragma unroll
+  for (int j = 0; j < NV; ++j)
+    if (f + j < n) acc[j] += x[f + j];
+}
+
+JPP_HD float osum_vars(const float* x, u32 n, u32 nv) {
+  float a[8];
+  switch (nv) {
+    case 8: osum<8>(x, n, a); return ((((((a[0] + a[1]) + a[2]) + a[3]) + a[4]) + a[5]) + a[6]) + a[7];
+    case 4: osum<4>(x, n, a); return ((a[0] + a[1]) + a[2]) + a[3];
+    case 2: osum<2>(x, n, a); return a[0] + a[1];
+    default: osum<1>(x, n, a); return a[0];
+  }
+}
+
+JPP_HD float osum_unrolled4(const float* x, u32 n) {
+  float a[4];
+  osum<4>(x, n, a);
+  return ((a[0] + a[1]) + a[2]) + a[3];
+}
+
+// max over the 32 per-lane values a region left in sm.red
+JPP_HD u64 uniform_max_u64(const u64* red) {
+#if defined(__CUDA_ARCH__)
+  u64 v = red[threadIdx.x & 31u];
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const u64 t = __shfl_xor_sync(0xffffffffu, v, o);
+    v = t > v ? t : v;
+  }
+  return v;
+#else
+  u64 m = 0;
+  for (int l = 0; l < 32; ++l) if (red[l] > m) m = red[l];
+  return m;
+#endif
+}
+
+#if defined(__CUDACC__)
+#define JPP_NOINLINE __noinline__
+#else
+#define JPP_NOINLINE
+#endif
+
 // Writes the beam row of one right node from `n` candidate totals.
-JPP_HD void write_beam(const BatchView& bv, const ScoreCfg& cfg, u32 node, const u64* gbeam, int n,
+JPP_NOINLINE
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline void write_beam(const BatchView& bv, const ScoreCfg& cfg, u32 node, const u64* gbeam, int n,
                        const float* totals, const float* local) {
   u32 idx[MAX_BEAM];
   const int maxBeam = cfg.beam;
-  const int len = beam_order(idx, n, totals, maxBeam);
+  int len;
+  if (n <= 1) {
+    idx[0] = 0;
+    len = n;
+  } else {
+    len = beam_order(idx, n, totals, maxBeam);
+  }
   jpp_b200_beam_element* row = bv.beam + (size_t)node * maxBeam;
   float* srow = bv.beamScores + (size_t)node * maxBeam * cfg.S;
   int k = 0;
@@ -682,6 +708,12 @@ JPP_HD void write_beam(const BatchView& bv, const ScoreCfg& cfg, u32 node, const
 
 // One warp, one sentence: makeGlobalBeam + computeGbeamScores for every
 // boundary (analyzer_impl.cc:260-284, score_processor.cc:246-361).
+//
+// The hot work of a boundary is flattened over the lanes as (row, feature)
+// items: each lane hashes one n-gram feature and gathers one weight per
+// iteration (all 32 lanes busy even when a boundary has only a few right
+// nodes), staging the weights in shared memory; the float sums are then
+// replayed from shared memory in the reference's accumulator order.
 JPP_HD void walk_sentence(const FeatTables& ft, const BatchView& bv, const ScoreCfg& cfg, const float* __restrict__ w,
                           WarpSmem sm, u32 sent) {
   const u32 b0 = bv.sentBndOff[sent];
@@ -689,6 +721,7 @@ JPP_HD void walk_sentence(const FeatTables& ft, const BatchView& bv, const Score
   const u32 B = (u32)cfg.beam;
   const u32 SP = ft.nStored;
   const u32 nB = ft.nBi, nT = ft.nTri, mask = ft.mask;
+  const u32 NF = nB + nT;
   const u32 GMAX = (u32)cfg.gbeam;
   unsigned long long gathers = 0, streamBytes = 0;
 
@@ -738,7 +771,7 @@ JPP_HD void walk_sentence(const FeatTables& ft, const BatchView& bv, const Score
       JPP_LANES
       u64 best = 0;
       for (u32 c = (u32)lane; c < nc; c += 32) {
-        const u32 left = c / B, slot = c % B;
+        const u32 left = c / B, slot = c - left * B;
         const u32 lnode = bv.endNode[e0 + left];
         const jpp_b200_beam_element el = bv.beam[(size_t)lnode * B + slot];
         if (!is_fake(el)) {
@@ -748,8 +781,7 @@ JPP_HD void walk_sentence(const FeatTables& ft, const BatchView& bv, const Score
       }
       sm.red[lane] = best;
       JPP_LANES_END
-      u64 m = 0;
-      for (int l = 0; l < 32; ++l) { const u64 v = sm.red[l]; if (v > m) m = v; }
+      const u64 m = uniform_max_u64(sm.red);
       JPP_SYNC();
       if (m == 0) break;
       if (JPP_LANE0) sm.gbeam[j] = m;
@@ -807,28 +839,50 @@ JPP_HD void walk_sentence(const FeatTables& ft, const BatchView& bv, const Score
       remaining = G - full;
       const u32 theMax = (u32)cfg.rcheck < G ? (u32)cfg.rcheck : G;  // computeT0Prescores :497-511
 
-      // ---- T0 prescores: T0 + bigrams (8 accumulators; last row Unrolled4) +
-      // trigrams (partial_ngram_feature_codegen.cc:13-153)
-      JPP_LANES
-      for (u32 r = (u32)lane; r < R; r += 32) {
-        const u32 node = n0 + r;
-        const u64* P = bv.patterns + (size_t)node * SP;
-        const bool lastRow = (r + 1 == R);
-        for (u32 i = 0; i < theMax; ++i) {
-          const u64* t1 = sm.t1pat + (size_t)sm.t1idx[i] * SP;
-          const u64* t2 = sm.t2pat + (size_t)i * SP;
-          float sc = bv.t0[node];
-          auto biIdx = [&](u32 f) -> u32 { return (u32)mix(mix(ft.biState[f], P[ft.biT0[f]]), t1[ft.biT1[f]]) & mask; };
-          auto triIdx = [&](u32 f) -> u32 {
-            return (u32)mix(mix(mix(ft.triState[f], P[ft.triT0[f]]), t1[ft.triT1[f]]), t2[ft.triT2[f]]) & mask;
-          };
-          sc += lastRow ? sum_unrolled4(w, nB, biIdx) : sum_vars(w, nB, ft.biVars, biIdx);
-          sc += lastRow ? sum_unrolled4(w, nT, triIdx) : sum_vars(w, nT, ft.triVars, triIdx);
-          bv.pre[(size_t)i * bv.totalNodes + node] = sc;
+      // ---- T0 prescores: T0 + bigrams (biVars accumulators; last row Unrolled4)
+      // + trigrams (partial_ngram_feature_codegen.cc:13-153)
+      u32 RC = sm.wcap / NF;
+      if (RC > KCHUNK) RC = KCHUNK;
+      for (u32 i = 0; i < theMax; ++i) {
+        const u64* t1 = sm.t1pat + (size_t)sm.t1idx[i] * SP;
+        const u64* t2 = sm.t2pat + (size_t)i * SP;
+        for (u32 r0 = 0; r0 < R; r0 += RC) {
+          const u32 rc = (R - r0) < RC ? (R - r0) : RC;
+          JPP_LANES
+          const u64* src = bv.patterns + (size_t)(n0 + r0) * SP;
+          for (u32 x = (u32)lane; x < rc * SP; x += 32) sm.t0pat[x] = src[x];
+          JPP_LANES_END
+          JPP_LANES
+          u32 row = 0, f = (u32)lane;
+          while (f >= NF) { f -= NF; ++row; }
+          for (u32 it = (u32)lane; it < rc * NF; it += 32) {
+            const u64* P = sm.t0pat + (size_t)row * SP;
+            u32 idx;
+            if (f < nB) {
+              idx = (u32)mix(mix(ft.biState[f], P[ft.biT0[f]]), t1[ft.biT1[f]]) & mask;
+            } else {
+              const u32 g = f - nB;
+              idx = (u32)mix(mix(mix(ft.triState[g], P[ft.triT0[g]]), t1[ft.triT1[g]]), t2[ft.triT2[g]]) & mask;
+            }
+            sm.wbuf[it] = JPP_LDG(w + idx);
+            f += 32;
+            while (f >= NF) { f -= NF; ++row; }
+          }
+          JPP_LANES_END
+          JPP_LANES
+          for (u32 r = (u32)lane; r < rc; r += 32) {
+            const u32 node = n0 + r0 + r;
+            const bool lastRow = (r0 + r + 1 == R);
+            const float* x = sm.wbuf + (size_t)r * NF;
+            float sc = bv.t0[node];
+            sc += lastRow ? osum_unrolled4(x, nB) : osum_vars(x, nB, ft.biVars);
+            sc += lastRow ? osum_unrolled4(x + nB, nT) : osum_vars(x + nB, nT, ft.triVars);
+            bv.pre[(size_t)i * bv.totalNodes + node] = sc;
+          }
+          JPP_LANES_END
         }
       }
-      JPP_LANES_END
-      gathers += (unsigned long long)theMax * R * (nB + nT);
+      gathers += (unsigned long long)theMax * R * NF;
 
       // ---- makeT0cutoffBeam (:471-495): which toKeep right nodes get full beams
       if (R > toKeep) {
@@ -879,14 +933,19 @@ JPP_HD void walk_sentence(const FeatTables& ft, const BatchView& bv, const Score
       JPP_LANES_END
     }
 
-    // ---- selected right nodes, KCHUNK at a time: full scoring against the
+    // ---- selected right nodes, a chunk at a time: full scoring against the
     // global beam (applyBiTri -> applyBiTriFullKernel, feature_impl_ngram_partial_kernels.h:19-110)
+    const bool scoreTail = remaining > 0 && G > 0;
+    const u32 perNode = scoreTail ? (U * nB + remaining * nT) : 1u;
+    u32 KCH = sm.wcap / (perNode ? perNode : 1u);
+    if (KCH > KCHUNK) KCH = KCHUNK;
+    if (KCH < 1) KCH = 1;
     u32 rScan = 0;
     while (rScan < R) {
       u32 K = 0;
       if (JPP_LANE0) {
         u32 r = rScan;
-        for (; r < R && K < KCHUNK; ++r) {
+        for (; r < R && K < KCH; ++r) {
           if (bv.selK[n0 + r] != 0xFFFFu) { sm.selNode[K] = r; bv.selK[n0 + r] = (u16)K; ++K; }
         }
         sm.misc[3] = K;
@@ -896,42 +955,68 @@ JPP_HD void walk_sentence(const FeatTables& ft, const BatchView& bv, const Score
       K = sm.misc[3];
       rScan = sm.misc[4];
       if (K == 0) break;
-      const bool scoreTail = remaining > 0 && G > 0;
       if (scoreTail) {
         JPP_LANES
+        for (u32 x = (u32)lane; x < K * SP; x += 32)
+          sm.t0pat[x] = bv.patterns[(size_t)(n0 + sm.selNode[x / SP]) * SP + x % SP];
+        JPP_LANES_END
+        const u32 triBase = K * U * nB;
+        JPP_LANES
+        {  // bigram items (k, u, f)
+          u32 k = 0, u = 0, f = (u32)lane;
+          while (f >= nB) { f -= nB; if (++u == U) { u = 0; ++k; } }
+          for (u32 it = (u32)lane; it < triBase; it += 32) {
+            const u64* P = sm.t0pat + (size_t)k * SP;
+            const u64* t1 = sm.t1pat + (size_t)u * SP;
+            const u32 idx = (u32)mix(mix(ft.biState[f], P[ft.biT0[f]]), t1[ft.biT1[f]]) & mask;
+            sm.wbuf[it] = JPP_LDG(w + idx);
+            f += 32;
+            while (f >= nB) { f -= nB; if (++u == U) { u = 0; ++k; } }
+          }
+        }
+        {  // trigram items (k, j, f) of the tail elements
+          const u32 nTri = K * remaining * nT;
+          u32 k = 0, j = 0, f = (u32)lane;
+          while (nT && f >= nT) { f -= nT; if (++j == remaining) { j = 0; ++k; } }
+          for (u32 it = (u32)lane; it < nTri; it += 32) {
+            const u32 gi = full + j;
+            const u64* P = sm.t0pat + (size_t)k * SP;
+            const u64* t1 = sm.t1pat + (size_t)sm.t1idx[gi] * SP;
+            const u64* t2 = sm.t2pat + (size_t)gi * SP;
+            const u32 idx = (u32)mix(mix(mix(ft.triState[f], P[ft.triT0[f]]), t1[ft.triT1[f]]), t2[ft.triT2[f]]) & mask;
+            sm.wbuf[triBase + it] = JPP_LDG(w + idx);
+            f += 32;
+            while (f >= nT) { f -= nT; if (++j == remaining) { j = 0; ++k; } }
+          }
+        }
+        JPP_LANES_END
+        JPP_LANES
         for (u32 it = (u32)lane; it < K * U; it += 32) {
-          const u32 k = it / U, u = it % U;
-          const u64* P = bv.patterns + (size_t)(n0 + sm.selNode[k]) * SP;
-          const u64* t1 = sm.t1pat + (size_t)u * SP;
-          auto biIdx = [&](u32 f) -> u32 { return (u32)mix(mix(ft.biState[f], P[ft.biT0[f]]), t1[ft.biT1[f]]) & mask; };
+          const u32 k = it / U, u = it - k * U;
+          const float* x = sm.wbuf + (size_t)it * nB;
           float v;
           if (u + 1 < U) {
-            float r1, r2;
-            sum_two(w, nB, biIdx, &r1, &r2);
-            v = r1 + r2;
+            float a[2];
+            osum<2>(x, nB, a);
+            v = a[0] + a[1];
           } else {
-            v = sum_unrolled4(w, nB, biIdx);
+            v = osum_unrolled4(x, nB);
           }
           sm.scbuf[k * GMAX + u] = v;
         }
         JPP_LANES_END
         JPP_LANES
         for (u32 it = (u32)lane; it < K * remaining; it += 32) {
-          const u32 k = it / remaining, j = it % remaining, gi = full + j;
+          const u32 k = it / remaining, j = it - k * remaining, gi = full + j;
           const u32 node = n0 + sm.selNode[k];
-          const u64* P = bv.patterns + (size_t)node * SP;
-          const u64* t1 = sm.t1pat + (size_t)sm.t1idx[gi] * SP;
-          const u64* t2 = sm.t2pat + (size_t)gi * SP;
-          auto triIdx = [&](u32 f) -> u32 {
-            return (u32)mix(mix(mix(ft.triState[f], P[ft.triT0[f]]), t1[ft.triT1[f]]), t2[ft.triT2[f]]) & mask;
-          };
+          const float* x = sm.wbuf + triBase + (size_t)it * nT;
           float v;
           if (j + 1 < remaining) {
-            float r1, r2;
-            sum_two(w, nT, triIdx, &r1, &r2);
-            v = sm.scbuf[k * GMAX + sm.t1idx[gi]] + r1 + r2;
+            float a[2];
+            osum<2>(x, nT, a);
+            v = sm.scbuf[k * GMAX + sm.t1idx[gi]] + a[0] + a[1];
           } else {
-            v = sm.scbuf[k * GMAX + sm.t1idx[gi]] + sum_unrolled4(w, nT, triIdx);
+            v = sm.scbuf[k * GMAX + sm.t1idx[gi]] + osum_unrolled4(x, nT);
           }
           v += bv.t0[node];  // copyT0Scores(tail, t0Score), score_processor.cc:411-424
           sm.loc[k * GMAX + gi] = v;
@@ -943,7 +1028,7 @@ JPP_HD void walk_sentence(const FeatTables& ft, const BatchView& bv, const Score
       }
       JPP_LANES
       for (u32 it = (u32)lane; it < K * full; it += 32) {
-        const u32 k = it / full, i = it % full;
+        const u32 k = it / full, i = it - k * full;
         float v = bv.pre[(size_t)i * bv.totalNodes + n0 + sm.selNode[k]];
         v += 0.0f;  // copyT0Scores(head, 0)
         sm.loc[k * GMAX + i] = v;

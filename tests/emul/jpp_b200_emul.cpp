@@ -64,8 +64,9 @@ extern "C" int jpp_b200_emul_score_batch(const jpp_b200_model* model, const jpp_
   bv.gbNode = gbNode.data(); bv.gbSlot = gbSlot.data(); bv.gbLeftBnd = gbLeftBnd.data(); bv.gbCount = gbCount.data();
   bv.eosGbeam = eosGbeam.data(); bv.eosLocal = eosLocal.data(); bv.eosRnn = eosRnn.data(); bv.counters = counters;
   for (u32 n = 0; n < NN; ++n) t0_node(ft, bv, weights, n);
-  std::vector<unsigned char> smem(warp_smem_bytes(G, SP) + 64);
-  WarpSmem sm = carve_warp_smem(smem.data(), G, SP);
+  const u32 wcap = warp_wcap(G, (u32)std::max(0, cfg.rbeam), ft.nBi + ft.nTri);
+  std::vector<unsigned char> smem(warp_smem_bytes(G, SP, wcap) + 64);
+  WarpSmem sm = carve_warp_smem(smem.data(), G, SP, wcap);
   for (u32 s = 0; s < NS; ++s) walk_sentence(ft, bv, cfg, weights, sm, s);
   if (model->num_scorers == 2) {
     const jpp_b200_rnn_model* rm = model->rnn;
