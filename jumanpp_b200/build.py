@@ -21,12 +21,25 @@ def nvcc() -> str:
     raise RuntimeError("nvcc not found")
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
+def build(force: bool = False, verbose: bool = False, defines: list[str] | None = None, out: Path | None = None) -> Path:
+    """`defines`/`out` build tuning variants (tools/tune_walk.py); the default build is the product."""
     newest = max(p.stat().st_mtime for p in SOURCES + HEADERS)
+    if out is not None:
+        global LIB
+        lib_default, LIB = LIB, Path(out)
+        try:
+            return _compile(verbose, defines or [])
+        finally:
+            LIB = lib_default
     if not force and LIB.exists() and LIB.stat().st_mtime >= newest:
         return LIB
+    return _compile(verbose, defines or [])
+
+
+def _compile(verbose: bool, defines: list[str]) -> Path:
     cmd = [nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
            "-fmad=false", "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v" if verbose else "-O3",
+           *[f"-D{d}" for d in defines],
            f"-I{ROOT / 'include'}", f"-I{PKG / 'csrc'}", *map(str, SOURCES), "-o", str(LIB), "-lcudart"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

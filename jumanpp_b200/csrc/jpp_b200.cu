@@ -20,6 +20,10 @@
 
 using namespace jppb200;
 
+#ifndef JPP_WALK_MINBLOCKS
+#define JPP_WALK_MINBLOCKS 6
+#endif
+
 namespace {
 
 thread_local std::string g_create_error;
@@ -72,7 +76,7 @@ __global__ void __launch_bounds__(128) k_t0(const FeatTables* __restrict__ ftg, 
 }
 
 // persistent warps pull sentences (longest first) from a global counter
-__global__ void __launch_bounds__(128, 4) k_walk(const FeatTables* __restrict__ ftg, BatchView bv, ScoreCfg cfg,
+__global__ void __launch_bounds__(128, JPP_WALK_MINBLOCKS) k_walk(const FeatTables* __restrict__ ftg, BatchView bv, ScoreCfg cfg,
                                              const float* __restrict__ w, u32* workCounter, u32 warpSmemBytes, u32 wcap) {
   extern __shared__ __align__(16) unsigned char smem[];
   FeatTables* ft = reinterpret_cast<FeatTables*>(smem);

@@ -53,11 +53,18 @@ typedef int32_t i32;
 typedef uint16_t u16;
 typedef uint8_t u8;
 
+#ifndef JPP_GATHER_BATCH
+#define JPP_GATHER_BATCH 1
+#endif
+#ifndef JPP_KCHUNK
+#define JPP_KCHUNK 16
+#endif
+
 // ---------------------------------------------------------------- limits ----
 enum {
   MAX_UNI = 64, MAX_BI = 64, MAX_TRI = 16, MAX_PAT = 64, MAX_PRIM = 48, MAX_COMP = 64, MAX_POOL = 256,
   MAX_BEAM = 32,   // beam_size, global_beam_size, right_gbeam_size upper bound on the GPU path
-  KCHUNK = 32      // right nodes scored per chunk
+  KCHUNK = JPP_KCHUNK  // right nodes scored per chunk
 };
 
 // util/seahash.h:15-17, impl/feature_impl_types.h:21-24
@@ -767,16 +774,43 @@ JPP_HD void walk_sentence(const FeatTables& ft, const BatchView& bv, const Score
     u64 last = ~(u64)0;
     u32 G = 0;
     const u32 nc = L * B;
+    // candidates are packed once into shared memory (the gathered-weight buffer is
+    // idle here); a boundary with more candidates than fit re-reads the beams
+    u64* candS = reinterpret_cast<u64*>(sm.wbuf);
+#ifndef JPP_STAGE_CANDS
+#define JPP_STAGE_CANDS 1
+#endif
+    const bool staged = JPP_STAGE_CANDS && nc <= sm.wcap / 2;
+    if (staged) {
+      JPP_LANES
+      for (u32 left = (u32)lane; left < L; left += 32) {
+        const u32 lnode = bv.endNode[e0 + left];
+        const jpp_b200_beam_element* row = bv.beam + (size_t)lnode * B;
+        for (u32 slot = 0; slot < B; ++slot) {
+          const jpp_b200_beam_element el = row[slot];
+          candS[left * B + slot] = is_fake(el) ? 0 : pack_cand(el.total_score, left, slot);
+        }
+      }
+      JPP_LANES_END
+    }
     for (u32 j = 0; j < GMAX; ++j) {
       JPP_LANES
       u64 best = 0;
-      for (u32 c = (u32)lane; c < nc; c += 32) {
-        const u32 left = c / B, slot = c - left * B;
-        const u32 lnode = bv.endNode[e0 + left];
-        const jpp_b200_beam_element el = bv.beam[(size_t)lnode * B + slot];
-        if (!is_fake(el)) {
-          const u64 key = pack_cand(el.total_score, left, slot);
+      if (staged) {
+        for (u32 c = (u32)lane; c < nc; c += 32) {
+          const u64 key = candS[c];
           if (key < last && key > best) best = key;
+        }
+      } else {
+        for (u32 left = (u32)lane; left < L; left += 32) {
+          const u32 lnode = bv.endNode[e0 + left];
+          for (u32 slot = 0; slot < B; ++slot) {
+            const jpp_b200_beam_element el = bv.beam[(size_t)lnode * B + slot];
+            if (!is_fake(el)) {
+              const u64 key = pack_cand(el.total_score, left, slot);
+              if (key < last && key > best) best = key;
+            }
+          }
         }
       }
       sm.red[lane] = best;
@@ -855,18 +889,30 @@ JPP_HD void walk_sentence(const FeatTables& ft, const BatchView& bv, const Score
           JPP_LANES
           u32 row = 0, f = (u32)lane;
           while (f >= NF) { f -= NF; ++row; }
-          for (u32 it = (u32)lane; it < rc * NF; it += 32) {
-            const u64* P = sm.t0pat + (size_t)row * SP;
-            u32 idx;
-            if (f < nB) {
-              idx = (u32)mix(mix(ft.biState[f], P[ft.biT0[f]]), t1[ft.biT1[f]]) & mask;
-            } else {
-              const u32 g = f - nB;
-              idx = (u32)mix(mix(mix(ft.triState[g], P[ft.triT0[g]]), t1[ft.triT1[g]]), t2[ft.triT2[g]]) & mask;
+          const u32 total = rc * NF;
+          for (u32 it = (u32)lane; it < total; it += 32u * JPP_GATHER_BATCH) {
+            u32 idx[JPP_GATHER_BATCH];
+            float v[JPP_GATHER_BATCH];
+#pragma unroll
+            for (int q = 0; q < JPP_GATHER_BATCH; ++q) {
+              idx[q] = 0;
+              if (it + 32u * q < total) {
+                const u64* P = sm.t0pat + (size_t)row * SP;
+                if (f < nB) {
+                  idx[q] = (u32)mix(mix(ft.biState[f], P[ft.biT0[f]]), t1[ft.biT1[f]]) & mask;
+                } else {
+                  const u32 g = f - nB;
+                  idx[q] = (u32)mix(mix(mix(ft.triState[g], P[ft.triT0[g]]), t1[ft.triT1[g]]), t2[ft.triT2[g]]) & mask;
+                }
+              }
+              f += 32;
+              while (f >= NF) { f -= NF; ++row; }
             }
-            sm.wbuf[it] = JPP_LDG(w + idx);
-            f += 32;
-            while (f >= NF) { f -= NF; ++row; }
+#pragma unroll
+            for (int q = 0; q < JPP_GATHER_BATCH; ++q) v[q] = JPP_LDG(w + idx[q]);
+#pragma unroll
+            for (int q = 0; q < JPP_GATHER_BATCH; ++q)
+              if (it + 32u * q < total) sm.wbuf[it + 32u * q] = v[q];
           }
           JPP_LANES_END
           JPP_LANES
@@ -962,16 +1008,28 @@ JPP_HD void walk_sentence(const FeatTables& ft, const BatchView& bv, const Score
         JPP_LANES_END
         const u32 triBase = K * U * nB;
         JPP_LANES
-        {  // bigram items (k, u, f)
+        {  // bigram items (k, u, f), four gathers in flight per lane
           u32 k = 0, u = 0, f = (u32)lane;
           while (f >= nB) { f -= nB; if (++u == U) { u = 0; ++k; } }
-          for (u32 it = (u32)lane; it < triBase; it += 32) {
-            const u64* P = sm.t0pat + (size_t)k * SP;
-            const u64* t1 = sm.t1pat + (size_t)u * SP;
-            const u32 idx = (u32)mix(mix(ft.biState[f], P[ft.biT0[f]]), t1[ft.biT1[f]]) & mask;
-            sm.wbuf[it] = JPP_LDG(w + idx);
-            f += 32;
-            while (f >= nB) { f -= nB; if (++u == U) { u = 0; ++k; } }
+          for (u32 it = (u32)lane; it < triBase; it += 32u * JPP_GATHER_BATCH) {
+            u32 idx[JPP_GATHER_BATCH];
+            float v[JPP_GATHER_BATCH];
+#pragma unroll
+            for (int q = 0; q < JPP_GATHER_BATCH; ++q) {
+              idx[q] = 0;
+              if (it + 32u * q < triBase) {
+                const u64* P = sm.t0pat + (size_t)k * SP;
+                const u64* t1 = sm.t1pat + (size_t)u * SP;
+                idx[q] = (u32)mix(mix(ft.biState[f], P[ft.biT0[f]]), t1[ft.biT1[f]]) & mask;
+              }
+              f += 32;
+              while (f >= nB) { f -= nB; if (++u == U) { u = 0; ++k; } }
+            }
+#pragma unroll
+            for (int q = 0; q < JPP_GATHER_BATCH; ++q) v[q] = JPP_LDG(w + idx[q]);
+#pragma unroll
+            for (int q = 0; q < JPP_GATHER_BATCH; ++q)
+              if (it + 32u * q < triBase) sm.wbuf[it + 32u * q] = v[q];
           }
         }
         {  // trigram items (k, j, f) of the tail elements

@@ -20,7 +20,9 @@ import numpy as np
 from . import abi
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "libjpp_b200.so"
+import os
+
+LIB_PATH = Path(os.environ.get("JPP_B200_LIB", PKG / "libjpp_b200.so"))  # override: kernel tuning variants
 
 _STATUS_NAMES = {abi.OK: "Ok", abi.INVALID_PARAMETER: "InvalidParameter", abi.INVALID_STATE: "InvalidState",
                  abi.NOT_IMPLEMENTED: "NotImplemented", abi.CUDA_ERROR: "InvalidState(CUDA)"}
