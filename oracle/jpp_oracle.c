@@ -1310,6 +1310,13 @@ int jpp_oracle_score_batch(const jpp_b200_model* model, const jpp_b200_config* c
   return rc;
 }
 
+/* test hooks: the building blocks the reference's own unit tests pin
+ * (score_processor_test.cc:48-113, perceptron_test.cc:11-44) */
+uint64_t jpp_oracle_pack_candidate(float score, uint16_t left, uint16_t beam) { return pack_cand(score, left, beam); }
+float jpp_oracle_candidate_score(uint64_t packed) { return cand_score(packed); }
+float jpp_oracle_unrolled4(const float* weights, const uint32_t* idx, int n) { return unrolled4(weights, idx, n); }
+uint64_t jpp_oracle_mix(uint64_t state, uint64_t data) { return mix(state, data); }
+
 void jpp_oracle_fill_weights(float* out, uint32_t log2_size, uint64_t seed, float scale) {
   uint64_t n = 1ull << log2_size;
   for (uint64_t i = 0; i < n; ++i) out[i] = jpp_oracle_synth_weight(seed, i, scale);

@@ -28,6 +28,11 @@ void jpp_oracle_std_sort(uint32_t* first, long n, const float* score);
 void jpp_oracle_std_nth_element(uint32_t* first, long nth, long n, const float* score);
 long jpp_oracle_ref_partition(uint32_t* first, long n, const float* score, long min_size, long max_size);
 
+uint64_t jpp_oracle_pack_candidate(float score, uint16_t left, uint16_t beam);
+float jpp_oracle_candidate_score(uint64_t packed);
+float jpp_oracle_unrolled4(const float* weights, const uint32_t* idx, int n);
+uint64_t jpp_oracle_mix(uint64_t state, uint64_t data);
+
 float jpp_oracle_synth_weight(uint64_t seed, uint64_t i, float scale);
 void jpp_oracle_fill_weights(float* out, uint32_t log2_size, uint64_t seed, float scale);
 
