@@ -295,7 +295,7 @@ def product_arm(args, rank: int, world: int, local_rank: int) -> None:
             "gpu_launches": int(cnt["launches"]) * args.steps,
             "wall_ms_per_step_resident": 1000.0 * wall_s / args.steps,
             "stage_ms": {k: statistics.mean(x[k] for x in kms) for k in kms[0]},
-            "roofline": {"bound": "hbm", "kernel": "k_walk (beam walk: n-gram hash + weight gather + beams)",
+            "roofline": {"bound": "hbm", "kernel": "wavefront walk: k_w_gbeam + k_w_prescore + k_w_cutoff + k_w_score + k_w_rest per boundary index (n-gram hash + weight gather + beams)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                          "algorithmic_bytes_per_launch": int(cnt["walk_bytes"]), "kernel_ms": walk_ms,

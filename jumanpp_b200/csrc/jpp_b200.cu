@@ -20,10 +20,6 @@
 
 using namespace jppb200;
 
-#ifndef JPP_WALK_MINBLOCKS
-#define JPP_WALK_MINBLOCKS 6
-#endif
-
 namespace {
 
 thread_local std::string g_create_error;
@@ -64,6 +60,7 @@ __global__ void k_node_index(BatchView bv) {
 }
 
 __global__ void __launch_bounds__(128) k_t0(const FeatTables* __restrict__ ftg, BatchView bv, const float* __restrict__ w) {
+  // per-thread (divergent) table indices here: shared memory, not the constant bank
   __shared__ FeatTables ft;
   {
     const u32* src = reinterpret_cast<const u32*>(ftg);
@@ -75,29 +72,59 @@ __global__ void __launch_bounds__(128) k_t0(const FeatTables* __restrict__ ftg, 
   if (node < bv.totalNodes) t0_node(ft, bv, w, node);
 }
 
-// persistent warps pull sentences (longest first) from a global counter
-__global__ void __launch_bounds__(128, JPP_WALK_MINBLOCKS) k_walk(const FeatTables* __restrict__ ftg, BatchView bv, ScoreCfg cfg,
-                                             const float* __restrict__ w, u32* workCounter, u32 warpSmemBytes, u32 wcap) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  FeatTables* ft = reinterpret_cast<FeatTables*>(smem);
-  {
-    const u32* src = reinterpret_cast<const u32*>(ftg);
-    u32* dst = reinterpret_cast<u32*>(ft);
-    for (u32 i = threadIdx.x; i < sizeof(FeatTables) / 4; i += blockDim.x) dst[i] = src[i];
-  }
-  __syncthreads();
-  const u32 warp = threadIdx.x >> 5;
-  unsigned char* base = smem + ((sizeof(FeatTables) + 15) & ~(size_t)15) + (size_t)warp * warpSmemBytes;
-  WarpSmem sm = carve_warp_smem(base, (u32)cfg.gbeam, ft->nStored, wcap);
-  for (;;) {
-    u32 item = 0;
-    if ((threadIdx.x & 31u) == 0) item = atomicAdd(workCounter, 1u);
-    item = __shfl_sync(0xffffffffu, item, 0);
-    if (item >= bv.numSentences) break;
-    const u32 sent = bv.sentOrder ? bv.sentOrder[item] : item;
-    walk_sentence(*ft, bv, cfg, w, sm, sent);
-    __syncwarp();
-  }
+// ---- wavefront walk kernels (see jpp_b200_kernels.h "wavefront walk") ----
+// wave index: nodes grouped by their local boundary index
+__global__ void k_wave_count(BatchView bv, u32* cnt) {
+  const u32 gB = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gB >= bv.totalBoundaries) return;
+  const u32 R = bv.bndNodeOff[gB + 1] - bv.bndNodeOff[gB];
+  if (R) atomicAdd(cnt + (gB - bv.sentBndOff[bv.bndSent[gB]]), R);
+}
+
+__global__ void k_wave_fill(BatchView bv, const u32* off, u32* cursor, u32* waveNodes) {
+  const u32 gB = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gB >= bv.totalBoundaries) return;
+  const u32 n0 = bv.bndNodeOff[gB];
+  const u32 R = bv.bndNodeOff[gB + 1] - n0;
+  if (!R) return;
+  const u32 lb = gB - bv.sentBndOff[bv.bndSent[gB]];
+  const u32 base = off[lb] + atomicAdd(cursor + lb, R);
+  for (u32 r = 0; r < R; ++r) waveNodes[base + r] = n0 + r;
+}
+
+__global__ void __launch_bounds__(128) k_w_init(BatchView bv, ScoreCfg cfg) {
+  const u32 s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < bv.numSentences) wave_init_sentence(bv, cfg, s);
+}
+
+__global__ void __launch_bounds__(128) k_w_gbeam(BatchView bv, ScoreCfg cfg, WaveView wv, u32 nActive, u32 bnd) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) *wv.selCount = 0;  // consumed by k_w_cutoff, a later launch on the same stream
+  if (i < nActive) wave_gbeam(bv, cfg, wv, bv.sentOrder[i], bnd);
+}
+
+__global__ void __launch_bounds__(128) k_w_prescore(const __grid_constant__ FeatTables ft, BatchView bv, ScoreCfg cfg,
+                                                   WaveView wv, const float* __restrict__ w, u32 first, u32 count) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) wave_prescore(ft, bv, cfg, wv, w, wv.waveNodes[first + i]);
+}
+
+__global__ void __launch_bounds__(128) k_w_cutoff(const __grid_constant__ FeatTables ft, BatchView bv, ScoreCfg cfg,
+                                                 WaveView wv, u32 nActive, u32 bnd) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nActive) wave_cutoff(ft, bv, cfg, wv, bv.sentOrder[i], bnd);
+}
+
+__global__ void __launch_bounds__(128) k_w_score(const __grid_constant__ FeatTables ft, BatchView bv, ScoreCfg cfg, WaveView wv,
+                                                const float* __restrict__ w) {
+  const u32 n = *wv.selCount;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    wave_score_node(ft, bv, cfg, wv, w, wv.selList[i]);
+}
+
+__global__ void __launch_bounds__(128) k_w_rest(BatchView bv, ScoreCfg cfg, WaveView wv, u32 first, u32 count) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) wave_rest_node(bv, cfg, wv, wv.waveNodes[first + i]);
 }
 
 __global__ void k_fill_i32(i32* p, size_t n, i32 v) {
@@ -300,13 +327,18 @@ struct jpp_b200_handle {
   enum { B_SBO, B_SCO, B_BNO, B_BEO, B_INFO, B_ENTRY, B_PH, B_RNNID, B_ENDS, B_CPS, B_NODEBND, B_BNDSENT, B_ENDNODE,
          B_ORDER, B_BEAM, B_BSCORES, B_PATS, B_T0, B_PRE, B_CUT, B_CUTIDX, B_SELK, B_GBNODE, B_GBSLOT, B_GBLBND, B_GBCNT,
          B_EOSG, B_EOSLOC, B_EOSRNN, B_COUNTERS, B_WORK,
+         W_GBKEY, W_GBLNODE, W_GBT2, W_GBT1IDX, W_T1NODE, W_GCNT, W_UCNT, W_SELLIST, W_SELCNT, W_NODES, W_OFF, W_CURSOR,
          R_OFF, R_ID, R_PREV, R_NEXT, R_BND, R_LEN, R_DEPTH, R_HASH, R_RNCNT, R_RSNODE, R_RSSLOT, R_RSEOSG, R_RSRNODE,
          R_RSCNT, R_CONN, R_BNDHEAD, R_CTX, R_LVLCNT, R_LVLOFF, R_LVLLIST, R_CTXOFF, R_RNSENT, R_CURSOR, R_CUBTMP,
          NUM_BUFS };
   DevBuf buf[NUM_BUFS];
   BatchView bv{};
+  WaveView wv{};
+  std::vector<u32> waveActive;   // [maxNb] sentences that have local boundary b
+  std::vector<u32> waveNodeOff;  // [maxNb+1] host copy
   RnnWork rw{};
   bool resident = false;
+  u32 walkLaunches = 0;
   u32 maxNb = 0;
   size_t rnTotal = 0;
   jpp_b200_counters counters{};
@@ -550,6 +582,37 @@ jpp_b200_status jpp_b200_upload_batch(jpp_b200_handle* h, const jpp_b200_batch* 
   k_boundary_index<<<(NS + 127) / 128, 128, 0, st>>>(bv);
   k_node_index<<<(NB + 127) / 128, 128, 0, st>>>(bv);
   CU_CHECK(h, cudaGetLastError());
+  {
+    // wave index (nodes grouped by local boundary) + per-sentence wave state
+    ENSURE(W_GBKEY, (size_t)NS * G * 8); ENSURE(W_GBLNODE, (size_t)NS * G * 4); ENSURE(W_GBT2, (size_t)NS * G * 4);
+    ENSURE(W_GBT1IDX, (size_t)NS * G); ENSURE(W_T1NODE, (size_t)NS * G * 4); ENSURE(W_GCNT, NS); ENSURE(W_UCNT, NS);
+    ENSURE(W_SELLIST, (size_t)NN * 4 + 16); ENSURE(W_SELCNT, 16); ENSURE(W_NODES, (size_t)NN * 4 + 16);
+    ENSURE(W_OFF, (size_t)(maxNb + 4) * 4); ENSURE(W_CURSOR, (size_t)(maxNb + 4) * 4 * 2);
+    u32* cnt = P(W_CURSOR, u32);
+    u32* cursor = cnt + (maxNb + 4);
+    CU_CHECK(h, cudaMemsetAsync(cnt, 0, (size_t)(maxNb + 4) * 4 * 2, st));
+    k_wave_count<<<(NB + 255) / 256, 256, 0, st>>>(bv, cnt);
+    size_t tmpBytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, cnt, P(W_OFF, u32), (int)(maxNb + 2), st);
+    CU_CHECK(h, bf[jpp_b200_handle::R_CUBTMP].ensure(tmpBytes + 16));
+    cub::DeviceScan::ExclusiveSum(bf[jpp_b200_handle::R_CUBTMP].p, tmpBytes, cnt, P(W_OFF, u32), (int)(maxNb + 2), st);
+    k_wave_fill<<<(NB + 255) / 256, 256, 0, st>>>(bv, P(W_OFF, u32), cursor, P(W_NODES, u32));
+    CU_CHECK(h, cudaGetLastError());
+    h->waveNodeOff.assign(maxNb + 2, 0);
+    CU_CHECK(h, cudaMemcpyAsync(h->waveNodeOff.data(), P(W_OFF, u32), (size_t)(maxNb + 2) * 4, cudaMemcpyDeviceToHost, st));
+    h->waveActive.assign(maxNb + 1, 0);
+    for (u32 s = 0; s < NS; ++s) {
+      const u32 nb = b->sent_boundary_off[s + 1] - b->sent_boundary_off[s];
+      h->waveActive[0] += 1;               // difference array: active for b < nb
+      if (nb <= maxNb) h->waveActive[nb] -= 1;
+    }
+    for (u32 i = 1; i <= maxNb; ++i) h->waveActive[i] += h->waveActive[i - 1];
+    WaveView& wv = h->wv;
+    wv = WaveView{};
+    wv.gbKey = P(W_GBKEY, u64); wv.gbLnode = P(W_GBLNODE, u32); wv.gbT2node = P(W_GBT2, u32); wv.gbT1idx = P(W_GBT1IDX, u8);
+    wv.t1node = P(W_T1NODE, u32); wv.gCount = P(W_GCNT, u8); wv.uCount = P(W_UCNT, u8); wv.selList = P(W_SELLIST, u32);
+    wv.selCount = P(W_SELCNT, u32); wv.waveNodes = P(W_NODES, u32); wv.waveNodeOff = P(W_OFF, u32);
+  }
   if (h->hasRnn) {
     ENSURE(R_OFF, (size_t)(NS + 1) * 4);
     H2D(R_OFF, rnOff.data(), (size_t)(NS + 1) * 4);
@@ -591,18 +654,31 @@ jpp_b200_status jpp_b200_score_resident(jpp_b200_handle* h) {
   CU_CHECK(h, cudaGetLastError());
   CU_CHECK(h, cudaEventRecord(h->ev[3], st));
   {
-    const u32 wcap = warp_wcap((u32)h->cfg.gbeam, (u32)std::max(0, h->cfg.rbeam), h->hm.ft.nBi + h->hm.ft.nTri);
-    const u32 warpBytes = (u32)warp_smem_bytes((u32)h->cfg.gbeam, h->hm.ft.nStored, wcap);
-    const u32 warpsPerBlock = 4;
-    const size_t smem = ((sizeof(FeatTables) + 15) & ~(size_t)15) + (size_t)warpsPerBlock * warpBytes;
-    if (smem > 200 * 1024) return fail(h, JPP_B200_NOT_IMPLEMENTED, "configuration needs more shared memory than one CTA has");
-    CU_CHECK(h, cudaFuncSetAttribute(k_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int perSm = 0;
-    CU_CHECK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_walk, 128, smem));
-    if (perSm < 1) perSm = 1;
-    const u32 grid = std::min<u32>((u32)h->smCount * (u32)perSm, (NS + warpsPerBlock - 1) / warpsPerBlock);
-    k_walk<<<std::max(1u, grid), 128, smem, st>>>(h->dFt, bv, h->cfg, h->dWeights, bf[jpp_b200_handle::B_WORK].as<u32>(), warpBytes, wcap);
+    const ScoreCfg& cfg = h->cfg;
+    const FeatTables& ft = h->hm.ft;
+    const WaveView& wv = h->wv;
+    k_w_init<<<(NS + 127) / 128, 128, 0, st>>>(bv, cfg);
+    u32 launches = 1;
+    for (u32 bnd = 2; bnd < h->maxNb; ++bnd) {
+      const u32 nAct = h->waveActive[bnd];
+      if (nAct == 0) break;
+      const u32 first = h->waveNodeOff[bnd], count = h->waveNodeOff[bnd + 1] - first;
+      if (count == 0) continue;
+      k_w_gbeam<<<(nAct + 127) / 128, 128, 0, st>>>(bv, cfg, wv, nAct, bnd);
+      if (cfg.rcheck > 0) k_w_prescore<<<(count + 127) / 128, 128, 0, st>>>(ft, bv, cfg, wv, h->dWeights, first, count);
+      k_w_cutoff<<<(nAct + 127) / 128, 128, 0, st>>>(ft, bv, cfg, wv, nAct, bnd);
+      u32 selBound = count;
+      if (cfg.rcheck > 0) selBound = std::min<u64>(count, (u64)nAct * (u32)cfg.rbeam);
+      const u32 blocks = std::min<u32>((selBound + 127) / 128, (u32)h->smCount * 16);
+      k_w_score<<<std::max(1u, blocks), 128, 0, st>>>(ft, bv, cfg, wv, h->dWeights);
+      launches += 3;
+      if (cfg.rcheck > 0) {
+        k_w_rest<<<(count + 127) / 128, 128, 0, st>>>(bv, cfg, wv, first, count);
+        launches += 2;
+      }
+    }
     CU_CHECK(h, cudaGetLastError());
+    h->walkLaunches = launches;
   }
   CU_CHECK(h, cudaEventRecord(h->ev[4], st));
   if (h->hasRnn) {
@@ -663,7 +739,7 @@ jpp_b200_status jpp_b200_score_resident(jpp_b200_handle* h) {
   c.gathers = dc[0] + t0Nodes * h->hm.ft.nUni;
   c.walk_gathers = dc[0];
   c.walk_bytes = 4ull * dc[0] + dc[1];
-  c.launches = 2 + (h->hasRnn ? (12ull + h->maxNb) : 0ull);
+  c.launches = 1 + h->walkLaunches + (h->hasRnn ? (12ull + h->maxNb) : 0ull);
   // BASELINE.md roofline accounting: 4 B per gather + streaming terms
   const u32 B = (u32)h->cfg.beam, SP = h->hm.ft.nStored;
   // T0 kernel: entry + NodeInfo + placeholders in, pattern row + score out; walk kernel: see walk_sentence

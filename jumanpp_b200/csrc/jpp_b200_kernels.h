@@ -1,18 +1,15 @@
 // jpp_b200_kernels.h -- device code of the B200 lattice scorer.
 //
-// One warp walks one sentence: boundaries are sequential (the beams of boundary
-// b depend on every earlier boundary: reference analyzer_impl.cc:260-284), the
-// work inside a boundary (candidate scan, pattern staging, n-gram hash + weight
-// gather, beam build) is spread over the 32 lanes.
+// Every stage is a flat data-parallel function of an index (a node, a sentence,
+// a selected node); jpp_b200.cu wraps each in a __global__ kernel.  The beam
+// walk is organised as a wavefront over the boundary index (see "wavefront
+// walk" below): sentences are independent, so at wave b every sentence that
+// has a boundary b is processed at once.
 //
-// Lane-region discipline.  Every cross-lane exchange goes through shared
-// memory between JPP_LANES / JPP_LANES_END regions (the end of a region is a
-// __syncwarp()).  Code outside a region is warp-uniform: every lane computes
-// the same values from shared / global data; uniform writes are guarded by
-// JPP_LANE0 and followed by JPP_SYNC().  Because of that discipline the very
-// same source also compiles as plain C++ with the lanes run one after another
-// (tests/emul, TEST ONLY -- it lets the kernel logic be checked against the
-// oracle on a machine without a GPU; it is never part of libjpp_b200.so).
+// The functions are __host__ __device__: tests/emul compiles this very source
+// as plain C++ and calls the functions in loops (TEST ONLY -- it lets the kernel
+// logic be checked against the oracle on a machine without a GPU; it is never
+// part of libjpp_b200.so).
 //
 // Float semantics: every sum replays the accumulator interleaving of the code
 // the reference CLI runs (file:line at each site); this file must be compiled
@@ -32,16 +29,8 @@
 #endif
 
 #if defined(__CUDA_ARCH__)
-#define JPP_LANES { const int lane = (int)(threadIdx.x & 31u);
-#define JPP_LANES_END } __syncwarp();
-#define JPP_LANE0 ((threadIdx.x & 31u) == 0)
-#define JPP_SYNC() __syncwarp()
 #define JPP_LDG(p) __ldg(p)
 #else
-#define JPP_LANES for (int lane = 0; lane < 32; ++lane) {
-#define JPP_LANES_END }
-#define JPP_LANE0 true
-#define JPP_SYNC() ((void)0)
 #define JPP_LDG(p) (*(p))
 #endif
 
@@ -53,18 +42,10 @@ typedef int32_t i32;
 typedef uint16_t u16;
 typedef uint8_t u8;
 
-#ifndef JPP_GATHER_BATCH
-#define JPP_GATHER_BATCH 1
-#endif
-#ifndef JPP_KCHUNK
-#define JPP_KCHUNK 16
-#endif
-
 // ---------------------------------------------------------------- limits ----
 enum {
   MAX_UNI = 64, MAX_BI = 64, MAX_TRI = 16, MAX_PAT = 64, MAX_PRIM = 48, MAX_COMP = 64, MAX_POOL = 256,
-  MAX_BEAM = 32,   // beam_size, global_beam_size, right_gbeam_size upper bound on the GPU path
-  KCHUNK = JPP_KCHUNK  // right nodes scored per chunk
+  MAX_BEAM = 32    // beam_size, global_beam_size, right_gbeam_size upper bound on the GPU path
 };
 
 // util/seahash.h:15-17, impl/feature_impl_types.h:21-24
@@ -554,123 +535,36 @@ JPP_HD int beam_order(u32* idx, int n, const float* totals, int maxBeam) {
   return (int)len;
 }
 
-// -------------------------------------------------------- beam walk ---------
-// Shared memory of one warp (sizes depend on the scoring configuration).
-struct WarpSmem {
-  u64* red;        // [32]
-  u64* gbeam;      // [G]   packed BeamCandidate, descending
-  u32* gbLnode;    // [G]
-  u32* gbT2node;   // [G]
-  u32* t1node;     // [G]   unique left nodes in first-seen order
-  u32* t1idx;      // [G]
-  u64* t1pat;      // [G][SP]
-  u64* t2pat;      // [G][SP]
-  u64* t0pat;      // [KCHUNK][SP]  pattern rows of the right nodes being scored
-  u32* selNode;    // [KCHUNK] right-node offsets (in boundary) of the current chunk
-  float* scbuf;    // [KCHUNK][G]  bigram score per (selected node, unique t1)
-  float* tot;      // [KCHUNK][G]
-  float* loc;      // [KCHUNK][G]
-  float* wbuf;     // [wcap] gathered weights, summed in reference order afterwards
-  u32* misc;       // [8] uniform scalars
-  u32 wcap;
+// ------------------------------------------------------- wavefront walk -----
+// The beams of boundary b depend on every earlier boundary of the SAME
+// sentence (reference analyzer_impl.cc:260-284) but sentences are independent.
+// So all sentences advance one boundary index at a time ("wave" b = local
+// boundary b of every sentence that has one), and inside a wave every phase is
+// a flat data-parallel kernel:
+//   W1 wave_gbeam      thread per sentence      makeGlobalBeam, dedupT1, gatherT2 ids
+//   W2 wave_prescore   thread per right node    T0 + bigram + trigram vs the head elements
+//   W3 wave_cutoff     thread per sentence      makeT0cutoffBeam -> list of selected nodes
+//   W4 wave_score_node thread per selected node applyBiTri vs the whole global beam, beam
+//   W5 wave_rest_node  thread per other node    beam of the head elements only
+// Threads of one warp run the same feature loop in lockstep, so the feature
+// tables (kernel parameter -> constant bank) are broadcast reads, the weight
+// gathers of a warp are 32 independent requests, and no lane idles because a
+// boundary has few right nodes: the parallelism is across sentences.
+
+// per-sentence state of the current wave (device arrays)
+struct WaveView {
+  u64* gbKey;      // [NS][G]  packed BeamCandidate of the global beam, descending
+  u32* gbLnode;    // [NS][G]  left node of each element
+  u32* gbT2node;   // [NS][G]  node before the left node
+  u8* gbT1idx;     // [NS][G]  index into the unique-t1 list
+  u32* t1node;     // [NS][G]  unique left nodes, first-seen order
+  u8* gCount;      // [NS]
+  u8* uCount;      // [NS]
+  u32* selList;    // [cap]    selected right nodes of the wave (global node ids)
+  u32* selCount;   // [1]
+  const u32* waveNodes;    // [NN] node ids grouped by local boundary index
+  const u32* waveNodeOff;  // [maxNb+1]
 };
-
-// gathered-weight staging capacity (floats) for a configuration
-JPP_HD u32 warp_wcap(u32 G, u32 rbeam, u32 NF) {
-  u32 k = rbeam ? rbeam : 8u;
-  if (k > 8u) k = 8u;
-  u32 a = 16u * NF, b = k * G * NF;
-  u32 c = a > b ? a : b;
-  if (c < G * NF) c = G * NF;
-  return c;
-}
-
-JPP_HD size_t warp_smem_bytes(u32 G, u32 SP, u32 wcap) {
-  size_t b = 0;
-  b += 32 * 8;                 // red
-  b += (size_t)G * 8;          // gbeam
-  b += (size_t)G * SP * 8 * 2; // t1pat, t2pat
-  b += (size_t)KCHUNK * SP * 8;// t0pat
-  b += (size_t)G * 4 * 4;      // gbLnode, gbT2node, t1node, t1idx
-  b += KCHUNK * 4;             // selNode
-  b += (size_t)KCHUNK * G * 4 * 3;
-  b += (size_t)wcap * 4;
-  b += 8 * 4;
-  return (b + 15) & ~(size_t)15;
-}
-
-JPP_HD WarpSmem carve_warp_smem(unsigned char* base, u32 G, u32 SP, u32 wcap) {
-  WarpSmem s;
-  unsigned char* p = base;
-  s.red = (u64*)p; p += 32 * 8;
-  s.gbeam = (u64*)p; p += (size_t)G * 8;
-  s.t1pat = (u64*)p; p += (size_t)G * SP * 8;
-  s.t2pat = (u64*)p; p += (size_t)G * SP * 8;
-  s.t0pat = (u64*)p; p += (size_t)KCHUNK * SP * 8;
-  s.gbLnode = (u32*)p; p += (size_t)G * 4;
-  s.gbT2node = (u32*)p; p += (size_t)G * 4;
-  s.t1node = (u32*)p; p += (size_t)G * 4;
-  s.t1idx = (u32*)p; p += (size_t)G * 4;
-  s.selNode = (u32*)p; p += KCHUNK * 4;
-  s.scbuf = (float*)p; p += (size_t)KCHUNK * G * 4;
-  s.tot = (float*)p; p += (size_t)KCHUNK * G * 4;
-  s.loc = (float*)p; p += (size_t)KCHUNK * G * 4;
-  s.wbuf = (float*)p; p += (size_t)wcap * 4;
-  s.misc = (u32*)p;
-  s.wcap = wcap;
-  return s;
-}
-
-// Ordered sums over gathered weights x[0..n): NV interleaved accumulators
-// started at 0 ("f_j = 0; f_j += w", partial_ngram_feature_codegen.cc:44-66;
-// NV = 4 is also computeUnrolled4RawPerceptron, perceptron.h:46-72; NV = 2 is
-// the r1/r2 pair of applyBiTriFullKernel, feature_impl_ngram_partial_kernels.h:35-61).
-template <int NV>
-JPP_HD void osum(const float* x, u32 n, float* acc) {
-#pragma unroll
-  for (int j = 0; j < NV; ++j) acc[j] = 0.0f;
-  u32 f = 0;
-  for (; f + NV <= n; f += NV) {
-#pragma unroll
-    for (int j = 0; j < NV; ++j) acc[j] += x[f + j];
-  }
-#pragma unroll
-  for (int j = 0; j < NV; ++j)
-    if (f + j < n) acc[j] += x[f + j];
-}
-
-JPP_HD float osum_vars(const float* x, u32 n, u32 nv) {
-  float a[8];
-  switch (nv) {
-    case 8: osum<8>(x, n, a); return ((((((a[0] + a[1]) + a[2]) + a[3]) + a[4]) + a[5]) + a[6]) + a[7];
-    case 4: osum<4>(x, n, a); return ((a[0] + a[1]) + a[2]) + a[3];
-    case 2: osum<2>(x, n, a); return a[0] + a[1];
-    default: osum<1>(x, n, a); return a[0];
-  }
-}
-
-JPP_HD float osum_unrolled4(const float* x, u32 n) {
-  float a[4];
-  osum<4>(x, n, a);
-  return ((a[0] + a[1]) + a[2]) + a[3];
-}
-
-// max over the 32 per-lane values a region left in sm.red
-JPP_HD u64 uniform_max_u64(const u64* red) {
-#if defined(__CUDA_ARCH__)
-  u64 v = red[threadIdx.x & 31u];
-#pragma unroll
-  for (int o = 16; o >= 1; o >>= 1) {
-    const u64 t = __shfl_xor_sync(0xffffffffu, v, o);
-    v = t > v ? t : v;
-  }
-  return v;
-#else
-  u64 m = 0;
-  for (int l = 0; l < 32; ++l) if (red[l] > m) m = red[l];
-  return m;
-#endif
-}
 
 #if defined(__CUDACC__)
 #define JPP_NOINLINE __noinline__
@@ -678,12 +572,48 @@ JPP_HD u64 uniform_max_u64(const u64* red) {
 #define JPP_NOINLINE
 #endif
 
+// Ordered sum of n gathered weights with NV interleaved accumulators started at
+// 0 ("f_j = 0; f_j += w", partial_ngram_feature_codegen.cc:44-66; NV = 4 is also
+// computeUnrolled4RawPerceptron, perceptron.h:46-72; NV = 2 is the r1/r2 pair
+// of applyBiTriFullKernel, feature_impl_ngram_partial_kernels.h:35-61).
+// idxOf(f) yields the table index; NV loads are in flight at a time.
+template <int NV, typename IdxFn>
+JPP_HD void gsum(const float* __restrict__ w, u32 n, IdxFn idxOf, float* acc) {
+#pragma unroll
+  for (int j = 0; j < NV; ++j) acc[j] = 0.0f;
+  u32 f = 0;
+  for (; f + NV <= n; f += NV) {
+    float x[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) x[j] = JPP_LDG(w + idxOf(f + j));
+#pragma unroll
+    for (int j = 0; j < NV; ++j) acc[j] += x[j];
+  }
+#pragma unroll
+  for (int j = 0; j < NV; ++j)
+    if (f + j < n) acc[j] += JPP_LDG(w + idxOf(f + j));
+}
+
+template <typename IdxFn>
+JPP_HD float gsum_vars(const float* __restrict__ w, u32 n, u32 nv, IdxFn idxOf) {
+  float a[8];
+  switch (nv) {
+    case 8: gsum<8>(w, n, idxOf, a); return ((((((a[0] + a[1]) + a[2]) + a[3]) + a[4]) + a[5]) + a[6]) + a[7];
+    case 4: gsum<4>(w, n, idxOf, a); return ((a[0] + a[1]) + a[2]) + a[3];
+    case 2: gsum<2>(w, n, idxOf, a); return a[0] + a[1];
+    default: gsum<1>(w, n, idxOf, a); return a[0];
+  }
+}
+
+template <typename IdxFn>
+JPP_HD float gsum_unrolled4(const float* __restrict__ w, u32 n, IdxFn idxOf) {
+  float a[4];
+  gsum<4>(w, n, idxOf, a);
+  return ((a[0] + a[1]) + a[2]) + a[3];
+}
+
 // Writes the beam row of one right node from `n` candidate totals.
-JPP_NOINLINE
-#if defined(__CUDACC__)
-__host__ __device__
-#endif
-inline void write_beam(const BatchView& bv, const ScoreCfg& cfg, u32 node, const u64* gbeam, int n,
+JPP_HD void write_beam(const BatchView& bv, const ScoreCfg& cfg, u32 node, const u64* gbeam, int n,
                        const float* totals, const float* local) {
   u32 idx[MAX_BEAM];
   const int maxBeam = cfg.beam;
@@ -713,430 +643,287 @@ inline void write_beam(const BatchView& bv, const ScoreCfg& cfg, u32 node, const
   }
 }
 
-// One warp, one sentence: makeGlobalBeam + computeGbeamScores for every
-// boundary (analyzer_impl.cc:260-284, score_processor.cc:246-361).
-//
-// The hot work of a boundary is flattened over the lanes as (row, feature)
-// items: each lane hashes one n-gram feature and gathers one weight per
-// iteration (all 32 lanes busy even when a boundary has only a few right
-// nodes), staging the weights in shared memory; the float sums are then
-// replayed from shared memory in the reference's accumulator order.
-JPP_HD void walk_sentence(const FeatTables& ft, const BatchView& bv, const ScoreCfg& cfg, const float* __restrict__ w,
-                          WarpSmem sm, u32 sent) {
+// W0: BOS beams of every sentence (analyzer_impl.cc:185-192) and the degenerate
+// "no codepoints" lattice (:255-258)
+JPP_HD void wave_init_sentence(const BatchView& bv, const ScoreCfg& cfg, u32 sent) {
   const u32 b0 = bv.sentBndOff[sent];
   const u32 nb = bv.sentBndOff[sent + 1] - b0;
   const u32 B = (u32)cfg.beam;
-  const u32 SP = ft.nStored;
-  const u32 nB = ft.nBi, nT = ft.nTri, mask = ft.mask;
-  const u32 NF = nB + nT;
-  const u32 GMAX = (u32)cfg.gbeam;
-  unsigned long long gathers = 0, streamBytes = 0;
-
-  // BOS beams (analyzer_impl.cc:185-192)
-  JPP_LANES
-  for (u32 i = (u32)lane; i < 2 * B && nb >= 2; i += 32) {
-    const u32 bb = i / B, k = i % B;
+  for (u32 bb = 0; bb < 2 && bb < nb; ++bb) {
     const u32 n0 = bv.bndNodeOff[b0 + bb];
-    jpp_b200_beam_element e;
-    if (k == 0) { e.left = 0; e.prev_beam = 0; e.total_score = 0.0f; }
-    else { e.left = 0xFFFFu; e.prev_beam = 0xFFFFu; e.total_score = -3.402823466e+38f; }  // EntryBeam::fake()
-    bv.beam[(size_t)n0 * B + k] = e;
-    for (u32 q = 0; q < cfg.S; ++q) bv.beamScores[((size_t)n0 * B + k) * cfg.S + q] = 0.0f;
-  }
-  JPP_LANES_END
-  if (nb <= 3) {  // analyzer_impl.cc:255-258
-    if (nb == 3) {
-      JPP_LANES
-      const u32 n0 = bv.bndNodeOff[b0 + 2];
-      for (u32 k = (u32)lane; k < B; k += 32) {
-        bv.beam[(size_t)n0 * B + k] = fake_elem();
-        for (u32 q = 0; q < cfg.S; ++q) bv.beamScores[((size_t)n0 * B + k) * cfg.S + q] = 0.0f;
-      }
-      JPP_LANES_END
+    for (u32 k = 0; k < B; ++k) {
+      jpp_b200_beam_element e;
+      if (k == 0) { e.left = 0; e.prev_beam = 0; e.total_score = 0.0f; }
+      else { e.left = 0xFFFFu; e.prev_beam = 0xFFFFu; e.total_score = -3.402823466e+38f; }  // EntryBeam::fake()
+      bv.beam[(size_t)n0 * B + k] = e;
+      for (u32 q = 0; q < cfg.S; ++q) bv.beamScores[((size_t)n0 * B + k) * cfg.S + q] = 0.0f;
     }
+  }
+  if (nb == 3) {
+    const u32 n0 = bv.bndNodeOff[b0 + 2];
+    for (u32 k = 0; k < B; ++k) {
+      bv.beam[(size_t)n0 * B + k] = fake_elem();
+      for (u32 q = 0; q < cfg.S; ++q) bv.beamScores[((size_t)n0 * B + k) * cfg.S + q] = 0.0f;
+    }
+    bv.gbCount[b0 + 2] = 0;
+  }
+}
+
+// W1: makeGlobalBeam (score_processor.cc:246-282) + dedupT1 / gatherT2 ids (:363-409).
+// One thread scans the L x B left beam elements and keeps the G largest packed
+// keys (distinct by construction: score_processor.h:81-115) in sorted order.
+JPP_HD void wave_gbeam(const BatchView& bv, const ScoreCfg& cfg, const WaveView& wv, u32 sent, u32 bnd) {
+  const u32 b0 = bv.sentBndOff[sent];
+  const u32 nb = bv.sentBndOff[sent + 1] - b0;
+  if (bnd >= nb || nb <= 3) return;
+  const u32 gB = b0 + bnd;
+  const u32 R = bv.bndNodeOff[gB + 1] - bv.bndNodeOff[gB];
+  const u32 B = (u32)cfg.beam, GMAX = (u32)cfg.gbeam;
+  wv.gCount[sent] = 0;
+  wv.uCount[sent] = 0;
+  if (R == 0) {  // analyzer_impl.cc:263-266
+    bv.gbCount[gB] = 0;
     return;
   }
-
-  for (u32 bnd = 2; bnd < nb; ++bnd) {
-    const u32 gB = b0 + bnd;
-    const u32 n0 = bv.bndNodeOff[gB];
-    const u32 R = bv.bndNodeOff[gB + 1] - n0;
-    const u32 e0 = bv.bndEndOff[gB];
-    const u32 L = bv.bndEndOff[gB + 1] - e0;
-    if (R == 0) {  // analyzer_impl.cc:263-266
-      if (JPP_LANE0) bv.gbCount[gB] = 0;
-      continue;
-    }
-
-    // ---- makeGlobalBeam (score_processor.cc:246-282): the G largest packed
-    // candidates; keys are distinct, so round j takes the largest key below
-    // the one taken in round j-1.
-    u64 last = ~(u64)0;
-    u32 G = 0;
-    const u32 nc = L * B;
-    // candidates are packed once into shared memory (the gathered-weight buffer is
-    // idle here); a boundary with more candidates than fit re-reads the beams
-    u64* candS = reinterpret_cast<u64*>(sm.wbuf);
-#ifndef JPP_STAGE_CANDS
-#define JPP_STAGE_CANDS 1
-#endif
-    const bool staged = JPP_STAGE_CANDS && nc <= sm.wcap / 2;
-    if (staged) {
-      JPP_LANES
-      for (u32 left = (u32)lane; left < L; left += 32) {
-        const u32 lnode = bv.endNode[e0 + left];
-        const jpp_b200_beam_element* row = bv.beam + (size_t)lnode * B;
-        for (u32 slot = 0; slot < B; ++slot) {
-          const jpp_b200_beam_element el = row[slot];
-          candS[left * B + slot] = is_fake(el) ? 0 : pack_cand(el.total_score, left, slot);
-        }
-      }
-      JPP_LANES_END
-    }
-    for (u32 j = 0; j < GMAX; ++j) {
-      JPP_LANES
-      u64 best = 0;
-      if (staged) {
-        for (u32 c = (u32)lane; c < nc; c += 32) {
-          const u64 key = candS[c];
-          if (key < last && key > best) best = key;
-        }
-      } else {
-        for (u32 left = (u32)lane; left < L; left += 32) {
-          const u32 lnode = bv.endNode[e0 + left];
-          for (u32 slot = 0; slot < B; ++slot) {
-            const jpp_b200_beam_element el = bv.beam[(size_t)lnode * B + slot];
-            if (!is_fake(el)) {
-              const u64 key = pack_cand(el.total_score, left, slot);
-              if (key < last && key > best) best = key;
-            }
-          }
-        }
-      }
-      sm.red[lane] = best;
-      JPP_LANES_END
-      const u64 m = uniform_max_u64(sm.red);
-      JPP_SYNC();
-      if (m == 0) break;
-      if (JPP_LANE0) sm.gbeam[j] = m;
-      last = m;
-      G = j + 1;
-    }
-    JPP_SYNC();
-
-    // ---- global beam bookkeeping, t1 de-duplication, t2 lookup (:363-409)
-    JPP_LANES
-    if ((u32)lane < G) {
-      const u64 key = sm.gbeam[lane];
-      const u32 left = (u32)(key >> 16) & 0xFFFFu, slot = (u32)key & 0xFFFFu;
-      const u32 lnode = bv.endNode[e0 + left];
-      const u32 lbnd = bv.ends[e0 + left].boundary;
-      const jpp_b200_beam_element el = bv.beam[(size_t)lnode * B + slot];
-      const u32 t2node = bv.endNode[bv.bndEndOff[b0 + lbnd] + el.left];
-      sm.gbLnode[lane] = lnode;
-      sm.gbT2node[lane] = t2node;
-      bv.gbNode[(size_t)gB * GMAX + lane] = lnode;
-      bv.gbSlot[(size_t)gB * GMAX + lane] = (u16)slot;
-      bv.gbLeftBnd[(size_t)gB * GMAX + lane] = (u16)lbnd;
-    }
-    if (lane == 0) bv.gbCount[gB] = (u8)G;
-    JPP_LANES_END
-    u32 U = 0;
-    if (JPP_LANE0) {
-      for (u32 g = 0; g < G; ++g) {
-        const u32 ln = sm.gbLnode[g];
-        u32 u = 0;
-        for (; u < U; ++u) if (sm.t1node[u] == ln) break;
-        if (u == U) { sm.t1node[U] = ln; ++U; }
-        sm.t1idx[g] = u;
-      }
-      sm.misc[1] = U;
-    }
-    JPP_SYNC();
-    U = sm.misc[1];
-    // algorithmic streaming bytes of this boundary (DESIGN.md "roofline accounting"):
-    // left beams read, pattern rows of right / unique-t1 / t2 nodes, ends, beams + scores written
-    streamBytes += 8ull * L * B + 8ull * SP * ((unsigned long long)R + U + G) + 4ull * L +
-                   (8ull + 4ull * cfg.S) * R * B;
-    JPP_LANES
-    for (u32 i = (u32)lane; i < U * SP; i += 32) sm.t1pat[i] = bv.patterns[(size_t)sm.t1node[i / SP] * SP + i % SP];
-    for (u32 i = (u32)lane; i < G * SP; i += 32) sm.t2pat[i] = bv.patterns[(size_t)sm.gbT2node[i / SP] * SP + i % SP];
-    JPP_LANES_END
-
-    const bool rightCheck = cfg.rcheck > 0;
-    u32 full = 0, toKeep = R, remaining = G;
-    if (rightCheck) {
-      full = (u32)cfg.rcheck;
-      if (R < full) full = R;
-      if (G < full) full = G;  // fullBeamApplySize, score_processor.cc:299-301
-      toKeep = (u32)cfg.rbeam < R ? (u32)cfg.rbeam : R;
-      remaining = G - full;
-      const u32 theMax = (u32)cfg.rcheck < G ? (u32)cfg.rcheck : G;  // computeT0Prescores :497-511
-
-      // ---- T0 prescores: T0 + bigrams (biVars accumulators; last row Unrolled4)
-      // + trigrams (partial_ngram_feature_codegen.cc:13-153)
-      u32 RC = sm.wcap / NF;
-      if (RC > KCHUNK) RC = KCHUNK;
-      for (u32 i = 0; i < theMax; ++i) {
-        const u64* t1 = sm.t1pat + (size_t)sm.t1idx[i] * SP;
-        const u64* t2 = sm.t2pat + (size_t)i * SP;
-        for (u32 r0 = 0; r0 < R; r0 += RC) {
-          const u32 rc = (R - r0) < RC ? (R - r0) : RC;
-          JPP_LANES
-          const u64* src = bv.patterns + (size_t)(n0 + r0) * SP;
-          for (u32 x = (u32)lane; x < rc * SP; x += 32) sm.t0pat[x] = src[x];
-          JPP_LANES_END
-          JPP_LANES
-          u32 row = 0, f = (u32)lane;
-          while (f >= NF) { f -= NF; ++row; }
-          const u32 total = rc * NF;
-          for (u32 it = (u32)lane; it < total; it += 32u * JPP_GATHER_BATCH) {
-            u32 idx[JPP_GATHER_BATCH];
-            float v[JPP_GATHER_BATCH];
-#pragma unroll
-            for (int q = 0; q < JPP_GATHER_BATCH; ++q) {
-              idx[q] = 0;
-              if (it + 32u * q < total) {
-                const u64* P = sm.t0pat + (size_t)row * SP;
-                if (f < nB) {
-                  idx[q] = (u32)mix(mix(ft.biState[f], P[ft.biT0[f]]), t1[ft.biT1[f]]) & mask;
-                } else {
-                  const u32 g = f - nB;
-                  idx[q] = (u32)mix(mix(mix(ft.triState[g], P[ft.triT0[g]]), t1[ft.triT1[g]]), t2[ft.triT2[g]]) & mask;
-                }
-              }
-              f += 32;
-              while (f >= NF) { f -= NF; ++row; }
-            }
-#pragma unroll
-            for (int q = 0; q < JPP_GATHER_BATCH; ++q) v[q] = JPP_LDG(w + idx[q]);
-#pragma unroll
-            for (int q = 0; q < JPP_GATHER_BATCH; ++q)
-              if (it + 32u * q < total) sm.wbuf[it + 32u * q] = v[q];
-          }
-          JPP_LANES_END
-          JPP_LANES
-          for (u32 r = (u32)lane; r < rc; r += 32) {
-            const u32 node = n0 + r0 + r;
-            const bool lastRow = (r0 + r + 1 == R);
-            const float* x = sm.wbuf + (size_t)r * NF;
-            float sc = bv.t0[node];
-            sc += lastRow ? osum_unrolled4(x, nB) : osum_vars(x, nB, ft.biVars);
-            sc += lastRow ? osum_unrolled4(x + nB, nT) : osum_vars(x + nB, nT, ft.triVars);
-            bv.pre[(size_t)i * bv.totalNodes + node] = sc;
-          }
-          JPP_LANES_END
-        }
-      }
-      gathers += (unsigned long long)theMax * R * NF;
-
-      // ---- makeT0cutoffBeam (:471-495): which toKeep right nodes get full beams
-      if (R > toKeep) {
-        JPP_LANES
-        for (u32 r = (u32)lane; r < R; r += 32) {
-          float v = 0;
-          for (u32 j = 0; j < full; ++j) v += bv.pre[(size_t)j * bv.totalNodes + n0 + r];
-          bv.cut[n0 + r] = v;
-        }
-        JPP_LANES_END
-        if (JPP_LANE0) sm.misc[2] = 0;
-        JPP_SYNC();
-        JPP_LANES
-        for (u32 r = (u32)lane; r < R; r += 32) {
-          const float mine = bv.cut[n0 + r];
-          u32 gt = 0, ge = 0;
-          for (u32 j = 0; j < R; ++j) {
-            const float o = bv.cut[n0 + j];
-            gt += (o > mine);
-            ge += (o >= mine);
-          }
-          // ge <= toKeep: certainly inside the top toKeep; gt >= toKeep: certainly outside;
-          // otherwise a run of equal scores straddles the cut -> replay nth_element
-          u16 v = 0xFFFFu;
-          if (ge <= toKeep) v = 1;
-          else if (gt < toKeep) { v = 2; sm.misc[2] = 1; }
-          bv.selK[n0 + r] = v;
-        }
-        JPP_LANES_END
-        if (sm.misc[2] != 0) {
-          if (JPP_LANE0) {
-            u32* idx = bv.cutIdx + n0;
-            for (u32 r = 0; r < R; ++r) idx[r] = r;
-            em_std_nth_element(idx, (long)toKeep, (long)R, ScoreCmp{bv.cut + n0});
-            for (u32 r = 0; r < R; ++r) bv.selK[n0 + r] = 0xFFFFu;
-            for (u32 k = 0; k < toKeep; ++k) bv.selK[n0 + idx[k]] = 1;
-          }
-          JPP_SYNC();
-        }
-      } else {
-        JPP_LANES
-        for (u32 r = (u32)lane; r < R; r += 32) bv.selK[n0 + r] = 1;
-        JPP_LANES_END
-      }
-    } else {
-      JPP_LANES
-      for (u32 r = (u32)lane; r < R; r += 32) bv.selK[n0 + r] = 1;
-      JPP_LANES_END
-    }
-
-    // ---- selected right nodes, a chunk at a time: full scoring against the
-    // global beam (applyBiTri -> applyBiTriFullKernel, feature_impl_ngram_partial_kernels.h:19-110)
-    const bool scoreTail = remaining > 0 && G > 0;
-    const u32 perNode = scoreTail ? (U * nB + remaining * nT) : 1u;
-    u32 KCH = sm.wcap / (perNode ? perNode : 1u);
-    if (KCH > KCHUNK) KCH = KCHUNK;
-    if (KCH < 1) KCH = 1;
-    u32 rScan = 0;
-    while (rScan < R) {
-      u32 K = 0;
-      if (JPP_LANE0) {
-        u32 r = rScan;
-        for (; r < R && K < KCH; ++r) {
-          if (bv.selK[n0 + r] != 0xFFFFu) { sm.selNode[K] = r; bv.selK[n0 + r] = (u16)K; ++K; }
-        }
-        sm.misc[3] = K;
-        sm.misc[4] = r;
-      }
-      JPP_SYNC();
-      K = sm.misc[3];
-      rScan = sm.misc[4];
-      if (K == 0) break;
-      if (scoreTail) {
-        JPP_LANES
-        for (u32 x = (u32)lane; x < K * SP; x += 32)
-          sm.t0pat[x] = bv.patterns[(size_t)(n0 + sm.selNode[x / SP]) * SP + x % SP];
-        JPP_LANES_END
-        const u32 triBase = K * U * nB;
-        JPP_LANES
-        {  // bigram items (k, u, f), four gathers in flight per lane
-          u32 k = 0, u = 0, f = (u32)lane;
-          while (f >= nB) { f -= nB; if (++u == U) { u = 0; ++k; } }
-          for (u32 it = (u32)lane; it < triBase; it += 32u * JPP_GATHER_BATCH) {
-            u32 idx[JPP_GATHER_BATCH];
-            float v[JPP_GATHER_BATCH];
-#pragma unroll
-            for (int q = 0; q < JPP_GATHER_BATCH; ++q) {
-              idx[q] = 0;
-              if (it + 32u * q < triBase) {
-                const u64* P = sm.t0pat + (size_t)k * SP;
-                const u64* t1 = sm.t1pat + (size_t)u * SP;
-                idx[q] = (u32)mix(mix(ft.biState[f], P[ft.biT0[f]]), t1[ft.biT1[f]]) & mask;
-              }
-              f += 32;
-              while (f >= nB) { f -= nB; if (++u == U) { u = 0; ++k; } }
-            }
-#pragma unroll
-            for (int q = 0; q < JPP_GATHER_BATCH; ++q) v[q] = JPP_LDG(w + idx[q]);
-#pragma unroll
-            for (int q = 0; q < JPP_GATHER_BATCH; ++q)
-              if (it + 32u * q < triBase) sm.wbuf[it + 32u * q] = v[q];
-          }
-        }
-        {  // trigram items (k, j, f) of the tail elements
-          const u32 nTri = K * remaining * nT;
-          u32 k = 0, j = 0, f = (u32)lane;
-          while (nT && f >= nT) { f -= nT; if (++j == remaining) { j = 0; ++k; } }
-          for (u32 it = (u32)lane; it < nTri; it += 32) {
-            const u32 gi = full + j;
-            const u64* P = sm.t0pat + (size_t)k * SP;
-            const u64* t1 = sm.t1pat + (size_t)sm.t1idx[gi] * SP;
-            const u64* t2 = sm.t2pat + (size_t)gi * SP;
-            const u32 idx = (u32)mix(mix(mix(ft.triState[f], P[ft.triT0[f]]), t1[ft.triT1[f]]), t2[ft.triT2[f]]) & mask;
-            sm.wbuf[triBase + it] = JPP_LDG(w + idx);
-            f += 32;
-            while (f >= nT) { f -= nT; if (++j == remaining) { j = 0; ++k; } }
-          }
-        }
-        JPP_LANES_END
-        JPP_LANES
-        for (u32 it = (u32)lane; it < K * U; it += 32) {
-          const u32 k = it / U, u = it - k * U;
-          const float* x = sm.wbuf + (size_t)it * nB;
-          float v;
-          if (u + 1 < U) {
-            float a[2];
-            osum<2>(x, nB, a);
-            v = a[0] + a[1];
-          } else {
-            v = osum_unrolled4(x, nB);
-          }
-          sm.scbuf[k * GMAX + u] = v;
-        }
-        JPP_LANES_END
-        JPP_LANES
-        for (u32 it = (u32)lane; it < K * remaining; it += 32) {
-          const u32 k = it / remaining, j = it - k * remaining, gi = full + j;
-          const u32 node = n0 + sm.selNode[k];
-          const float* x = sm.wbuf + triBase + (size_t)it * nT;
-          float v;
-          if (j + 1 < remaining) {
-            float a[2];
-            osum<2>(x, nT, a);
-            v = sm.scbuf[k * GMAX + sm.t1idx[gi]] + a[0] + a[1];
-          } else {
-            v = sm.scbuf[k * GMAX + sm.t1idx[gi]] + osum_unrolled4(x, nT);
-          }
-          v += bv.t0[node];  // copyT0Scores(tail, t0Score), score_processor.cc:411-424
-          sm.loc[k * GMAX + gi] = v;
-          v += cand_score(sm.gbeam[gi]);
-          sm.tot[k * GMAX + gi] = v;
-        }
-        JPP_LANES_END
-        gathers += (unsigned long long)K * ((unsigned long long)U * nB + (unsigned long long)remaining * nT);
-      }
-      JPP_LANES
-      for (u32 it = (u32)lane; it < K * full; it += 32) {
-        const u32 k = it / full, i = it - k * full;
-        float v = bv.pre[(size_t)i * bv.totalNodes + n0 + sm.selNode[k]];
-        v += 0.0f;  // copyT0Scores(head, 0)
-        sm.loc[k * GMAX + i] = v;
-        v += cand_score(sm.gbeam[i]);
-        sm.tot[k * GMAX + i] = v;
-      }
-      JPP_LANES_END
-      JPP_LANES
-      for (u32 k = (u32)lane; k < K; k += 32) {
-        const u32 node = n0 + sm.selNode[k];
-        write_beam(bv, cfg, node, sm.gbeam, (int)G, sm.tot + k * GMAX, sm.loc + k * GMAX);
-        if (bnd == nb - 1) {
-          for (u32 g = 0; g < G; ++g) {
-            bv.eosGbeam[(size_t)sent * GMAX + g] = sm.gbeam[g];
-            bv.eosLocal[(size_t)sent * GMAX + g] = sm.loc[k * GMAX + g];
-          }
-        }
-      }
-      JPP_LANES_END
-    }
-
-    // ---- right nodes outside the cutoff: beam of the head elements only
-    if (rightCheck && R > toKeep) {
-      JPP_LANES
-      for (u32 r = (u32)lane; r < R; r += 32) {
-        const u32 node = n0 + r;
-        if (bv.selK[node] == 0xFFFFu) {
-          float tot[MAX_BEAM], loc[MAX_BEAM];
-          for (u32 i = 0; i < full; ++i) {
-            float v = bv.pre[(size_t)i * bv.totalNodes + node];
-            v += 0.0f;
-            loc[i] = v;
-            v += cand_score(sm.gbeam[i]);
-            tot[i] = v;
-          }
-          write_beam(bv, cfg, node, sm.gbeam, (int)full, tot, loc);
-        }
-      }
-      JPP_LANES_END
+  const u32 e0 = bv.bndEndOff[gB];
+  const u32 L = bv.bndEndOff[gB + 1] - e0;
+  u64 top[MAX_BEAM];
+  u32 G = 0;
+  for (u32 left = 0; left < L; ++left) {
+    const u32 lnode = bv.endNode[e0 + left];
+    const jpp_b200_beam_element* row = bv.beam + (size_t)lnode * B;
+    for (u32 slot = 0; slot < B; ++slot) {
+      const jpp_b200_beam_element el = row[slot];
+      if (is_fake(el)) break;  // beams are filled front to back (score_processor.cc:257-260)
+      const u64 key = pack_cand(el.total_score, left, slot);
+      if (G == GMAX && key < top[G - 1]) continue;
+      u32 pos = G < GMAX ? G : GMAX - 1;
+      while (pos > 0 && top[pos - 1] < key) { top[pos] = top[pos - 1]; --pos; }
+      top[pos] = key;
+      if (G < GMAX) ++G;
     }
   }
-  if (JPP_LANE0 && bv.counters) {
+  u64* gbKey = wv.gbKey + (size_t)sent * GMAX;
+  u32* gbLnode = wv.gbLnode + (size_t)sent * GMAX;
+  u32* gbT2 = wv.gbT2node + (size_t)sent * GMAX;
+  u8* t1idx = wv.gbT1idx + (size_t)sent * GMAX;
+  u32* t1node = wv.t1node + (size_t)sent * GMAX;
+  u32 U = 0;
+  for (u32 g = 0; g < G; ++g) {
+    const u64 key = top[g];
+    const u32 left = (u32)(key >> 16) & 0xFFFFu, slot = (u32)key & 0xFFFFu;
+    const u32 lnode = bv.endNode[e0 + left];
+    const u32 lbnd = bv.ends[e0 + left].boundary;
+    const jpp_b200_beam_element el = bv.beam[(size_t)lnode * B + slot];
+    gbKey[g] = key;
+    gbLnode[g] = lnode;
+    gbT2[g] = bv.endNode[bv.bndEndOff[b0 + lbnd] + el.left];
+    u32 u = 0;
+    for (; u < U; ++u) if (t1node[u] == lnode) break;
+    if (u == U) { t1node[U] = lnode; ++U; }
+    t1idx[g] = (u8)u;
+    bv.gbNode[(size_t)gB * GMAX + g] = lnode;
+    bv.gbSlot[(size_t)gB * GMAX + g] = (u16)slot;
+    bv.gbLeftBnd[(size_t)gB * GMAX + g] = (u16)lbnd;
+  }
+  bv.gbCount[gB] = (u8)G;
+  wv.gCount[sent] = (u8)G;
+  wv.uCount[sent] = (u8)U;
+}
+
+// W2: computeT0Prescores (score_processor.cc:497-511) for one right node:
+// T0 + bigrams against t1 of head element i + trigrams (generated applyBiStep2 /
+// applyTriStep3: biVars / triVars accumulators, last row of the boundary through
+// computeUnrolled4RawPerceptron; partial_ngram_feature_codegen.cc:13-153)
+JPP_HD void wave_prescore(const FeatTables& ft, const BatchView& bv, const ScoreCfg& cfg, const WaveView& wv,
+                          const float* __restrict__ w, u32 node) {
+  const u32 gB = bv.nodeBnd[node];
+  const u32 sent = bv.bndSent[gB];
+  const u32 G = wv.gCount[sent];
+  const u32 theMax = (u32)cfg.rcheck < G ? (u32)cfg.rcheck : G;
+  if (theMax == 0) return;
+  const u32 GMAX = (u32)cfg.gbeam, SP = ft.nStored, mask = ft.mask;
+  const bool lastRow = (node + 1 == bv.bndNodeOff[gB + 1]);
+  const u64* P = bv.patterns + (size_t)node * SP;
+  const float t0 = bv.t0[node];
+  for (u32 i = 0; i < theMax; ++i) {
+    const u64* t1 = bv.patterns + (size_t)wv.gbLnode[(size_t)sent * GMAX + i] * SP;
+    const u64* t2 = bv.patterns + (size_t)wv.gbT2node[(size_t)sent * GMAX + i] * SP;
+    auto biIdx = [&](u32 f) -> u32 { return (u32)mix(mix(ft.biState[f], P[ft.biT0[f]]), t1[ft.biT1[f]]) & mask; };
+    auto triIdx = [&](u32 f) -> u32 {
+      return (u32)mix(mix(mix(ft.triState[f], P[ft.triT0[f]]), t1[ft.triT1[f]]), t2[ft.triT2[f]]) & mask;
+    };
+    float sc = t0;
+    sc += lastRow ? gsum_unrolled4(w, ft.nBi, biIdx) : gsum_vars(w, ft.nBi, ft.biVars, biIdx);
+    sc += lastRow ? gsum_unrolled4(w, ft.nTri, triIdx) : gsum_vars(w, ft.nTri, ft.triVars, triIdx);
+    bv.pre[(size_t)i * bv.totalNodes + node] = sc;
+  }
+}
+
+// W3: makeT0cutoffBeam (score_processor.cc:471-495) -- exact std::nth_element
+// replay -- and the work counters of the boundary.  Selected nodes are appended
+// to the wave's list.
+JPP_HD void wave_cutoff(const FeatTables& ft, const BatchView& bv, const ScoreCfg& cfg, const WaveView& wv, u32 sent, u32 bnd) {
+  const u32 b0 = bv.sentBndOff[sent];
+  const u32 nb = bv.sentBndOff[sent + 1] - b0;
+  if (bnd >= nb || nb <= 3) return;
+  const u32 gB = b0 + bnd;
+  const u32 n0 = bv.bndNodeOff[gB];
+  const u32 R = bv.bndNodeOff[gB + 1] - n0;
+  if (R == 0) return;
+  const u32 G = wv.gCount[sent], U = wv.uCount[sent];
+  const u32 B = (u32)cfg.beam, SP = ft.nStored;
+  const u32 L = bv.bndEndOff[gB + 1] - bv.bndEndOff[gB];
+  u32 full = 0, toKeep = R, remaining = G, theMax = 0;
+  if (cfg.rcheck > 0) {
+    full = (u32)cfg.rcheck;
+    if (R < full) full = R;
+    if (G < full) full = G;  // fullBeamApplySize, :299-301
+    toKeep = (u32)cfg.rbeam < R ? (u32)cfg.rbeam : R;
+    remaining = G - full;
+    theMax = (u32)cfg.rcheck < G ? (u32)cfg.rcheck : G;
+  }
+  if (cfg.rcheck > 0 && R > toKeep) {
+    u32* idx = bv.cutIdx + n0;
+    float* cut = bv.cut + n0;
+    for (u32 r = 0; r < R; ++r) {
+      float v = 0;
+      for (u32 j = 0; j < full; ++j) v += bv.pre[(size_t)j * bv.totalNodes + n0 + r];
+      cut[r] = v;
+      idx[r] = r;
+      bv.selK[n0 + r] = 0xFFFFu;
+    }
+    em_std_nth_element(idx, (long)toKeep, (long)R, ScoreCmp{cut});
+    for (u32 k = 0; k < toKeep; ++k) bv.selK[n0 + idx[k]] = 1;
+  } else {
+    for (u32 r = 0; r < R; ++r) bv.selK[n0 + r] = 1;
+  }
+  // append the selected nodes (in node order) to the wave list
+  u32 nsel = 0;
+  for (u32 r = 0; r < R; ++r) nsel += (bv.selK[n0 + r] != 0xFFFFu);
+  u32 base;
 #if defined(__CUDA_ARCH__)
-    atomicAdd(bv.counters + 0, gathers);
-    atomicAdd(bv.counters + 1, streamBytes);
+  base = atomicAdd(wv.selCount, nsel);
 #else
-    bv.counters[0] += gathers;
-    bv.counters[1] += streamBytes;
+  base = *wv.selCount;
+  *wv.selCount += nsel;
+#endif
+  for (u32 r = 0, k = 0; r < R; ++r)
+    if (bv.selK[n0 + r] != 0xFFFFu) wv.selList[base + k++] = n0 + r;
+  if (bv.counters) {
+    const bool scoreTail = remaining > 0 && G > 0;
+    unsigned long long g = (unsigned long long)theMax * R * (ft.nBi + ft.nTri);
+    if (scoreTail) g += (unsigned long long)nsel * ((unsigned long long)U * ft.nBi + (unsigned long long)remaining * ft.nTri);
+    // streaming bytes of the boundary (DESIGN.md "roofline accounting")
+    const unsigned long long sb = 8ull * L * B + 8ull * SP * ((unsigned long long)R + U + G) + 4ull * L +
+                                  (8ull + 4ull * cfg.S) * R * B;
+#if defined(__CUDA_ARCH__)
+    atomicAdd(bv.counters + 0, g);
+    atomicAdd(bv.counters + 1, sb);
+#else
+    bv.counters[0] += g;
+    bv.counters[1] += sb;
 #endif
   }
+}
+
+// W4: one selected right node against the whole global beam: applyBiTri ->
+// applyBiTriFullKernel (feature_impl_ngram_partial_kernels.h:19-110: two
+// accumulators, last rows through Unrolled4), copyT0Scores (score_processor.cc:411-424),
+// makeT0Beam (:426-469).
+JPP_HD void wave_score_node(const FeatTables& ft, const BatchView& bv, const ScoreCfg& cfg, const WaveView& wv,
+                            const float* __restrict__ w, u32 node) {
+  const u32 gB = bv.nodeBnd[node];
+  const u32 sent = bv.bndSent[gB];
+  const u32 G = wv.gCount[sent], U = wv.uCount[sent];
+  const u32 GMAX = (u32)cfg.gbeam, SP = ft.nStored, mask = ft.mask, nB = ft.nBi, nT = ft.nTri;
+  const u32 R = bv.bndNodeOff[gB + 1] - bv.bndNodeOff[gB];
+  u32 full = 0, remaining = G;
+  if (cfg.rcheck > 0) {
+    full = (u32)cfg.rcheck;
+    if (R < full) full = R;
+    if (G < full) full = G;
+    remaining = G - full;
+  }
+  const u64* gbKey = wv.gbKey + (size_t)sent * GMAX;
+  const u32* t1node = wv.t1node + (size_t)sent * GMAX;
+  const u8* t1idx = wv.gbT1idx + (size_t)sent * GMAX;
+  const u32* gbT2 = wv.gbT2node + (size_t)sent * GMAX;
+  const u64* P = bv.patterns + (size_t)node * SP;
+  float tot[MAX_BEAM], loc[MAX_BEAM], scbuf[MAX_BEAM];
+  for (u32 i = 0; i < full; ++i) {
+    float v = bv.pre[(size_t)i * bv.totalNodes + node];
+    v += 0.0f;  // copyT0Scores(head, 0)
+    loc[i] = v;
+    v += cand_score(gbKey[i]);
+    tot[i] = v;
+  }
+  if (remaining > 0 && G > 0) {
+    for (u32 u = 0; u < U; ++u) {
+      const u64* t1 = bv.patterns + (size_t)t1node[u] * SP;
+      auto biIdx = [&](u32 f) -> u32 { return (u32)mix(mix(ft.biState[f], P[ft.biT0[f]]), t1[ft.biT1[f]]) & mask; };
+      if (u + 1 < U) {
+        float a[2];
+        gsum<2>(w, nB, biIdx, a);
+        scbuf[u] = a[0] + a[1];
+      } else {
+        scbuf[u] = gsum_unrolled4(w, nB, biIdx);
+      }
+    }
+    const float t0 = bv.t0[node];
+    for (u32 j = 0; j < remaining; ++j) {
+      const u32 gi = full + j;
+      const u64* t1 = bv.patterns + (size_t)t1node[t1idx[gi]] * SP;
+      const u64* t2 = bv.patterns + (size_t)gbT2[gi] * SP;
+      auto triIdx = [&](u32 f) -> u32 {
+        return (u32)mix(mix(mix(ft.triState[f], P[ft.triT0[f]]), t1[ft.triT1[f]]), t2[ft.triT2[f]]) & mask;
+      };
+      float v;
+      if (j + 1 < remaining) {
+        float a[2];
+        gsum<2>(w, nT, triIdx, a);
+        v = scbuf[t1idx[gi]] + a[0] + a[1];
+      } else {
+        v = scbuf[t1idx[gi]] + gsum_unrolled4(w, nT, triIdx);
+      }
+      v += t0;  // copyT0Scores(tail, t0Score)
+      loc[gi] = v;
+      v += cand_score(gbKey[gi]);
+      tot[gi] = v;
+    }
+  }
+  write_beam(bv, cfg, node, gbKey, (int)G, tot, loc);
+  const u32 b0 = bv.sentBndOff[sent];
+  if (gB + 1 == bv.sentBndOff[sent + 1]) {  // EOS boundary: keep every connection for the re-rank
+    for (u32 g = 0; g < G; ++g) {
+      bv.eosGbeam[(size_t)sent * GMAX + g] = gbKey[g];
+      bv.eosLocal[(size_t)sent * GMAX + g] = loc[g];
+    }
+  }
+  (void)b0;
+}
+
+// W5: right nodes outside the cutoff keep a beam of the head elements only
+// (score_processor.cc:336-346)
+JPP_HD void wave_rest_node(const BatchView& bv, const ScoreCfg& cfg, const WaveView& wv, u32 node) {
+  if (bv.selK[node] != 0xFFFFu) return;
+  const u32 gB = bv.nodeBnd[node];
+  const u32 sent = bv.bndSent[gB];
+  const u32 G = wv.gCount[sent];
+  const u32 R = bv.bndNodeOff[gB + 1] - bv.bndNodeOff[gB];
+  u32 full = (u32)cfg.rcheck;
+  if (R < full) full = R;
+  if (G < full) full = G;
+  const u64* gbKey = wv.gbKey + (size_t)sent * (u32)cfg.gbeam;
+  float tot[MAX_BEAM], loc[MAX_BEAM];
+  for (u32 i = 0; i < full; ++i) {
+    float v = bv.pre[(size_t)i * bv.totalNodes + node];
+    v += 0.0f;
+    loc[i] = v;
+    v += cand_score(gbKey[i]);
+    tot[i] = v;
+  }
+  write_beam(bv, cfg, node, gbKey, (int)full, tot, loc);
 }
 
 }  // namespace jppb200

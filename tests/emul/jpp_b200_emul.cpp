@@ -1,7 +1,6 @@
-// TEST ONLY.  Lane-serial CPU build of the *device* code in
+// TEST ONLY.  Serial CPU build of the *device* code in
 // jumanpp_b200/csrc/jpp_b200_kernels.h and jpp_b200_rnn.h: the same source the
-// GPU runs, with the 32 lanes of a warp executed one after another (see the
-// lane-region discipline in jpp_b200_kernels.h).  It exists so that kernel
+// GPU runs, with every kernel "launch" executed as a plain loop over its index.  It exists so that kernel
 // logic can be compared with the oracle on a machine without a GPU.  It is
 // built into tests/emul/libjpp_b200_emul.so, never into libjpp_b200.so, and
 // nothing in the product loads it.
@@ -64,10 +63,35 @@ extern "C" int jpp_b200_emul_score_batch(const jpp_b200_model* model, const jpp_
   bv.gbNode = gbNode.data(); bv.gbSlot = gbSlot.data(); bv.gbLeftBnd = gbLeftBnd.data(); bv.gbCount = gbCount.data();
   bv.eosGbeam = eosGbeam.data(); bv.eosLocal = eosLocal.data(); bv.eosRnn = eosRnn.data(); bv.counters = counters;
   for (u32 n = 0; n < NN; ++n) t0_node(ft, bv, weights, n);
-  const u32 wcap = warp_wcap(G, (u32)std::max(0, cfg.rbeam), ft.nBi + ft.nTri);
-  std::vector<unsigned char> smem(warp_smem_bytes(G, SP, wcap) + 64);
-  WarpSmem sm = carve_warp_smem(smem.data(), G, SP, wcap);
-  for (u32 s = 0; s < NS; ++s) walk_sentence(ft, bv, cfg, weights, sm, s);
+  // wavefront walk: the kernels of jpp_b200.cu, one "launch" = one loop
+  u32 maxNb = 0;
+  for (u32 s = 0; s < NS; ++s) maxNb = std::max(maxNb, b->sent_boundary_off[s + 1] - b->sent_boundary_off[s]);
+  std::vector<u32> waveNodeOff(maxNb + 2, 0), waveNodes(NN);
+  for (u32 n = 0; n < NN; ++n) waveNodeOff[nodeBnd[n] - b->sent_boundary_off[bndSent[nodeBnd[n]]] + 1]++;
+  for (u32 i = 0; i <= maxNb; ++i) waveNodeOff[i + 1] += waveNodeOff[i];
+  {
+    std::vector<u32> cur(waveNodeOff.begin(), waveNodeOff.end() - 1);
+    for (u32 n = 0; n < NN; ++n) waveNodes[cur[nodeBnd[n] - b->sent_boundary_off[bndSent[nodeBnd[n]]]]++] = n;
+  }
+  std::vector<u64> gbKey((size_t)NS * G);
+  std::vector<u32> gbLnode((size_t)NS * G), gbT2node((size_t)NS * G), t1node((size_t)NS * G), selList(NN + 1);
+  std::vector<u8> gbT1idx((size_t)NS * G), gCount(NS), uCount(NS);
+  u32 selCount = 0;
+  WaveView wv{};
+  wv.gbKey = gbKey.data(); wv.gbLnode = gbLnode.data(); wv.gbT2node = gbT2node.data(); wv.gbT1idx = gbT1idx.data();
+  wv.t1node = t1node.data(); wv.gCount = gCount.data(); wv.uCount = uCount.data(); wv.selList = selList.data();
+  wv.selCount = &selCount; wv.waveNodes = waveNodes.data(); wv.waveNodeOff = waveNodeOff.data();
+  for (u32 s = 0; s < NS; ++s) wave_init_sentence(bv, cfg, s);
+  for (u32 bnd = 2; bnd < maxNb; ++bnd) {
+    selCount = 0;
+    for (u32 s = 0; s < NS; ++s) wave_gbeam(bv, cfg, wv, s, bnd);
+    if (cfg.rcheck > 0)
+      for (u32 i = waveNodeOff[bnd]; i < waveNodeOff[bnd + 1]; ++i) wave_prescore(ft, bv, cfg, wv, weights, waveNodes[i]);
+    for (u32 s = 0; s < NS; ++s) wave_cutoff(ft, bv, cfg, wv, s, bnd);
+    for (u32 i = 0; i < selCount; ++i) wave_score_node(ft, bv, cfg, wv, weights, selList[i]);
+    if (cfg.rcheck > 0)
+      for (u32 i = waveNodeOff[bnd]; i < waveNodeOff[bnd + 1]; ++i) wave_rest_node(bv, cfg, wv, waveNodes[i]);
+  }
   if (model->num_scorers == 2) {
     const jpp_b200_rnn_model* rm = model->rnn;
     RnnTables rt{rm->layer_size, rm->maxent_order, rm->maxent_size, rm->vocab_size, rm->nce_constant, rm->unk_constant,
