@@ -136,20 +136,7 @@ __global__ void k_rnn_tree(BatchView bv, ScoreCfg cfg, RnnWork rw) {
   if (s < bv.numSentences) rnn_build_tree(bv, cfg, rw, s);
 }
 
-// level histogram / lists; ctxSlot[rnode] = compact context row
-__global__ void k_rnn_level_count(BatchView bv, RnnWork rw, const u32* ctxOff) {
-  const u32 s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= bv.numSentences) return;
-  const u32 base0 = rw.rnOff[s];
-  const u32 n = rw.rnCount[s];
-  const u32 nb = bv.sentBndOff[s + 1] - bv.sentBndOff[s];
-  for (u32 i = 2; i < n; ++i) {
-    const u32 q = base0 + i;
-    if ((u32)rw.bnd[q] + 1 < nb) atomicAdd(rw.levelCount + rw.depth[q], 1u);
-  }
-  (void)ctxOff;
-}
-
+// level lists (the histogram is accumulated by k_rnn_tree)
 __global__ void k_rnn_level_fill(BatchView bv, RnnWork rw, u32* cursor) {
   const u32 s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= bv.numSentences) return;
@@ -177,7 +164,8 @@ __global__ void k_rnn_mark_sentence(BatchView bv, RnnWork rw, u32* rnSent) {
   if (s >= bv.numSentences) return;
   const u32 base0 = rw.rnOff[s];
   const u32 n = rw.rnCount[s];
-  for (u32 i = 0; i < n; ++i) rnSent[base0 + i] = s;
+  const u32 m = rw.rsCount[s] > n ? rw.rsCount[s] : n;
+  for (u32 i = 0; i < m; ++i) rnSent[base0 + i] = s;
 }
 
 // BOS context of every sentence: sigmoid(W^T 0 + emb[0]) (rnn_scorer_gbeam.cc:37-46);
@@ -193,87 +181,124 @@ __global__ void k_rnn_bos(BatchView bv, RnnWork rw, RnnTables rt, const u32* ctx
   (void)bv;
 }
 
-// One warp per tree node of the level: ctx' = sigmoid(W^T ctx + emb[id])
-// (mikolov_rnn_impl.h:202-214).  Lane l owns output i = i0 + l and keeps the 32
-// interleaved partial sums of the eigen_shim order in registers (partial j
-// accumulates k = j, j+32, ...), then folds them with the 16/8/4/2/1 tree --
-// the same additions, in the same order, as the shuffle formulation, without
-// cross-lane traffic.  Wt is the transposed recurrent matrix, so the 32 lanes
-// read 128 contiguous bytes per k; the input context is staged in shared memory.
-__global__ void __launch_bounds__(256) k_rnn_level(RnnWork rw, RnnTables rt, const float* __restrict__ Wt,
+// Level kernel: ctx' = sigmoid(W^T ctx + emb[id]) (mikolov_rnn_impl.h:202-214) for
+// the tree nodes of one depth.  A warp takes a tile of NT nodes; lane l owns
+// output i = i0 + l for all NT nodes, so every load of the (transposed)
+// recurrent matrix is reused NT times from a register.
+// Dot-product order = oracle/eigen_shim: 32 residue partials (k = r, r+32, ...)
+// folded by the 16/8/4/2/1 tree.  The residues are visited in bit-reversed
+// order, which is the depth-first order of that tree, so a partial is folded
+// into its parent as soon as its sibling exists and only <= 6 values per
+// (output, node) are live instead of 32 -- same additions, same operands, same
+// order as the serial definition.
+template <int NT>
+__global__ void __launch_bounds__(128) k_rnn_level(RnnWork rw, RnnTables rt, const float* __restrict__ Wt,
                                                  const u32* ctxOff, const u32* rnSent, u32 level) {
-  extern __shared__ float sctx[];
+  extern __shared__ __align__(16) float sctx[];
   const u32 cnt = rw.levelCount[level];
   const u32 off = rw.levelOff[level];
   const int lane = threadIdx.x & 31;
   const u32 warp = threadIdx.x >> 5;
   const u32 warpsPerBlock = blockDim.x >> 5;
   const u32 H = rt.H;
-  float* cinS = sctx + (size_t)warp * H;
-  for (u32 item = blockIdx.x * warpsPerBlock + warp; item < cnt; item += gridDim.x * warpsPerBlock) {
-    const u32 q = rw.levelList[off + item];
-    const u32 p = (u32)rw.prev[q];
-    const float* cin = rw.ctx + ctx_row(rw, ctxOff, rnSent, p) * H;
-    float* cout = rw.ctx + ctx_row(rw, ctxOff, rnSent, q) * H;
-    i32 id = rw.id[q];
-    if (id == -1) id = 0;  // rnn_scorer_gbeam.cc:126-129
-    const float* emb = rt.emb + (size_t)id * H;
+  float* cS = sctx + (size_t)warp * H * NT;  // [k][NT]
+  const u32 tiles = (cnt + NT - 1) / NT;
+  for (u32 tile = blockIdx.x * warpsPerBlock + warp; tile < tiles; tile += gridDim.x * warpsPerBlock) {
+    const u32 first = tile * NT;
+    const u32 nvalid = (cnt - first) < (u32)NT ? (cnt - first) : (u32)NT;
+    u32 qn[NT];
+    const float* emb[NT];
+    float* cout[NT];
     __syncwarp();
-    for (u32 k = (u32)lane; k < H; k += 32) cinS[k] = cin[k];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      const u32 q = rw.levelList[off + first + ((u32)j < nvalid ? (u32)j : 0u)];
+      qn[j] = q;
+      const u32 p = (u32)rw.prev[q];
+      const float* cin = rw.ctx + ctx_row(rw, ctxOff, rnSent, p) * H;
+      cout[j] = rw.ctx + ctx_row(rw, ctxOff, rnSent, q) * H;
+      i32 id = rw.id[q];
+      if (id == -1) id = 0;  // rnn_scorer_gbeam.cc:126-129
+      emb[j] = rt.emb + (size_t)id * H;
+      for (u32 k = (u32)lane; k < H; k += 32) cS[(size_t)k * NT + j] = cin[k];
+    }
     __syncwarp();
     for (u32 i0 = 0; i0 < H; i0 += 32) {
       const u32 i = i0 + (u32)lane;
-      float part[32];
+      const u32 ic = i < H ? i : H - 1;
+      float st[6][NT];
+      int sp = 0;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) part[j] = 0.0f;
-      if (i < H) {
-        for (u32 k0 = 0; k0 < H; k0 += 32) {
+      for (int r = 0; r < 32; ++r) {
+        // residue of the r-th leaf in depth-first order = 5-bit reversal of r
+        const int l = ((r & 1) << 4) | ((r & 2) << 2) | (r & 4) | ((r & 8) >> 2) | ((r & 16) >> 4);
+        float part[NT];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const u32 k = k0 + (u32)j;
-            if (k < H) part[j] = __fadd_rn(part[j], __fmul_rn(Wt[(size_t)k * H + i], cinS[k]));
+        for (int j = 0; j < NT; ++j) part[j] = 0.0f;
+        for (u32 k = (u32)l; k < H; k += 32) {
+          const float wv = Wt[(size_t)k * H + ic];
+          const float4* c4 = reinterpret_cast<const float4*>(cS + (size_t)k * NT);
+#pragma unroll
+          for (int j4 = 0; j4 < NT / 4; ++j4) {
+            const float4 c = c4[j4];
+            part[j4 * 4 + 0] = __fadd_rn(part[j4 * 4 + 0], __fmul_rn(wv, c.x));
+            part[j4 * 4 + 1] = __fadd_rn(part[j4 * 4 + 1], __fmul_rn(wv, c.y));
+            part[j4 * 4 + 2] = __fadd_rn(part[j4 * 4 + 2], __fmul_rn(wv, c.z));
+            part[j4 * 4 + 3] = __fadd_rn(part[j4 * 4 + 3], __fmul_rn(wv, c.w));
           }
         }
 #pragma unroll
-        for (int stride = 16; stride >= 1; stride >>= 1) {
+        for (int j = 0; j < NT; ++j) st[sp][j] = part[j];
+        ++sp;
+        // binary-counter folding: after leaf r, fold once per trailing one bit of r
 #pragma unroll
-          for (int l = 0; l < stride; ++l) part[l] = __fadd_rn(part[l], part[l + stride]);
+        for (int b = 0; b < 5; ++b) {
+          if (((r >> b) & 1) && ((r & ((1 << b) - 1)) == ((1 << b) - 1))) {
+#pragma unroll
+            for (int j = 0; j < NT; ++j) st[sp - 2][j] = __fadd_rn(st[sp - 2][j], st[sp - 1][j]);
+            --sp;
+          }
         }
-        const float v = __fadd_rn(part[0], emb[i]);
-        cout[i] = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-v)));
+      }
+      if (i < H) {
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          if ((u32)j < nvalid) {
+            const float v = __fadd_rn(st[0][j], emb[j][i]);
+            cout[j][i] = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-v)));
+          }
+        }
       }
     }
+    (void)qn;
   }
 }
 
-// one warp per score entry
+// one warp per score entry of the batch-wide flat list
 __global__ void __launch_bounds__(256) k_rnn_scores(BatchView bv, ScoreCfg cfg, RnnWork rw, RnnTables rt, const u32* ctxOff,
                                                   const u32* rnSent) {
   const int lane = threadIdx.x & 31;
   const u32 warpsPerBlock = blockDim.x >> 5;
   const u32 H = rt.H;
-  // sentences are few relative to warps: iterate (sentence, entry) with a flat loop per sentence
-  for (u32 s = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); s < bv.numSentences; s += gridDim.x * warpsPerBlock) {
-    const u32 base0 = rw.rnOff[s];
-    const u32 n = rw.rsCount[s];
-    for (u32 i = 0; i < n; ++i) {
-      const u32 si = base0 + i;
-      const i32 q = rw.rsRnode[si];
-      const i32 id = rw.id[q];
-      float sc;
-      if (id == rt.unkId) {
-        sc = __fadd_rn(rt.unkConstant, __fmul_rn(rt.unkLengthPenalty, (float)rw.length[q]));  // rnn_scorer_gbeam.cc:236-240
-      } else {
-        const i32 p = rw.prev[q];
-        const i32 eid = id == -1 ? 0 : id;
-        const float d = warp_dot32(rt.nce + (size_t)eid * H, rw.ctx + ctx_row(rw, ctxOff, rnSent, (u32)p) * H, H, lane);
-        sc = rnn_finish_score(rt, d, rw.id[p], id);
-      }
-      if (lane == 0) {
-        const u16 g = rw.rsEosG[si];
-        if (g != 0xFFFFu) bv.eosRnn[(size_t)s * cfg.gbeam + g] = sc;
-        else bv.beamScores[((size_t)rw.rsNode[si] * cfg.beam + rw.rsSlot[si]) * cfg.S + 1] = sc;
-      }
+  const u32 total = *rw.scoreTotal;
+  for (u32 e = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); e < total; e += gridDim.x * warpsPerBlock) {
+    const u32 si = rw.scoreList[e];
+    const u32 s = rnSent[si];
+    const i32 q = rw.rsRnode[si];
+    const i32 id = rw.id[q];
+    float sc;
+    if (id == rt.unkId) {
+      sc = __fadd_rn(rt.unkConstant, __fmul_rn(rt.unkLengthPenalty, (float)rw.length[q]));  // rnn_scorer_gbeam.cc:236-240
+    } else {
+      const i32 p = rw.prev[q];
+      const i32 eid = id == -1 ? 0 : id;
+      const float d = warp_dot32(rt.nce + (size_t)eid * H, rw.ctx + ctx_row(rw, ctxOff, rnSent, (u32)p) * H, H, lane);
+      sc = rnn_finish_score(rt, d, rw.id[p], id);
+    }
+    if (lane == 0) {
+      const u16 g = rw.rsEosG[si];
+      if (g != 0xFFFFu) bv.eosRnn[(size_t)s * cfg.gbeam + g] = sc;
+      else bv.beamScores[((size_t)rw.rsNode[si] * cfg.beam + rw.rsSlot[si]) * cfg.S + 1] = sc;
     }
   }
 }
@@ -329,7 +354,7 @@ struct jpp_b200_handle {
          B_EOSG, B_EOSLOC, B_EOSRNN, B_COUNTERS, B_WORK,
          W_GBKEY, W_GBLNODE, W_GBT2, W_GBT1IDX, W_T1NODE, W_GCNT, W_UCNT, W_SELLIST, W_SELCNT, W_NODES, W_OFF, W_CURSOR,
          R_OFF, R_ID, R_PREV, R_NEXT, R_BND, R_LEN, R_DEPTH, R_HASH, R_RNCNT, R_RSNODE, R_RSSLOT, R_RSEOSG, R_RSRNODE,
-         R_RSCNT, R_CONN, R_BNDHEAD, R_CTX, R_LVLCNT, R_LVLOFF, R_LVLLIST, R_CTXOFF, R_RNSENT, R_CURSOR, R_CUBTMP,
+         R_RSCNT, R_CONN, R_BNDHEAD, R_CTX, R_CHNODE, R_CHSLOT, R_CHBND, R_SCLIST, R_SCTOTAL, R_LVLCNT, R_LVLOFF, R_LVLLIST, R_CTXOFF, R_RNSENT, R_CURSOR, R_CUBTMP,
          NUM_BUFS };
   DevBuf buf[NUM_BUFS];
   BatchView bv{};
@@ -451,8 +476,12 @@ jpp_b200_status jpp_b200_create(const jpp_b200_model* model, const jpp_b200_conf
         for (u32 k = 0; k < H; ++k) wt[(size_t)k * H + i] = r->matrix[(size_t)i * H + k];
       CREATE_CHECK(cudaMalloc(&h->dRnnWt, wt.size() * sizeof(float)));
       CREATE_CHECK(cudaMemcpy(h->dRnnWt, wt.data(), wt.size() * sizeof(float), cudaMemcpyHostToDevice));
-      if (8 * H * sizeof(float) > 48 * 1024)
-        CREATE_CHECK(cudaFuncSetAttribute(k_rnn_level, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * H * sizeof(float))));
+      if (32 * H * sizeof(float) > 200 * 1024) {
+        g_create_error = "rnn layer too large for the level kernel's shared-memory tile";
+        jpp_b200_destroy(h);
+        return JPP_B200_NOT_IMPLEMENTED;
+      }
+      CREATE_CHECK(cudaFuncSetAttribute(k_rnn_level<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(32 * H * sizeof(float))));
     }
     h->rt = RnnTables{r->layer_size, r->maxent_order, r->maxent_size, r->vocab_size, r->nce_constant, r->unk_constant,
                       r->unk_length_penalty, r->unk_id, h->dRnnBlocks[0], h->dRnnBlocks[1], h->dRnnBlocks[2],
@@ -622,6 +651,8 @@ jpp_b200_status jpp_b200_upload_batch(jpp_b200_handle* h, const jpp_b200_batch* 
     ENSURE(R_RSCNT, (size_t)NS * 4); ENSURE(R_CONN, (size_t)NN * B * 4); ENSURE(R_BNDHEAD, (size_t)NB * 4);
     ENSURE(R_LVLCNT, (size_t)(maxNb + 4) * 4); ENSURE(R_LVLOFF, (size_t)(maxNb + 4) * 4); ENSURE(R_CURSOR, (size_t)(maxNb + 4) * 4);
     ENSURE(R_LVLLIST, rnTotal * 4); ENSURE(R_CTXOFF, (size_t)(NS + 1) * 4); ENSURE(R_RNSENT, rnTotal * 4);
+    ENSURE(R_CHNODE, rnTotal * 4); ENSURE(R_CHSLOT, rnTotal * 2); ENSURE(R_CHBND, rnTotal * 2); ENSURE(R_SCLIST, rnTotal * 4);
+    ENSURE(R_SCTOTAL, 16);
     RnnWork& rw = h->rw;
     rw = RnnWork{};
     rw.rnOff = P(R_OFF, u32); rw.id = P(R_ID, i32); rw.prev = P(R_PREV, i32); rw.next = P(R_NEXT, i32); rw.bnd = P(R_BND, i32);
@@ -629,6 +660,8 @@ jpp_b200_status jpp_b200_upload_batch(jpp_b200_handle* h, const jpp_b200_batch* 
     rw.rsNode = P(R_RSNODE, u32); rw.rsSlot = P(R_RSSLOT, u16); rw.rsEosG = P(R_RSEOSG, u16); rw.rsRnode = P(R_RSRNODE, i32);
     rw.rsCount = P(R_RSCNT, u32); rw.connNode = P(R_CONN, i32); rw.bndHead = P(R_BNDHEAD, i32);
     rw.levelCount = P(R_LVLCNT, u32); rw.levelOff = P(R_LVLOFF, u32); rw.levelList = P(R_LVLLIST, u32);
+    rw.chainNode = P(R_CHNODE, u32); rw.chainSlot = P(R_CHSLOT, u16); rw.chainBnd = P(R_CHBND, u16);
+    rw.scoreList = P(R_SCLIST, u32); rw.scoreTotal = P(R_SCTOTAL, u32);
     rw.maxDepth = maxNb + 1;
   }
   CU_CHECK(h, cudaEventRecord(h->ev[1], st));
@@ -687,6 +720,7 @@ jpp_b200_status jpp_b200_score_resident(jpp_b200_handle* h) {
     k_fill_i32<<<h->smCount * 4, 256, 0, st>>>(rw.connNode, (size_t)NN * B, -1);
     k_fill_i32<<<h->smCount, 256, 0, st>>>(rw.bndHead, (size_t)NB, -1);
     CU_CHECK(h, cudaMemsetAsync(rw.levelCount, 0, (size_t)(h->maxNb + 4) * 4, st));
+    CU_CHECK(h, cudaMemsetAsync(rw.scoreTotal, 0, 4, st));
     CU_CHECK(h, cudaMemsetAsync(bf[jpp_b200_handle::R_CURSOR].p, 0, (size_t)(h->maxNb + 4) * 4, st));
     k_rnn_tree<<<(NS + 63) / 64, 64, 0, st>>>(bv, h->cfg, rw);
     CU_CHECK(h, cudaGetLastError());
@@ -706,7 +740,6 @@ jpp_b200_status jpp_b200_score_resident(jpp_b200_handle* h) {
     rw.ctx = bf[jpp_b200_handle::R_CTX].as<float>();
     u32* rnSent = bf[jpp_b200_handle::R_RNSENT].as<u32>();
     k_rnn_mark_sentence<<<(NS + 127) / 128, 128, 0, st>>>(bv, rw, rnSent);
-    k_rnn_level_count<<<(NS + 127) / 128, 128, 0, st>>>(bv, rw, ctxOff);
     cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, rw.levelCount, rw.levelOff, (int)(h->maxNb + 2), st);
     CU_CHECK(h, bf[jpp_b200_handle::R_CUBTMP].ensure(tmpBytes + 16));
     cub::DeviceScan::ExclusiveSum(bf[jpp_b200_handle::R_CUBTMP].p, tmpBytes, rw.levelCount, rw.levelOff, (int)(h->maxNb + 2), st);
@@ -715,11 +748,11 @@ jpp_b200_status jpp_b200_score_resident(jpp_b200_handle* h) {
     CU_CHECK(h, cudaGetLastError());
     CU_CHECK(h, cudaEventRecord(h->ev[5], st));
     for (u32 level = 1; level <= h->maxNb; ++level) {
-      k_rnn_level<<<h->smCount * 2, 256, 8 * h->rt.H * sizeof(float), st>>>(rw, h->rt, h->dRnnWt, ctxOff, rnSent, level);
+      k_rnn_level<8><<<h->smCount * 4, 128, 4 * 8 * h->rt.H * sizeof(float), st>>>(rw, h->rt, h->dRnnWt, ctxOff, rnSent, level);
     }
     CU_CHECK(h, cudaGetLastError());
     CU_CHECK(h, cudaEventRecord(h->ev[6], st));
-    k_rnn_scores<<<h->smCount * 2, 256, 0, st>>>(bv, h->cfg, rw, h->rt, ctxOff, rnSent);
+    k_rnn_scores<<<h->smCount * 8, 256, 0, st>>>(bv, h->cfg, rw, h->rt, ctxOff, rnSent);
     CU_CHECK(h, cudaGetLastError());
     CU_CHECK(h, cudaEventRecord(h->ev[7], st));
     k_rerank<<<(NS + 63) / 64, 64, 0, st>>>(bv, h->cfg, h->scoreW[0], h->scoreW[1]);

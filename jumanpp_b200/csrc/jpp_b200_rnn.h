@@ -46,6 +46,11 @@ struct RnnWork {
   u32* rsCount;       // [sentences]
   i32* connNode;      // [nodes][B]  ptrCache_: connection -> rnode, -1 = unseen
   i32* bndHead;       // [boundaries] head of the published list of the boundary
+  u32* chainNode;     // [rnode capacity] scratch: connections of the path being added
+  u16* chainSlot;
+  u16* chainBnd;
+  u32* scoreList;     // [rnode capacity] flat list of score entries of the whole batch
+  u32* scoreTotal;    // [1]
   float* ctx;         // [total rnodes][H]
   // level lists
   u32* levelCount;    // [maxDepth+2]
@@ -85,13 +90,19 @@ JPP_HD void rnn_build_tree(const BatchView& bv, const ScoreCfg& cfg, const RnnWo
   for (u32 g = 0; g < eosG; ++g) {
     const u64 key = bv.eosGbeam[(size_t)sent * GMAX + g];
     const u32 left0 = (u32)(key >> 16) & 0xFFFFu;
-    // pass 1: walk back to the first connection already in ptrCache_
+    // addPrevChain: walk back to the first connection already in ptrCache_,
+    // remembering the new connections (deepest last)
     u32 len = 0;
+    i32 first, prev;
     {
       u32 curNode = bv.endNode[eosE0 + left0];
       u32 curBnd = bv.ends[eosE0 + left0].boundary;
       u32 curSlot = (u32)key & 0xFFFFu;
-      while (rw.connNode[(size_t)curNode * B + curSlot] == -1) {
+      i32 known;
+      while ((known = rw.connNode[(size_t)curNode * B + curSlot]) == -1) {
+        rw.chainNode[base0 + len] = curNode;
+        rw.chainSlot[base0 + len] = (u16)curSlot;
+        rw.chainBnd[base0 + len] = (u16)curBnd;
         ++len;
         const jpp_b200_beam_element el = bv.beam[(size_t)curNode * B + curSlot];
         const u32 e = bv.bndEndOff[b0 + curBnd] + el.left;
@@ -99,35 +110,14 @@ JPP_HD void rnn_build_tree(const BatchView& bv, const ScoreCfg& cfg, const RnnWo
         curBnd = bv.ends[e].boundary;
         curNode = bv.endNode[e];
       }
+      first = prev = known;
     }
-    // pass 2: for depth d = len-1 .. 0 (deepest new connection first) then the EOS
-    // fake connection; connection at distance d from the tip is found by walking
-    // d steps (paths are short, and this keeps the kernel free of scratch arrays)
-    i32 first, prev;
-    {
-      u32 curNode = bv.endNode[eosE0 + left0];
-      u32 curBnd = bv.ends[eosE0 + left0].boundary;
-      u32 curSlot = (u32)key & 0xFFFFu;
-      for (u32 t = 0; t < len; ++t) {
-        const jpp_b200_beam_element el = bv.beam[(size_t)curNode * B + curSlot];
-        const u32 e = bv.bndEndOff[b0 + curBnd] + el.left;
-        curSlot = el.prev_beam; curBnd = bv.ends[e].boundary; curNode = bv.endNode[e];
-      }
-      first = prev = rw.connNode[(size_t)curNode * B + curSlot];
-    }
+    // unwind: deepest new connection first, the EOS fake connection (k == -1) last
     for (i32 k = (i32)len - 1; k >= -1; --k) {
       u32 cNode = 0, cSlot = 0, cb;
       i32 id, length;
       if (k >= 0) {
-        u32 curNode = bv.endNode[eosE0 + left0];
-        u32 curBnd = bv.ends[eosE0 + left0].boundary;
-        u32 curSlot = (u32)key & 0xFFFFu;
-        for (i32 t = 0; t < k; ++t) {
-          const jpp_b200_beam_element el = bv.beam[(size_t)curNode * B + curSlot];
-          const u32 e = bv.bndEndOff[b0 + curBnd] + el.left;
-          curSlot = el.prev_beam; curBnd = bv.ends[e].boundary; curNode = bv.endNode[e];
-        }
-        cNode = curNode; cSlot = curSlot; cb = curBnd;
+        cNode = rw.chainNode[base0 + k]; cSlot = rw.chainSlot[base0 + k]; cb = rw.chainBnd[base0 + k];
         id = bv.nodeRnnId[cNode];
         length = (i32)bv.nodeInfo[cNode].end - (i32)bv.nodeInfo[cNode].start;
       } else {
@@ -154,6 +144,13 @@ JPP_HD void rnn_build_tree(const BatchView& bv, const ScoreCfg& cfg, const RnnWo
         mine = (i32)(base0 + nrn++);
         rw.id[mine] = id; rw.prev[mine] = prev; rw.next[mine] = -1; rw.bnd[mine] = (i32)cb;
         rw.length[mine] = length; rw.hash[mine] = hv; rw.depth[mine] = rw.depth[prev] + 1;
+        if (cb + 1 < nb && rw.levelCount) {  // a context is needed for every node before EOS
+#if defined(__CUDA_ARCH__)
+          atomicAdd(rw.levelCount + rw.depth[mine], 1u);
+#else
+          rw.levelCount[rw.depth[mine]] += 1;
+#endif
+        }
       }
       if (k >= 0) rw.connNode[(size_t)cNode * B + cSlot] = mine;
       prev = mine;
@@ -162,9 +159,6 @@ JPP_HD void rnn_build_tree(const BatchView& bv, const ScoreCfg& cfg, const RnnWo
     {
       i32 lastN = prev;
       i32 k = -1;
-      u32 curNode = bv.endNode[eosE0 + left0];
-      u32 curBnd = bv.ends[eosE0 + left0].boundary;
-      u32 curSlot = (u32)key & 0xFFFFu;
       while (lastN != first) {
         const u32 cb = (u32)rw.bnd[lastN];
         rw.next[lastN] = rw.bndHead[b0 + cb];
@@ -173,10 +167,7 @@ JPP_HD void rnn_build_tree(const BatchView& bv, const ScoreCfg& cfg, const RnnWo
         if (k < 0) {
           rw.rsNode[si] = 0; rw.rsSlot[si] = 0; rw.rsEosG[si] = (u16)g;
         } else {
-          rw.rsNode[si] = curNode; rw.rsSlot[si] = (u16)curSlot; rw.rsEosG[si] = (u16)0xFFFFu;
-          const jpp_b200_beam_element el = bv.beam[(size_t)curNode * B + curSlot];
-          const u32 e = bv.bndEndOff[b0 + curBnd] + el.left;
-          curSlot = el.prev_beam; curBnd = bv.ends[e].boundary; curNode = bv.endNode[e];
+          rw.rsNode[si] = rw.chainNode[base0 + k]; rw.rsSlot[si] = rw.chainSlot[base0 + k]; rw.rsEosG[si] = (u16)0xFFFFu;
         }
         rw.rsRnode[si] = lastN;
         lastN = rw.prev[lastN];
@@ -186,6 +177,16 @@ JPP_HD void rnn_build_tree(const BatchView& bv, const ScoreCfg& cfg, const RnnWo
   }
   rw.rnCount[sent] = nrn;
   rw.rsCount[sent] = nrs;
+  if (rw.scoreList && nrs) {  // flat list of this batch's score entries
+    u32 base;
+#if defined(__CUDA_ARCH__)
+    base = atomicAdd(rw.scoreTotal, nrs);
+#else
+    base = *rw.scoreTotal;
+    *rw.scoreTotal += nrs;
+#endif
+    for (u32 i = 0; i < nrs; ++i) rw.scoreList[base + i] = base0 + i;
+  }
 }
 
 // dot product, oracle/eigen_shim order
