@@ -274,14 +274,14 @@ __global__ void __launch_bounds__(128) k_rnn_level(RnnWork rw, RnnTables rt, con
   }
 }
 
-// one warp per score entry of the batch-wide flat list
-__global__ void __launch_bounds__(256) k_rnn_scores(BatchView bv, ScoreCfg cfg, RnnWork rw, RnnTables rt, const u32* ctxOff,
+// One thread per score entry of the batch-wide flat list: nce[id] . ctx(prev) in the
+// eigen_shim order (32 residue partials in registers, then the 16/8/4/2/1 fold),
+// maxent hash, nce constant (mikolov_rnn_impl.h:216-257).
+__global__ void __launch_bounds__(128) k_rnn_scores(BatchView bv, ScoreCfg cfg, RnnWork rw, RnnTables rt, const u32* ctxOff,
                                                   const u32* rnSent) {
-  const int lane = threadIdx.x & 31;
-  const u32 warpsPerBlock = blockDim.x >> 5;
   const u32 H = rt.H;
   const u32 total = *rw.scoreTotal;
-  for (u32 e = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); e < total; e += gridDim.x * warpsPerBlock) {
+  for (u32 e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
     const u32 si = rw.scoreList[e];
     const u32 s = rnSent[si];
     const i32 q = rw.rsRnode[si];
@@ -292,14 +292,41 @@ __global__ void __launch_bounds__(256) k_rnn_scores(BatchView bv, ScoreCfg cfg, 
     } else {
       const i32 p = rw.prev[q];
       const i32 eid = id == -1 ? 0 : id;
-      const float d = warp_dot32(rt.nce + (size_t)eid * H, rw.ctx + ctx_row(rw, ctxOff, rnSent, (u32)p) * H, H, lane);
-      sc = rnn_finish_score(rt, d, rw.id[p], id);
+      const float* a = rt.nce + (size_t)eid * H;
+      const float* b = rw.ctx + ctx_row(rw, ctxOff, rnSent, (u32)p) * H;
+      float part[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) part[j] = 0.0f;
+      u32 k0 = 0;
+      if ((H & 3u) == 0) {
+        for (; k0 + 32 <= H; k0 += 32) {
+          const float4* a4 = reinterpret_cast<const float4*>(a + k0);
+          const float4* b4 = reinterpret_cast<const float4*>(b + k0);
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 x = a4[j4], y = b4[j4];
+            part[j4 * 4 + 0] = __fadd_rn(part[j4 * 4 + 0], __fmul_rn(x.x, y.x));
+            part[j4 * 4 + 1] = __fadd_rn(part[j4 * 4 + 1], __fmul_rn(x.y, y.y));
+            part[j4 * 4 + 2] = __fadd_rn(part[j4 * 4 + 2], __fmul_rn(x.z, y.z));
+            part[j4 * 4 + 3] = __fadd_rn(part[j4 * 4 + 3], __fmul_rn(x.w, y.w));
+          }
+        }
+      }
+      for (; k0 < H; k0 += 32) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (k0 + j < H) part[j] = __fadd_rn(part[j], __fmul_rn(a[k0 + j], b[k0 + j]));
+      }
+#pragma unroll
+      for (int stride = 16; stride >= 1; stride >>= 1) {
+#pragma unroll
+        for (int l = 0; l < stride; ++l) part[l] = __fadd_rn(part[l], part[l + stride]);
+      }
+      sc = rnn_finish_score(rt, part[0], rw.id[p], id);
     }
-    if (lane == 0) {
-      const u16 g = rw.rsEosG[si];
-      if (g != 0xFFFFu) bv.eosRnn[(size_t)s * cfg.gbeam + g] = sc;
-      else bv.beamScores[((size_t)rw.rsNode[si] * cfg.beam + rw.rsSlot[si]) * cfg.S + 1] = sc;
-    }
+    const u16 g = rw.rsEosG[si];
+    if (g != 0xFFFFu) bv.eosRnn[(size_t)s * cfg.gbeam + g] = sc;
+    else bv.beamScores[((size_t)rw.rsNode[si] * cfg.beam + rw.rsSlot[si]) * cfg.S + 1] = sc;
   }
 }
 
@@ -752,7 +779,7 @@ jpp_b200_status jpp_b200_score_resident(jpp_b200_handle* h) {
     }
     CU_CHECK(h, cudaGetLastError());
     CU_CHECK(h, cudaEventRecord(h->ev[6], st));
-    k_rnn_scores<<<h->smCount * 8, 256, 0, st>>>(bv, h->cfg, rw, h->rt, ctxOff, rnSent);
+    k_rnn_scores<<<h->smCount * 16, 128, 0, st>>>(bv, h->cfg, rw, h->rt, ctxOff, rnSent);
     CU_CHECK(h, cudaGetLastError());
     CU_CHECK(h, cudaEventRecord(h->ev[7], st));
     k_rerank<<<(NS + 63) / 64, 64, 0, st>>>(bv, h->cfg, h->scoreW[0], h->scoreW[1]);

@@ -577,11 +577,21 @@ struct WaveView {
 // computeUnrolled4RawPerceptron, perceptron.h:46-72; NV = 2 is the r1/r2 pair
 // of applyBiTriFullKernel, feature_impl_ngram_partial_kernels.h:35-61).
 // idxOf(f) yields the table index; NV loads are in flight at a time.
-template <int NV, typename IdxFn>
+// idxOf(f) yields the table index; LB (a multiple of NV) independent loads are
+// issued before their values are added, in feature order, into accumulator f % NV
+// -- the order of additions inside each accumulator is unchanged.
+template <int NV, int LB, typename IdxFn>
 JPP_HD void gsum(const float* __restrict__ w, u32 n, IdxFn idxOf, float* acc) {
 #pragma unroll
   for (int j = 0; j < NV; ++j) acc[j] = 0.0f;
   u32 f = 0;
+  for (; f + LB <= n; f += LB) {
+    float x[LB];
+#pragma unroll
+    for (int j = 0; j < LB; ++j) x[j] = JPP_LDG(w + idxOf(f + j));
+#pragma unroll
+    for (int j = 0; j < LB; ++j) acc[j % NV] += x[j];
+  }
   for (; f + NV <= n; f += NV) {
     float x[NV];
 #pragma unroll
@@ -598,17 +608,17 @@ template <typename IdxFn>
 JPP_HD float gsum_vars(const float* __restrict__ w, u32 n, u32 nv, IdxFn idxOf) {
   float a[8];
   switch (nv) {
-    case 8: gsum<8>(w, n, idxOf, a); return ((((((a[0] + a[1]) + a[2]) + a[3]) + a[4]) + a[5]) + a[6]) + a[7];
-    case 4: gsum<4>(w, n, idxOf, a); return ((a[0] + a[1]) + a[2]) + a[3];
-    case 2: gsum<2>(w, n, idxOf, a); return a[0] + a[1];
-    default: gsum<1>(w, n, idxOf, a); return a[0];
+    case 8: gsum<8, 8>(w, n, idxOf, a); return ((((((a[0] + a[1]) + a[2]) + a[3]) + a[4]) + a[5]) + a[6]) + a[7];
+    case 4: gsum<4, 8>(w, n, idxOf, a); return ((a[0] + a[1]) + a[2]) + a[3];
+    case 2: gsum<2, 8>(w, n, idxOf, a); return a[0] + a[1];
+    default: gsum<1, 8>(w, n, idxOf, a); return a[0];
   }
 }
 
 template <typename IdxFn>
 JPP_HD float gsum_unrolled4(const float* __restrict__ w, u32 n, IdxFn idxOf) {
   float a[4];
-  gsum<4>(w, n, idxOf, a);
+  gsum<4, 8>(w, n, idxOf, a);
   return ((a[0] + a[1]) + a[2]) + a[3];
 }
 
@@ -689,18 +699,26 @@ JPP_HD void wave_gbeam(const BatchView& bv, const ScoreCfg& cfg, const WaveView&
   const u32 L = bv.bndEndOff[gB + 1] - e0;
   u64 top[MAX_BEAM];
   u32 G = 0;
-  for (u32 left = 0; left < L; ++left) {
-    const u32 lnode = bv.endNode[e0 + left];
-    const jpp_b200_beam_element* row = bv.beam + (size_t)lnode * B;
+  // beams are filled front to back (score_processor.cc:257-260), so fake slots
+  // can simply be skipped: every load below is independent of the others
+  for (u32 left0 = 0; left0 < L; left0 += 4) {
+    u32 ln[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) ln[q] = bv.endNode[e0 + (left0 + q < L ? left0 + q : left0)];
     for (u32 slot = 0; slot < B; ++slot) {
-      const jpp_b200_beam_element el = row[slot];
-      if (is_fake(el)) break;  // beams are filled front to back (score_processor.cc:257-260)
-      const u64 key = pack_cand(el.total_score, left, slot);
-      if (G == GMAX && key < top[G - 1]) continue;
-      u32 pos = G < GMAX ? G : GMAX - 1;
-      while (pos > 0 && top[pos - 1] < key) { top[pos] = top[pos - 1]; --pos; }
-      top[pos] = key;
-      if (G < GMAX) ++G;
+      jpp_b200_beam_element el[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) el[q] = bv.beam[(size_t)ln[q] * B + slot];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (left0 + q >= L || is_fake(el[q])) continue;
+        const u64 key = pack_cand(el[q].total_score, left0 + q, slot);
+        if (G == GMAX && key < top[G - 1]) continue;
+        u32 pos = G < GMAX ? G : GMAX - 1;
+        while (pos > 0 && top[pos - 1] < key) { top[pos] = top[pos - 1]; --pos; }
+        top[pos] = key;
+        if (G < GMAX) ++G;
+      }
     }
   }
   u64* gbKey = wv.gbKey + (size_t)sent * GMAX;
@@ -798,33 +816,56 @@ JPP_HD void wave_cutoff(const FeatTables& ft, const BatchView& bv, const ScoreCf
   } else {
     for (u32 r = 0; r < R; ++r) bv.selK[n0 + r] = 1;
   }
-  // append the selected nodes (in node order) to the wave list
+  // append the selected nodes (in node order) to the wave list; one atomic per
+  // warp (the lanes of a warp are different sentences)
   u32 nsel = 0;
   for (u32 r = 0; r < R; ++r) nsel += (bv.selK[n0 + r] != 0xFFFFu);
+  unsigned long long g = 0, sb = 0;
+  if (bv.counters) {
+    const bool scoreTail = remaining > 0 && G > 0;
+    g = (unsigned long long)theMax * R * (ft.nBi + ft.nTri);
+    if (scoreTail) g += (unsigned long long)nsel * ((unsigned long long)U * ft.nBi + (unsigned long long)remaining * ft.nTri);
+    // streaming bytes of the boundary (DESIGN.md "roofline accounting")
+    sb = 8ull * L * B + 8ull * SP * ((unsigned long long)R + U + G) + 4ull * L + (8ull + 4ull * cfg.S) * R * B;
+  }
   u32 base;
 #if defined(__CUDA_ARCH__)
-  base = atomicAdd(wv.selCount, nsel);
+  {
+    const unsigned m = __activemask();
+    const int lane = (int)(threadIdx.x & 31u);
+    const int leader = __ffs(m) - 1;
+    unsigned long long gs = g, sbs = sb;
+    // the mask may have holes (threads that returned early or diverged): plain broadcast reduction
+    u32 total = 0, excl = 0;
+    for (int l = 0; l < 32; ++l) {
+      if (!((m >> l) & 1u)) continue;
+      const u32 v = __shfl_sync(m, nsel, l);
+      if (l < lane) excl += v;
+      total += v;
+    }
+    unsigned long long gt = 0, st = 0;
+    if (bv.counters) {
+      for (int l = 0; l < 32; ++l) {
+        if (!((m >> l) & 1u)) continue;
+        gt += __shfl_sync(m, gs, l);
+        st += __shfl_sync(m, sbs, l);
+      }
+    }
+    u32 wbase = 0;
+    if (lane == leader) {
+      wbase = atomicAdd(wv.selCount, total);
+      if (bv.counters) { atomicAdd(bv.counters + 0, gt); atomicAdd(bv.counters + 1, st); }
+    }
+    wbase = __shfl_sync(m, wbase, leader);
+    base = wbase + excl;
+  }
 #else
   base = *wv.selCount;
   *wv.selCount += nsel;
+  if (bv.counters) { bv.counters[0] += g; bv.counters[1] += sb; }
 #endif
   for (u32 r = 0, k = 0; r < R; ++r)
     if (bv.selK[n0 + r] != 0xFFFFu) wv.selList[base + k++] = n0 + r;
-  if (bv.counters) {
-    const bool scoreTail = remaining > 0 && G > 0;
-    unsigned long long g = (unsigned long long)theMax * R * (ft.nBi + ft.nTri);
-    if (scoreTail) g += (unsigned long long)nsel * ((unsigned long long)U * ft.nBi + (unsigned long long)remaining * ft.nTri);
-    // streaming bytes of the boundary (DESIGN.md "roofline accounting")
-    const unsigned long long sb = 8ull * L * B + 8ull * SP * ((unsigned long long)R + U + G) + 4ull * L +
-                                  (8ull + 4ull * cfg.S) * R * B;
-#if defined(__CUDA_ARCH__)
-    atomicAdd(bv.counters + 0, g);
-    atomicAdd(bv.counters + 1, sb);
-#else
-    bv.counters[0] += g;
-    bv.counters[1] += sb;
-#endif
-  }
 }
 
 // W4: one selected right node against the whole global beam: applyBiTri ->
@@ -864,7 +905,7 @@ JPP_HD void wave_score_node(const FeatTables& ft, const BatchView& bv, const Sco
       auto biIdx = [&](u32 f) -> u32 { return (u32)mix(mix(ft.biState[f], P[ft.biT0[f]]), t1[ft.biT1[f]]) & mask; };
       if (u + 1 < U) {
         float a[2];
-        gsum<2>(w, nB, biIdx, a);
+        gsum<2, 8>(w, nB, biIdx, a);
         scbuf[u] = a[0] + a[1];
       } else {
         scbuf[u] = gsum_unrolled4(w, nB, biIdx);
@@ -881,7 +922,7 @@ JPP_HD void wave_score_node(const FeatTables& ft, const BatchView& bv, const Sco
       float v;
       if (j + 1 < remaining) {
         float a[2];
-        gsum<2>(w, nT, triIdx, a);
+        gsum<2, 4>(w, nT, triIdx, a);
         v = scbuf[t1idx[gi]] + a[0] + a[1];
       } else {
         v = scbuf[t1idx[gi]] + gsum_unrolled4(w, nT, triIdx);
