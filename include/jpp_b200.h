@@ -239,6 +239,15 @@ typedef struct jpp_b200_result {
   uint64_t* node_patterns;
   /* [total_nodes] ScoreProcessor scores_.bufferT0() (unigram score of the node) */
   float* node_t0_score;
+  /* The 1-best path of every sentence, i.e. what AnalysisPath::fillIn
+   * (analysis_result.cc:25-76) walks from EOS beam[0] through the `previous`
+   * links, already resolved on the device: best_path_len[s] node indices (global
+   * node index into the batch, BOS and EOS excluded, in sentence order) stored
+   * at best_path_nodes[sent_boundary_off[s] ...].  A caller that only prints the
+   * 1-best analysis (the CLI default) downloads these few MB instead of every
+   * beam.  best_path_len: [num_sentences]; best_path_nodes: [total_boundaries]. */
+  uint32_t* best_path_len;
+  uint32_t* best_path_nodes;
 } jpp_b200_result;
 
 /* Work counters of the last scored batch (roofline accounting). */

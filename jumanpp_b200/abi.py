@@ -78,7 +78,8 @@ class Batch(C.Structure):
 
 class Result(C.Structure):
     _fields_ = [("node_beam", C.c_void_p), ("node_beam_scores", C.c_void_p),
-                ("node_patterns", C.c_void_p), ("node_t0_score", C.c_void_p)]
+                ("node_patterns", C.c_void_p), ("node_t0_score", C.c_void_p),
+                ("best_path_len", C.c_void_p), ("best_path_nodes", C.c_void_p)]
 
 
 class Counters(C.Structure):
@@ -341,16 +342,29 @@ class ScoreResult:
     node_beam_scores: np.ndarray   # [nodes][beam][S] f32
     node_patterns: np.ndarray      # [nodes][stored] u64
     node_t0_score: np.ndarray      # [nodes] f32
+    best_path_len: np.ndarray | None = None     # [sentences] u32
+    best_path_nodes: np.ndarray | None = None   # [boundaries] u32, sentence s at sent_boundary_off[s]
 
     @staticmethod
-    def allocate(num_nodes: int, beam: int, num_scorers: int, stored: int) -> "ScoreResult":
-        return ScoreResult(np.zeros((num_nodes, beam), BEAM_EL_DT),
-                           np.zeros((num_nodes, beam, num_scorers), np.float32),
-                           np.zeros((num_nodes, stored), np.uint64), np.zeros(num_nodes, np.float32))
+    def allocate(num_nodes: int, beam: int, num_scorers: int, stored: int, num_sentences: int = 0,
+                 num_boundaries: int = 0) -> "ScoreResult":
+        r = ScoreResult(np.zeros((num_nodes, beam), BEAM_EL_DT),
+                        np.zeros((num_nodes, beam, num_scorers), np.float32),
+                        np.zeros((num_nodes, stored), np.uint64), np.zeros(num_nodes, np.float32))
+        if num_sentences:
+            r.best_path_len = np.zeros(num_sentences, np.uint32)
+            r.best_path_nodes = np.zeros(num_boundaries, np.uint32)
+        return r
 
     def as_struct(self) -> Result:
         return Result(_ptr(self.node_beam), _ptr(self.node_beam_scores), _ptr(self.node_patterns),
-                      _ptr(self.node_t0_score))
+                      _ptr(self.node_t0_score), _ptr(self.best_path_len), _ptr(self.best_path_nodes))
+
+    def paths(self, batch: "StagedBatch") -> list[list[int]]:
+        """1-best node indices per sentence from the device-resolved paths."""
+        off = batch.sent_boundary_off
+        return [self.best_path_nodes[int(off[s]):int(off[s]) + int(self.best_path_len[s])].tolist()
+                for s in range(batch.num_sentences)]
 
 
 def best_paths(batch: StagedBatch, res: ScoreResult) -> list[list[tuple[int, int]]]:

@@ -330,6 +330,11 @@ __global__ void __launch_bounds__(128) k_rnn_scores(BatchView bv, ScoreCfg cfg, 
   }
 }
 
+__global__ void k_best_path(BatchView bv, ScoreCfg cfg, u32* pathLen, u32* pathNodes) {
+  const u32 s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < bv.numSentences) best_path_sentence(bv, cfg, pathLen, pathNodes, s);
+}
+
 __global__ void k_rerank(BatchView bv, ScoreCfg cfg, float w0, float w1) {
   const u32 s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s < bv.numSentences) rerank_sentence(bv, cfg, w0, w1, s);
@@ -379,6 +384,7 @@ struct jpp_b200_handle {
   enum { B_SBO, B_SCO, B_BNO, B_BEO, B_INFO, B_ENTRY, B_PH, B_RNNID, B_ENDS, B_CPS, B_NODEBND, B_BNDSENT, B_ENDNODE,
          B_ORDER, B_BEAM, B_BSCORES, B_PATS, B_T0, B_PRE, B_CUT, B_CUTIDX, B_SELK, B_GBNODE, B_GBSLOT, B_GBLBND, B_GBCNT,
          B_EOSG, B_EOSLOC, B_EOSRNN, B_COUNTERS, B_WORK,
+         B_PATHLEN, B_PATHNODES,
          W_GBKEY, W_GBLNODE, W_GBT2, W_GBT1IDX, W_T1NODE, W_GCNT, W_UCNT, W_SELLIST, W_SELCNT, W_NODES, W_OFF, W_CURSOR,
          R_OFF, R_ID, R_PREV, R_NEXT, R_BND, R_LEN, R_DEPTH, R_HASH, R_RNCNT, R_RSNODE, R_RSSLOT, R_RSEOSG, R_RSRNODE,
          R_RSCNT, R_CONN, R_BNDHEAD, R_CTX, R_CHNODE, R_CHSLOT, R_CHBND, R_SCLIST, R_SCTOTAL, R_LVLCNT, R_LVLOFF, R_LVLLIST, R_CTXOFF, R_RNSENT, R_CURSOR, R_CUBTMP,
@@ -606,6 +612,7 @@ jpp_b200_status jpp_b200_upload_batch(jpp_b200_handle* h, const jpp_b200_batch* 
   ENSURE(B_GBCNT, (size_t)NB);
   ENSURE(B_EOSG, (size_t)NS * G * 8); ENSURE(B_EOSLOC, (size_t)NS * G * 4); ENSURE(B_EOSRNN, (size_t)NS * G * 4);
   ENSURE(B_COUNTERS, 64); ENSURE(B_WORK, 16);
+  ENSURE(B_PATHLEN, (size_t)NS * 4); ENSURE(B_PATHNODES, (size_t)NB * 4);
   cudaStream_t st = h->stream;
 #define H2D(idx, src, bytes) CU_CHECK(h, cudaMemcpyAsync(bf[jpp_b200_handle::idx].p, src, bytes, cudaMemcpyHostToDevice, st))
   CU_CHECK(h, cudaEventRecord(h->ev[0], st));
@@ -787,6 +794,8 @@ jpp_b200_status jpp_b200_score_resident(jpp_b200_handle* h) {
     // counters: tree nodes and scores
     h->counters.rnn_nodes = rows;
   }
+  k_best_path<<<(NS + 127) / 128, 128, 0, st>>>(bv, h->cfg, bf[jpp_b200_handle::B_PATHLEN].as<u32>(), bf[jpp_b200_handle::B_PATHNODES].as<u32>());
+  CU_CHECK(h, cudaGetLastError());
   CU_CHECK(h, cudaEventRecord(h->ev[8], st));
   CU_CHECK(h, cudaStreamSynchronize(st));
   // counters
@@ -799,7 +808,7 @@ jpp_b200_status jpp_b200_score_resident(jpp_b200_handle* h) {
   c.gathers = dc[0] + t0Nodes * h->hm.ft.nUni;
   c.walk_gathers = dc[0];
   c.walk_bytes = 4ull * dc[0] + dc[1];
-  c.launches = 1 + h->walkLaunches + (h->hasRnn ? (12ull + h->maxNb) : 0ull);
+  c.launches = 2 + h->walkLaunches + (h->hasRnn ? (12ull + h->maxNb) : 0ull);
   // BASELINE.md roofline accounting: 4 B per gather + streaming terms
   const u32 B = (u32)h->cfg.beam, SP = h->hm.ft.nStored;
   // T0 kernel: entry + NodeInfo + placeholders in, pattern row + score out; walk kernel: see walk_sentence
@@ -832,6 +841,8 @@ jpp_b200_status jpp_b200_download_result(jpp_b200_handle* h, jpp_b200_result* r)
   if (r->node_beam_scores) CU_CHECK(h, cudaMemcpyAsync(r->node_beam_scores, bv.beamScores, NN * B * S * 4, cudaMemcpyDeviceToHost, st));
   if (r->node_patterns) CU_CHECK(h, cudaMemcpyAsync(r->node_patterns, bv.patterns, NN * SP * 8, cudaMemcpyDeviceToHost, st));
   if (r->node_t0_score) CU_CHECK(h, cudaMemcpyAsync(r->node_t0_score, bv.t0, NN * 4, cudaMemcpyDeviceToHost, st));
+  if (r->best_path_len) CU_CHECK(h, cudaMemcpyAsync(r->best_path_len, h->buf[jpp_b200_handle::B_PATHLEN].p, (size_t)bv.numSentences * 4, cudaMemcpyDeviceToHost, st));
+  if (r->best_path_nodes) CU_CHECK(h, cudaMemcpyAsync(r->best_path_nodes, h->buf[jpp_b200_handle::B_PATHNODES].p, (size_t)bv.totalBoundaries * 4, cudaMemcpyDeviceToHost, st));
   CU_CHECK(h, cudaStreamSynchronize(st));
   return JPP_B200_OK;
 }

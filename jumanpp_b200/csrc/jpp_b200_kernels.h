@@ -967,4 +967,32 @@ JPP_HD void wave_rest_node(const BatchView& bv, const ScoreCfg& cfg, const WaveV
   write_beam(bv, cfg, node, gbKey, (int)full, tot, loc);
 }
 
+// 1-best path of a sentence: walk EOS beam[0] back through the (left, prev_beam)
+// links (analysis_result.cc:25-76) and store the node indices in sentence order.
+JPP_HD void best_path_sentence(const BatchView& bv, const ScoreCfg& cfg, u32* pathLen, u32* pathNodes, u32 sent) {
+  const u32 b0 = bv.sentBndOff[sent];
+  const u32 nb = bv.sentBndOff[sent + 1] - b0;
+  const u32 B = (u32)cfg.beam;
+  pathLen[sent] = 0;
+  if (nb <= 3) return;
+  u32 len = 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    u32 node = bv.bndNodeOff[b0 + nb - 1], bnd = nb - 1, slot = 0, i = 0;
+    for (;;) {
+      const jpp_b200_beam_element el = bv.beam[(size_t)node * B + slot];
+      if (is_fake(el)) { len = 0; i = 0; break; }  // unreachable EOS: no path
+      const u32 e = bv.bndEndOff[b0 + bnd] + el.left;
+      slot = el.prev_beam;
+      bnd = bv.ends[e].boundary;
+      node = bv.endNode[e];
+      if (bnd < 2) break;
+      if (pass == 1) pathNodes[b0 + (len - 1 - i)] = node;
+      ++i;
+    }
+    if (pass == 0) len = i;
+    if (len == 0) break;
+  }
+  pathLen[sent] = len;
+}
+
 }  // namespace jppb200

@@ -104,7 +104,7 @@ class LatticeScorer:
 
     def allocate_result(self, batch: abi.StagedBatch) -> abi.ScoreResult:
         return abi.ScoreResult.allocate(batch.num_nodes, self.config.beam_size, self.model.num_scorers,
-                                        self.model.num_stored_patterns)
+                                        self.model.num_stored_patterns, batch.num_sentences, batch.num_boundaries)
 
     # -- reference: AnalyzerImpl::computeScores for every sentence of the batch
     def compute_scores(self, batch: abi.StagedBatch, result: abi.ScoreResult | None = None) -> abi.ScoreResult:
@@ -121,12 +121,16 @@ class LatticeScorer:
     def score_resident(self) -> None:
         self._check(self._lib.jpp_b200_score_resident(self._h))
 
-    def download(self, result: abi.ScoreResult, beams_only: bool = False) -> abi.ScoreResult:
+    def download(self, result: abi.ScoreResult, beams_only: bool = False, paths_only: bool = False) -> abi.ScoreResult:
+        """Copy back the requested part of the post-state: everything, the beams (+ paths), or only
+        the device-resolved 1-best paths (what the CLI's default output needs)."""
         rs = result.as_struct()
-        if beams_only:
+        if beams_only or paths_only:
             rs.node_beam_scores = None
             rs.node_patterns = None
             rs.node_t0_score = None
+        if paths_only:
+            rs.node_beam = None
         self._check(self._lib.jpp_b200_download_result(self._h, C.byref(rs)))
         return result
 

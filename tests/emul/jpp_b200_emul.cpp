@@ -157,5 +157,7 @@ extern "C" int jpp_b200_emul_score_batch(const jpp_b200_model* model, const jpp_
       rerank_sentence(bv, cfg, model->score_weights[0], model->score_weights[1], s);
     }
   }
+  if (r->best_path_len && r->best_path_nodes)
+    for (u32 s = 0; s < NS; ++s) best_path_sentence(bv, cfg, r->best_path_len, r->best_path_nodes, s);
   return 0;
 }

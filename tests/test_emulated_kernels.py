@@ -30,7 +30,8 @@ def emul():
 
 
 def run_emul(emul, model, cfg, batch):
-    res = abi.ScoreResult.allocate(batch.num_nodes, cfg.beam_size, model.num_scorers, model.num_stored_patterns)
+    res = abi.ScoreResult.allocate(batch.num_nodes, cfg.beam_size, model.num_scorers, model.num_stored_patterns,
+                                   batch.num_sentences, batch.num_boundaries)
     w = oracle_lib.weights_for(model)
     ms, cs, bs, rs = model.as_struct(), cfg.as_struct(), batch.as_struct(), res.as_struct()
     err = C.create_string_buffer(512)
@@ -46,6 +47,10 @@ def test_linear_kernels(emul, name):
     res = run_emul(emul, model, cfg, batch)
     rep = parity.compare_with_expected(d, batch, res, rnn=False)
     assert rep == {"patterns": 0, "beam_links": 0, "beam_totals": 0, "conn_scores": 0}, rep
+    # device-resolved 1-best paths == the walk a host would do over the beams
+    bno, sbo = batch.boundary_node_off, batch.sent_boundary_off
+    want = [[int(bno[int(sbo[s]) + b]) + p for b, p in path[:-1]] for s, path in enumerate(abi.best_paths(batch, res))]
+    assert res.paths(batch) == want
 
 
 @pytest.mark.parametrize("name", RNN)

@@ -38,6 +38,10 @@ def test_linear_path_matches_reference_and_oracle(name):
     assert res.node_t0_score.tobytes() == ora.node_t0_score.tobytes()
     assert cnt["gathers"] == stats.gathers
     assert cnt["kernel_ms"]["beam_walk"] > 0
+    from jumanpp_b200 import abi
+    bno, sbo = batch.boundary_node_off, batch.sent_boundary_off
+    want = [[int(bno[int(sbo[s]) + b]) + p for b, p in path[:-1]] for s, path in enumerate(abi.best_paths(batch, res))]
+    assert res.paths(batch) == want
 
 
 @pytest.mark.parametrize("name", RNN)
