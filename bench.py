@@ -259,43 +259,43 @@ def product_arm(args, rank: int, world: int, local_rank: int) -> None:
         scorer.download(res, paths_only=True)
     torch.cuda.synchronize()
     dt_single = time.perf_counter() - t0
-    # (b) pipelined: the batch in `e2e_chunks` pieces over two handles / host threads, so the
-    # copies of one piece overlap the kernels of the other
-    nchunk = max(2, args.e2e_chunks)
-    bounds = shard.shard_bounds(np.diff(batch.sent_codepoint_off.astype(np.int64)), nchunk)
-    chunks = []
-    for c in range(nchunk):
-        sub = batch.select(int(bounds[c]), int(bounds[c + 1]))
-        sub = abi.StagedBatch.concat([sub], pin=pinned_copy)
-        r = abi.ScoreResult.allocate(0, cfg.beam_size, model.num_scorers, model.num_stored_patterns, sub.num_sentences,
-                                     sub.num_boundaries)
-        r.best_path_len, r.best_path_nodes = pinned_copy(r.best_path_len), pinned_copy(r.best_path_nodes)
-        chunks.append((sub, r))
-    scorer.close()
-    workers = [LatticeScorer(model, cfg, device=local_rank) for _ in range(2)]
+    dt_e2e = dt_single
+    pipelined = None
+    workers = [scorer]
+    if args.e2e_chunks >= 2:
+        # (b) optional: the batch in pieces over two handles / host threads (copies of one piece
+        # overlap the kernels of the other).  Measured slower than the single call at this size
+        # (profiles/README.md), so it is off by default.
+        nchunk = args.e2e_chunks
+        bounds = shard.shard_bounds(np.diff(batch.sent_codepoint_off.astype(np.int64)), nchunk)
+        chunks = []
+        for c in range(nchunk):
+            sub = abi.StagedBatch.concat([batch.select(int(bounds[c]), int(bounds[c + 1]))], pin=pinned_copy)
+            r = abi.ScoreResult.allocate(0, cfg.beam_size, model.num_scorers, model.num_stored_patterns,
+                                         sub.num_sentences, sub.num_boundaries)
+            r.best_path_len, r.best_path_nodes = pinned_copy(r.best_path_len), pinned_copy(r.best_path_nodes)
+            chunks.append((sub, r))
+        workers = [scorer, LatticeScorer(model, cfg, device=local_rank)]
 
-    def run_worker(wi):
-        sc = workers[wi]
-        for ci in range(wi, nchunk, 2):
-            sub, r = chunks[ci]
-            sc.upload(sub); sc.score_resident(); sc.download(r, paths_only=True)
+        def run_worker(wi):
+            for ci in range(wi, nchunk, 2):
+                sub, r = chunks[ci]
+                workers[wi].upload(sub); workers[wi].score_resident(); workers[wi].download(r, paths_only=True)
 
-    def pipelined_step():
-        ts = [threading.Thread(target=run_worker, args=(wi,)) for wi in range(2)]
-        for t in ts: t.start()
-        for t in ts: t.join()
+        def pipelined_step():
+            ts = [threading.Thread(target=run_worker, args=(wi,)) for wi in range(2)]
+            for t in ts: t.start()
+            for t in ts: t.join()
 
-    for _ in range(min(2, args.warmup)):
-        pipelined_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        pipelined_step()
-    torch.cuda.synchronize()
-    dt_e2e = time.perf_counter() - t0
-    # the pipelined pieces must give the same 1-best paths as the single call
-    got = np.concatenate([r.best_path_len for _, r in chunks])
-    assert np.array_equal(got, res.best_path_len), "pipelined e2e disagrees with the single-call result"
+        for _ in range(2):
+            pipelined_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            pipelined_step()
+        torch.cuda.synchronize()
+        pipelined = {"chunks": nchunk, "ms_per_step": 1000.0 * (time.perf_counter() - t0) / args.steps}
+        assert np.array_equal(np.concatenate([r.best_path_len for _, r in chunks]), res.best_path_len)
     t_e2e = torch.tensor([dt_e2e, dt_single], dtype=torch.float64, device="cuda")
     counts = torch.tensor([batch.num_sentences, cnt["gathers"], cnt["nodes"]], dtype=torch.float64, device="cuda")
     if dist:
@@ -334,8 +334,9 @@ def product_arm(args, rank: int, world: int, local_rank: int) -> None:
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "sentences/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": 1000.0 * e2e_s / args.steps,
-                    "how": f"{nchunk} pieces over 2 handles/host threads (copies overlap kernels); D2H = device-resolved 1-best paths",
-                    "single_call_value": total_sent * args.steps / single_s, "single_call_ms_per_step": 1000.0 * single_s / args.steps},
+                    "how": "one jpp_b200_upload_batch + score_resident + download_result per step from pinned host buffers; "
+                           "D2H = device-resolved 1-best paths (jpp_b200_result.best_path_*)",
+                    "pipelined_two_handles": pipelined},
             "gpu_launches": int(cnt["launches"]) * args.steps,
             "wall_ms_per_step_resident": 1000.0 * wall_s / args.steps,
             "stage_ms": {k: statistics.mean(x[k] for x in kms) for k in kms[0]},
@@ -419,7 +420,7 @@ def main() -> None:
     ap.add_argument("--cache", default=os.environ.get("JPP_B200_CACHE", "/tmp/jpp_b200_cache"))
     ap.add_argument("--cpu-sample-per-core", type=int, default=1500)
     ap.add_argument("--parity-sample", type=int, default=2000)
-    ap.add_argument("--e2e-chunks", type=int, default=4)
+    ap.add_argument("--e2e-chunks", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
