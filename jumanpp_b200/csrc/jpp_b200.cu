@@ -59,17 +59,28 @@ __global__ void k_node_index(BatchView bv) {
   }
 }
 
-__global__ void __launch_bounds__(128) k_t0(const FeatTables* __restrict__ ftg, BatchView bv, const float* __restrict__ w) {
+// Shared-memory hot-weight cache of a CTA (WLoadCached): kCacheSlots 8-byte slots.
+constexpr u32 kCacheSlots = 16384;  // 128 KB: the hottest 16k indices are ~3/4 of all gathers
+constexpr u32 kCacheThreads = 1024; // one CTA per SM shares one cache
+
+__device__ __forceinline__ WLoadCached make_cache(const float* w, unsigned long long* slots) {
+  for (u32 i = threadIdx.x; i < kCacheSlots; i += blockDim.x) slots[i] = 0xFFFFFFFFull;  // empty tag
+  __syncthreads();
+  return WLoadCached{w, slots, kCacheSlots - 1};
+}
+
+__global__ void __launch_bounds__(kCacheThreads) k_t0(const FeatTables* __restrict__ ftg, BatchView bv, const float* __restrict__ w) {
   // per-thread (divergent) table indices here: shared memory, not the constant bank
   __shared__ FeatTables ft;
+  extern __shared__ __align__(16) unsigned long long cacheSlots[];
   {
     const u32* src = reinterpret_cast<const u32*>(ftg);
     u32* dst = reinterpret_cast<u32*>(&ft);
     for (u32 i = threadIdx.x; i < sizeof(FeatTables) / 4; i += blockDim.x) dst[i] = src[i];
   }
-  __syncthreads();
-  const u32 node = blockIdx.x * blockDim.x + threadIdx.x;
-  if (node < bv.totalNodes) t0_node(ft, bv, w, node);
+  const WLoadCached wl = make_cache(w, cacheSlots);
+  for (u32 node = blockIdx.x * blockDim.x + threadIdx.x; node < bv.totalNodes; node += gridDim.x * blockDim.x)
+    t0_node(ft, bv, wl, node);
 }
 
 // ---- wavefront walk kernels (see jpp_b200_kernels.h "wavefront walk") ----
@@ -103,10 +114,12 @@ __global__ void __launch_bounds__(128) k_w_gbeam(BatchView bv, ScoreCfg cfg, Wav
   if (i < nActive) wave_gbeam(bv, cfg, wv, bv.sentOrder[i], bnd);
 }
 
-__global__ void __launch_bounds__(128) k_w_prescore(const __grid_constant__ FeatTables ft, BatchView bv, ScoreCfg cfg,
-                                                   WaveView wv, const float* __restrict__ w, u32 first, u32 count) {
-  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < count) wave_prescore(ft, bv, cfg, wv, w, wv.waveNodes[first + i]);
+__global__ void __launch_bounds__(kCacheThreads) k_w_prescore(const __grid_constant__ FeatTables ft, BatchView bv, ScoreCfg cfg,
+                                                           WaveView wv, const float* __restrict__ w, u32 first, u32 count) {
+  extern __shared__ __align__(16) unsigned long long cacheSlots[];
+  const WLoadCached wl = make_cache(w, cacheSlots);
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
+    wave_prescore(ft, bv, cfg, wv, wl, wv.waveNodes[first + i]);
 }
 
 __global__ void __launch_bounds__(128) k_w_cutoff(const __grid_constant__ FeatTables ft, BatchView bv, ScoreCfg cfg,
@@ -115,11 +128,13 @@ __global__ void __launch_bounds__(128) k_w_cutoff(const __grid_constant__ FeatTa
   if (i < nActive) wave_cutoff(ft, bv, cfg, wv, bv.sentOrder[i], bnd);
 }
 
-__global__ void __launch_bounds__(128) k_w_score(const __grid_constant__ FeatTables ft, BatchView bv, ScoreCfg cfg, WaveView wv,
-                                                const float* __restrict__ w) {
+__global__ void __launch_bounds__(kCacheThreads) k_w_score(const __grid_constant__ FeatTables ft, BatchView bv, ScoreCfg cfg,
+                                                        WaveView wv, const float* __restrict__ w) {
+  extern __shared__ __align__(16) unsigned long long cacheSlots[];
+  const WLoadCached wl = make_cache(w, cacheSlots);
   const u32 n = *wv.selCount;
   for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-    wave_score_node(ft, bv, cfg, wv, w, wv.selList[i]);
+    wave_score_node(ft, bv, cfg, wv, wl, wv.selList[i]);
 }
 
 __global__ void __launch_bounds__(128) k_w_rest(BatchView bv, ScoreCfg cfg, WaveView wv, u32 first, u32 count) {
@@ -481,6 +496,9 @@ jpp_b200_status jpp_b200_create(const jpp_b200_model* model, const jpp_b200_conf
   CREATE_CHECK(cudaGetDeviceProperties(&prop, device));
   h->smCount = prop.multiProcessorCount;
   CREATE_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CREATE_CHECK(cudaFuncSetAttribute(k_t0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kCacheSlots * 8)));
+  CREATE_CHECK(cudaFuncSetAttribute(k_w_prescore, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kCacheSlots * 8)));
+  CREATE_CHECK(cudaFuncSetAttribute(k_w_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kCacheSlots * 8)));
   for (auto& e : h->ev) CREATE_CHECK(cudaEventCreate(&e));
   CREATE_CHECK(cudaMalloc(&h->dFt, sizeof(FeatTables)));
   CREATE_CHECK(cudaMemcpyAsync(h->dFt, &h->hm.ft, sizeof(FeatTables), cudaMemcpyHostToDevice, h->stream));
@@ -717,7 +735,7 @@ jpp_b200_status jpp_b200_score_resident(jpp_b200_handle* h) {
   CU_CHECK(h, cudaMemsetAsync(bf[jpp_b200_handle::B_COUNTERS].p, 0, 64, st));
   CU_CHECK(h, cudaMemsetAsync(bf[jpp_b200_handle::B_WORK].p, 0, 16, st));
   CU_CHECK(h, cudaEventRecord(h->ev[2], st));
-  k_t0<<<(NN + 127) / 128, 128, 0, st>>>(h->dFt, bv, h->dWeights);
+  k_t0<<<h->smCount, kCacheThreads, kCacheSlots * 8, st>>>(h->dFt, bv, h->dWeights);
   CU_CHECK(h, cudaGetLastError());
   CU_CHECK(h, cudaEventRecord(h->ev[3], st));
   {
@@ -732,12 +750,15 @@ jpp_b200_status jpp_b200_score_resident(jpp_b200_handle* h) {
       const u32 first = h->waveNodeOff[bnd], count = h->waveNodeOff[bnd + 1] - first;
       if (count == 0) continue;
       k_w_gbeam<<<(nAct + 127) / 128, 128, 0, st>>>(bv, cfg, wv, nAct, bnd);
-      if (cfg.rcheck > 0) k_w_prescore<<<(count + 127) / 128, 128, 0, st>>>(ft, bv, cfg, wv, h->dWeights, first, count);
+      if (cfg.rcheck > 0) {
+        const u32 pb = std::min<u32>((count + kCacheThreads - 1) / kCacheThreads, (u32)h->smCount);
+        k_w_prescore<<<std::max(1u, pb), kCacheThreads, kCacheSlots * 8, st>>>(ft, bv, cfg, wv, h->dWeights, first, count);
+      }
       k_w_cutoff<<<(nAct + 127) / 128, 128, 0, st>>>(ft, bv, cfg, wv, nAct, bnd);
       u32 selBound = count;
       if (cfg.rcheck > 0) selBound = std::min<u64>(count, (u64)nAct * (u32)cfg.rbeam);
-      const u32 blocks = std::min<u32>((selBound + 127) / 128, (u32)h->smCount * 16);
-      k_w_score<<<std::max(1u, blocks), 128, 0, st>>>(ft, bv, cfg, wv, h->dWeights);
+      const u32 blocks = std::min<u32>((selBound + kCacheThreads - 1) / kCacheThreads, (u32)h->smCount);
+      k_w_score<<<std::max(1u, blocks), kCacheThreads, kCacheSlots * 8, st>>>(ft, bv, cfg, wv, h->dWeights);
       launches += 3;
       if (cfg.rcheck > 0) {
         k_w_rest<<<(count + 127) / 128, 128, 0, st>>>(bv, cfg, wv, first, count);

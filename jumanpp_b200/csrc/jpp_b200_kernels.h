@@ -177,6 +177,55 @@ JPP_HD jpp_b200_beam_element fake_elem() {
   return e;  // memset 0xff, score_processor.cc:466-468
 }
 
+// ------------------------------------------------------ weight loaders ------
+// Every perceptron-table read goes through a loader.  The gathered indices are
+// hashes, i.e. uniformly spread over the table (256 MiB at k = 26), but their
+// FREQUENCIES are extremely skewed (the 16 384 hottest indices are 73 % of all
+// gathers on the benchmark corpus: DESIGN.md section 5), and a warp-wide gather of 32
+// different lines costs the L1TEX pipe ~64 cycles however well it caches.
+// WLoadCached therefore keeps a direct-mapped (index -> weight) cache of the hot
+// slice in shared memory: one 8-byte slot {tag = index, value}, filled on a
+// miss.  A slot is written with a single 64-bit store, so concurrent fills of
+// the same slot by different threads cannot produce a torn pair; the value is a
+// pure function of the index, so whoever wins, a hit returns exactly what the
+// table holds -- results are bit-identical to WLoadDirect.
+struct WLoadDirect {
+  const float* __restrict__ w;
+  template <int N>
+  JPP_HD void get(const u32 (&id)[N], float (&x)[N]) const {
+#pragma unroll
+    for (int j = 0; j < N; ++j) x[j] = JPP_LDG(w + id[j]);
+  }
+  JPP_HD float one(u32 id) const { return JPP_LDG(w + id); }
+};
+
+#if defined(__CUDACC__)
+struct WLoadCached {
+  const float* __restrict__ w;
+  unsigned long long* slots;  // shared memory, [cmask + 1], tag 0xFFFFFFFF = empty
+  u32 cmask;
+  template <int N>
+  __device__ __forceinline__ void get(const u32 (&id)[N], float (&x)[N]) const {
+    unsigned long long e[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) e[j] = slots[id[j] & cmask];
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      const bool hit = (u32)e[j] == id[j];
+      x[j] = hit ? __uint_as_float((u32)(e[j] >> 32)) : __ldg(w + id[j]);
+      if (!hit) slots[id[j] & cmask] = ((unsigned long long)__float_as_uint(x[j]) << 32) | id[j];
+    }
+  }
+  __device__ __forceinline__ float one(u32 id) const {
+    const unsigned long long e = slots[id & cmask];
+    if ((u32)e == id) return __uint_as_float((u32)(e >> 32));
+    const float v = __ldg(w + id);
+    slots[id & cmask] = ((unsigned long long)__float_as_uint(v) << 32) | id;
+    return v;
+  }
+};
+#endif
+
 // ------------------------------------------------------------ T0 kernel -----
 // One thread per node: primitive features -> 38 pattern hashes -> 32 unigram
 // hashes -> weight gather + ordered sum.  Replaces the generated
@@ -217,7 +266,8 @@ JPP_HD u64 prim_value(const FeatTables& ft, u32 p, const i32* entry, const i32* 
   }
 }
 
-JPP_HD void t0_node(const FeatTables& ft, const BatchView& bv, const float* __restrict__ w, u32 node) {
+template <typename WL>
+JPP_HD void t0_node(const FeatTables& ft, const BatchView& bv, const WL& wl, u32 node) {
   const u32 gb = bv.nodeBnd[node];
   const u32 sent = bv.bndSent[gb];
   const u32 localBnd = gb - bv.sentBndOff[sent];
@@ -264,14 +314,13 @@ JPP_HD void t0_node(const FeatTables& ft, const BatchView& bv, const float* __re
   const u32 nU = ft.nUni, mask = ft.mask;
   for (u32 u0 = 0; u0 < nU; u0 += 4) {
     float wv[4];
+    u32 id[4];
 #pragma unroll
     for (u32 j = 0; j < 4; ++j) {
-      const u32 u = u0 + j;
-      if (u < nU) {
-        const u32 idx = (u32)mix(ft.uniState[u], pat[ft.uniT0[u]]) & mask;
-        wv[j] = JPP_LDG(w + idx);
-      }
+      const u32 u = u0 + j < nU ? u0 + j : nU - 1;
+      id[j] = (u32)mix(ft.uniState[u], pat[ft.uniT0[u]]) & mask;
     }
+    wl.get(id, wv);
 #pragma unroll
     for (u32 j = 0; j < 4; ++j) {
       const u32 u = u0 + j;
@@ -580,45 +629,49 @@ struct WaveView {
 // idxOf(f) yields the table index; LB (a multiple of NV) independent loads are
 // issued before their values are added, in feature order, into accumulator f % NV
 // -- the order of additions inside each accumulator is unchanged.
-template <int NV, int LB, typename IdxFn>
-JPP_HD void gsum(const float* __restrict__ w, u32 n, IdxFn idxOf, float* acc) {
+template <int NV, int LB, typename WL, typename IdxFn>
+JPP_HD void gsum(const WL& wl, u32 n, IdxFn idxOf, float* acc) {
 #pragma unroll
   for (int j = 0; j < NV; ++j) acc[j] = 0.0f;
   u32 f = 0;
   for (; f + LB <= n; f += LB) {
+    u32 id[LB];
     float x[LB];
 #pragma unroll
-    for (int j = 0; j < LB; ++j) x[j] = JPP_LDG(w + idxOf(f + j));
+    for (int j = 0; j < LB; ++j) id[j] = idxOf(f + j);
+    wl.get(id, x);
 #pragma unroll
     for (int j = 0; j < LB; ++j) acc[j % NV] += x[j];
   }
   for (; f + NV <= n; f += NV) {
+    u32 id[NV];
     float x[NV];
 #pragma unroll
-    for (int j = 0; j < NV; ++j) x[j] = JPP_LDG(w + idxOf(f + j));
+    for (int j = 0; j < NV; ++j) id[j] = idxOf(f + j);
+    wl.get(id, x);
 #pragma unroll
     for (int j = 0; j < NV; ++j) acc[j] += x[j];
   }
 #pragma unroll
   for (int j = 0; j < NV; ++j)
-    if (f + j < n) acc[j] += JPP_LDG(w + idxOf(f + j));
+    if (f + j < n) acc[j] += wl.one(idxOf(f + j));
 }
 
-template <typename IdxFn>
-JPP_HD float gsum_vars(const float* __restrict__ w, u32 n, u32 nv, IdxFn idxOf) {
+template <typename WL, typename IdxFn>
+JPP_HD float gsum_vars(const WL& wl, u32 n, u32 nv, IdxFn idxOf) {
   float a[8];
   switch (nv) {
-    case 8: gsum<8, 8>(w, n, idxOf, a); return ((((((a[0] + a[1]) + a[2]) + a[3]) + a[4]) + a[5]) + a[6]) + a[7];
-    case 4: gsum<4, 8>(w, n, idxOf, a); return ((a[0] + a[1]) + a[2]) + a[3];
-    case 2: gsum<2, 8>(w, n, idxOf, a); return a[0] + a[1];
-    default: gsum<1, 8>(w, n, idxOf, a); return a[0];
+    case 8: gsum<8, 8>(wl, n, idxOf, a); return ((((((a[0] + a[1]) + a[2]) + a[3]) + a[4]) + a[5]) + a[6]) + a[7];
+    case 4: gsum<4, 8>(wl, n, idxOf, a); return ((a[0] + a[1]) + a[2]) + a[3];
+    case 2: gsum<2, 8>(wl, n, idxOf, a); return a[0] + a[1];
+    default: gsum<1, 8>(wl, n, idxOf, a); return a[0];
   }
 }
 
-template <typename IdxFn>
-JPP_HD float gsum_unrolled4(const float* __restrict__ w, u32 n, IdxFn idxOf) {
+template <typename WL, typename IdxFn>
+JPP_HD float gsum_unrolled4(const WL& wl, u32 n, IdxFn idxOf) {
   float a[4];
-  gsum<4, 8>(w, n, idxOf, a);
+  gsum<4, 8>(wl, n, idxOf, a);
   return ((a[0] + a[1]) + a[2]) + a[3];
 }
 
@@ -753,8 +806,9 @@ JPP_HD void wave_gbeam(const BatchView& bv, const ScoreCfg& cfg, const WaveView&
 // T0 + bigrams against t1 of head element i + trigrams (generated applyBiStep2 /
 // applyTriStep3: biVars / triVars accumulators, last row of the boundary through
 // computeUnrolled4RawPerceptron; partial_ngram_feature_codegen.cc:13-153)
+template <typename WL>
 JPP_HD void wave_prescore(const FeatTables& ft, const BatchView& bv, const ScoreCfg& cfg, const WaveView& wv,
-                          const float* __restrict__ w, u32 node) {
+                          const WL& wl, u32 node) {
   const u32 gB = bv.nodeBnd[node];
   const u32 sent = bv.bndSent[gB];
   const u32 G = wv.gCount[sent];
@@ -772,8 +826,8 @@ JPP_HD void wave_prescore(const FeatTables& ft, const BatchView& bv, const Score
       return (u32)mix(mix(mix(ft.triState[f], P[ft.triT0[f]]), t1[ft.triT1[f]]), t2[ft.triT2[f]]) & mask;
     };
     float sc = t0;
-    sc += lastRow ? gsum_unrolled4(w, ft.nBi, biIdx) : gsum_vars(w, ft.nBi, ft.biVars, biIdx);
-    sc += lastRow ? gsum_unrolled4(w, ft.nTri, triIdx) : gsum_vars(w, ft.nTri, ft.triVars, triIdx);
+    sc += lastRow ? gsum_unrolled4(wl, ft.nBi, biIdx) : gsum_vars(wl, ft.nBi, ft.biVars, biIdx);
+    sc += lastRow ? gsum_unrolled4(wl, ft.nTri, triIdx) : gsum_vars(wl, ft.nTri, ft.triVars, triIdx);
     bv.pre[(size_t)i * bv.totalNodes + node] = sc;
   }
 }
@@ -872,8 +926,9 @@ JPP_HD void wave_cutoff(const FeatTables& ft, const BatchView& bv, const ScoreCf
 // applyBiTriFullKernel (feature_impl_ngram_partial_kernels.h:19-110: two
 // accumulators, last rows through Unrolled4), copyT0Scores (score_processor.cc:411-424),
 // makeT0Beam (:426-469).
+template <typename WL>
 JPP_HD void wave_score_node(const FeatTables& ft, const BatchView& bv, const ScoreCfg& cfg, const WaveView& wv,
-                            const float* __restrict__ w, u32 node) {
+                            const WL& wl, u32 node) {
   const u32 gB = bv.nodeBnd[node];
   const u32 sent = bv.bndSent[gB];
   const u32 G = wv.gCount[sent], U = wv.uCount[sent];
@@ -905,10 +960,10 @@ JPP_HD void wave_score_node(const FeatTables& ft, const BatchView& bv, const Sco
       auto biIdx = [&](u32 f) -> u32 { return (u32)mix(mix(ft.biState[f], P[ft.biT0[f]]), t1[ft.biT1[f]]) & mask; };
       if (u + 1 < U) {
         float a[2];
-        gsum<2, 8>(w, nB, biIdx, a);
+        gsum<2, 8>(wl, nB, biIdx, a);
         scbuf[u] = a[0] + a[1];
       } else {
-        scbuf[u] = gsum_unrolled4(w, nB, biIdx);
+        scbuf[u] = gsum_unrolled4(wl, nB, biIdx);
       }
     }
     const float t0 = bv.t0[node];
@@ -922,10 +977,10 @@ JPP_HD void wave_score_node(const FeatTables& ft, const BatchView& bv, const Sco
       float v;
       if (j + 1 < remaining) {
         float a[2];
-        gsum<2, 4>(w, nT, triIdx, a);
+        gsum<2, 4>(wl, nT, triIdx, a);
         v = scbuf[t1idx[gi]] + a[0] + a[1];
       } else {
-        v = scbuf[t1idx[gi]] + gsum_unrolled4(w, nT, triIdx);
+        v = scbuf[t1idx[gi]] + gsum_unrolled4(wl, nT, triIdx);
       }
       v += t0;  // copyT0Scores(tail, t0Score)
       loc[gi] = v;

@@ -139,8 +139,23 @@ static int compile_model(const jpp_b200_model* m, const float* w, CModel* c) {
   return 0;
 }
 
+/* optional debugging aid: JPP_ORACLE_DUMP_IDX=<file> appends every gathered table
+ * index (u32) -- used once to measure how skewed the gather distribution is */
+#include <stdio.h>
+static FILE* g_dump;
+static int g_dump_init;
+static void dump_idx(const u32* idx, int n) {
+  if (!g_dump_init) {
+    const char* p = getenv("JPP_ORACLE_DUMP_IDX");
+    g_dump = p ? fopen(p, "ab") : NULL;
+    g_dump_init = 1;
+  }
+  if (g_dump) fwrite(idx, 4, (size_t)n, g_dump);
+}
+
 /* computeUnrolled4RawPerceptron, perceptron.h:46-72 */
 static float unrolled4(const float* w, const u32* idx, int n) {
+  dump_idx(idx, n);
   float r1 = 0, r2 = 0, r3 = 0, r4 = 0;
   int i;
   for (i = 0; (i + 4) <= n; i += 4) {
@@ -163,6 +178,7 @@ static float unrolled4(const float* w, const u32* idx, int n) {
  * first == 0: "float f_j = 0; f_j += w" (partial_ngram_feature_codegen.cc:49-56). */
 static float accum_sum(const float* w, const u32* idx, int n, int nv, int assign_first) {
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  dump_idx(idx, n);
   for (int i = 0; i < n; ++i) {
     float x = w[idx[i]];
     if (assign_first && i < nv) acc[i % nv] = x; else acc[i % nv] += x;
@@ -175,6 +191,7 @@ static float accum_sum(const float* w, const u32* idx, int n, int nv, int assign
 /* 2-accumulator loop of applyBiTriFullKernel (feature_impl_ngram_partial_kernels.h:35-61) */
 static void accum2(const float* w, const u32* idx, int n, float* r1o, float* r2o) {
   float r1 = 0, r2 = 0;
+  dump_idx(idx, n);
   int f = 0;
   for (; (f + 2) <= n; f += 2) {
     r1 += w[idx[f]];

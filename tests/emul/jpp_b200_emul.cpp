@@ -62,7 +62,8 @@ extern "C" int jpp_b200_emul_score_batch(const jpp_b200_model* model, const jpp_
   bv.pre = pre.data(); bv.cut = cut.data(); bv.cutIdx = cutIdx.data(); bv.selK = selK.data();
   bv.gbNode = gbNode.data(); bv.gbSlot = gbSlot.data(); bv.gbLeftBnd = gbLeftBnd.data(); bv.gbCount = gbCount.data();
   bv.eosGbeam = eosGbeam.data(); bv.eosLocal = eosLocal.data(); bv.eosRnn = eosRnn.data(); bv.counters = counters;
-  for (u32 n = 0; n < NN; ++n) t0_node(ft, bv, weights, n);
+  const WLoadDirect wl{weights};
+  for (u32 n = 0; n < NN; ++n) t0_node(ft, bv, wl, n);
   // wavefront walk: the kernels of jpp_b200.cu, one "launch" = one loop
   u32 maxNb = 0;
   for (u32 s = 0; s < NS; ++s) maxNb = std::max(maxNb, b->sent_boundary_off[s + 1] - b->sent_boundary_off[s]);
@@ -86,9 +87,9 @@ extern "C" int jpp_b200_emul_score_batch(const jpp_b200_model* model, const jpp_
     selCount = 0;
     for (u32 s = 0; s < NS; ++s) wave_gbeam(bv, cfg, wv, s, bnd);
     if (cfg.rcheck > 0)
-      for (u32 i = waveNodeOff[bnd]; i < waveNodeOff[bnd + 1]; ++i) wave_prescore(ft, bv, cfg, wv, weights, waveNodes[i]);
+      for (u32 i = waveNodeOff[bnd]; i < waveNodeOff[bnd + 1]; ++i) wave_prescore(ft, bv, cfg, wv, wl, waveNodes[i]);
     for (u32 s = 0; s < NS; ++s) wave_cutoff(ft, bv, cfg, wv, s, bnd);
-    for (u32 i = 0; i < selCount; ++i) wave_score_node(ft, bv, cfg, wv, weights, selList[i]);
+    for (u32 i = 0; i < selCount; ++i) wave_score_node(ft, bv, cfg, wv, wl, selList[i]);
     if (cfg.rcheck > 0)
       for (u32 i = waveNodeOff[bnd]; i < waveNodeOff[bnd + 1]; ++i) wave_rest_node(bv, cfg, wv, waveNodes[i]);
   }
