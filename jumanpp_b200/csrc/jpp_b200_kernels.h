@@ -117,7 +117,10 @@ struct BatchView {
   // results
   jpp_b200_beam_element* beam;  // [nodes][B]
   float* beamScores;            // [nodes][B][S]
-  u64* patterns;                // [nodes][stored]
+  u64* patterns;                // stored pattern p of node n at patterns[n * patNodeStride + p * patPStride]
+  size_t patNodeStride, patPStride;  // device: (1, nodes) = structure of arrays, so that
+                                // adjacent nodes' values of one pattern share a cache line;
+                                // the ABI layout [nodes][stored] is (stored, 1)
   float* t0;                    // [nodes]
   // scratch
   float* pre;        // [rcheck][nodes]  T0 prescores
@@ -161,6 +164,14 @@ JPP_HD float cand_score(u64 d) {
   return f;
 #endif
 }
+
+// stored pattern p of a node
+struct PatRow {
+  const u64* base;
+  size_t pstride;
+  JPP_HD u64 operator[](u32 p) const { return base[(size_t)p * pstride]; }
+};
+JPP_HD PatRow pat_row(const BatchView& bv, u32 node) { return PatRow{bv.patterns + (size_t)node * bv.patNodeStride, bv.patPStride}; }
 
 JPP_HD bool is_fake(const jpp_b200_beam_element& e) { return e.left == 0xFFFFu && e.prev_beam == 0xFFFFu; }
 
@@ -272,10 +283,11 @@ JPP_HD void t0_node(const FeatTables& ft, const BatchView& bv, const WL& wl, u32
   const u32 sent = bv.bndSent[gb];
   const u32 localBnd = gb - bv.sentBndOff[sent];
   const u32 SP = ft.nStored;
-  u64* pout = bv.patterns + (size_t)node * SP;
+  u64* pout = bv.patterns + (size_t)node * bv.patNodeStride;
+  const size_t pstr = bv.patPStride;
   const jpp_b200_node_info ni = bv.nodeInfo[node];
   if (localBnd < 2) {  // BOS rows, lattice_builder.cc:171-176
-    for (u32 p = 0; p < SP; ++p) pout[p] = (u64)(u32)ni.entry_ptr;
+    for (u32 p = 0; p < SP; ++p) pout[p * pstr] = (u64)(u32)ni.entry_ptr;
     bv.t0[node] = 0.0f;
     return;
   }
@@ -303,7 +315,7 @@ JPP_HD void t0_node(const FeatTables& ft, const BatchView& bv, const WL& wl, u32
     }
     pat[ft.patIndex[p]] = h;
   }
-  for (u32 p = 0; p < SP; ++p) pout[p] = pat[p];
+  for (u32 p = 0; p < SP; ++p) pout[p * pstr] = pat[p];
   // unigram score.  Rows 0..R-2 of a boundary: "float score_part_j = w" for the
   // first uniVars terms then "+=" (pattern_feature_codegen.cc:229-236), summed
   // p0 + p1 + ...; the last row goes through computeUnrolled4RawPerceptron
@@ -816,11 +828,11 @@ JPP_HD void wave_prescore(const FeatTables& ft, const BatchView& bv, const Score
   if (theMax == 0) return;
   const u32 GMAX = (u32)cfg.gbeam, SP = ft.nStored, mask = ft.mask;
   const bool lastRow = (node + 1 == bv.bndNodeOff[gB + 1]);
-  const u64* P = bv.patterns + (size_t)node * SP;
+  const PatRow P = pat_row(bv, node);
   const float t0 = bv.t0[node];
   for (u32 i = 0; i < theMax; ++i) {
-    const u64* t1 = bv.patterns + (size_t)wv.gbLnode[(size_t)sent * GMAX + i] * SP;
-    const u64* t2 = bv.patterns + (size_t)wv.gbT2node[(size_t)sent * GMAX + i] * SP;
+    const PatRow t1 = pat_row(bv, wv.gbLnode[(size_t)sent * GMAX + i]);
+    const PatRow t2 = pat_row(bv, wv.gbT2node[(size_t)sent * GMAX + i]);
     auto biIdx = [&](u32 f) -> u32 { return (u32)mix(mix(ft.biState[f], P[ft.biT0[f]]), t1[ft.biT1[f]]) & mask; };
     auto triIdx = [&](u32 f) -> u32 {
       return (u32)mix(mix(mix(ft.triState[f], P[ft.triT0[f]]), t1[ft.triT1[f]]), t2[ft.triT2[f]]) & mask;
@@ -945,7 +957,7 @@ JPP_HD void wave_score_node(const FeatTables& ft, const BatchView& bv, const Sco
   const u32* t1node = wv.t1node + (size_t)sent * GMAX;
   const u8* t1idx = wv.gbT1idx + (size_t)sent * GMAX;
   const u32* gbT2 = wv.gbT2node + (size_t)sent * GMAX;
-  const u64* P = bv.patterns + (size_t)node * SP;
+  const PatRow P = pat_row(bv, node);
   float tot[MAX_BEAM], loc[MAX_BEAM], scbuf[MAX_BEAM];
   for (u32 i = 0; i < full; ++i) {
     float v = bv.pre[(size_t)i * bv.totalNodes + node];
@@ -956,7 +968,7 @@ JPP_HD void wave_score_node(const FeatTables& ft, const BatchView& bv, const Sco
   }
   if (remaining > 0 && G > 0) {
     for (u32 u = 0; u < U; ++u) {
-      const u64* t1 = bv.patterns + (size_t)t1node[u] * SP;
+      const PatRow t1 = pat_row(bv, t1node[u]);
       auto biIdx = [&](u32 f) -> u32 { return (u32)mix(mix(ft.biState[f], P[ft.biT0[f]]), t1[ft.biT1[f]]) & mask; };
       if (u + 1 < U) {
         float a[2];
@@ -969,8 +981,8 @@ JPP_HD void wave_score_node(const FeatTables& ft, const BatchView& bv, const Sco
     const float t0 = bv.t0[node];
     for (u32 j = 0; j < remaining; ++j) {
       const u32 gi = full + j;
-      const u64* t1 = bv.patterns + (size_t)t1node[t1idx[gi]] * SP;
-      const u64* t2 = bv.patterns + (size_t)gbT2[gi] * SP;
+      const PatRow t1 = pat_row(bv, t1node[t1idx[gi]]);
+      const PatRow t2 = pat_row(bv, gbT2[gi]);
       auto triIdx = [&](u32 f) -> u32 {
         return (u32)mix(mix(mix(ft.triState[f], P[ft.triT0[f]]), t1[ft.triT1[f]]), t2[ft.triT2[f]]) & mask;
       };

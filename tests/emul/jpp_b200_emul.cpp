@@ -57,7 +57,7 @@ extern "C" int jpp_b200_emul_score_batch(const jpp_b200_model* model, const jpp_
   bv.nodePlaceholders = ft.nPlaceholders ? b->node_placeholders : nullptr; bv.nodeRnnId = b->node_rnn_id;
   bv.ends = b->ends; bv.cps = b->codepoints;
   bv.nodeBnd = nodeBnd.data(); bv.bndSent = bndSent.data(); bv.endNode = endNode.data(); bv.sentOrder = nullptr;
-  bv.beam = r->node_beam; bv.beamScores = r->node_beam_scores; bv.patterns = r->node_patterns;
+  bv.beam = r->node_beam; bv.beamScores = r->node_beam_scores; bv.patterns = r->node_patterns; bv.patNodeStride = SP; bv.patPStride = 1;
   bv.t0 = r->node_t0_score ? r->node_t0_score : t0tmp.data();
   bv.pre = pre.data(); bv.cut = cut.data(); bv.cutIdx = cutIdx.data(); bv.selK = selK.data();
   bv.gbNode = gbNode.data(); bv.gbSlot = gbSlot.data(); bv.gbLeftBnd = gbLeftBnd.data(); bv.gbCount = gbCount.data();
