@@ -69,18 +69,20 @@ __device__ __forceinline__ WLoadCached make_cache(const float* w, unsigned long 
   return WLoadCached{w, slots, kCacheSlots - 1};
 }
 
-__global__ void __launch_bounds__(kCacheThreads) k_t0(const FeatTables* __restrict__ ftg, BatchView bv, const float* __restrict__ w) {
+// T0: one thread per node.  No hot-weight cache here: measured 13.4 ms without vs 19.9 ms with
+// (profiles/README.md r1h) -- most unigram features are high-cardinality (surface, base form).
+__global__ void __launch_bounds__(128) k_t0(const FeatTables* __restrict__ ftg, BatchView bv, const float* __restrict__ w) {
   // per-thread (divergent) table indices here: shared memory, not the constant bank
   __shared__ FeatTables ft;
-  extern __shared__ __align__(16) unsigned long long cacheSlots[];
   {
     const u32* src = reinterpret_cast<const u32*>(ftg);
     u32* dst = reinterpret_cast<u32*>(&ft);
     for (u32 i = threadIdx.x; i < sizeof(FeatTables) / 4; i += blockDim.x) dst[i] = src[i];
   }
-  const WLoadCached wl = make_cache(w, cacheSlots);
-  for (u32 node = blockIdx.x * blockDim.x + threadIdx.x; node < bv.totalNodes; node += gridDim.x * blockDim.x)
-    t0_node(ft, bv, wl, node);
+  __syncthreads();
+  const WLoadDirect wl{w};
+  const u32 node = blockIdx.x * blockDim.x + threadIdx.x;
+  if (node < bv.totalNodes) t0_node(ft, bv, wl, node);
 }
 
 // ---- wavefront walk kernels (see jpp_b200_kernels.h "wavefront walk") ----
@@ -345,14 +347,6 @@ __global__ void __launch_bounds__(128) k_rnn_scores(BatchView bv, ScoreCfg cfg, 
   }
 }
 
-__global__ void k_patterns_to_aos(const u64* soa, u64* aos, u32 nn, u32 sp) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < (size_t)nn * sp) {
-    const u32 node = (u32)(i / sp), p = (u32)(i % sp);
-    aos[i] = soa[(size_t)p * nn + node];
-  }
-}
-
 __global__ void k_best_path(BatchView bv, ScoreCfg cfg, u32* pathLen, u32* pathNodes) {
   const u32 s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s < bv.numSentences) best_path_sentence(bv, cfg, pathLen, pathNodes, s);
@@ -407,7 +401,7 @@ struct jpp_b200_handle {
   enum { B_SBO, B_SCO, B_BNO, B_BEO, B_INFO, B_ENTRY, B_PH, B_RNNID, B_ENDS, B_CPS, B_NODEBND, B_BNDSENT, B_ENDNODE,
          B_ORDER, B_BEAM, B_BSCORES, B_PATS, B_T0, B_PRE, B_CUT, B_CUTIDX, B_SELK, B_GBNODE, B_GBSLOT, B_GBLBND, B_GBCNT,
          B_EOSG, B_EOSLOC, B_EOSRNN, B_COUNTERS, B_WORK,
-         B_PATHLEN, B_PATHNODES, B_PATS_AOS,
+         B_PATHLEN, B_PATHNODES,
          W_GBKEY, W_GBLNODE, W_GBT2, W_GBT1IDX, W_T1NODE, W_GCNT, W_UCNT, W_SELLIST, W_SELCNT, W_NODES, W_OFF, W_CURSOR,
          R_OFF, R_ID, R_PREV, R_NEXT, R_BND, R_LEN, R_DEPTH, R_HASH, R_RNCNT, R_RSNODE, R_RSSLOT, R_RSEOSG, R_RSRNODE,
          R_RSCNT, R_CONN, R_BNDHEAD, R_CTX, R_CHNODE, R_CHSLOT, R_CHBND, R_SCLIST, R_SCTOTAL, R_LVLCNT, R_LVLOFF, R_LVLLIST, R_CTXOFF, R_RNSENT, R_CURSOR, R_CUBTMP,
@@ -504,7 +498,6 @@ jpp_b200_status jpp_b200_create(const jpp_b200_model* model, const jpp_b200_conf
   CREATE_CHECK(cudaGetDeviceProperties(&prop, device));
   h->smCount = prop.multiProcessorCount;
   CREATE_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-  CREATE_CHECK(cudaFuncSetAttribute(k_t0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kCacheSlots * 8)));
   CREATE_CHECK(cudaFuncSetAttribute(k_w_prescore, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kCacheSlots * 8)));
   CREATE_CHECK(cudaFuncSetAttribute(k_w_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kCacheSlots * 8)));
   for (auto& e : h->ev) CREATE_CHECK(cudaEventCreate(&e));
@@ -664,7 +657,9 @@ jpp_b200_status jpp_b200_upload_batch(jpp_b200_handle* h, const jpp_b200_batch* 
   bv.ends = P(B_ENDS, jpp_b200_node_ptr); bv.cps = P(B_CPS, jpp_b200_codepoint);
   bv.nodeBnd = P(B_NODEBND, u32); bv.bndSent = P(B_BNDSENT, u32); bv.endNode = P(B_ENDNODE, u32); bv.sentOrder = P(B_ORDER, u32);
   bv.beam = P(B_BEAM, jpp_b200_beam_element); bv.beamScores = P(B_BSCORES, float); bv.patterns = P(B_PATS, u64);
-  bv.patNodeStride = 1; bv.patPStride = NN;  // structure of arrays on the device
+  // [nodes][stored] (the ABI layout).  A structure-of-arrays layout was measured and is 29 % slower
+  // for the walk kernels (profiles/README.md r1i): rows of left / t2 nodes are read whole, one line each.
+  bv.patNodeStride = SP; bv.patPStride = 1;
   bv.t0 = P(B_T0, float); bv.pre = P(B_PRE, float); bv.cut = P(B_CUT, float); bv.cutIdx = P(B_CUTIDX, u32);
   bv.selK = P(B_SELK, u16); bv.gbNode = P(B_GBNODE, u32); bv.gbSlot = P(B_GBSLOT, u16); bv.gbLeftBnd = P(B_GBLBND, u16);
   bv.gbCount = P(B_GBCNT, u8); bv.eosGbeam = P(B_EOSG, u64); bv.eosLocal = P(B_EOSLOC, float); bv.eosRnn = P(B_EOSRNN, float);
@@ -744,7 +739,7 @@ jpp_b200_status jpp_b200_score_resident(jpp_b200_handle* h) {
   CU_CHECK(h, cudaMemsetAsync(bf[jpp_b200_handle::B_COUNTERS].p, 0, 64, st));
   CU_CHECK(h, cudaMemsetAsync(bf[jpp_b200_handle::B_WORK].p, 0, 16, st));
   CU_CHECK(h, cudaEventRecord(h->ev[2], st));
-  k_t0<<<h->smCount, kCacheThreads, kCacheSlots * 8, st>>>(h->dFt, bv, h->dWeights);
+  k_t0<<<(NN + 127) / 128, 128, 0, st>>>(h->dFt, bv, h->dWeights);
   CU_CHECK(h, cudaGetLastError());
   CU_CHECK(h, cudaEventRecord(h->ev[3], st));
   {
@@ -869,14 +864,7 @@ jpp_b200_status jpp_b200_download_result(jpp_b200_handle* h, jpp_b200_result* r)
   const size_t NN = bv.totalNodes, B = (size_t)h->cfg.beam, S = h->cfg.S, SP = h->hm.ft.nStored;
   if (r->node_beam) CU_CHECK(h, cudaMemcpyAsync(r->node_beam, bv.beam, NN * B * sizeof(jpp_b200_beam_element), cudaMemcpyDeviceToHost, st));
   if (r->node_beam_scores) CU_CHECK(h, cudaMemcpyAsync(r->node_beam_scores, bv.beamScores, NN * B * S * 4, cudaMemcpyDeviceToHost, st));
-  if (r->node_patterns) {
-    // the ABI layout is [nodes][stored]; the device keeps [stored][nodes]
-    CU_CHECK(h, h->buf[jpp_b200_handle::B_PATS_AOS].ensure(NN * SP * 8));
-    u64* aos = h->buf[jpp_b200_handle::B_PATS_AOS].as<u64>();
-    k_patterns_to_aos<<<(unsigned)((NN * SP + 255) / 256), 256, 0, st>>>(bv.patterns, aos, (u32)NN, (u32)SP);
-    CU_CHECK(h, cudaGetLastError());
-    CU_CHECK(h, cudaMemcpyAsync(r->node_patterns, aos, NN * SP * 8, cudaMemcpyDeviceToHost, st));
-  }
+  if (r->node_patterns) CU_CHECK(h, cudaMemcpyAsync(r->node_patterns, bv.patterns, NN * SP * 8, cudaMemcpyDeviceToHost, st));
   if (r->node_t0_score) CU_CHECK(h, cudaMemcpyAsync(r->node_t0_score, bv.t0, NN * 4, cudaMemcpyDeviceToHost, st));
   if (r->best_path_len) CU_CHECK(h, cudaMemcpyAsync(r->best_path_len, h->buf[jpp_b200_handle::B_PATHLEN].p, (size_t)bv.numSentences * 4, cudaMemcpyDeviceToHost, st));
   if (r->best_path_nodes) CU_CHECK(h, cudaMemcpyAsync(r->best_path_nodes, h->buf[jpp_b200_handle::B_PATHNODES].p, (size_t)bv.totalBoundaries * 4, cudaMemcpyDeviceToHost, st));
