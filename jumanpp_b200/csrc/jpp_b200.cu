@@ -258,10 +258,10 @@ __global__ void __launch_bounds__(128) k_rnn_level(RnnWork rw, RnnTables rt, con
 #pragma unroll
           for (int j4 = 0; j4 < NT / 4; ++j4) {
             const float4 c = c4[j4];
-            part[j4 * 4 + 0] = __fadd_rn(part[j4 * 4 + 0], __fmul_rn(wv, c.x));
-            part[j4 * 4 + 1] = __fadd_rn(part[j4 * 4 + 1], __fmul_rn(wv, c.y));
-            part[j4 * 4 + 2] = __fadd_rn(part[j4 * 4 + 2], __fmul_rn(wv, c.z));
-            part[j4 * 4 + 3] = __fadd_rn(part[j4 * 4 + 3], __fmul_rn(wv, c.w));
+            part[j4 * 4 + 0] = __fmaf_rn(wv, c.x, part[j4 * 4 + 0]);
+            part[j4 * 4 + 1] = __fmaf_rn(wv, c.y, part[j4 * 4 + 1]);
+            part[j4 * 4 + 2] = __fmaf_rn(wv, c.z, part[j4 * 4 + 2]);
+            part[j4 * 4 + 3] = __fmaf_rn(wv, c.w, part[j4 * 4 + 3]);
           }
         }
 #pragma unroll
@@ -322,17 +322,17 @@ __global__ void __launch_bounds__(128) k_rnn_scores(BatchView bv, ScoreCfg cfg, 
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
             const float4 x = a4[j4], y = b4[j4];
-            part[j4 * 4 + 0] = __fadd_rn(part[j4 * 4 + 0], __fmul_rn(x.x, y.x));
-            part[j4 * 4 + 1] = __fadd_rn(part[j4 * 4 + 1], __fmul_rn(x.y, y.y));
-            part[j4 * 4 + 2] = __fadd_rn(part[j4 * 4 + 2], __fmul_rn(x.z, y.z));
-            part[j4 * 4 + 3] = __fadd_rn(part[j4 * 4 + 3], __fmul_rn(x.w, y.w));
+            part[j4 * 4 + 0] = __fmaf_rn(x.x, y.x, part[j4 * 4 + 0]);
+            part[j4 * 4 + 1] = __fmaf_rn(x.y, y.y, part[j4 * 4 + 1]);
+            part[j4 * 4 + 2] = __fmaf_rn(x.z, y.z, part[j4 * 4 + 2]);
+            part[j4 * 4 + 3] = __fmaf_rn(x.w, y.w, part[j4 * 4 + 3]);
           }
         }
       }
       for (; k0 < H; k0 += 32) {
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          if (k0 + j < H) part[j] = __fadd_rn(part[j], __fmul_rn(a[k0 + j], b[k0 + j]));
+          if (k0 + j < H) part[j] = __fmaf_rn(a[k0 + j], b[k0 + j], part[j]);
       }
 #pragma unroll
       for (int stride = 16; stride >= 1; stride >>= 1) {

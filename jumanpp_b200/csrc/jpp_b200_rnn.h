@@ -13,8 +13,8 @@
 //                       (score_processor.cc:521-576).
 //
 // Dot products use the order of oracle/eigen_shim (which stands in for the
-// un-vendored Eigen): lane l sums k = l, l+32, ... with separate mul and add,
-// then a xor-shuffle tree 16, 8, 4, 2, 1.
+// un-vendored Eigen): partial l sums k = l, l+32, ... with one fused multiply-add
+// per term, then the 16, 8, 4, 2, 1 fold of the 32 partials.
 #pragma once
 #include "jpp_b200_kernels.h"
 
@@ -189,26 +189,16 @@ JPP_HD void rnn_build_tree(const BatchView& bv, const ScoreCfg& cfg, const RnnWo
   }
 }
 
-// dot product, oracle/eigen_shim order
-#if defined(__CUDACC__)
-JPP_D float warp_dot32(const float* __restrict__ a, const float* __restrict__ b, u32 n, int lane) {
-  float part = 0.0f;
-  for (u32 k = (u32)lane; k < n; k += 32) {
-    const float prod = __fmul_rn(a[k], b[k]);
-    part = __fadd_rn(part, prod);
-  }
-#pragma unroll
-  for (int stride = 16; stride >= 1; stride >>= 1) part = __fadd_rn(part, __shfl_xor_sync(0xffffffffu, part, stride));
-  return part;  // every lane holds part[0]'s value only in lane 0 semantics; lane 0 is authoritative
-}
-#endif
-
+// dot product, oracle/eigen_shim order (serial form; the kernels keep the 32 partials in registers)
 JPP_HD float serial_dot32(const float* a, const float* b, u32 n) {
   float part[32];
   for (int l = 0; l < 32; ++l) part[l] = 0.0f;
   for (u32 k = 0; k < n; ++k) {
-    const float prod = a[k] * b[k];
-    part[k & 31] = part[k & 31] + prod;
+#if defined(__CUDA_ARCH__)
+    part[k & 31] = __fmaf_rn(a[k], b[k], part[k & 31]);
+#else
+    part[k & 31] = fmaf(a[k], b[k], part[k & 31]);
+#endif
   }
   for (int stride = 16; stride >= 1; stride >>= 1)
     for (int l = 0; l < stride; ++l) part[l] = part[l] + part[l + stride];

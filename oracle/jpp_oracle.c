@@ -631,13 +631,12 @@ static const u64 PRIMES[] = {108641969, 116049371, 125925907, 133333309, 1456789
                              940740127, 953085797, 985184539, 990122807};
 #define PRIMES_SIZE 36
 
-/* dot product in the order of oracle/eigen_shim (32 interleaved partials + xor tree) */
+/* dot product in the order of oracle/eigen_shim (32 interleaved fmaf partials + tree) */
 static float dot32(const float* a, const float* b, u32 n) {
   float part[32];
   for (int l = 0; l < 32; ++l) part[l] = 0.0f;
   for (u32 k = 0; k < n; ++k) {
-    float prod = a[k] * b[k];
-    part[k & 31] = part[k & 31] + prod;
+    part[k & 31] = fmaf(a[k], b[k], part[k & 31]);
   }
   for (int stride = 16; stride >= 1; stride >>= 1)
     for (int l = 0; l < stride; ++l) part[l] = part[l] + part[l + stride];

@@ -26,7 +26,7 @@ class OracleStats(C.Structure):
 def build_oracle(force: bool = False) -> Path:
     src = ORACLE_DIR / "jpp_oracle.c"
     if force or not LIB.exists() or LIB.stat().st_mtime < src.stat().st_mtime:
-        subprocess.run(["gcc", "-O2", "-std=c11", "-ffp-contract=off", "-march=x86-64-v2", "-fPIC", "-shared",
+        subprocess.run(["gcc", "-O2", "-std=c11", "-ffp-contract=off", "-march=x86-64-v3", "-fPIC", "-shared",
                         f"-I{ROOT / 'include'}", f"-I{ORACLE_DIR}", str(src), "-o", str(LIB), "-lpthread", "-lm"],
                        check=True)
     return LIB

@@ -23,7 +23,7 @@ def emul():
     lib = EMUL / "libjpp_b200_emul.so"
     deps = [src] + list((ROOT / "jumanpp_b200" / "csrc").glob("*.h")) + [ROOT / "include" / "jpp_b200.h"]
     if not lib.exists() or lib.stat().st_mtime < max(p.stat().st_mtime for p in deps):
-        subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-march=x86-64-v2", "-fPIC", "-shared", "-w",
+        subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-march=x86-64-v3", "-fPIC", "-shared", "-w",
                         f"-I{ROOT / 'include'}", f"-I{ROOT / 'jumanpp_b200' / 'csrc'}", str(src), "-o", str(lib)],
                        check=True)
     return C.CDLL(str(lib))
