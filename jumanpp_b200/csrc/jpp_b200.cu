@@ -144,6 +144,19 @@ __global__ void __launch_bounds__(128) k_w_rest(BatchView bv, ScoreCfg cfg, Wave
   if (i < count) wave_rest_node(bv, cfg, wv, wv.waveNodes[first + i]);
 }
 
+// full-beam mode: the whole boundary step of a right node in one thread
+__global__ void __launch_bounds__(128) k_w_full(const __grid_constant__ FeatTables ft, BatchView bv, ScoreCfg cfg, WaveView wv,
+                                                const float* __restrict__ w, u32 first, u32 count) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  const WLoadDirect wl{w};
+  u32 g = 0;
+  if (i < count) g = wave_full_node(ft, bv, cfg, wl, wv.waveNodes[first + i]);
+  if (bv.counters) {
+    g = __reduce_add_sync(0xffffffffu, g);
+    if ((threadIdx.x & 31) == 0 && g) atomicAdd(bv.counters + 0, (unsigned long long)g);
+  }
+}
+
 __global__ void k_fill_i32(i32* p, size_t n, i32 v) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
 }
@@ -440,8 +453,6 @@ jpp_b200_status check_config(jpp_b200_handle* h, const jpp_b200_config* c, u32 n
     return fail(h, JPP_B200_INVALID_PARAMETER, "right global beam size should not be zero if you enable it");  // :58-61
   if (numScorers > 1 && c->global_beam_size <= 0)
     return fail(h, JPP_B200_INVALID_STATE, "additional scorers are supported only with global beam enabled");  // :83-88
-  if (c->global_beam_size <= 0)
-    return fail(h, JPP_B200_NOT_IMPLEMENTED, "full-beam scoring (global_beam_size <= 0, computeScoresFull) is not on the GPU path yet");
   if (c->beam_size > MAX_BEAM || c->global_beam_size > MAX_BEAM || c->right_gbeam_size > MAX_BEAM || c->right_gbeam_check > MAX_BEAM)
     return fail(h, JPP_B200_NOT_IMPLEMENTED, "beam sizes above 32 are not supported by the GPU path");
   return JPP_B200_OK;
@@ -587,7 +598,7 @@ jpp_b200_status jpp_b200_upload_batch(jpp_b200_handle* h, const jpp_b200_batch* 
   const u32 NN = b->boundary_node_off[NB];
   const u32 NE = b->boundary_end_off[NB];
   const u32 NC = b->sent_codepoint_off[NS];
-  const u32 B = (u32)h->cfg.beam, G = (u32)h->cfg.gbeam, S = h->cfg.S, SP = h->hm.ft.nStored;
+  const u32 B = (u32)h->cfg.beam, G = (u32)std::max(1, h->cfg.gbeam), S = h->cfg.S, SP = h->hm.ft.nStored;
   const u32 RC = h->cfg.rcheck > 0 ? (u32)h->cfg.rcheck : 1u;
   // work order: longest sentence first; validate shapes on the way
   std::vector<u32> order(NS);
@@ -753,6 +764,11 @@ jpp_b200_status jpp_b200_score_resident(jpp_b200_handle* h) {
       if (nAct == 0) break;
       const u32 first = h->waveNodeOff[bnd], count = h->waveNodeOff[bnd + 1] - first;
       if (count == 0) continue;
+      if (cfg.gbeam <= 0) {  // computeScoresFull
+        k_w_full<<<(count + 127) / 128, 128, 0, st>>>(ft, bv, cfg, wv, h->dWeights, first, count);
+        ++launches;
+        continue;
+      }
       k_w_gbeam<<<(nAct + 127) / 128, 128, 0, st>>>(bv, cfg, wv, nAct, bnd);
       if (cfg.rcheck > 0) {
         const u32 pb = std::min<u32>((count + kCacheThreads - 1) / kCacheThreads, (u32)h->smCount);

@@ -1034,6 +1034,71 @@ JPP_HD void wave_rest_node(const BatchView& bv, const ScoreCfg& cfg, const WaveV
   write_beam(bv, cfg, node, gbKey, (int)full, tot, loc);
 }
 
+// Full-beam scoring (computeScoresFull, analyzer_impl.cc:197-248; selected when the global
+// beam is off): every (left node, beam entry of it) is scored against the right node.
+// One thread per right node: applyT1 per left node (bigrams, score_processor.cc:136-144),
+// applyT2 per beam entry (trigrams, :146-156), then makeBeams (:208-244): the `beam` largest
+// packed (total, left, beam) keys.  Returns the number of table reads it made.
+template <typename WL>
+JPP_HD u32 wave_full_node(const FeatTables& ft, const BatchView& bv, const ScoreCfg& cfg, const WL& wl, u32 node) {
+  const u32 gB = bv.nodeBnd[node];
+  const u32 sent = bv.bndSent[gB];
+  const u32 b0 = bv.sentBndOff[sent];
+  const u32 B = (u32)cfg.beam, mask = ft.mask;
+  const u32 e0 = bv.bndEndOff[gB];
+  const u32 L = bv.bndEndOff[gB + 1] - e0;
+  const bool lastRow = (node + 1 == bv.bndNodeOff[gB + 1]);
+  const PatRow P = pat_row(bv, node);
+  const float t0 = bv.t0[node];
+  u64 top[MAX_BEAM];
+  float topLocal[MAX_BEAM];
+  u32 n = 0, gathers = 0;
+  for (u32 left = 0; left < L; ++left) {
+    const u32 lnode = bv.endNode[e0 + left];
+    const u32 lbnd = bv.ends[e0 + left].boundary;
+    const jpp_b200_beam_element* lrow = bv.beam + (size_t)lnode * B;
+    const PatRow t1 = pat_row(bv, lnode);
+    auto biIdx = [&](u32 f) -> u32 { return (u32)mix(mix(ft.biState[f], P[ft.biT0[f]]), t1[ft.biT1[f]]) & mask; };
+    float T1 = t0;
+    T1 += lastRow ? gsum_unrolled4(wl, ft.nBi, biIdx) : gsum_vars(wl, ft.nBi, ft.biVars, biIdx);
+    gathers += ft.nBi;
+    for (u32 slot = 0; slot < B; ++slot) {
+      const jpp_b200_beam_element el = lrow[slot];
+      if (is_fake(el)) break;
+      const PatRow t2 = pat_row(bv, bv.endNode[bv.bndEndOff[b0 + lbnd] + el.left]);
+      auto triIdx = [&](u32 f) -> u32 {
+        return (u32)mix(mix(mix(ft.triState[f], P[ft.triT0[f]]), t1[ft.triT1[f]]), t2[ft.triT2[f]]) & mask;
+      };
+      float T2 = T1;
+      T2 += lastRow ? gsum_unrolled4(wl, ft.nTri, triIdx) : gsum_vars(wl, ft.nTri, ft.triVars, triIdx);
+      gathers += ft.nTri;
+      const u64 key = pack_cand(el.total_score + T2, left, slot);  // fillBeamCandidates, :165-191
+      if (n == B && key < top[n - 1]) continue;
+      u32 pos = n < B ? n : B - 1;
+      while (pos > 0 && top[pos - 1] < key) { top[pos] = top[pos - 1]; topLocal[pos] = topLocal[pos - 1]; --pos; }
+      top[pos] = key;
+      topLocal[pos] = T2;
+      if (n < B) ++n;
+    }
+  }
+  jpp_b200_beam_element* row = bv.beam + (size_t)node * B;
+  float* srow = bv.beamScores + (size_t)node * B * cfg.S;
+  for (u32 k = 0; k < B; ++k) {
+    if (k < n) {
+      jpp_b200_beam_element e;
+      e.left = (u16)(top[k] >> 16);
+      e.prev_beam = (u16)top[k];
+      e.total_score = cand_score(top[k]);
+      row[k] = e;
+      srow[(size_t)k * cfg.S] = topLocal[k];
+    } else {
+      row[k] = fake_elem();
+      srow[(size_t)k * cfg.S] = 0.0f;
+    }
+  }
+  return gathers;
+}
+
 // 1-best path of a sentence: walk EOS beam[0] back through the (left, prev_beam)
 // links (analysis_result.cc:25-76) and store the node indices in sentence order.
 JPP_HD void best_path_sentence(const BatchView& bv, const ScoreCfg& cfg, u32* pathLen, u32* pathNodes, u32 sent) {

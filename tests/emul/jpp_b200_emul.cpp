@@ -33,7 +33,7 @@ extern "C" int jpp_b200_emul_score_batch(const jpp_b200_model* model, const jpp_
                model->num_scorers};
   const u32 NS = b->num_sentences, NB = b->sent_boundary_off[NS], NN = b->boundary_node_off[NB],
             NE = b->boundary_end_off[NB];
-  const u32 B = (u32)cfg.beam, G = (u32)cfg.gbeam, S = cfg.S, SP = ft.nStored;
+  const u32 B = (u32)cfg.beam, G = (u32)std::max(1, cfg.gbeam), S = cfg.S, SP = ft.nStored;
   const u32 RC = cfg.rcheck > 0 ? (u32)cfg.rcheck : 1u;
   std::vector<u32> nodeBnd(NN), bndSent(NB), endNode(NE), cutIdx(NN), gbNode((size_t)NB * G);
   std::vector<u16> selK(NN), gbSlot((size_t)NB * G), gbLeftBnd((size_t)NB * G);
@@ -83,7 +83,9 @@ extern "C" int jpp_b200_emul_score_batch(const jpp_b200_model* model, const jpp_
   wv.t1node = t1node.data(); wv.gCount = gCount.data(); wv.uCount = uCount.data(); wv.selList = selList.data();
   wv.selCount = &selCount; wv.waveNodes = waveNodes.data(); wv.waveNodeOff = waveNodeOff.data();
   for (u32 s = 0; s < NS; ++s) wave_init_sentence(bv, cfg, s);
-  for (u32 bnd = 2; bnd < maxNb; ++bnd) {
+  for (u32 bnd = 2; bnd < maxNb && cfg.gbeam <= 0; ++bnd)  // full-beam loop
+    for (u32 i = waveNodeOff[bnd]; i < waveNodeOff[bnd + 1]; ++i) counters[0] += wave_full_node(ft, bv, cfg, wl, waveNodes[i]);
+  for (u32 bnd = 2; bnd < maxNb && cfg.gbeam > 0; ++bnd) {
     selCount = 0;
     for (u32 s = 0; s < NS; ++s) wave_gbeam(bv, cfg, wv, s, bnd);
     if (cfg.rcheck > 0)

@@ -10,7 +10,7 @@ import pytest
 
 import oracle_lib
 import parity
-from conftest import LINEAR_GBEAM, RNN, load_golden
+from conftest import FULL_BEAM, LINEAR_GBEAM, RNN, load_golden
 from jumanpp_b200 import abi
 
 ROOT = Path(__file__).resolve().parent.parent
@@ -41,7 +41,7 @@ def run_emul(emul, model, cfg, batch):
     return res
 
 
-@pytest.mark.parametrize("name", LINEAR_GBEAM)
+@pytest.mark.parametrize("name", LINEAR_GBEAM + FULL_BEAM)
 def test_linear_kernels(emul, name):
     d, model, cfg, batch = load_golden(name)
     res = run_emul(emul, model, cfg, batch)

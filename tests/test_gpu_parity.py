@@ -10,7 +10,7 @@ import pytest
 
 import oracle_lib
 import parity
-from conftest import LINEAR_GBEAM, RNN, load_golden
+from conftest import FULL_BEAM, LINEAR_GBEAM, RNN, load_golden
 
 pytestmark = pytest.mark.gpu
 
@@ -26,7 +26,7 @@ def gpu_score(model, cfg, batch):
     return res, cnt
 
 
-@pytest.mark.parametrize("name", LINEAR_GBEAM)
+@pytest.mark.parametrize("name", LINEAR_GBEAM + FULL_BEAM)
 def test_linear_path_matches_reference_and_oracle(name):
     d, model, cfg, batch = load_golden(name)
     res, cnt = gpu_score(model, cfg, batch)
@@ -98,5 +98,5 @@ def test_errors_are_reported_not_swallowed():
         LatticeScorer(model, abi.ScoringConfig(5, 6, 1, 0))
     assert e.value.code == abi.INVALID_PARAMETER
     with pytest.raises(ScorerError) as e:
-        LatticeScorer(model, abi.ScoringConfig(5, 0, 0, 0))   # full-beam loop not on the GPU path yet
+        LatticeScorer(model, abi.ScoringConfig(40, 6, 1, 5))   # beams above 32 are refused, not truncated
     assert e.value.code == abi.NOT_IMPLEMENTED
