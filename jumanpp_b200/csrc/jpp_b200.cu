@@ -112,8 +112,108 @@ __global__ void __launch_bounds__(128) k_w_init(BatchView bv, ScoreCfg cfg) {
 
 __global__ void __launch_bounds__(128) k_w_gbeam(BatchView bv, ScoreCfg cfg, WaveView wv, u32 nActive, u32 bnd) {
   const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0) *wv.selCount = 0;  // consumed by k_w_cutoff, a later launch on the same stream
+  if (i == 0) wv.selCount[0] = wv.selCount[1] = 0;  // consumed by k_w_cutoff, a later launch on the same stream
   if (i < nActive) wave_gbeam(bv, cfg, wv, bv.sentOrder[i], bnd);
+}
+
+// W1, warp per sentence (the same function as wave_gbeam, which stays the serial statement of it
+// for tests/emul): lane l owns left node l (+32, +64, ...), loads its B beam elements at once,
+// and G rounds of a warp-wide maximum over the packed keys pick the global beam -- keys are
+// distinct (score_processor.h:81-115), so the selection has one answer whatever the order.
+// Lane g then resolves element g (left node, its boundary, the node before it) and the
+// first-seen numbering of the unique left nodes (dedupT1, score_processor.cc:363-385).
+template <int KB>
+__global__ void __launch_bounds__(128) k_w_gbeam_warp(BatchView bv, ScoreCfg cfg, WaveView wv, u32 nActive, u32 bnd) {
+  const u32 tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid == 0) wv.selCount[0] = wv.selCount[1] = 0;
+  const u32 w = tid >> 5, lane = threadIdx.x & 31u;
+  if (w >= nActive) return;
+  const u32 sent = bv.sentOrder[w];
+  const u32 b0 = bv.sentBndOff[sent];
+  const u32 nb = bv.sentBndOff[sent + 1] - b0;
+  if (bnd >= nb || nb <= 3) return;
+  const u32 gB = b0 + bnd;
+  const u32 R = bv.bndNodeOff[gB + 1] - bv.bndNodeOff[gB];
+  const u32 B = (u32)cfg.beam, GMAX = (u32)cfg.gbeam;
+  if (R == 0) {  // analyzer_impl.cc:263-266
+    if (lane == 0) { wv.gCount[sent] = 0; wv.uCount[sent] = 0; bv.gbCount[gB] = 0; }
+    return;
+  }
+  const u32 e0 = bv.bndEndOff[gB];
+  const u32 L = bv.bndEndOff[gB + 1] - e0;
+  const unsigned full = 0xffffffffu;
+  u64 carried = 0;  // lane g: g-th largest key so far (0 = none; no real key is 0)
+  for (u32 c0 = 0; c0 < L; c0 += 32) {
+    const u32 left = c0 + lane;
+    u64 k[KB];
+#pragma unroll
+    for (int q = 0; q < KB; ++q) k[q] = 0;
+    if (left < L) {
+      const jpp_b200_beam_element* row = bv.beam + (size_t)bv.endNode[e0 + left] * B;
+#pragma unroll
+      for (int q = 0; q < KB; ++q) {
+        if ((u32)q < B) {
+          const jpp_b200_beam_element el = row[q];
+          k[q] = is_fake(el) ? 0ull : pack_cand(el.total_score, left, (u32)q);
+        }
+      }
+    }
+    u64 next = 0;
+    for (u32 g = 0; g < GMAX; ++g) {
+      u64 m = carried;
+      int mi = -1;
+#pragma unroll
+      for (int q = 0; q < KB; ++q)
+        if (k[q] > m) { m = k[q]; mi = q; }
+      const u32 hi = (u32)(m >> 32);
+      const u32 whi = __reduce_max_sync(full, hi);
+      const u32 wlo = __reduce_max_sync(full, hi == whi ? (u32)m : 0u);
+      const u64 wm = ((u64)whi << 32) | wlo;
+      if (wm == 0) break;
+      if (m == wm) {
+        if (mi < 0) carried = 0;
+#pragma unroll
+        for (int q = 0; q < KB; ++q)
+          if (q == mi) k[q] = 0;
+      }
+      if (lane == g) next = wm;
+    }
+    carried = next;
+  }
+  const u32 G = __popc(__ballot_sync(full, carried != 0));
+  const bool have = lane < G;
+  u32 lnode = 0xFFFFFFFFu, slot = 0, lbnd = 0, t2 = 0;
+  if (have) {
+    const u32 left = (u32)(carried >> 16) & 0xFFFFu;
+    slot = (u32)carried & 0xFFFFu;
+    lnode = bv.endNode[e0 + left];
+    lbnd = bv.ends[e0 + left].boundary;
+    const jpp_b200_beam_element el = bv.beam[(size_t)lnode * B + slot];
+    t2 = bv.endNode[bv.bndEndOff[b0 + lbnd] + el.left];
+  }
+  u32 firstIdx = lane;
+  for (u32 j = 0; j < G; ++j) {
+    const u32 lj = __shfl_sync(full, lnode, j);
+    if (have && lj == lnode && j < firstIdx) firstIdx = j;
+  }
+  const unsigned firstMask = __ballot_sync(full, have && firstIdx == lane);
+  const u32 u = __popc(firstMask & ((1u << firstIdx) - 1u));
+  if (have) {
+    const size_t o = (size_t)sent * GMAX;
+    wv.gbKey[o + lane] = carried;
+    wv.gbLnode[o + lane] = lnode;
+    wv.gbT2node[o + lane] = t2;
+    wv.gbT1idx[o + lane] = (u8)u;
+    if (firstIdx == lane) wv.t1node[o + u] = lnode;
+    bv.gbNode[(size_t)gB * GMAX + lane] = lnode;
+    bv.gbSlot[(size_t)gB * GMAX + lane] = (u16)slot;
+    bv.gbLeftBnd[(size_t)gB * GMAX + lane] = (u16)lbnd;
+  }
+  if (lane == 0) {
+    bv.gbCount[gB] = (u8)G;
+    wv.gCount[sent] = (u8)G;
+    wv.uCount[sent] = (u8)__popc(firstMask);
+  }
 }
 
 __global__ void __launch_bounds__(kCacheThreads) k_w_prescore(const __grid_constant__ FeatTables ft, BatchView bv, ScoreCfg cfg,
@@ -134,9 +234,18 @@ __global__ void __launch_bounds__(kCacheThreads) k_w_score(const __grid_constant
                                                         WaveView wv, const float* __restrict__ w) {
   extern __shared__ __align__(16) unsigned long long cacheSlots[];
   const WLoadCached wl = make_cache(w, cacheSlots);
-  const u32 n = *wv.selCount;
+  const u32 n = wv.selCount[0];
   for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-    wave_score_node(ft, bv, cfg, wv, wl, wv.selList[i]);
+    wave_score_node(ft, bv, cfg, wv, wl, i);
+}
+
+__global__ void __launch_bounds__(kCacheThreads) k_w_bigram(const __grid_constant__ FeatTables ft, BatchView bv, ScoreCfg cfg,
+                                                         WaveView wv, const float* __restrict__ w) {
+  extern __shared__ __align__(16) unsigned long long cacheSlots[];
+  const WLoadCached wl = make_cache(w, cacheSlots);
+  const u32 n = wv.selCount[1];
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    wave_score_bigram(ft, bv, cfg, wv, wl, wv.itemList[i]);
 }
 
 __global__ void __launch_bounds__(128) k_w_rest(BatchView bv, ScoreCfg cfg, WaveView wv, u32 first, u32 count) {
@@ -415,7 +524,7 @@ struct jpp_b200_handle {
          B_ORDER, B_BEAM, B_BSCORES, B_PATS, B_T0, B_PRE, B_CUT, B_CUTIDX, B_SELK, B_GBNODE, B_GBSLOT, B_GBLBND, B_GBCNT,
          B_EOSG, B_EOSLOC, B_EOSRNN, B_COUNTERS, B_WORK,
          B_PATHLEN, B_PATHNODES,
-         W_GBKEY, W_GBLNODE, W_GBT2, W_GBT1IDX, W_T1NODE, W_GCNT, W_UCNT, W_SELLIST, W_SELCNT, W_NODES, W_OFF, W_CURSOR,
+         W_GBKEY, W_GBLNODE, W_GBT2, W_GBT1IDX, W_T1NODE, W_GCNT, W_UCNT, W_SELLIST, W_SELCNT, W_ITEMS, W_SCB, W_NODES, W_OFF, W_CURSOR,
          R_OFF, R_ID, R_PREV, R_NEXT, R_BND, R_LEN, R_DEPTH, R_HASH, R_RNCNT, R_RSNODE, R_RSSLOT, R_RSEOSG, R_RSRNODE,
          R_RSCNT, R_CONN, R_BNDHEAD, R_CTX, R_CHNODE, R_CHSLOT, R_CHBND, R_SCLIST, R_SCTOTAL, R_LVLCNT, R_LVLOFF, R_LVLLIST, R_CTXOFF, R_RNSENT, R_CURSOR, R_CUBTMP,
          NUM_BUFS };
@@ -446,6 +555,45 @@ jpp_b200_status fail(jpp_b200_handle* h, jpp_b200_status st, const std::string& 
     if (e_ != cudaSuccess)                                                                        \
       return fail(h, JPP_B200_CUDA_ERROR, std::string(#expr) + ": " + cudaGetErrorString(e_));    \
   } while (0)
+
+// JPP_B200_PROFILE=1: CUDA events around every launch of the wave loop, summed per kernel and
+// printed to stderr (diagnostic only: the extra events perturb the step a little)
+struct WaveProfile {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;
+  std::vector<int> kind;
+  size_t used = 0;
+  void begin(cudaStream_t st, int k) {
+    if (!on) return;
+    if (used + 2 > ev.size()) {
+      ev.resize(used + 2);
+      cudaEventCreate(&ev[used]);
+      cudaEventCreate(&ev[used + 1]);
+    }
+    cudaEventRecord(ev[used], st);
+    kind.push_back(k);
+  }
+  void end(cudaStream_t st) {
+    if (!on) return;
+    cudaEventRecord(ev[used + 1], st);
+    used += 2;
+  }
+  void report(const char* const* names, int nk) {
+    if (!on) return;
+    std::vector<double> ms(nk, 0.0);
+    std::vector<int> cnt(nk, 0);
+    for (size_t i = 0; i < kind.size(); ++i) {
+      float t = 0;
+      cudaEventElapsedTime(&t, ev[2 * i], ev[2 * i + 1]);
+      ms[kind[i]] += t;
+      cnt[kind[i]] += 1;
+    }
+    for (int k = 0; k < nk; ++k)
+      if (cnt[k]) fprintf(stderr, "[jpp_b200 profile] %-12s %5d launches %9.3f ms\n", names[k], cnt[k], ms[k]);
+    used = 0;
+    kind.clear();
+  }
+};
 
 jpp_b200_status check_config(jpp_b200_handle* h, const jpp_b200_config* c, u32 numScorers) {
   if (c->beam_size <= 0) return fail(h, JPP_B200_INVALID_PARAMETER, "beam size can not be zero for scoring");  // analyzer_impl.cc:53-56
@@ -511,6 +659,7 @@ jpp_b200_status jpp_b200_create(const jpp_b200_model* model, const jpp_b200_conf
   CREATE_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CREATE_CHECK(cudaFuncSetAttribute(k_w_prescore, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kCacheSlots * 8)));
   CREATE_CHECK(cudaFuncSetAttribute(k_w_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kCacheSlots * 8)));
+  CREATE_CHECK(cudaFuncSetAttribute(k_w_bigram, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kCacheSlots * 8)));
   for (auto& e : h->ev) CREATE_CHECK(cudaEventCreate(&e));
   CREATE_CHECK(cudaMalloc(&h->dFt, sizeof(FeatTables)));
   CREATE_CHECK(cudaMemcpyAsync(h->dFt, &h->hm.ft, sizeof(FeatTables), cudaMemcpyHostToDevice, h->stream));
@@ -683,6 +832,12 @@ jpp_b200_status jpp_b200_upload_batch(jpp_b200_handle* h, const jpp_b200_batch* 
     ENSURE(W_GBKEY, (size_t)NS * G * 8); ENSURE(W_GBLNODE, (size_t)NS * G * 4); ENSURE(W_GBT2, (size_t)NS * G * 4);
     ENSURE(W_GBT1IDX, (size_t)NS * G); ENSURE(W_T1NODE, (size_t)NS * G * 4); ENSURE(W_GCNT, NS); ENSURE(W_UCNT, NS);
     ENSURE(W_SELLIST, (size_t)NN * 4 + 16); ENSURE(W_SELCNT, 16); ENSURE(W_NODES, (size_t)NN * 4 + 16);
+    {
+      // selected right nodes of one wave: at most right_gbeam_size per active sentence (makeT0cutoffBeam)
+      size_t selCap = NN;
+      if (h->cfg.rcheck > 0) selCap = std::min<size_t>(NN, (size_t)NS * (u32)h->cfg.rbeam);
+      ENSURE(W_ITEMS, (selCap * G + 4) * 4); ENSURE(W_SCB, (selCap * G + 4) * 4);
+    }
     ENSURE(W_OFF, (size_t)(maxNb + 4) * 4); ENSURE(W_CURSOR, (size_t)(maxNb + 4) * 4 * 2);
     u32* cnt = P(W_CURSOR, u32);
     u32* cursor = cnt + (maxNb + 4);
@@ -707,7 +862,7 @@ jpp_b200_status jpp_b200_upload_batch(jpp_b200_handle* h, const jpp_b200_batch* 
     wv = WaveView{};
     wv.gbKey = P(W_GBKEY, u64); wv.gbLnode = P(W_GBLNODE, u32); wv.gbT2node = P(W_GBT2, u32); wv.gbT1idx = P(W_GBT1IDX, u8);
     wv.t1node = P(W_T1NODE, u32); wv.gCount = P(W_GCNT, u8); wv.uCount = P(W_UCNT, u8); wv.selList = P(W_SELLIST, u32);
-    wv.selCount = P(W_SELCNT, u32); wv.waveNodes = P(W_NODES, u32); wv.waveNodeOff = P(W_OFF, u32);
+    wv.selCount = P(W_SELCNT, u32); wv.itemList = P(W_ITEMS, u32); wv.scb = P(W_SCB, float); wv.waveNodes = P(W_NODES, u32); wv.waveNodeOff = P(W_OFF, u32);
   }
   if (h->hasRnn) {
     ENSURE(R_OFF, (size_t)(NS + 1) * 4);
@@ -757,6 +912,12 @@ jpp_b200_status jpp_b200_score_resident(jpp_b200_handle* h) {
     const ScoreCfg& cfg = h->cfg;
     const FeatTables& ft = h->hm.ft;
     const WaveView& wv = h->wv;
+    static const bool profileOn = getenv("JPP_B200_PROFILE") != nullptr;
+    static const bool serialGbeam = getenv("JPP_B200_SERIAL_GBEAM") != nullptr;  // A/B switch for W1
+    static WaveProfile prof;
+    prof.on = profileOn;
+    enum { K_GBEAM, K_PRESCORE, K_CUTOFF, K_BIGRAM, K_SCORE, K_REST, K_FULL, K_KINDS };
+    static const char* const kindNames[K_KINDS] = {"k_w_gbeam", "k_w_prescore", "k_w_cutoff", "k_w_bigram", "k_w_score", "k_w_rest", "k_w_full"};
     k_w_init<<<(NS + 127) / 128, 128, 0, st>>>(bv, cfg);
     u32 launches = 1;
     for (u32 bnd = 2; bnd < h->maxNb; ++bnd) {
@@ -765,25 +926,47 @@ jpp_b200_status jpp_b200_score_resident(jpp_b200_handle* h) {
       const u32 first = h->waveNodeOff[bnd], count = h->waveNodeOff[bnd + 1] - first;
       if (count == 0) continue;
       if (cfg.gbeam <= 0) {  // computeScoresFull
+        prof.begin(st, K_FULL);
         k_w_full<<<(count + 127) / 128, 128, 0, st>>>(ft, bv, cfg, wv, h->dWeights, first, count);
+        prof.end(st);
         ++launches;
         continue;
       }
-      k_w_gbeam<<<(nAct + 127) / 128, 128, 0, st>>>(bv, cfg, wv, nAct, bnd);
+      prof.begin(st, K_GBEAM);
+      if (serialGbeam) k_w_gbeam<<<(nAct + 127) / 128, 128, 0, st>>>(bv, cfg, wv, nAct, bnd);
+      else if (cfg.beam <= 8) k_w_gbeam_warp<8><<<(nAct + 3) / 4, 128, 0, st>>>(bv, cfg, wv, nAct, bnd);
+      else k_w_gbeam_warp<MAX_BEAM><<<(nAct + 3) / 4, 128, 0, st>>>(bv, cfg, wv, nAct, bnd);
+      prof.end(st);
       if (cfg.rcheck > 0) {
         const u32 pb = std::min<u32>((count + kCacheThreads - 1) / kCacheThreads, (u32)h->smCount);
+        prof.begin(st, K_PRESCORE);
         k_w_prescore<<<std::max(1u, pb), kCacheThreads, kCacheSlots * 8, st>>>(ft, bv, cfg, wv, h->dWeights, first, count);
+        prof.end(st);
       }
+      prof.begin(st, K_CUTOFF);
       k_w_cutoff<<<(nAct + 127) / 128, 128, 0, st>>>(ft, bv, cfg, wv, nAct, bnd);
+      prof.end(st);
       u32 selBound = count;
       if (cfg.rcheck > 0) selBound = std::min<u64>(count, (u64)nAct * (u32)cfg.rbeam);
+      const u32 iblocks = std::min<u32>((u32)(((u64)selBound * (u32)cfg.gbeam + kCacheThreads - 1) / kCacheThreads), (u32)h->smCount);
+      prof.begin(st, K_BIGRAM);
+      k_w_bigram<<<std::max(1u, iblocks), kCacheThreads, kCacheSlots * 8, st>>>(ft, bv, cfg, wv, h->dWeights);
+      prof.end(st);
       const u32 blocks = std::min<u32>((selBound + kCacheThreads - 1) / kCacheThreads, (u32)h->smCount);
+      prof.begin(st, K_SCORE);
       k_w_score<<<std::max(1u, blocks), kCacheThreads, kCacheSlots * 8, st>>>(ft, bv, cfg, wv, h->dWeights);
-      launches += 3;
+      prof.end(st);
+      launches += 4;
       if (cfg.rcheck > 0) {
+        prof.begin(st, K_REST);
         k_w_rest<<<(count + 127) / 128, 128, 0, st>>>(bv, cfg, wv, first, count);
+        prof.end(st);
         launches += 2;
       }
+    }
+    if (prof.on) {
+      cudaStreamSynchronize(st);
+      prof.report(kindNames, K_KINDS);
     }
     CU_CHECK(h, cudaGetLastError());
     h->walkLaunches = launches;

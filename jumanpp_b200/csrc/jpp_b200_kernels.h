@@ -622,7 +622,9 @@ struct WaveView {
   u8* gCount;      // [NS]
   u8* uCount;      // [NS]
   u32* selList;    // [cap]    selected right nodes of the wave (global node ids)
-  u32* selCount;   // [1]
+  u32* selCount;   // [2]      [0] selected nodes, [1] bigram items
+  u32* itemList;   // [cap*G]  (position in selList) << 5 | index into the unique-t1 list
+  float* scb;      // [cap*G]  bigram part of applyBiTri per (selected node, unique t1)
   const u32* waveNodes;    // [NN] node ids grouped by local boundary index
   const u32* waveNodeOff;  // [maxNb+1]
 };
@@ -677,6 +679,74 @@ JPP_HD float gsum_vars(const WL& wl, u32 n, u32 nv, IdxFn idxOf) {
     case 4: gsum<4, 8>(wl, n, idxOf, a); return ((a[0] + a[1]) + a[2]) + a[3];
     case 2: gsum<2, 8>(wl, n, idxOf, a); return a[0] + a[1];
     default: gsum<1, 8>(wl, n, idxOf, a); return a[0];
+  }
+}
+
+// One row of a generated n-gram step: rows 0..R-2 use NV interleaved accumulators, the last
+// row goes through computeUnrolled4RawPerceptron (4 accumulators).  Neighbouring threads
+// hold rows of both kinds, so both accumulator sets are fed from the same gathered values
+// (the additions are free next to the gathers) and the result is selected at the end: no
+// divergent gather loops.  Per accumulator the order of additions is that of gsum<NV> /
+// gsum<4>, so the result is bit-identical to gsum_vars / gsum_unrolled4.
+template <int NV, int LB, typename WL, typename IdxFn>
+JPP_HD void gsum_dual(const WL& wl, u32 n, IdxFn idxOf, float (&a)[NV], float& unrolled4) {
+  static_assert(LB % 4 == 0 && LB % NV == 0, "batch must cover whole accumulator rounds");
+  float b[4];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) a[j] = 0.0f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) b[j] = 0.0f;
+  u32 f = 0;
+  for (; f + LB <= n; f += LB) {
+    u32 id[LB];
+    float x[LB];
+#pragma unroll
+    for (int j = 0; j < LB; ++j) id[j] = idxOf(f + j);
+    wl.get(id, x);
+#pragma unroll
+    for (int j = 0; j < LB; ++j) {
+      a[j % NV] += x[j];
+      if (NV != 4) b[j % 4] += x[j];
+    }
+  }
+  if (f < n) {  // f is a multiple of LB (hence of NV and of 4): accumulator of feature f + j is j % NV
+    u32 id[LB];
+    float x[LB];
+#pragma unroll
+    for (int j = 0; j < LB; ++j) id[j] = idxOf(f + j < n ? f + j : n - 1);
+    wl.get(id, x);
+#pragma unroll
+    for (int j = 0; j < LB; ++j) {
+      if (f + j < n) {
+        a[j % NV] += x[j];
+        if (NV != 4) b[j % 4] += x[j];
+      }
+    }
+  }
+  if (NV == 4) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) b[j] = a[j % NV];
+  }
+  unrolled4 = ((b[0] + b[1]) + b[2]) + b[3];
+}
+
+template <int NV, typename WL, typename IdxFn>
+JPP_HD float gsum_row_nv(const WL& wl, u32 n, IdxFn idxOf, bool last) {
+  float a[NV], s4;
+  gsum_dual<NV, 8>(wl, n, idxOf, a, s4);
+  float sa = a[0];
+#pragma unroll
+  for (int j = 1; j < NV; ++j) sa += a[j];
+  return last ? s4 : sa;
+}
+
+template <typename WL, typename IdxFn>
+JPP_HD float gsum_row(const WL& wl, u32 n, u32 nv, IdxFn idxOf, bool last) {
+  switch (nv) {
+    case 8: return gsum_row_nv<8>(wl, n, idxOf, last);
+    case 4: return gsum_row_nv<4>(wl, n, idxOf, last);
+    case 2: return gsum_row_nv<2>(wl, n, idxOf, last);
+    default: return gsum_row_nv<1>(wl, n, idxOf, last);
   }
 }
 
@@ -838,8 +908,8 @@ JPP_HD void wave_prescore(const FeatTables& ft, const BatchView& bv, const Score
       return (u32)mix(mix(mix(ft.triState[f], P[ft.triT0[f]]), t1[ft.triT1[f]]), t2[ft.triT2[f]]) & mask;
     };
     float sc = t0;
-    sc += lastRow ? gsum_unrolled4(wl, ft.nBi, biIdx) : gsum_vars(wl, ft.nBi, ft.biVars, biIdx);
-    sc += lastRow ? gsum_unrolled4(wl, ft.nTri, triIdx) : gsum_vars(wl, ft.nTri, ft.triVars, triIdx);
+    sc += gsum_row(wl, ft.nBi, ft.biVars, biIdx, lastRow);
+    sc += gsum_row(wl, ft.nTri, ft.triVars, triIdx, lastRow);
     bv.pre[(size_t)i * bv.totalNodes + node] = sc;
   }
 }
@@ -894,53 +964,78 @@ JPP_HD void wave_cutoff(const FeatTables& ft, const BatchView& bv, const ScoreCf
     // streaming bytes of the boundary (DESIGN.md "roofline accounting")
     sb = 8ull * L * B + 8ull * SP * ((unsigned long long)R + U + G) + 4ull * L + (8ull + 4ull * cfg.S) * R * B;
   }
-  u32 base;
+  const u32 nitems = (remaining > 0 && G > 0) ? nsel * U : 0u;
+  u32 base, ibase;
 #if defined(__CUDA_ARCH__)
   {
     const unsigned m = __activemask();
     const int lane = (int)(threadIdx.x & 31u);
     const int leader = __ffs(m) - 1;
-    unsigned long long gs = g, sbs = sb;
     // the mask may have holes (threads that returned early or diverged): plain broadcast reduction
-    u32 total = 0, excl = 0;
+    u32 total = 0, excl = 0, itotal = 0, iexcl = 0;
+    unsigned long long gt = 0, st = 0;
     for (int l = 0; l < 32; ++l) {
       if (!((m >> l) & 1u)) continue;
       const u32 v = __shfl_sync(m, nsel, l);
-      if (l < lane) excl += v;
+      const u32 vi = __shfl_sync(m, nitems, l);
+      if (l < lane) { excl += v; iexcl += vi; }
       total += v;
-    }
-    unsigned long long gt = 0, st = 0;
-    if (bv.counters) {
-      for (int l = 0; l < 32; ++l) {
-        if (!((m >> l) & 1u)) continue;
-        gt += __shfl_sync(m, gs, l);
-        st += __shfl_sync(m, sbs, l);
+      itotal += vi;
+      if (bv.counters) {
+        gt += __shfl_sync(m, g, l);
+        st += __shfl_sync(m, sb, l);
       }
     }
-    u32 wbase = 0;
+    u32 wbase = 0, wibase = 0;
     if (lane == leader) {
       wbase = atomicAdd(wv.selCount, total);
+      wibase = atomicAdd(wv.selCount + 1, itotal);
       if (bv.counters) { atomicAdd(bv.counters + 0, gt); atomicAdd(bv.counters + 1, st); }
     }
-    wbase = __shfl_sync(m, wbase, leader);
-    base = wbase + excl;
+    base = __shfl_sync(m, wbase, leader) + excl;
+    ibase = __shfl_sync(m, wibase, leader) + iexcl;
   }
 #else
-  base = *wv.selCount;
-  *wv.selCount += nsel;
+  base = wv.selCount[0];
+  ibase = wv.selCount[1];
+  wv.selCount[0] += nsel;
+  wv.selCount[1] += nitems;
   if (bv.counters) { bv.counters[0] += g; bv.counters[1] += sb; }
 #endif
-  for (u32 r = 0, k = 0; r < R; ++r)
-    if (bv.selK[n0 + r] != 0xFFFFu) wv.selList[base + k++] = n0 + r;
+  for (u32 r = 0, k = 0; r < R; ++r) {
+    if (bv.selK[n0 + r] == 0xFFFFu) continue;
+    wv.selList[base + k] = n0 + r;
+    if (nitems)
+      for (u32 u = 0; u < U; ++u) wv.itemList[ibase + k * U + u] = ((base + k) << 5) | u;
+    ++k;
+  }
 }
 
-// W4: one selected right node against the whole global beam: applyBiTri ->
-// applyBiTriFullKernel (feature_impl_ngram_partial_kernels.h:19-110: two
-// accumulators, last rows through Unrolled4), copyT0Scores (score_processor.cc:411-424),
-// makeT0Beam (:426-469).
+// W4a: bigram part of applyBiTri for one (selected right node, unique t1) pair
+// (applyBiTriFullKernel, feature_impl_ngram_partial_kernels.h:19-110: the r1/r2 accumulator
+// pair; the last t1 row goes through Unrolled4).  Every item is exactly nBi gathers, so the
+// lanes of a warp stay converged whatever the number of unique t1 nodes of their sentences.
+template <typename WL>
+JPP_HD void wave_score_bigram(const FeatTables& ft, const BatchView& bv, const ScoreCfg& cfg, const WaveView& wv,
+                              const WL& wl, u32 item) {
+  const u32 pos = item >> 5, u = item & 31u;
+  const u32 node = wv.selList[pos];
+  const u32 sent = bv.bndSent[bv.nodeBnd[node]];
+  const u32 U = wv.uCount[sent], mask = ft.mask;
+  const PatRow P = pat_row(bv, node);
+  const PatRow t1 = pat_row(bv, wv.t1node[(size_t)sent * (u32)cfg.gbeam + u]);
+  auto biIdx = [&](u32 f) -> u32 { return (u32)mix(mix(ft.biState[f], P[ft.biT0[f]]), t1[ft.biT1[f]]) & mask; };
+  float a[2], s4;
+  gsum_dual<2, 8>(wl, ft.nBi, biIdx, a, s4);
+  wv.scb[(size_t)pos * (u32)cfg.gbeam + u] = (u + 1 == U) ? s4 : a[0] + a[1];
+}
+
+// W4b: one selected right node against the whole global beam: trigram part of applyBiTri
+// on top of the W4a bigram sums, copyT0Scores (score_processor.cc:411-424), makeT0Beam (:426-469).
 template <typename WL>
 JPP_HD void wave_score_node(const FeatTables& ft, const BatchView& bv, const ScoreCfg& cfg, const WaveView& wv,
-                            const WL& wl, u32 node) {
+                            const WL& wl, u32 pos) {
+  const u32 node = wv.selList[pos];
   const u32 gB = bv.nodeBnd[node];
   const u32 sent = bv.bndSent[gB];
   const u32 G = wv.gCount[sent], U = wv.uCount[sent];
@@ -958,7 +1053,8 @@ JPP_HD void wave_score_node(const FeatTables& ft, const BatchView& bv, const Sco
   const u8* t1idx = wv.gbT1idx + (size_t)sent * GMAX;
   const u32* gbT2 = wv.gbT2node + (size_t)sent * GMAX;
   const PatRow P = pat_row(bv, node);
-  float tot[MAX_BEAM], loc[MAX_BEAM], scbuf[MAX_BEAM];
+  float tot[MAX_BEAM], loc[MAX_BEAM];
+  const float* scbuf = wv.scb + (size_t)pos * GMAX;
   for (u32 i = 0; i < full; ++i) {
     float v = bv.pre[(size_t)i * bv.totalNodes + node];
     v += 0.0f;  // copyT0Scores(head, 0)
@@ -967,17 +1063,6 @@ JPP_HD void wave_score_node(const FeatTables& ft, const BatchView& bv, const Sco
     tot[i] = v;
   }
   if (remaining > 0 && G > 0) {
-    for (u32 u = 0; u < U; ++u) {
-      const PatRow t1 = pat_row(bv, t1node[u]);
-      auto biIdx = [&](u32 f) -> u32 { return (u32)mix(mix(ft.biState[f], P[ft.biT0[f]]), t1[ft.biT1[f]]) & mask; };
-      if (u + 1 < U) {
-        float a[2];
-        gsum<2, 8>(wl, nB, biIdx, a);
-        scbuf[u] = a[0] + a[1];
-      } else {
-        scbuf[u] = gsum_unrolled4(wl, nB, biIdx);
-      }
-    }
     const float t0 = bv.t0[node];
     for (u32 j = 0; j < remaining; ++j) {
       const u32 gi = full + j;
@@ -986,14 +1071,10 @@ JPP_HD void wave_score_node(const FeatTables& ft, const BatchView& bv, const Sco
       auto triIdx = [&](u32 f) -> u32 {
         return (u32)mix(mix(mix(ft.triState[f], P[ft.triT0[f]]), t1[ft.triT1[f]]), t2[ft.triT2[f]]) & mask;
       };
-      float v;
-      if (j + 1 < remaining) {
-        float a[2];
-        gsum<2, 4>(wl, nT, triIdx, a);
-        v = scbuf[t1idx[gi]] + a[0] + a[1];
-      } else {
-        v = scbuf[t1idx[gi]] + gsum_unrolled4(wl, nT, triIdx);
-      }
+      float a[2], s4;
+      gsum_dual<2, 4>(wl, nT, triIdx, a, s4);
+      const float sc = scbuf[t1idx[gi]];
+      float v = (j + 1 == remaining) ? sc + s4 : sc + a[0] + a[1];
       v += t0;  // copyT0Scores(tail, t0Score)
       loc[gi] = v;
       v += cand_score(gbKey[gi]);
@@ -1060,7 +1141,7 @@ JPP_HD u32 wave_full_node(const FeatTables& ft, const BatchView& bv, const Score
     const PatRow t1 = pat_row(bv, lnode);
     auto biIdx = [&](u32 f) -> u32 { return (u32)mix(mix(ft.biState[f], P[ft.biT0[f]]), t1[ft.biT1[f]]) & mask; };
     float T1 = t0;
-    T1 += lastRow ? gsum_unrolled4(wl, ft.nBi, biIdx) : gsum_vars(wl, ft.nBi, ft.biVars, biIdx);
+    T1 += gsum_row(wl, ft.nBi, ft.biVars, biIdx, lastRow);
     gathers += ft.nBi;
     for (u32 slot = 0; slot < B; ++slot) {
       const jpp_b200_beam_element el = lrow[slot];
@@ -1070,7 +1151,7 @@ JPP_HD u32 wave_full_node(const FeatTables& ft, const BatchView& bv, const Score
         return (u32)mix(mix(mix(ft.triState[f], P[ft.triT0[f]]), t1[ft.triT1[f]]), t2[ft.triT2[f]]) & mask;
       };
       float T2 = T1;
-      T2 += lastRow ? gsum_unrolled4(wl, ft.nTri, triIdx) : gsum_vars(wl, ft.nTri, ft.triVars, triIdx);
+      T2 += gsum_row(wl, ft.nTri, ft.triVars, triIdx, lastRow);
       gathers += ft.nTri;
       const u64 key = pack_cand(el.total_score + T2, left, slot);  // fillBeamCandidates, :165-191
       if (n == B && key < top[n - 1]) continue;

@@ -77,21 +77,24 @@ extern "C" int jpp_b200_emul_score_batch(const jpp_b200_model* model, const jpp_
   std::vector<u64> gbKey((size_t)NS * G);
   std::vector<u32> gbLnode((size_t)NS * G), gbT2node((size_t)NS * G), t1node((size_t)NS * G), selList(NN + 1);
   std::vector<u8> gbT1idx((size_t)NS * G), gCount(NS), uCount(NS);
-  u32 selCount = 0;
+  u32 selCount[2] = {0, 0};
+  std::vector<u32> itemList((size_t)(NN + 1) * G);
+  std::vector<float> scb((size_t)(NN + 1) * G);
   WaveView wv{};
   wv.gbKey = gbKey.data(); wv.gbLnode = gbLnode.data(); wv.gbT2node = gbT2node.data(); wv.gbT1idx = gbT1idx.data();
   wv.t1node = t1node.data(); wv.gCount = gCount.data(); wv.uCount = uCount.data(); wv.selList = selList.data();
-  wv.selCount = &selCount; wv.waveNodes = waveNodes.data(); wv.waveNodeOff = waveNodeOff.data();
+  wv.selCount = selCount; wv.itemList = itemList.data(); wv.scb = scb.data(); wv.waveNodes = waveNodes.data(); wv.waveNodeOff = waveNodeOff.data();
   for (u32 s = 0; s < NS; ++s) wave_init_sentence(bv, cfg, s);
   for (u32 bnd = 2; bnd < maxNb && cfg.gbeam <= 0; ++bnd)  // full-beam loop
     for (u32 i = waveNodeOff[bnd]; i < waveNodeOff[bnd + 1]; ++i) counters[0] += wave_full_node(ft, bv, cfg, wl, waveNodes[i]);
   for (u32 bnd = 2; bnd < maxNb && cfg.gbeam > 0; ++bnd) {
-    selCount = 0;
+    selCount[0] = selCount[1] = 0;
     for (u32 s = 0; s < NS; ++s) wave_gbeam(bv, cfg, wv, s, bnd);
     if (cfg.rcheck > 0)
       for (u32 i = waveNodeOff[bnd]; i < waveNodeOff[bnd + 1]; ++i) wave_prescore(ft, bv, cfg, wv, wl, waveNodes[i]);
     for (u32 s = 0; s < NS; ++s) wave_cutoff(ft, bv, cfg, wv, s, bnd);
-    for (u32 i = 0; i < selCount; ++i) wave_score_node(ft, bv, cfg, wv, wl, selList[i]);
+    for (u32 i = 0; i < selCount[1]; ++i) wave_score_bigram(ft, bv, cfg, wv, wl, itemList[i]);
+    for (u32 i = 0; i < selCount[0]; ++i) wave_score_node(ft, bv, cfg, wv, wl, i);
     if (cfg.rcheck > 0)
       for (u32 i = waveNodeOff[bnd]; i < waveNodeOff[bnd + 1]; ++i) wave_rest_node(bv, cfg, wv, waveNodes[i]);
   }
