@@ -116,18 +116,22 @@ __global__ void __launch_bounds__(128) k_w_gbeam(BatchView bv, ScoreCfg cfg, Wav
   if (i < nActive) wave_gbeam(bv, cfg, wv, bv.sentOrder[i], bnd);
 }
 
-// W1, warp per sentence (the same function as wave_gbeam, which stays the serial statement of it
-// for tests/emul): lane l owns left node l (+32, +64, ...), loads its B beam elements at once,
-// and G rounds of a warp-wide maximum over the packed keys pick the global beam -- keys are
-// distinct (score_processor.h:81-115), so the selection has one answer whatever the order.
-// Lane g then resolves element g (left node, its boundary, the node before it) and the
-// first-seen numbering of the unique left nodes (dedupT1, score_processor.cc:363-385).
-template <int KB>
+// W1, a group of GW lanes per sentence (the same function as wave_gbeam, which stays the serial
+// statement of it for tests/emul): lane l of the group owns left node l (+GW, +2GW, ...), loads
+// its B beam elements at once, and G rounds of a group-wide maximum over the packed keys pick
+// the global beam -- keys are distinct (score_processor.h:81-115), so the selection has one
+// answer whatever the order.  Lane g then resolves element g (left node, its boundary, the node
+// before it) and the first-seen numbering of the unique left nodes (dedupT1,
+// score_processor.cc:363-385).  GW = 8 (four sentences per warp) when the global beam has at
+// most 8 elements -- a boundary has ~7 left nodes, so a full warp per sentence idles -- else 32.
+template <int KB, int GW>
 __global__ void __launch_bounds__(128) k_w_gbeam_warp(BatchView bv, ScoreCfg cfg, WaveView wv, u32 nActive, u32 bnd) {
   const u32 tid = blockIdx.x * blockDim.x + threadIdx.x;
   if (tid == 0) wv.selCount[0] = wv.selCount[1] = 0;
-  const u32 w = tid >> 5, lane = threadIdx.x & 31u;
+  const u32 w = tid / GW, lane = threadIdx.x & 31u, sub = lane % GW;
   if (w >= nActive) return;
+  const unsigned gshift = lane - sub;
+  const unsigned gmask = (GW == 32 ? 0xffffffffu : ((1u << GW) - 1u)) << gshift;
   const u32 sent = bv.sentOrder[w];
   const u32 b0 = bv.sentBndOff[sent];
   const u32 nb = bv.sentBndOff[sent + 1] - b0;
@@ -136,15 +140,14 @@ __global__ void __launch_bounds__(128) k_w_gbeam_warp(BatchView bv, ScoreCfg cfg
   const u32 R = bv.bndNodeOff[gB + 1] - bv.bndNodeOff[gB];
   const u32 B = (u32)cfg.beam, GMAX = (u32)cfg.gbeam;
   if (R == 0) {  // analyzer_impl.cc:263-266
-    if (lane == 0) { wv.gCount[sent] = 0; wv.uCount[sent] = 0; bv.gbCount[gB] = 0; }
+    if (sub == 0) { wv.gCount[sent] = 0; wv.uCount[sent] = 0; bv.gbCount[gB] = 0; }
     return;
   }
   const u32 e0 = bv.bndEndOff[gB];
   const u32 L = bv.bndEndOff[gB + 1] - e0;
-  const unsigned full = 0xffffffffu;
-  u64 carried = 0;  // lane g: g-th largest key so far (0 = none; no real key is 0)
-  for (u32 c0 = 0; c0 < L; c0 += 32) {
-    const u32 left = c0 + lane;
+  u64 carried = 0;  // lane g of the group: g-th largest key so far (0 = none; no real key is 0)
+  for (u32 c0 = 0; c0 < L; c0 += GW) {
+    const u32 left = c0 + sub;
     u64 k[KB];
 #pragma unroll
     for (int q = 0; q < KB; ++q) k[q] = 0;
@@ -166,8 +169,8 @@ __global__ void __launch_bounds__(128) k_w_gbeam_warp(BatchView bv, ScoreCfg cfg
       for (int q = 0; q < KB; ++q)
         if (k[q] > m) { m = k[q]; mi = q; }
       const u32 hi = (u32)(m >> 32);
-      const u32 whi = __reduce_max_sync(full, hi);
-      const u32 wlo = __reduce_max_sync(full, hi == whi ? (u32)m : 0u);
+      const u32 whi = __reduce_max_sync(gmask, hi);
+      const u32 wlo = __reduce_max_sync(gmask, hi == whi ? (u32)m : 0u);
       const u64 wm = ((u64)whi << 32) | wlo;
       if (wm == 0) break;
       if (m == wm) {
@@ -176,12 +179,12 @@ __global__ void __launch_bounds__(128) k_w_gbeam_warp(BatchView bv, ScoreCfg cfg
         for (int q = 0; q < KB; ++q)
           if (q == mi) k[q] = 0;
       }
-      if (lane == g) next = wm;
+      if (sub == g) next = wm;
     }
     carried = next;
   }
-  const u32 G = __popc(__ballot_sync(full, carried != 0));
-  const bool have = lane < G;
+  const u32 G = __popc(__ballot_sync(gmask, carried != 0));
+  const bool have = sub < G;
   u32 lnode = 0xFFFFFFFFu, slot = 0, lbnd = 0, t2 = 0;
   if (have) {
     const u32 left = (u32)(carried >> 16) & 0xFFFFu;
@@ -191,25 +194,25 @@ __global__ void __launch_bounds__(128) k_w_gbeam_warp(BatchView bv, ScoreCfg cfg
     const jpp_b200_beam_element el = bv.beam[(size_t)lnode * B + slot];
     t2 = bv.endNode[bv.bndEndOff[b0 + lbnd] + el.left];
   }
-  u32 firstIdx = lane;
+  u32 firstIdx = sub;
   for (u32 j = 0; j < G; ++j) {
-    const u32 lj = __shfl_sync(full, lnode, j);
+    const u32 lj = __shfl_sync(gmask, lnode, j, GW);
     if (have && lj == lnode && j < firstIdx) firstIdx = j;
   }
-  const unsigned firstMask = __ballot_sync(full, have && firstIdx == lane);
+  const unsigned firstMask = (__ballot_sync(gmask, have && firstIdx == sub) & gmask) >> gshift;
   const u32 u = __popc(firstMask & ((1u << firstIdx) - 1u));
   if (have) {
     const size_t o = (size_t)sent * GMAX;
-    wv.gbKey[o + lane] = carried;
-    wv.gbLnode[o + lane] = lnode;
-    wv.gbT2node[o + lane] = t2;
-    wv.gbT1idx[o + lane] = (u8)u;
-    if (firstIdx == lane) wv.t1node[o + u] = lnode;
-    bv.gbNode[(size_t)gB * GMAX + lane] = lnode;
-    bv.gbSlot[(size_t)gB * GMAX + lane] = (u16)slot;
-    bv.gbLeftBnd[(size_t)gB * GMAX + lane] = (u16)lbnd;
+    wv.gbKey[o + sub] = carried;
+    wv.gbLnode[o + sub] = lnode;
+    wv.gbT2node[o + sub] = t2;
+    wv.gbT1idx[o + sub] = (u8)u;
+    if (firstIdx == sub) wv.t1node[o + u] = lnode;
+    bv.gbNode[(size_t)gB * GMAX + sub] = lnode;
+    bv.gbSlot[(size_t)gB * GMAX + sub] = (u16)slot;
+    bv.gbLeftBnd[(size_t)gB * GMAX + sub] = (u16)lbnd;
   }
-  if (lane == 0) {
+  if (sub == 0) {
     bv.gbCount[gB] = (u8)G;
     wv.gCount[sent] = (u8)G;
     wv.uCount[sent] = (u8)__popc(firstMask);
@@ -230,13 +233,16 @@ __global__ void __launch_bounds__(128) k_w_cutoff(const __grid_constant__ FeatTa
   if (i < nActive) wave_cutoff(ft, bv, cfg, wv, bv.sentOrder[i], bnd);
 }
 
+template <bool SMALL>
 __global__ void __launch_bounds__(kCacheThreads) k_w_score(const __grid_constant__ FeatTables ft, BatchView bv, ScoreCfg cfg,
                                                         WaveView wv, const float* __restrict__ w) {
   extern __shared__ __align__(16) unsigned long long cacheSlots[];
   const WLoadCached wl = make_cache(w, cacheSlots);
   const u32 n = wv.selCount[0];
-  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-    wave_score_node(ft, bv, cfg, wv, wl, i);
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (SMALL) wave_score_node_small(ft, bv, cfg, wv, wl, i);
+    else wave_score_node(ft, bv, cfg, wv, wl, i);
+  }
 }
 
 __global__ void __launch_bounds__(kCacheThreads) k_w_bigram(const __grid_constant__ FeatTables ft, BatchView bv, ScoreCfg cfg,
@@ -410,6 +416,119 @@ __global__ void __launch_bounds__(128) k_rnn_level(RnnWork rw, RnnTables rt, con
       }
     }
     (void)qn;
+  }
+}
+
+// Level kernel, layer sizes that are a multiple of 32 (KI = H / 32 <= 6): the same sums as
+// k_rnn_level, arranged so that the additions of the 16/8/4/2/1 tree happen ACROSS lanes.
+// Lane l owns residue l of every dot product: p_l = fma chain over k = l, l+32, ... (KI terms).
+// A warp takes 8 tree nodes (their previous contexts sit in registers, lane l holding elements
+// l + 32 i) and walks the outputs four at a time: 32 (node, output) pairs, 32 partials per lane,
+// 4*KI*8 FMAs per lane against 4*KI shared-memory reads of the recurrent matrix.  The 32 x 32
+// partials are then folded by a transpose-reduce: at lane distance 16 every lane keeps half of
+// its pairs and receives the matching partials of its partner (p_l + p_{l+16}), then distance 8,
+// 4, 2, 1 -- 31 shuffles for 32 complete dot products, and lane L ends up with pair L.  Operands
+// and association are exactly those of oracle/eigen_shim dot32 (float + is commutative).
+template <int KI>
+__global__ void __launch_bounds__(256) k_rnn_level_x(RnnWork rw, RnnTables rt, const u32* ctxOff, const u32* rnSent, u32 level) {
+  constexpr int TN = 8, TO = 4;
+  extern __shared__ __align__(16) float Ws[];  // recurrent matrix as stored: Ws[o * H + k]
+  const u32 cnt = rw.levelCount[level];
+  const u32 tiles = (cnt + TN - 1) / TN;
+  const u32 warpsPerBlock = blockDim.x >> 5;
+  if (blockIdx.x * warpsPerBlock >= tiles) return;
+  constexpr u32 H = 32u * KI;
+  {
+    const float4* src = reinterpret_cast<const float4*>(rt.matrix);
+    float4* dst = reinterpret_cast<float4*>(Ws);
+    for (u32 i = threadIdx.x; i < H * H / 4; i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+  const u32 off = rw.levelOff[level];
+  const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const unsigned full = 0xffffffffu;
+  for (u32 tile = blockIdx.x * warpsPerBlock + warp; tile < tiles; tile += gridDim.x * warpsPerBlock) {
+    const u32 first = tile * TN;
+    const u32 nvalid = (cnt - first) < (u32)TN ? (cnt - first) : (u32)TN;
+    // lane j < 8 resolves node j; everyone then reads the 8 previous contexts
+    u32 inRow = 0, outRow = 0, embRow = 0;
+    {
+      const u32 j = lane & 7u;
+      const u32 q = rw.levelList[off + first + (j < nvalid ? j : 0u)];
+      inRow = (u32)ctx_row(rw, ctxOff, rnSent, (u32)rw.prev[q]);
+      outRow = (u32)ctx_row(rw, ctxOff, rnSent, q);
+      i32 id = rw.id[q];
+      if (id == -1) id = 0;  // rnn_scorer_gbeam.cc:126-129
+      embRow = (u32)id;
+    }
+    float c[TN][KI];
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const u32 r = __shfl_sync(full, inRow, j);
+      const float* cin = rw.ctx + (size_t)r * H;
+#pragma unroll
+      for (int i = 0; i < KI; ++i) c[j][i] = cin[lane + 32u * i];
+    }
+    // lane L finishes pair L = j * TO + t: node j = L / 4, output o0 + (L % 4)
+    const u32 myJ = lane >> 2, myT = lane & 3u;
+    const float* myEmb = rt.emb + (size_t)__shfl_sync(full, embRow, myJ) * H;
+    float* myOut = rw.ctx + (size_t)__shfl_sync(full, outRow, myJ) * H;
+    for (u32 o0 = 0; o0 < H; o0 += TO) {
+      float P[TN * TO];
+#pragma unroll
+      for (int x = 0; x < TN * TO; ++x) P[x] = 0.0f;
+#pragma unroll
+      for (int t = 0; t < TO; ++t) {
+#pragma unroll
+        for (int i = 0; i < KI; ++i) {
+          const float w = Ws[(o0 + t) * H + 32u * i + lane];
+#pragma unroll
+          for (int j = 0; j < TN; ++j) P[j * TO + t] = __fmaf_rn(w, c[j][i], P[j * TO + t]);
+        }
+      }
+      float v16[16], v8[8], v4[4], v2[2], v1;
+      {
+        const bool up = (lane & 16u) != 0;
+#pragma unroll
+        for (int x = 0; x < 16; ++x) {
+          const float a = P[x], b = P[x + 16];
+          v16[x] = __fadd_rn(up ? b : a, __shfl_xor_sync(full, up ? a : b, 16));
+        }
+      }
+      {
+        const bool up = (lane & 8u) != 0;
+#pragma unroll
+        for (int x = 0; x < 8; ++x) {
+          const float a = v16[x], b = v16[x + 8];
+          v8[x] = __fadd_rn(up ? b : a, __shfl_xor_sync(full, up ? a : b, 8));
+        }
+      }
+      {
+        const bool up = (lane & 4u) != 0;
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+          const float a = v8[x], b = v8[x + 4];
+          v4[x] = __fadd_rn(up ? b : a, __shfl_xor_sync(full, up ? a : b, 4));
+        }
+      }
+      {
+        const bool up = (lane & 2u) != 0;
+#pragma unroll
+        for (int x = 0; x < 2; ++x) {
+          const float a = v4[x], b = v4[x + 2];
+          v2[x] = __fadd_rn(up ? b : a, __shfl_xor_sync(full, up ? a : b, 2));
+        }
+      }
+      {
+        const bool up = (lane & 1u) != 0;
+        const float a = v2[0], b = v2[1];
+        v1 = __fadd_rn(up ? b : a, __shfl_xor_sync(full, up ? a : b, 1));
+      }
+      const u32 o = o0 + myT;
+      const float v = __fadd_rn(v1, myEmb[o]);
+      const float r = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-v)));
+      if (myJ < nvalid) myOut[o] = r;
+    }
   }
 }
 
@@ -658,7 +777,8 @@ jpp_b200_status jpp_b200_create(const jpp_b200_model* model, const jpp_b200_conf
   h->smCount = prop.multiProcessorCount;
   CREATE_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CREATE_CHECK(cudaFuncSetAttribute(k_w_prescore, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kCacheSlots * 8)));
-  CREATE_CHECK(cudaFuncSetAttribute(k_w_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kCacheSlots * 8)));
+  CREATE_CHECK(cudaFuncSetAttribute(k_w_score<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kCacheSlots * 8)));
+  CREATE_CHECK(cudaFuncSetAttribute(k_w_score<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kCacheSlots * 8)));
   CREATE_CHECK(cudaFuncSetAttribute(k_w_bigram, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kCacheSlots * 8)));
   for (auto& e : h->ev) CREATE_CHECK(cudaEventCreate(&e));
   CREATE_CHECK(cudaMalloc(&h->dFt, sizeof(FeatTables)));
@@ -694,6 +814,15 @@ jpp_b200_status jpp_b200_create(const jpp_b200_model* model, const jpp_b200_conf
         return JPP_B200_NOT_IMPLEMENTED;
       }
       CREATE_CHECK(cudaFuncSetAttribute(k_rnn_level<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(32 * H * sizeof(float))));
+      if (H % 32 == 0 && H / 32 <= 6) {
+        const int wsBytes = (int)(H * H * sizeof(float));
+        CREATE_CHECK(cudaFuncSetAttribute(k_rnn_level_x<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, wsBytes));
+        CREATE_CHECK(cudaFuncSetAttribute(k_rnn_level_x<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, wsBytes));
+        CREATE_CHECK(cudaFuncSetAttribute(k_rnn_level_x<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, wsBytes));
+        CREATE_CHECK(cudaFuncSetAttribute(k_rnn_level_x<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, wsBytes));
+        CREATE_CHECK(cudaFuncSetAttribute(k_rnn_level_x<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, wsBytes));
+        CREATE_CHECK(cudaFuncSetAttribute(k_rnn_level_x<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, wsBytes));
+      }
     }
     h->rt = RnnTables{r->layer_size, r->maxent_order, r->maxent_size, r->vocab_size, r->nce_constant, r->unk_constant,
                       r->unk_length_penalty, r->unk_id, h->dRnnBlocks[0], h->dRnnBlocks[1], h->dRnnBlocks[2],
@@ -934,8 +1063,9 @@ jpp_b200_status jpp_b200_score_resident(jpp_b200_handle* h) {
       }
       prof.begin(st, K_GBEAM);
       if (serialGbeam) k_w_gbeam<<<(nAct + 127) / 128, 128, 0, st>>>(bv, cfg, wv, nAct, bnd);
-      else if (cfg.beam <= 8) k_w_gbeam_warp<8><<<(nAct + 3) / 4, 128, 0, st>>>(bv, cfg, wv, nAct, bnd);
-      else k_w_gbeam_warp<MAX_BEAM><<<(nAct + 3) / 4, 128, 0, st>>>(bv, cfg, wv, nAct, bnd);
+      else if (cfg.beam <= 8 && cfg.gbeam <= 8) k_w_gbeam_warp<8, 8><<<(nAct + 15) / 16, 128, 0, st>>>(bv, cfg, wv, nAct, bnd);
+      else if (cfg.beam <= 8) k_w_gbeam_warp<8, 32><<<(nAct + 3) / 4, 128, 0, st>>>(bv, cfg, wv, nAct, bnd);
+      else k_w_gbeam_warp<MAX_BEAM, 32><<<(nAct + 3) / 4, 128, 0, st>>>(bv, cfg, wv, nAct, bnd);
       prof.end(st);
       if (cfg.rcheck > 0) {
         const u32 pb = std::min<u32>((count + kCacheThreads - 1) / kCacheThreads, (u32)h->smCount);
@@ -954,7 +1084,8 @@ jpp_b200_status jpp_b200_score_resident(jpp_b200_handle* h) {
       prof.end(st);
       const u32 blocks = std::min<u32>((selBound + kCacheThreads - 1) / kCacheThreads, (u32)h->smCount);
       prof.begin(st, K_SCORE);
-      k_w_score<<<std::max(1u, blocks), kCacheThreads, kCacheSlots * 8, st>>>(ft, bv, cfg, wv, h->dWeights);
+      if (small_gbeam_ok(cfg)) k_w_score<true><<<std::max(1u, blocks), kCacheThreads, kCacheSlots * 8, st>>>(ft, bv, cfg, wv, h->dWeights);
+      else k_w_score<false><<<std::max(1u, blocks), kCacheThreads, kCacheSlots * 8, st>>>(ft, bv, cfg, wv, h->dWeights);
       prof.end(st);
       launches += 4;
       if (cfg.rcheck > 0) {
@@ -1005,8 +1136,25 @@ jpp_b200_status jpp_b200_score_resident(jpp_b200_handle* h) {
     k_rnn_bos<<<NS, 64, 0, st>>>(bv, rw, h->rt, ctxOff);
     CU_CHECK(h, cudaGetLastError());
     CU_CHECK(h, cudaEventRecord(h->ev[5], st));
-    for (u32 level = 1; level <= h->maxNb; ++level) {
-      k_rnn_level<8><<<h->smCount * 4, 128, 4 * 8 * h->rt.H * sizeof(float), st>>>(rw, h->rt, h->dRnnWt, ctxOff, rnSent, level);
+    {
+      const u32 H = h->rt.H;
+      const bool crossLane = (H % 32 == 0) && H / 32 <= 6 && !getenv("JPP_B200_RNN_LEVEL_V1");
+      const u32 grid = (u32)h->smCount * 2;
+      const size_t wsBytes = (size_t)H * H * sizeof(float);
+      for (u32 level = 1; level <= h->maxNb; ++level) {
+        if (!crossLane) {
+          k_rnn_level<8><<<h->smCount * 4, 128, 4 * 8 * H * sizeof(float), st>>>(rw, h->rt, h->dRnnWt, ctxOff, rnSent, level);
+          continue;
+        }
+        switch (H / 32) {
+          case 1: k_rnn_level_x<1><<<grid, 256, wsBytes, st>>>(rw, h->rt, ctxOff, rnSent, level); break;
+          case 2: k_rnn_level_x<2><<<grid, 256, wsBytes, st>>>(rw, h->rt, ctxOff, rnSent, level); break;
+          case 3: k_rnn_level_x<3><<<grid, 256, wsBytes, st>>>(rw, h->rt, ctxOff, rnSent, level); break;
+          case 4: k_rnn_level_x<4><<<grid, 256, wsBytes, st>>>(rw, h->rt, ctxOff, rnSent, level); break;
+          case 5: k_rnn_level_x<5><<<grid, 256, wsBytes, st>>>(rw, h->rt, ctxOff, rnSent, level); break;
+          default: k_rnn_level_x<6><<<grid, 256, wsBytes, st>>>(rw, h->rt, ctxOff, rnSent, level); break;
+        }
+      }
     }
     CU_CHECK(h, cudaGetLastError());
     CU_CHECK(h, cudaEventRecord(h->ev[6], st));

@@ -1092,6 +1092,103 @@ JPP_HD void wave_score_node(const FeatTables& ft, const BatchView& bv, const Sco
   (void)b0;
 }
 
+// W4b for small global beams (G <= 8 and G <= beam*4/3, the CLI default 6 / 5): the same
+// result as wave_score_node with everything in registers.  With at most 16 candidates and
+// no partition step makeT0Beam's std::sort is libstdc++'s insertion sort, i.e. a stable
+// descending sort, so the slot of candidate i is the number of candidates that are larger
+// or equal-and-earlier (tests/test_sort_emulation.py checks exactly this equivalence).
+constexpr int SMALL_G = 8;
+JPP_HD bool small_gbeam_ok(const ScoreCfg& cfg) {
+  return cfg.gbeam <= SMALL_G && cfg.gbeam <= 16 && (long)cfg.gbeam <= (long)cfg.beam * 4 / 3;
+}
+
+template <typename WL>
+JPP_HD void wave_score_node_small(const FeatTables& ft, const BatchView& bv, const ScoreCfg& cfg, const WaveView& wv,
+                                  const WL& wl, u32 pos) {
+  const u32 node = wv.selList[pos];
+  const u32 gB = bv.nodeBnd[node];
+  const u32 sent = bv.bndSent[gB];
+  const u32 G = wv.gCount[sent];
+  const u32 GMAX = (u32)cfg.gbeam, mask = ft.mask, nT = ft.nTri, B = (u32)cfg.beam;
+  const u32 R = bv.bndNodeOff[gB + 1] - bv.bndNodeOff[gB];
+  u32 full = 0;
+  if (cfg.rcheck > 0) {
+    full = (u32)cfg.rcheck;
+    if (R < full) full = R;
+    if (G < full) full = G;
+  }
+  const u64* gbKey = wv.gbKey + (size_t)sent * GMAX;
+  const u32* t1node = wv.t1node + (size_t)sent * GMAX;
+  const u8* t1idx = wv.gbT1idx + (size_t)sent * GMAX;
+  const u32* gbT2 = wv.gbT2node + (size_t)sent * GMAX;
+  const float* scbuf = wv.scb + (size_t)pos * GMAX;
+  const PatRow P = pat_row(bv, node);
+  const float t0 = bv.t0[node];
+  float tot[SMALL_G], loc[SMALL_G];
+  u64 key[SMALL_G];
+#pragma unroll
+  for (int gi = 0; gi < SMALL_G; ++gi) {
+    tot[gi] = 0.0f;
+    loc[gi] = 0.0f;
+    key[gi] = 0;
+    if ((u32)gi >= G) continue;
+    key[gi] = gbKey[gi];
+    float v;
+    if ((u32)gi < full) {
+      v = bv.pre[(size_t)gi * bv.totalNodes + node];
+      v += 0.0f;  // copyT0Scores(head, 0)
+    } else {
+      const u32 ti = t1idx[gi];
+      const PatRow t1 = pat_row(bv, t1node[ti]);
+      const PatRow t2 = pat_row(bv, gbT2[gi]);
+      auto triIdx = [&](u32 f) -> u32 {
+        return (u32)mix(mix(mix(ft.triState[f], P[ft.triT0[f]]), t1[ft.triT1[f]]), t2[ft.triT2[f]]) & mask;
+      };
+      float a[2], s4;
+      gsum_dual<2, 4>(wl, nT, triIdx, a, s4);
+      const float sc = scbuf[ti];
+      v = ((u32)gi + 1 == G) ? sc + s4 : sc + a[0] + a[1];
+      v += t0;  // copyT0Scores(tail, t0Score)
+    }
+    loc[gi] = v;
+    tot[gi] = v + cand_score(key[gi]);
+  }
+  jpp_b200_beam_element* row = bv.beam + (size_t)node * B;
+  float* srow = bv.beamScores + (size_t)node * B * cfg.S;
+#pragma unroll
+  for (int i = 0; i < SMALL_G; ++i) {
+    if ((u32)i >= G) continue;
+    u32 rank = 0;
+#pragma unroll
+    for (int j = 0; j < SMALL_G; ++j) {
+      if ((u32)j >= G || j == i) continue;
+      const bool before = (tot[j] > tot[i]) || (j < i && !(tot[i] > tot[j]));
+      rank += before ? 1u : 0u;
+    }
+    if (rank < B) {
+      jpp_b200_beam_element e;
+      e.left = (u16)(key[i] >> 16);
+      e.prev_beam = (u16)key[i];
+      e.total_score = tot[i];
+      row[rank] = e;
+      srow[(size_t)rank * cfg.S] = loc[i];
+      for (u32 q = 1; q < cfg.S; ++q) srow[(size_t)rank * cfg.S + q] = 0.0f;
+    }
+  }
+  for (u32 k = G; k < B; ++k) {
+    row[k] = fake_elem();
+    for (u32 q = 0; q < cfg.S; ++q) srow[(size_t)k * cfg.S + q] = 0.0f;
+  }
+  if (gB + 1 == bv.sentBndOff[sent + 1]) {  // EOS boundary: keep every connection for the re-rank
+#pragma unroll
+    for (int g = 0; g < SMALL_G; ++g) {
+      if ((u32)g >= G) continue;
+      bv.eosGbeam[(size_t)sent * GMAX + g] = key[g];
+      bv.eosLocal[(size_t)sent * GMAX + g] = loc[g];
+    }
+  }
+}
+
 // W5: right nodes outside the cutoff keep a beam of the head elements only
 // (score_processor.cc:336-346)
 JPP_HD void wave_rest_node(const BatchView& bv, const ScoreCfg& cfg, const WaveView& wv, u32 node) {

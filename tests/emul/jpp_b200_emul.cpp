@@ -94,7 +94,10 @@ extern "C" int jpp_b200_emul_score_batch(const jpp_b200_model* model, const jpp_
       for (u32 i = waveNodeOff[bnd]; i < waveNodeOff[bnd + 1]; ++i) wave_prescore(ft, bv, cfg, wv, wl, waveNodes[i]);
     for (u32 s = 0; s < NS; ++s) wave_cutoff(ft, bv, cfg, wv, s, bnd);
     for (u32 i = 0; i < selCount[1]; ++i) wave_score_bigram(ft, bv, cfg, wv, wl, itemList[i]);
-    for (u32 i = 0; i < selCount[0]; ++i) wave_score_node(ft, bv, cfg, wv, wl, i);
+    for (u32 i = 0; i < selCount[0]; ++i) {
+      if (small_gbeam_ok(cfg)) wave_score_node_small(ft, bv, cfg, wv, wl, i);
+      else wave_score_node(ft, bv, cfg, wv, wl, i);
+    }
     if (cfg.rcheck > 0)
       for (u32 i = waveNodeOff[bnd]; i < waveNodeOff[bnd + 1]; ++i) wave_rest_node(bv, cfg, wv, waveNodes[i]);
   }

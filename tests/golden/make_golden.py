@@ -30,6 +30,8 @@ REF = Path("/root/reference")
 
 RNN_PARAMS = dict(layer_size=32, maxent_order=3, maxent_size=1 << 16, nce_lnz=9.0, seed=2, vocab=5000)
 RNN2_PARAMS = dict(layer_size=64, maxent_order=4, maxent_size=1 << 15, nce_lnz=7.5, seed=5, vocab=3000)
+RNN3_PARAMS = dict(layer_size=128, maxent_order=3, maxent_size=1 << 16, nce_lnz=9.0, seed=11, vocab=4000)  # bench size
+RNN4_PARAMS = dict(layer_size=48, maxent_order=2, maxent_size=1 << 14, nce_lnz=8.0, seed=13, vocab=2000)   # not a multiple of 32
 
 CONFIGS = {
     # name: (harness args, sentence count)
@@ -42,6 +44,8 @@ CONFIGS = {
     "rcheck0": ("beam=5 gbeam=6 rcheck=0 rbeam=0 log2w=16 wseed=13", 14),
     "rnn_default": ("beam=5 gbeam=6 rcheck=1 rbeam=5 log2w=18 wseed=1 rnn=RNN1", 16),
     "rnn_beam20": ("beam=20 gbeam=20 rcheck=1 rbeam=5 log2w=16 wseed=7 rnn=RNN2 rnn_weight=0.05 nce_bias=3.5", 10),
+    "rnn_h128": ("beam=5 gbeam=6 rcheck=1 rbeam=5 log2w=18 wseed=5 rnn=RNN3", 12),
+    "rnn_h48": ("beam=4 gbeam=5 rcheck=1 rbeam=4 log2w=16 wseed=6 rnn=RNN4", 10),
 }
 
 
@@ -66,7 +70,7 @@ def main() -> None:
     sents[0] = sents[0][:1]                 # one-codepoint sentence
     sents[1] = "abc12３４" + sents[1][:6]     # ascii / digit unk makers
     sents[2] = sents[2][:3] + "ゴロゴロ" + "ドキドキ"  # onomatopoeia maker
-    for name, prm in (("RNN1", RNN_PARAMS), ("RNN2", RNN2_PARAMS)):
+    for name, prm in (("RNN1", RNN_PARAMS), ("RNN2", RNN2_PARAMS), ("RNN3", RNN3_PARAMS), ("RNN4", RNN4_PARAMS)):
         words = synth.rnn_vocabulary(dic, prm["vocab"])
         synth.write_rnn_model(tmp / name, words, prm["layer_size"], prm["maxent_order"], prm["maxent_size"],
                               prm["nce_lnz"], prm["seed"])
@@ -89,7 +93,7 @@ def main() -> None:
                     break
             chosen = ok
         corpus.write_text("\n".join(chosen) + "\n", encoding="utf-8")
-        a = [x.replace("RNN1", str(tmp / "RNN1")).replace("RNN2", str(tmp / "RNN2")) for x in args.split()]
+        a = [re.sub(r"^rnn=(RNN\d)$", lambda m: f"rnn={tmp / m.group(1)}", x) for x in args.split()]
         out = tmp / f"{name}.jppb"
         run([str(HARNESS), "stage", f"dict={dic}", f"corpus={corpus}", f"out={out}", *a])
         gz(out, HERE / f"{name}.jppb.gz")

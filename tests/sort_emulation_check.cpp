@@ -51,6 +51,26 @@ int main() {
     }
     ++checked;
   }
+  // n <= 16: std::sort is a plain insertion sort, i.e. stable -- the register fast path
+  // (wave_score_node_small) ranks a candidate by "larger, or equal and earlier"
+  for (int t = 0; t < 40000; ++t) {
+    int n = 1 + (int)(rng() % 16);
+    int distinct = 1 + (int)(rng() % 5);
+    std::vector<float> sc(n);
+    for (auto& x : sc) x = (float)(rng() % distinct) * 0.5f - 1.0f;
+    std::vector<uint32_t> a(n);
+    std::iota(a.begin(), a.end(), 0u);
+    std::sort(a.begin(), a.end(), [&](uint32_t x, uint32_t y) { return sc[x] > sc[y]; });
+    for (int i = 0; i < n; ++i) {
+      uint32_t rank = 0;
+      for (int j = 0; j < n; ++j) {
+        if (j == i) continue;
+        rank += ((sc[j] > sc[i]) || (j < i && !(sc[i] > sc[j]))) ? 1u : 0u;
+      }
+      if (a[rank] != (uint32_t)i) { std::printf("stable-rank mismatch n=%d t=%d\n", n, t); return 1; }
+    }
+    ++checked;
+  }
   std::printf("ok %ld\n", checked);
   return 0;
 }
