@@ -27,6 +27,7 @@ buffers (H2D of the staged lattices + D2H of the beams inside the timed region).
 from __future__ import annotations
 
 import argparse
+import dataclasses
 import json
 import os
 import statistics
@@ -109,11 +110,17 @@ def load_staged(info, args, pin) -> tuple[abi.ModelSpec, abi.ScoringConfig, abi.
     for f in files:
         dd = jppb.load(f)
         first = first or dd
-        parts.append(abi.StagedBatch.from_jppb(dd))
+        part = abi.StagedBatch.from_jppb(dd)
+        parts.append(part if args.inline_entries else part.compact_entries())
     model = abi.ModelSpec.from_jppb(first, str(info["rnn"]) if info["rnn"] else None)
     model.log2_weights, model.weight_seed, model.weight_scale = args.log2w, args.wseed, 0.5
     cfg = abi.ScoringConfig.from_jppb(first)
-    batch = abi.StagedBatch.concat(parts, pin=pin)
+    if args.inline_entries:
+        batch = abi.StagedBatch.concat(parts, pin=pin)
+    else:   # one entry row per distinct entry of the whole batch (jpp_b200_batch.node_entry_row / entry_rows)
+        batch = abi.StagedBatch.concat(parts).compact_entries()
+        batch = dataclasses.replace(batch, **{f.name: pin(getattr(batch, f.name)) for f in dataclasses.fields(batch)
+                                              if getattr(batch, f.name) is not None})
     return model, cfg, batch
 
 
@@ -213,9 +220,7 @@ def product_arm(args, rank: int, world: int, local_rank: int) -> None:
         f"{batch.num_boundaries} boundaries ({time.time() - t0:.1f}s)")
     scorer = LatticeScorer(model, cfg, device=local_rank)
     res = scorer.allocate_result(batch)
-    h2d = sum(a.nbytes for a in (batch.sent_boundary_off, batch.sent_codepoint_off, batch.boundary_node_off,
-                                 batch.boundary_end_off, batch.node_info, batch.node_entry, batch.ends, batch.codepoints)
-              ) + sum(a.nbytes for a in (batch.node_placeholders, batch.node_rnn_id) if a is not None)
+    h2d = batch.h2d_bytes()
 
     def barrier():
         torch.cuda.synchronize()
@@ -334,7 +339,9 @@ def product_arm(args, rank: int, world: int, local_rank: int) -> None:
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "sentences/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": 1000.0 * e2e_s / args.steps,
-                    "how": "one jpp_b200_upload_batch + score_resident + download_result per step from pinned host buffers; "
+                    "entry_rows": (None if batch.entry_rows is None else int(len(batch.entry_rows))),
+                    "how": "one jpp_b200_upload_batch + score_resident + download_result per step from pinned host buffers "
+                           "(entry buffers sent " + ("inline, one per node" if batch.entry_rows is None else "as one row per distinct entry + a row index per node") + "); "
                            "D2H = device-resolved 1-best paths (jpp_b200_result.best_path_*)",
                     "pipelined_two_handles": pipelined},
             "gpu_launches": int(cnt["launches"]) * args.steps,
@@ -422,6 +429,8 @@ def main() -> None:
     ap.add_argument("--parity-sample", type=int, default=2000)
     ap.add_argument("--e2e-chunks", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--inline-entries", action="store_true",
+                    help="send one entry buffer per node (jpp_b200_batch.node_entry) instead of the compact row table")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define JPP_B200_ABI_VERSION 1u
+#define JPP_B200_ABI_VERSION 2u
 
 typedef enum jpp_b200_status {
   JPP_B200_OK = 0,
@@ -210,6 +210,15 @@ typedef struct jpp_b200_batch {
   const jpp_b200_node_ptr* ends;        /* [total_ends]                      */
   /* per sentence codepoints */
   const jpp_b200_codepoint* codepoints; /* [total_codepoints]                */
+  /* Compact alternative to node_entry (ABI 2).  When node_entry is NULL the entry
+   * buffer of node n is entry_rows[node_entry_row[n]]: the stager keeps ONE row per
+   * distinct entry of the batch -- a dictionary word's EntryPtr identifies its
+   * row (DictionaryEntries::entryAtPtr, dic_entries.h), unknown-word nodes add
+   * rows of their own -- and sends 4 bytes per node instead of 4*entry_size.
+   * The rows hold exactly what fillEntryBuffer would have written. */
+  const uint32_t* node_entry_row;       /* [total_nodes] or NULL              */
+  const int32_t* entry_rows;            /* [num_entry_rows][entry_size]       */
+  uint32_t num_entry_rows;
 } jpp_b200_batch;
 
 /* ConnectionBeamElement (lattice_config.h:70-73) without the raw pointer: the

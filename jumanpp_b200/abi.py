@@ -9,11 +9,12 @@ from arrays produced by any other host-side lattice builder.
 from __future__ import annotations
 
 import ctypes as C
+import dataclasses
 from dataclasses import dataclass, field
 
 import numpy as np
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # jpp_b200_status
 OK, INVALID_PARAMETER, INVALID_STATE, NOT_IMPLEMENTED, CUDA_ERROR = range(5)
@@ -73,7 +74,8 @@ class Batch(C.Structure):
                 ("sent_boundary_off", C.c_void_p), ("sent_codepoint_off", C.c_void_p),
                 ("boundary_node_off", C.c_void_p), ("boundary_end_off", C.c_void_p),
                 ("node_info", C.c_void_p), ("node_entry", C.c_void_p), ("node_placeholders", C.c_void_p),
-                ("node_rnn_id", C.c_void_p), ("ends", C.c_void_p), ("codepoints", C.c_void_p)]
+                ("node_rnn_id", C.c_void_p), ("ends", C.c_void_p), ("codepoints", C.c_void_p),
+                ("node_entry_row", C.c_void_p), ("entry_rows", C.c_void_p), ("num_entry_rows", C.c_uint32)]
 
 
 class Result(C.Structure):
@@ -242,11 +244,13 @@ class StagedBatch:
     boundary_node_off: np.ndarray
     boundary_end_off: np.ndarray
     node_info: np.ndarray        # NODE_INFO_DT
-    node_entry: np.ndarray       # [nodes][entry_size] i32
+    node_entry: np.ndarray | None   # [nodes][entry_size] i32, or None in the compact form
     node_placeholders: np.ndarray | None
     node_rnn_id: np.ndarray | None
     ends: np.ndarray             # NODE_PTR_DT
     codepoints: np.ndarray       # CODEPOINT_DT
+    node_entry_row: np.ndarray | None = None   # compact form: [nodes] u32 index into entry_rows
+    entry_rows: np.ndarray | None = None       # [rows][entry_size] i32
 
     @property
     def num_sentences(self) -> int:
@@ -288,6 +292,9 @@ class StagedBatch:
         b.boundary_end_off = _ptr(self.boundary_end_off)
         b.node_info = _ptr(self.node_info)
         b.node_entry = _ptr(self.node_entry)
+        b.node_entry_row = _ptr(self.node_entry_row)
+        b.entry_rows = _ptr(self.entry_rows)
+        b.num_entry_rows = 0 if self.entry_rows is None else len(self.entry_rows)
         b.node_placeholders = _ptr(self.node_placeholders)
         b.node_rnn_id = _ptr(self.node_rnn_id)
         b.ends = _ptr(self.ends)
@@ -312,11 +319,17 @@ class StagedBatch:
             arrs = [get(p) for p in parts]
             return None if arrs[0] is None else pin(np.concatenate(arrs))
 
+        rows = row_idx = None
+        if parts[0].node_entry is None:   # compact parts: stack the row tables, rebase the indices
+            bases = np.cumsum([0] + [len(p.entry_rows) for p in parts[:-1]])
+            rows = pin(np.concatenate([p.entry_rows for p in parts]))
+            row_idx = pin(np.concatenate([(p.node_entry_row.astype(np.uint64) + int(b)).astype(np.uint32)
+                                          for p, b in zip(parts, bases)]))
         return StagedBatch(
             pin(offs(lambda p: p.sent_boundary_off, None)), pin(offs(lambda p: p.sent_codepoint_off, None)),
             pin(offs(lambda p: p.boundary_node_off, None)), pin(offs(lambda p: p.boundary_end_off, None)),
             cat(lambda p: p.node_info), cat(lambda p: p.node_entry), cat(lambda p: p.node_placeholders),
-            cat(lambda p: p.node_rnn_id), cat(lambda p: p.ends), cat(lambda p: p.codepoints))
+            cat(lambda p: p.node_rnn_id), cat(lambda p: p.ends), cat(lambda p: p.codepoints), row_idx, rows)
 
     def select(self, lo: int, hi: int) -> "StagedBatch":
         """Sentences [lo, hi) as an independent batch (offsets rebased)."""
@@ -329,10 +342,44 @@ class StagedBatch:
             (self.sent_codepoint_off[lo:hi + 1] - c0).astype(np.uint32),
             (self.boundary_node_off[b0:b1 + 1] - n0).astype(np.uint32),
             (self.boundary_end_off[b0:b1 + 1] - e0).astype(np.uint32),
-            np.ascontiguousarray(self.node_info[n0:n1]), np.ascontiguousarray(self.node_entry[n0:n1]),
+            np.ascontiguousarray(self.node_info[n0:n1]),
+            None if self.node_entry is None else np.ascontiguousarray(self.node_entry[n0:n1]),
             None if self.node_placeholders is None else np.ascontiguousarray(self.node_placeholders[n0:n1]),
             None if self.node_rnn_id is None else np.ascontiguousarray(self.node_rnn_id[n0:n1]),
-            np.ascontiguousarray(self.ends[e0:e1]), np.ascontiguousarray(self.codepoints[c0:c1]))
+            np.ascontiguousarray(self.ends[e0:e1]), np.ascontiguousarray(self.codepoints[c0:c1]),
+            None if self.node_entry_row is None else np.ascontiguousarray(self.node_entry_row[n0:n1]),
+            self.entry_rows)
+
+    def compact_entries(self, pin=None) -> "StagedBatch":
+        """The same batch with one entry row per distinct entry buffer (jpp_b200_batch.node_entry_row /
+        entry_rows): what a stager that keys rows by EntryPtr sends.  Rows are matched by content here,
+        through a 64-bit hash whose collisions are checked.  A batch that is already compact (e.g. a
+        concatenation of compact parts) gets its row table de-duplicated once more."""
+        pin = pin or (lambda a: a)
+        rows = np.ascontiguousarray(self.node_entry if self.node_entry is not None else self.entry_rows, np.int32)
+        n, es = rows.shape
+        h = np.full(n, 0x9E3779B97F4A7C15, np.uint64)
+        with np.errstate(over="ignore"):
+            for c in range(es):
+                h ^= (rows[:, c].astype(np.uint32).astype(np.uint64) + np.uint64(0x9E3779B97F4A7C15)
+                      + (h << np.uint64(6)) + (h >> np.uint64(2)))
+                h *= np.uint64(0xFF51AFD7ED558CCD)
+                h ^= h >> np.uint64(33)
+        _, first, inverse = np.unique(h, return_index=True, return_inverse=True)
+        table = np.ascontiguousarray(rows[first])
+        if not np.array_equal(table[inverse], rows):
+            raise RuntimeError("entry-row hash collision; use the inline form")
+        inverse = inverse.astype(np.uint32)
+        idx = inverse if self.node_entry is not None else inverse[self.node_entry_row]
+        return dataclasses.replace(self, node_entry=None, node_entry_row=pin(np.ascontiguousarray(idx)),
+                                   entry_rows=pin(table))
+
+    def h2d_bytes(self) -> int:
+        """Bytes jpp_b200_upload_batch copies to the device for this batch."""
+        arrs = (self.sent_boundary_off, self.sent_codepoint_off, self.boundary_node_off, self.boundary_end_off,
+                self.node_info, self.node_entry, self.node_placeholders, self.node_rnn_id, self.ends, self.codepoints,
+                self.node_entry_row, self.entry_rows)
+        return int(sum(a.nbytes for a in arrs if a is not None))
 
 
 @dataclass

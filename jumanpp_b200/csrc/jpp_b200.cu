@@ -639,7 +639,7 @@ struct jpp_b200_handle {
   float scoreW[2] = {1.0f, 0.0f};
   int smCount = 148;
   // batch buffers
-  enum { B_SBO, B_SCO, B_BNO, B_BEO, B_INFO, B_ENTRY, B_PH, B_RNNID, B_ENDS, B_CPS, B_NODEBND, B_BNDSENT, B_ENDNODE,
+  enum { B_SBO, B_SCO, B_BNO, B_BEO, B_INFO, B_ENTRY, B_ENTRYROW, B_PH, B_RNNID, B_ENDS, B_CPS, B_NODEBND, B_BNDSENT, B_ENDNODE,
          B_ORDER, B_BEAM, B_BSCORES, B_PATS, B_T0, B_PRE, B_CUT, B_CUTIDX, B_SELK, B_GBNODE, B_GBSLOT, B_GBLBND, B_GBCNT,
          B_EOSG, B_EOSLOC, B_EOSRNN, B_COUNTERS, B_WORK,
          B_PATHLEN, B_PATHNODES,
@@ -866,7 +866,7 @@ jpp_b200_status jpp_b200_upload_batch(jpp_b200_handle* h, const jpp_b200_batch* 
   CU_CHECK(h, cudaSetDevice(h->device));
   if (b->num_sentences == 0) return fail(h, JPP_B200_INVALID_PARAMETER, "empty batch");
   if (!b->sent_boundary_off || !b->sent_codepoint_off || !b->boundary_node_off || !b->boundary_end_off || !b->node_info ||
-      !b->node_entry || !b->ends || (!b->codepoints && b->sent_codepoint_off[b->num_sentences] > 0))
+      (!b->node_entry && (!b->node_entry_row || !b->entry_rows || b->num_entry_rows == 0)) || !b->ends || (!b->codepoints && b->sent_codepoint_off[b->num_sentences] > 0))
     return fail(h, JPP_B200_INVALID_PARAMETER, "batch has null arrays");
   if (h->hm.ft.nPlaceholders > 0 && !b->node_placeholders)
     return fail(h, JPP_B200_INVALID_PARAMETER, "model has placeholders but batch.node_placeholders is null");
@@ -903,7 +903,9 @@ jpp_b200_status jpp_b200_upload_batch(jpp_b200_handle* h, const jpp_b200_batch* 
   ENSURE(B_SBO, (size_t)(NS + 1) * 4); ENSURE(B_SCO, (size_t)(NS + 1) * 4);
   ENSURE(B_BNO, (size_t)(NB + 1) * 4); ENSURE(B_BEO, (size_t)(NB + 1) * 4);
   ENSURE(B_INFO, (size_t)NN * sizeof(jpp_b200_node_info));
-  ENSURE(B_ENTRY, (size_t)NN * h->hm.ft.entrySize * 4);
+  const bool compactEntries = b->node_entry == nullptr;
+  ENSURE(B_ENTRY, (size_t)(compactEntries ? b->num_entry_rows : NN) * h->hm.ft.entrySize * 4);
+  if (compactEntries) ENSURE(B_ENTRYROW, (size_t)NN * 4);
   ENSURE(B_PH, (size_t)NN * std::max(1u, h->hm.ft.nPlaceholders) * 4);
   ENSURE(B_RNNID, (size_t)NN * 4);
   ENSURE(B_ENDS, (size_t)NE * sizeof(jpp_b200_node_ptr));
@@ -929,7 +931,12 @@ jpp_b200_status jpp_b200_upload_batch(jpp_b200_handle* h, const jpp_b200_batch* 
   H2D(B_BNO, b->boundary_node_off, (size_t)(NB + 1) * 4);
   H2D(B_BEO, b->boundary_end_off, (size_t)(NB + 1) * 4);
   H2D(B_INFO, b->node_info, (size_t)NN * sizeof(jpp_b200_node_info));
-  H2D(B_ENTRY, b->node_entry, (size_t)NN * h->hm.ft.entrySize * 4);
+  if (compactEntries) {
+    H2D(B_ENTRY, b->entry_rows, (size_t)b->num_entry_rows * h->hm.ft.entrySize * 4);
+    H2D(B_ENTRYROW, b->node_entry_row, (size_t)NN * 4);
+  } else {
+    H2D(B_ENTRY, b->node_entry, (size_t)NN * h->hm.ft.entrySize * 4);
+  }
   if (h->hm.ft.nPlaceholders) H2D(B_PH, b->node_placeholders, (size_t)NN * h->hm.ft.nPlaceholders * 4);
   if (h->hasRnn) H2D(B_RNNID, b->node_rnn_id, (size_t)NN * 4);
   H2D(B_ENDS, b->ends, (size_t)NE * sizeof(jpp_b200_node_ptr));
@@ -940,7 +947,9 @@ jpp_b200_status jpp_b200_upload_batch(jpp_b200_handle* h, const jpp_b200_batch* 
   bv.numSentences = NS; bv.totalBoundaries = NB; bv.totalNodes = NN; bv.totalEnds = NE;
 #define P(idx, T) bf[jpp_b200_handle::idx].as<T>()
   bv.sentBndOff = P(B_SBO, u32); bv.sentCpOff = P(B_SCO, u32); bv.bndNodeOff = P(B_BNO, u32); bv.bndEndOff = P(B_BEO, u32);
-  bv.nodeInfo = P(B_INFO, jpp_b200_node_info); bv.nodeEntry = P(B_ENTRY, i32);
+  bv.nodeInfo = P(B_INFO, jpp_b200_node_info); bv.nodeEntry = compactEntries ? nullptr : P(B_ENTRY, i32);
+  bv.nodeEntryRow = compactEntries ? P(B_ENTRYROW, u32) : nullptr; bv.entryRows = compactEntries ? P(B_ENTRY, i32) : nullptr;
+  bv.numEntryRows = compactEntries ? b->num_entry_rows : 0;
   bv.nodePlaceholders = h->hm.ft.nPlaceholders ? P(B_PH, i32) : nullptr;
   bv.nodeRnnId = h->hasRnn ? P(B_RNNID, i32) : nullptr;
   bv.ends = P(B_ENDS, jpp_b200_node_ptr); bv.cps = P(B_CPS, jpp_b200_codepoint);
@@ -1173,6 +1182,7 @@ jpp_b200_status jpp_b200_score_resident(jpp_b200_handle* h) {
   // counters
   unsigned long long dc[8] = {0};
   CU_CHECK(h, cudaMemcpy(dc, bf[jpp_b200_handle::B_COUNTERS].p, 64, cudaMemcpyDeviceToHost));
+  if (dc[7]) return fail(h, JPP_B200_INVALID_PARAMETER, "batch.node_entry_row holds an index >= num_entry_rows");
   jpp_b200_counters& c = h->counters;
   c.sentences = NS; c.boundaries = NB; c.nodes = NN;
   // T0 runs on every node except the two BOS nodes of each sentence

@@ -104,7 +104,10 @@ struct BatchView {
   const u32* bndNodeOff;
   const u32* bndEndOff;
   const jpp_b200_node_info* nodeInfo;
-  const i32* nodeEntry;
+  const i32* nodeEntry;      // [nodes][entrySize], or null: entryRows[nodeEntryRow[node]]
+  const u32* nodeEntryRow;
+  const i32* entryRows;
+  u32 numEntryRows;
   const i32* nodePlaceholders;  // may be null
   const i32* nodeRnnId;         // may be null
   const jpp_b200_node_ptr* ends;
@@ -294,7 +297,17 @@ JPP_HD void t0_node(const FeatTables& ft, const BatchView& bv, const WL& wl, u32
   const u32 cp0 = bv.sentCpOff[sent];
   const u32 ncp = bv.sentCpOff[sent + 1] - cp0;
   const jpp_b200_codepoint* cps = bv.cps + cp0;
-  const i32* entry = bv.nodeEntry + (size_t)node * ft.entrySize;
+  const i32* entry;
+  if (bv.nodeEntry) {
+    entry = bv.nodeEntry + (size_t)node * ft.entrySize;
+  } else {
+    u32 row = bv.nodeEntryRow[node];
+    if (row >= bv.numEntryRows) {  // reported as INVALID_PARAMETER after the step
+      row = 0;
+      if (bv.counters) bv.counters[7] = 1;
+    }
+    entry = bv.entryRows + (size_t)row * ft.entrySize;
+  }
   const i32* ph = bv.nodePlaceholders ? bv.nodePlaceholders + (size_t)node * ft.nPlaceholders : nullptr;
   u64 prim[MAX_PRIM];
   for (u32 i = 0; i < ft.nPrim; ++i) prim[i] = prim_value(ft, i, entry, ph, ni, cps, ncp);

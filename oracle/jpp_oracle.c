@@ -743,7 +743,8 @@ static int score_sentence(const Ctx* c, Scratch* s, u32 sent) {
     for (u32 r = 0; r < R; ++r) {
       u32 node = n0 + r;
       u64* P = s->pats + (size_t)r * NP;
-      node_patterns(cm, B->node_entry + (size_t)node * m->entry_size,
+      node_patterns(cm, B->node_entry ? B->node_entry + (size_t)node * m->entry_size
+                                      : B->entry_rows + (size_t)B->node_entry_row[node] * m->entry_size,
                     B->node_placeholders ? B->node_placeholders + (size_t)node * m->num_placeholders : NULL,
                     &B->node_info[node], cps, ncp, P);
       for (u32 p = 0; p < SP; ++p) patsOut[(size_t)node * SP + p] = P[p];

@@ -60,3 +60,28 @@ def test_rnn_kernels(emul, name, rnn_dir):
     rep = parity.compare_with_expected(d, batch, res, rnn=True)
     rep.pop("final_path_elements")
     assert all(v == 0 for v in rep.values()), rep
+
+
+def test_compact_entry_rows_give_the_same_result(emul):
+    """jpp_b200_batch.node_entry_row / entry_rows (one row per distinct entry) against the inline form;
+    also through concat (row tables stacked, indices rebased) and select."""
+    d, model, cfg, batch = load_golden("default")
+    inline = run_emul(emul, model, cfg, batch)
+    compact = batch.compact_entries()
+    assert compact.node_entry is None and len(compact.entry_rows) < batch.num_nodes
+    assert compact.h2d_bytes() < batch.h2d_bytes()
+    got = run_emul(emul, model, cfg, compact)
+    assert got.node_beam.tobytes() == inline.node_beam.tobytes()
+    assert (got.node_patterns == inline.node_patterns).all()
+    ns = batch.num_sentences
+    parts = [batch.select(0, ns // 2).compact_entries(), batch.select(ns // 2, ns).compact_entries()]
+    again = abi.StagedBatch.concat(parts)
+    got2 = run_emul(emul, model, cfg, again)
+    assert got2.node_beam.tobytes() == inline.node_beam.tobytes()
+    dedup = again.compact_entries()
+    assert len(dedup.entry_rows) == len(compact.entry_rows)
+    got3 = run_emul(emul, model, cfg, dedup.select(1, ns - 1))
+    ref3 = run_emul(emul, model, cfg, batch.select(1, ns - 1))
+    assert got3.node_beam.tobytes() == ref3.node_beam.tobytes()
+    ora, _ = oracle_lib.oracle_score(model, cfg, compact)
+    assert ora.node_beam.tobytes() == inline.node_beam.tobytes()

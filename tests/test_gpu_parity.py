@@ -87,6 +87,34 @@ def test_batch_split_and_order_invariance():
         off += n
 
 
+def test_compact_entry_rows():
+    """Entry buffers sent as one row per distinct entry + a row index per node (ABI 2)."""
+    import dataclasses
+    from jumanpp_b200.scorer import LatticeScorer, ScorerError
+    d, model, cfg, batch = load_golden("default")
+    inline, _ = gpu_score(model, cfg, batch)
+    compact = batch.compact_entries()
+    got, _ = gpu_score(model, cfg, compact)
+    assert got.node_beam.tobytes() == inline.node_beam.tobytes()
+    assert np.array_equal(got.node_patterns, inline.node_patterns)
+    bad = dataclasses.replace(compact, node_entry_row=compact.node_entry_row.copy())
+    bad.node_entry_row[3] = len(compact.entry_rows) + 5
+    sc = LatticeScorer(model, cfg)
+    try:
+        with pytest.raises(ScorerError) as e:
+            sc.compute_scores(bad)
+        assert e.value.code == abi_mod().INVALID_PARAMETER
+        again = sc.compute_scores(compact)        # the handle stays usable
+        assert again.node_beam.tobytes() == inline.node_beam.tobytes()
+    finally:
+        sc.close()
+
+
+def abi_mod():
+    from jumanpp_b200 import abi
+    return abi
+
+
 def test_errors_are_reported_not_swallowed():
     from jumanpp_b200 import abi
     from jumanpp_b200.scorer import LatticeScorer, ScorerError
