@@ -190,7 +190,16 @@ def reference_arm(args, rank: int, world: int) -> None:
                                    f"whole Analyzer::analyze runs at {outs[-1]['analyze_sentences_per_s']:.0f} sentences/s"},
         "e2e": {"value": value, "unit": "sentences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit_result(line)
+
+
+RESULT_OUT = None
+
+
+def emit_result(line: dict) -> None:
+    out = RESULT_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def workload_config(args, wl) -> dict:
@@ -347,17 +356,18 @@ def product_arm(args, rank: int, world: int, local_rank: int) -> None:
             "gpu_launches": int(cnt["launches"]) * args.steps,
             "wall_ms_per_step_resident": 1000.0 * wall_s / args.steps,
             "stage_ms": {k: statistics.mean(x[k] for x in kms) for k in kms[0]},
-            "roofline": {"bound": "hbm", "kernel": "wavefront walk: k_w_gbeam + k_w_prescore + k_w_cutoff + k_w_score + k_w_rest per boundary index (n-gram hash + weight gather + beams)",
+            "roofline": {"bound": "hbm", "kernel": "wave loop: k_w_gbeam_warp + k_w_prescore + k_w_cutoff_group + k_w_items + k_w_final per boundary number (n-gram hash + weight gather + beams)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                          "algorithmic_bytes_per_launch": int(cnt["walk_bytes"]), "kernel_ms": walk_ms,
-                         "gathers_per_launch": int(cnt["walk_gathers"]), "traffic": traffic},
+                         "gathers_per_launch": int(cnt["walk_gathers"]),
+                         "gathers_issued_per_launch": int(cnt["walk_gathers_issued"]), "traffic": traffic},
             "work": {"sentences": int(total_sent), "nodes": int(counts[2].item()), "gathers": int(counts[1].item()),
                      "rnn_nodes": int(cnt["rnn_nodes"])},
         }
         if not args.no_cpu_baseline:
             line.update(cpu_baseline_leg(args, info, model, cfg, batch, workers[0], res))
-        print(json.dumps(line), flush=True)
+        emit_result(line)
     for wk in workers:
         wk.close()
     if dist:
@@ -432,6 +442,12 @@ def main() -> None:
     ap.add_argument("--inline-entries", action="store_true",
                     help="send one entry buffer per node (jpp_b200_batch.node_entry) instead of the compact row table")
     args = ap.parse_args()
+    # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version
+    # banner to stdout at init): keep the real stdout aside for the result and point fd 1 at stderr.
+    global RESULT_OUT
+    sys.stdout.flush()
+    RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -264,16 +264,21 @@ typedef struct jpp_b200_counters {
   uint64_t sentences;
   uint64_t boundaries;
   uint64_t nodes;
-  uint64_t gathers;        /* perceptron-table reads issued (4 B each)          */
+  uint64_t gathers;        /* perceptron-table reads of the reference algorithm
+                              (nU*R + c*R*(nB+nT) + K*(U*nB+(G-c)*nT)
+                              per boundary; 4 B each)                          */
   uint64_t algorithmic_bytes; /* A of BASELINE.md "Roofline accounting"           */
   uint64_t rnn_nodes;      /* prefix-tree contexts computed (2*H*H flop each)   */
   uint64_t rnn_scores;
-  uint64_t walk_gathers;   /* table reads of the beam-walk kernel alone         */
+  uint64_t walk_gathers;   /* the same for the wave loop alone (without T0)     */
   uint64_t walk_bytes;     /* algorithmic bytes of the beam-walk kernel alone   */
   uint64_t launches;       /* kernels launched by the last score call           */
   float kernel_ms[8];      /* per stage, CUDA events on the scoring stream:
                               0 T0, 1 beam walk, 2 rnn tree, 3 rnn contexts, 4 rnn
                               scores, 5 re-rank, 6 upload (H2D + index), 7 all scoring */
+  uint64_t walk_gathers_issued; /* table reads the wave loop really made: the bigram
+                              weights of (node, head element's t1) are read once
+                              and summed in both orders, so this is smaller   */
 } jpp_b200_counters;
 
 typedef struct jpp_b200_handle jpp_b200_handle;

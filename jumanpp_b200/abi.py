@@ -88,7 +88,8 @@ class Counters(C.Structure):
     _fields_ = [("sentences", C.c_uint64), ("boundaries", C.c_uint64), ("nodes", C.c_uint64),
                 ("gathers", C.c_uint64), ("algorithmic_bytes", C.c_uint64),
                 ("rnn_nodes", C.c_uint64), ("rnn_scores", C.c_uint64), ("walk_gathers", C.c_uint64),
-                ("walk_bytes", C.c_uint64), ("launches", C.c_uint64), ("kernel_ms", C.c_float * 8)]
+                ("walk_bytes", C.c_uint64), ("launches", C.c_uint64), ("kernel_ms", C.c_float * 8),
+                ("walk_gathers_issued", C.c_uint64)]
 
 
 NODE_INFO_DT = np.dtype([("entry_ptr", "<i4"), ("start", "<u2"), ("end", "<u2")])

@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(128) k_w_init(BatchView bv, ScoreCfg cfg) {
 
 __global__ void __launch_bounds__(128) k_w_gbeam(BatchView bv, ScoreCfg cfg, WaveView wv, u32 nActive, u32 bnd) {
   const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0) wv.selCount[0] = wv.selCount[1] = 0;  // consumed by k_w_cutoff, a later launch on the same stream
+  if (i == 0) wv.selCount[0] = wv.selCount[1] = wv.selCount[2] = 0;  // consumed by k_w_cutoff_group, a later launch on the same stream
   if (i < nActive) wave_gbeam(bv, cfg, wv, bv.sentOrder[i], bnd);
 }
 
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(128) k_w_gbeam(BatchView bv, ScoreCfg cfg, Wav
 template <int KB, int GW>
 __global__ void __launch_bounds__(128) k_w_gbeam_warp(BatchView bv, ScoreCfg cfg, WaveView wv, u32 nActive, u32 bnd) {
   const u32 tid = blockIdx.x * blockDim.x + threadIdx.x;
-  if (tid == 0) wv.selCount[0] = wv.selCount[1] = 0;
+  if (tid == 0) wv.selCount[0] = wv.selCount[1] = wv.selCount[2] = 0;
   const u32 w = tid / GW, lane = threadIdx.x & 31u, sub = lane % GW;
   if (w >= nActive) return;
   const unsigned gshift = lane - sub;
@@ -227,36 +227,203 @@ __global__ void __launch_bounds__(kCacheThreads) k_w_prescore(const __grid_const
     wave_prescore(ft, bv, cfg, wv, wl, wv.waveNodes[first + i]);
 }
 
-__global__ void __launch_bounds__(128) k_w_cutoff(const __grid_constant__ FeatTables ft, BatchView bv, ScoreCfg cfg,
-                                                 WaveView wv, u32 nActive, u32 bnd) {
-  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < nActive) wave_cutoff(ft, bv, cfg, wv, bv.sentOrder[i], bnd);
-}
-
-template <bool SMALL>
-__global__ void __launch_bounds__(kCacheThreads) k_w_score(const __grid_constant__ FeatTables ft, BatchView bv, ScoreCfg cfg,
-                                                        WaveView wv, const float* __restrict__ w) {
-  extern __shared__ __align__(16) unsigned long long cacheSlots[];
-  const WLoadCached wl = make_cache(w, cacheSlots);
-  const u32 n = wv.selCount[0];
-  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    if (SMALL) wave_score_node_small(ft, bv, cfg, wv, wl, i);
-    else wave_score_node(ft, bv, cfg, wv, wl, i);
+// W3, 8 lanes per sentence, 32 sentences per block (serial statement: wave_cutoff).  A boundary
+// has ~7 right nodes: lane r holds the cut score of node r and counts how many scores are larger
+// / equal by shuffles; when no run of equal scores straddles the cut that count IS the
+// nth_element selection.  When it does (or with more than 8 right nodes) lane 0 replays
+// std::nth_element exactly as the serial code.  List positions come from a block-wide prefix
+// over the 32 sentences and one atomic per block and list.
+__global__ void __launch_bounds__(256) k_w_cutoff_group(const __grid_constant__ FeatTables ft, BatchView bv, ScoreCfg cfg,
+                                                       WaveView wv, u32 nActive, u32 bnd) {
+  constexpr u32 GW = 8, SPB = 256 / GW;
+  static_assert(SPB == 32, "the block prefix below is one warp wide");
+  __shared__ u32 sSel[SPB], sBi[SPB], sTri[SPB], sBase[3];
+  __shared__ unsigned long long sCnt[3];
+  const u32 lane = threadIdx.x & 31u, sub = lane % GW, grp = threadIdx.x / GW;
+  const unsigned gshift = lane - sub;
+  const unsigned gmask = ((1u << GW) - 1u) << gshift;
+  const u32 sentIdx = blockIdx.x * SPB + grp;
+  if (threadIdx.x < 3) sCnt[threadIdx.x] = 0;
+  __syncthreads();
+  bool active = sentIdx < nActive;
+  u32 sent = 0, gB = 0, n0 = 0, R = 0, G = 0, U = 0, L = 0;
+  if (active) {
+    sent = bv.sentOrder[sentIdx];
+    const u32 b0 = bv.sentBndOff[sent];
+    const u32 nb = bv.sentBndOff[sent + 1] - b0;
+    if (bnd >= nb || nb <= 3) {
+      active = false;
+    } else {
+      gB = b0 + bnd;
+      n0 = bv.bndNodeOff[gB];
+      R = bv.bndNodeOff[gB + 1] - n0;
+      if (R == 0) active = false;
+    }
+  }
+  StepSizes z = step_sizes(cfg, R, 0);
+  if (active) {
+    G = wv.gCount[sent];
+    U = wv.uCount[sent];
+    L = bv.bndEndOff[gB + 1] - bv.bndEndOff[gB];
+    z = step_sizes(cfg, R, G);
+  }
+  // Selection as a bit per right node (boundaries of up to 64 nodes; beyond that lane 0 marks
+  // selPos in global memory as the serial code does).
+  constexpr u32 SM_R = 64;
+  __shared__ float sCut[SPB][SM_R];
+  __shared__ u32 sIdx[SPB][SM_R];
+  const bool bits = active && R <= SM_R;
+  unsigned long long selBits = 0;
+  u32 nsel = 0;
+  if (active) {
+    if (!(cfg.rcheck > 0 && R > z.toKeep)) {
+      if (bits) selBits = ~0ull;
+      else for (u32 r = sub; r < R; r += GW) bv.selPos[n0 + r] = 0;
+      nsel = R;
+    } else {
+      nsel = z.toKeep;
+      bool exact = true;  // std::nth_element has to be replayed
+      if (R <= GW) {
+        // rank count: when no run of equal scores straddles the cut it IS the selection
+        const bool valid = sub < R;
+        float v = 0;
+        if (valid) for (u32 j = 0; j < z.full; ++j) v += bv.pre[(size_t)j * bv.totalNodes + n0 + sub];
+        u32 greater = 0, eq = 0;
+        for (u32 j = 0; j < R; ++j) {
+          const float vj = __shfl_sync(gmask, v, j, GW);
+          if (vj > v) ++greater;
+          else if (!(v > vj)) ++eq;  // counts the lane itself
+        }
+        const bool sure = valid && greater + eq <= z.toKeep;
+        const bool out = valid && greater >= z.toKeep;
+        const unsigned amb = __ballot_sync(gmask, valid && !sure && !out) & gmask;
+        if (amb == 0) {
+          exact = false;
+          selBits = (unsigned long long)((__ballot_sync(gmask, sure) & gmask) >> gshift);
+        } else {
+          if (valid) { sCut[grp][sub] = v; sIdx[grp][sub] = sub; }
+        }
+      } else if (bits) {
+        for (u32 r = sub; r < R; r += GW) {
+          float c = 0;
+          for (u32 j = 0; j < z.full; ++j) c += bv.pre[(size_t)j * bv.totalNodes + n0 + r];
+          sCut[grp][r] = c;
+          sIdx[grp][r] = r;
+        }
+      }
+      if (exact && bits) {
+        __syncwarp(gmask);
+        u32 lo = 0, hi = 0;
+        if (sub == 0) {
+          em_std_nth_element(sIdx[grp], (long)z.toKeep, (long)R, ScoreCmp{sCut[grp]});
+          for (u32 k = 0; k < z.toKeep; ++k) {
+            const u32 r = sIdx[grp][k];
+            if (r < 32) lo |= 1u << r; else hi |= 1u << (r - 32);
+          }
+        }
+        lo = __shfl_sync(gmask, lo, 0, GW);
+        hi = __shfl_sync(gmask, hi, 0, GW);
+        selBits = ((unsigned long long)hi << 32) | lo;
+      } else if (exact) {
+        if (sub == 0) {
+          u32* idx = bv.cutIdx + n0;
+          float* cut = bv.cut + n0;
+          for (u32 r = 0; r < R; ++r) {
+            float c = 0;
+            for (u32 j = 0; j < z.full; ++j) c += bv.pre[(size_t)j * bv.totalNodes + n0 + r];
+            cut[r] = c;
+            idx[r] = r;
+            bv.selPos[n0 + r] = NOT_SELECTED;
+          }
+          em_std_nth_element(idx, (long)z.toKeep, (long)R, ScoreCmp{cut});
+          for (u32 k = 0; k < z.toKeep; ++k) bv.selPos[n0 + idx[k]] = 0;
+        }
+        __syncwarp(gmask);
+      }
+    }
+  }
+  const bool scoreTail = active && z.remaining > 0 && G > 0;
+  const u32 u0 = first_bigram_item(cfg);
+  const u32 biPer = scoreTail && U > u0 ? U - u0 : 0u;
+  const u32 triPer = scoreTail ? z.remaining : 0u;
+  if (sub == 0) {
+    sSel[grp] = nsel;
+    sBi[grp] = nsel * biPer;
+    sTri[grp] = nsel * triPer;
+    if (active && bv.counters) {
+      unsigned long long g = 0, sb = 0, gi = 0;
+      step_counters(ft, cfg, z, R, L, G, U, nsel, g, sb, gi);
+      atomicAdd(&sCnt[0], g);
+      atomicAdd(&sCnt[1], sb);
+      atomicAdd(&sCnt[2], gi);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    u32 v[3] = {sSel[lane], sBi[lane], sTri[lane]};
+    u32 inc[3] = {v[0], v[1], v[2]};
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const u32 t = __shfl_up_sync(0xffffffffu, inc[q], d);
+        if ((int)lane >= d) inc[q] += t;
+      }
+    }
+    if (lane == 31) {
+      sBase[0] = inc[0] ? atomicAdd(wv.selCount + 0, inc[0]) : 0u;
+      sBase[1] = inc[1] ? atomicAdd(wv.selCount + 1, inc[1]) : 0u;
+      sBase[2] = inc[2] ? atomicAdd(wv.selCount + 2, inc[2]) : 0u;
+    }
+    sSel[lane] = inc[0] - v[0];
+    sBi[lane] = inc[1] - v[1];
+    sTri[lane] = inc[2] - v[2];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && bv.counters && (sCnt[0] | sCnt[1])) {
+    atomicAdd(bv.counters + 0, sCnt[0]);
+    atomicAdd(bv.counters + 1, sCnt[1]);
+    atomicAdd(bv.counters + 2, sCnt[2]);
+  }
+  if (!active) return;
+  const u32 base = sBase[0] + sSel[grp], biBase = sBase[1] + sBi[grp], triBase = sBase[2] + sTri[grp];
+  u32 run = 0;
+  for (u32 r0 = 0; r0 < R; r0 += GW) {
+    const u32 r = r0 + sub;
+    const bool valid = r < R;
+    const bool sel = valid && (bits ? ((selBits >> r) & 1ull) != 0 : bv.selPos[n0 + r] != NOT_SELECTED);
+    const unsigned m = (__ballot_sync(gmask, sel) & gmask) >> gshift;
+    if (sel) {
+      const u32 k = run + __popc(m & ((1u << sub) - 1u));
+      const u32 pos = base + k;
+      bv.selPos[n0 + r] = pos;
+      if (scoreTail)
+        emit_items(bv, cfg, wv, sent, z, G, U, n0 + r, pos, wv.biItems + biBase + (size_t)k * biPer,
+                   wv.triItems + triBase + (size_t)k * triPer);
+    } else if (valid) {
+      bv.selPos[n0 + r] = NOT_SELECTED;
+    }
+    run += __popc(m);
   }
 }
 
-__global__ void __launch_bounds__(kCacheThreads) k_w_bigram(const __grid_constant__ FeatTables ft, BatchView bv, ScoreCfg cfg,
-                                                         WaveView wv, const float* __restrict__ w) {
+// W4: bigram items first, trigram items after them; one 16-byte item per thread
+__global__ void __launch_bounds__(kCacheThreads) k_w_items(const __grid_constant__ FeatTables ft, BatchView bv, WaveView wv,
+                                                        const float* __restrict__ w) {
   extern __shared__ __align__(16) unsigned long long cacheSlots[];
   const WLoadCached wl = make_cache(w, cacheSlots);
-  const u32 n = wv.selCount[1];
-  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-    wave_score_bigram(ft, bv, cfg, wv, wl, wv.itemList[i]);
+  const u32 n1 = wv.selCount[1], n2 = wv.selCount[2];
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n1 + n2; i += gridDim.x * blockDim.x) {
+    if (i < n1) wave_item_bigram(ft, bv, wv, wl, wv.biItems[i]);
+    else wave_item_trigram(ft, bv, wv, wl, wv.triItems[i - n1]);
+  }
 }
 
-__global__ void __launch_bounds__(128) k_w_rest(BatchView bv, ScoreCfg cfg, WaveView wv, u32 first, u32 count) {
+// W5: thread per right node of the wave
+template <bool SMALL>
+__global__ void __launch_bounds__(128) k_w_final(BatchView bv, ScoreCfg cfg, WaveView wv, u32 first, u32 count) {
   const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < count) wave_rest_node(bv, cfg, wv, wv.waveNodes[first + i]);
+  if (i < count) wave_final_node<SMALL>(bv, cfg, wv, wv.waveNodes[first + i]);
 }
 
 // full-beam mode: the whole boundary step of a right node in one thread
@@ -640,10 +807,10 @@ struct jpp_b200_handle {
   int smCount = 148;
   // batch buffers
   enum { B_SBO, B_SCO, B_BNO, B_BEO, B_INFO, B_ENTRY, B_ENTRYROW, B_PH, B_RNNID, B_ENDS, B_CPS, B_NODEBND, B_BNDSENT, B_ENDNODE,
-         B_ORDER, B_BEAM, B_BSCORES, B_PATS, B_T0, B_PRE, B_CUT, B_CUTIDX, B_SELK, B_GBNODE, B_GBSLOT, B_GBLBND, B_GBCNT,
+         B_ORDER, B_BEAM, B_BSCORES, B_PATS, B_T0, B_PRE, B_CUT, B_CUTIDX, B_SELPOS, B_BI0, B_GBNODE, B_GBSLOT, B_GBLBND, B_GBCNT,
          B_EOSG, B_EOSLOC, B_EOSRNN, B_COUNTERS, B_WORK,
          B_PATHLEN, B_PATHNODES,
-         W_GBKEY, W_GBLNODE, W_GBT2, W_GBT1IDX, W_T1NODE, W_GCNT, W_UCNT, W_SELLIST, W_SELCNT, W_ITEMS, W_SCB, W_NODES, W_OFF, W_CURSOR,
+         W_GBKEY, W_GBLNODE, W_GBT2, W_GBT1IDX, W_T1NODE, W_GCNT, W_UCNT, W_SELCNT, W_BIITEMS, W_TRIITEMS, W_SCB, W_TRI, W_NODES, W_OFF, W_CURSOR,
          R_OFF, R_ID, R_PREV, R_NEXT, R_BND, R_LEN, R_DEPTH, R_HASH, R_RNCNT, R_RSNODE, R_RSSLOT, R_RSEOSG, R_RSRNODE,
          R_RSCNT, R_CONN, R_BNDHEAD, R_CTX, R_CHNODE, R_CHSLOT, R_CHBND, R_SCLIST, R_SCTOTAL, R_LVLCNT, R_LVLOFF, R_LVLLIST, R_CTXOFF, R_RNSENT, R_CURSOR, R_CUBTMP,
          NUM_BUFS };
@@ -777,9 +944,7 @@ jpp_b200_status jpp_b200_create(const jpp_b200_model* model, const jpp_b200_conf
   h->smCount = prop.multiProcessorCount;
   CREATE_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CREATE_CHECK(cudaFuncSetAttribute(k_w_prescore, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kCacheSlots * 8)));
-  CREATE_CHECK(cudaFuncSetAttribute(k_w_score<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kCacheSlots * 8)));
-  CREATE_CHECK(cudaFuncSetAttribute(k_w_score<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kCacheSlots * 8)));
-  CREATE_CHECK(cudaFuncSetAttribute(k_w_bigram, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kCacheSlots * 8)));
+  CREATE_CHECK(cudaFuncSetAttribute(k_w_items, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kCacheSlots * 8)));
   for (auto& e : h->ev) CREATE_CHECK(cudaEventCreate(&e));
   CREATE_CHECK(cudaMalloc(&h->dFt, sizeof(FeatTables)));
   CREATE_CHECK(cudaMemcpyAsync(h->dFt, &h->hm.ft, sizeof(FeatTables), cudaMemcpyHostToDevice, h->stream));
@@ -917,7 +1082,7 @@ jpp_b200_status jpp_b200_upload_batch(jpp_b200_handle* h, const jpp_b200_batch* 
   ENSURE(B_PATS, (size_t)NN * SP * 8);
   ENSURE(B_T0, (size_t)NN * 4);
   ENSURE(B_PRE, (size_t)NN * RC * 4);
-  ENSURE(B_CUT, (size_t)NN * 4); ENSURE(B_CUTIDX, (size_t)NN * 4); ENSURE(B_SELK, (size_t)NN * 2);
+  ENSURE(B_CUT, (size_t)NN * 4); ENSURE(B_CUTIDX, (size_t)NN * 4); ENSURE(B_SELPOS, (size_t)NN * 4); ENSURE(B_BI0, (size_t)NN * 4);
   ENSURE(B_GBNODE, (size_t)NB * G * 4); ENSURE(B_GBSLOT, (size_t)NB * G * 2); ENSURE(B_GBLBND, (size_t)NB * G * 2);
   ENSURE(B_GBCNT, (size_t)NB);
   ENSURE(B_EOSG, (size_t)NS * G * 8); ENSURE(B_EOSLOC, (size_t)NS * G * 4); ENSURE(B_EOSRNN, (size_t)NS * G * 4);
@@ -959,7 +1124,7 @@ jpp_b200_status jpp_b200_upload_batch(jpp_b200_handle* h, const jpp_b200_batch* 
   // for the walk kernels (profiles/README.md r1i): rows of left / t2 nodes are read whole, one line each.
   bv.patNodeStride = SP; bv.patPStride = 1;
   bv.t0 = P(B_T0, float); bv.pre = P(B_PRE, float); bv.cut = P(B_CUT, float); bv.cutIdx = P(B_CUTIDX, u32);
-  bv.selK = P(B_SELK, u16); bv.gbNode = P(B_GBNODE, u32); bv.gbSlot = P(B_GBSLOT, u16); bv.gbLeftBnd = P(B_GBLBND, u16);
+  bv.selPos = P(B_SELPOS, u32); bv.bi0 = P(B_BI0, float); bv.gbNode = P(B_GBNODE, u32); bv.gbSlot = P(B_GBSLOT, u16); bv.gbLeftBnd = P(B_GBLBND, u16);
   bv.gbCount = P(B_GBCNT, u8); bv.eosGbeam = P(B_EOSG, u64); bv.eosLocal = P(B_EOSLOC, float); bv.eosRnn = P(B_EOSRNN, float);
   bv.counters = P(B_COUNTERS, unsigned long long);
   k_boundary_index<<<(NS + 127) / 128, 128, 0, st>>>(bv);
@@ -969,12 +1134,14 @@ jpp_b200_status jpp_b200_upload_batch(jpp_b200_handle* h, const jpp_b200_batch* 
     // wave index (nodes grouped by local boundary) + per-sentence wave state
     ENSURE(W_GBKEY, (size_t)NS * G * 8); ENSURE(W_GBLNODE, (size_t)NS * G * 4); ENSURE(W_GBT2, (size_t)NS * G * 4);
     ENSURE(W_GBT1IDX, (size_t)NS * G); ENSURE(W_T1NODE, (size_t)NS * G * 4); ENSURE(W_GCNT, NS); ENSURE(W_UCNT, NS);
-    ENSURE(W_SELLIST, (size_t)NN * 4 + 16); ENSURE(W_SELCNT, 16); ENSURE(W_NODES, (size_t)NN * 4 + 16);
+    ENSURE(W_SELCNT, 16); ENSURE(W_NODES, (size_t)NN * 4 + 16);
     {
       // selected right nodes of one wave: at most right_gbeam_size per active sentence (makeT0cutoffBeam)
       size_t selCap = NN;
       if (h->cfg.rcheck > 0) selCap = std::min<size_t>(NN, (size_t)NS * (u32)h->cfg.rbeam);
-      ENSURE(W_ITEMS, (selCap * G + 4) * 4); ENSURE(W_SCB, (selCap * G + 4) * 4);
+      if (selCap * G >= 0x7FFFFFFFull) return fail(h, JPP_B200_INVALID_PARAMETER, "batch too large for the item lists; split it");
+      ENSURE(W_BIITEMS, (selCap * G + 4) * sizeof(WaveItem)); ENSURE(W_TRIITEMS, (selCap * G + 4) * sizeof(WaveItem));
+      ENSURE(W_SCB, (selCap * G + 4) * 4); ENSURE(W_TRI, (selCap * G + 4) * 8);
     }
     ENSURE(W_OFF, (size_t)(maxNb + 4) * 4); ENSURE(W_CURSOR, (size_t)(maxNb + 4) * 4 * 2);
     u32* cnt = P(W_CURSOR, u32);
@@ -999,8 +1166,8 @@ jpp_b200_status jpp_b200_upload_batch(jpp_b200_handle* h, const jpp_b200_batch* 
     WaveView& wv = h->wv;
     wv = WaveView{};
     wv.gbKey = P(W_GBKEY, u64); wv.gbLnode = P(W_GBLNODE, u32); wv.gbT2node = P(W_GBT2, u32); wv.gbT1idx = P(W_GBT1IDX, u8);
-    wv.t1node = P(W_T1NODE, u32); wv.gCount = P(W_GCNT, u8); wv.uCount = P(W_UCNT, u8); wv.selList = P(W_SELLIST, u32);
-    wv.selCount = P(W_SELCNT, u32); wv.itemList = P(W_ITEMS, u32); wv.scb = P(W_SCB, float); wv.waveNodes = P(W_NODES, u32); wv.waveNodeOff = P(W_OFF, u32);
+    wv.t1node = P(W_T1NODE, u32); wv.gCount = P(W_GCNT, u8); wv.uCount = P(W_UCNT, u8);
+    wv.selCount = P(W_SELCNT, u32); wv.biItems = P(W_BIITEMS, WaveItem); wv.triItems = P(W_TRIITEMS, WaveItem); wv.scb = P(W_SCB, float); wv.tri = P(W_TRI, float); wv.waveNodes = P(W_NODES, u32); wv.waveNodeOff = P(W_OFF, u32);
   }
   if (h->hasRnn) {
     ENSURE(R_OFF, (size_t)(NS + 1) * 4);
@@ -1054,8 +1221,8 @@ jpp_b200_status jpp_b200_score_resident(jpp_b200_handle* h) {
     static const bool serialGbeam = getenv("JPP_B200_SERIAL_GBEAM") != nullptr;  // A/B switch for W1
     static WaveProfile prof;
     prof.on = profileOn;
-    enum { K_GBEAM, K_PRESCORE, K_CUTOFF, K_BIGRAM, K_SCORE, K_REST, K_FULL, K_KINDS };
-    static const char* const kindNames[K_KINDS] = {"k_w_gbeam", "k_w_prescore", "k_w_cutoff", "k_w_bigram", "k_w_score", "k_w_rest", "k_w_full"};
+    enum { K_GBEAM, K_PRESCORE, K_CUTOFF, K_ITEMS, K_FINAL, K_FULL, K_KINDS };
+    static const char* const kindNames[K_KINDS] = {"k_w_gbeam", "k_w_prescore", "k_w_cutoff", "k_w_items", "k_w_final", "k_w_full"};
     k_w_init<<<(NS + 127) / 128, 128, 0, st>>>(bv, cfg);
     u32 launches = 1;
     for (u32 bnd = 2; bnd < h->maxNb; ++bnd) {
@@ -1083,26 +1250,20 @@ jpp_b200_status jpp_b200_score_resident(jpp_b200_handle* h) {
         prof.end(st);
       }
       prof.begin(st, K_CUTOFF);
-      k_w_cutoff<<<(nAct + 127) / 128, 128, 0, st>>>(ft, bv, cfg, wv, nAct, bnd);
+      k_w_cutoff_group<<<(nAct + 31) / 32, 256, 0, st>>>(ft, bv, cfg, wv, nAct, bnd);
       prof.end(st);
       u32 selBound = count;
       if (cfg.rcheck > 0) selBound = std::min<u64>(count, (u64)nAct * (u32)cfg.rbeam);
+      // at most (G - 1) + G items per selected node; a fraction of that in practice
       const u32 iblocks = std::min<u32>((u32)(((u64)selBound * (u32)cfg.gbeam + kCacheThreads - 1) / kCacheThreads), (u32)h->smCount);
-      prof.begin(st, K_BIGRAM);
-      k_w_bigram<<<std::max(1u, iblocks), kCacheThreads, kCacheSlots * 8, st>>>(ft, bv, cfg, wv, h->dWeights);
+      prof.begin(st, K_ITEMS);
+      k_w_items<<<std::max(1u, iblocks), kCacheThreads, kCacheSlots * 8, st>>>(ft, bv, wv, h->dWeights);
       prof.end(st);
-      const u32 blocks = std::min<u32>((selBound + kCacheThreads - 1) / kCacheThreads, (u32)h->smCount);
-      prof.begin(st, K_SCORE);
-      if (small_gbeam_ok(cfg)) k_w_score<true><<<std::max(1u, blocks), kCacheThreads, kCacheSlots * 8, st>>>(ft, bv, cfg, wv, h->dWeights);
-      else k_w_score<false><<<std::max(1u, blocks), kCacheThreads, kCacheSlots * 8, st>>>(ft, bv, cfg, wv, h->dWeights);
+      prof.begin(st, K_FINAL);
+      if (small_gbeam_ok(cfg)) k_w_final<true><<<(count + 127) / 128, 128, 0, st>>>(bv, cfg, wv, first, count);
+      else k_w_final<false><<<(count + 127) / 128, 128, 0, st>>>(bv, cfg, wv, first, count);
       prof.end(st);
-      launches += 4;
-      if (cfg.rcheck > 0) {
-        prof.begin(st, K_REST);
-        k_w_rest<<<(count + 127) / 128, 128, 0, st>>>(bv, cfg, wv, first, count);
-        prof.end(st);
-        launches += 2;
-      }
+      launches += 4 + (cfg.rcheck > 0 ? 1 : 0);
     }
     if (prof.on) {
       cudaStreamSynchronize(st);
@@ -1189,6 +1350,7 @@ jpp_b200_status jpp_b200_score_resident(jpp_b200_handle* h) {
   const unsigned long long t0Nodes = (unsigned long long)NN - 2ull * NS;
   c.gathers = dc[0] + t0Nodes * h->hm.ft.nUni;
   c.walk_gathers = dc[0];
+  c.walk_gathers_issued = h->cfg.gbeam > 0 ? dc[2] : dc[0];
   c.walk_bytes = 4ull * dc[0] + dc[1];
   c.launches = 2 + h->walkLaunches + (h->hasRnn ? (12ull + h->maxNb) : 0ull);
   // BASELINE.md roofline accounting: 4 B per gather + streaming terms

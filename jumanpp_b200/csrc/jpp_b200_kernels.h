@@ -129,7 +129,8 @@ struct BatchView {
   float* pre;        // [rcheck][nodes]  T0 prescores
   float* cut;        // [nodes]          cutoff score
   u32* cutIdx;       // [nodes]          index scratch for nth_element emulation
-  u16* selK;         // [nodes]          chunk-local index of a selected node / 0xFFFF
+  u32* selPos;       // [nodes]          position in the wave's list of selected nodes / NOT_SELECTED
+  float* bi0;        // [nodes]          applyBiTri bigram sum against unique t1 0 (written by W2)
   u32* gbNode;       // [boundaries][G]  global beam elements (left node)
   u16* gbSlot;       // [boundaries][G]
   u16* gbLeftBnd;    // [boundaries][G]  sentence-local boundary of the left node
@@ -337,17 +338,18 @@ JPP_HD void t0_node(const FeatTables& ft, const BatchView& bv, const WL& wl, u32
   const u32 nv = lastRow ? 4u : ft.uniVars;
   float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
   const u32 nU = ft.nUni, mask = ft.mask;
-  for (u32 u0 = 0; u0 < nU; u0 += 4) {
-    float wv[4];
-    u32 id[4];
+  constexpr u32 T0_LB = 8;  // table reads in flight per thread
+  for (u32 u0 = 0; u0 < nU; u0 += T0_LB) {
+    float wv[T0_LB];
+    u32 id[T0_LB];
 #pragma unroll
-    for (u32 j = 0; j < 4; ++j) {
+    for (u32 j = 0; j < T0_LB; ++j) {
       const u32 u = u0 + j < nU ? u0 + j : nU - 1;
       id[j] = (u32)mix(ft.uniState[u], pat[ft.uniT0[u]]) & mask;
     }
     wl.get(id, wv);
 #pragma unroll
-    for (u32 j = 0; j < 4; ++j) {
+    for (u32 j = 0; j < T0_LB; ++j) {
       const u32 u = u0 + j;
       if (u < nU) {
         const u32 a = u % nv;
@@ -618,8 +620,9 @@ JPP_HD int beam_order(u32* idx, int n, const float* totals, int maxBeam) {
 //   W1 wave_gbeam      thread per sentence      makeGlobalBeam, dedupT1, gatherT2 ids
 //   W2 wave_prescore   thread per right node    T0 + bigram + trigram vs the head elements
 //   W3 wave_cutoff     thread per sentence      makeT0cutoffBeam -> list of selected nodes
-//   W4 wave_score_node thread per selected node applyBiTri vs the whole global beam, beam
-//   W5 wave_rest_node  thread per other node    beam of the head elements only
+//   W4 wave_item_*     thread per (selected node, unique t1) / (selected node, gbeam element)
+//                                               bigram / trigram part of applyBiTri
+//   W5 wave_final_node thread per right node    connection scores, makeT0Beam, beam row
 // Threads of one warp run the same feature loop in lockstep, so the feature
 // tables (kernel parameter -> constant bank) are broadcast reads, the weight
 // gathers of a warp are 32 independent requests, and no lane idles because a
@@ -635,9 +638,11 @@ struct WaveView {
   u8* gCount;      // [NS]
   u8* uCount;      // [NS]
   u32* selList;    // [cap]    selected right nodes of the wave (global node ids)
-  u32* selCount;   // [2]      [0] selected nodes, [1] bigram items
-  u32* itemList;   // [cap*G]  (position in selList) << 5 | index into the unique-t1 list
-  float* scb;      // [cap*G]  bigram part of applyBiTri per (selected node, unique t1)
+  u32* selCount;   // [3]      [0] selected nodes, [1] bigram items, [2] trigram items
+  struct WaveItem* biItems;   // [cap*G]
+  struct WaveItem* triItems;  // [cap*G]
+  float* scb;      // [cap*G]     bigram part of applyBiTri per (selected node, unique t1)
+  float* tri;      // [cap*G][2]  trigram accumulators per (selected node, global beam element)
   const u32* waveNodes;    // [NN] node ids grouped by local boundary index
   const u32* waveNodeOff;  // [maxNb+1]
 };
@@ -897,19 +902,70 @@ JPP_HD void wave_gbeam(const BatchView& bv, const ScoreCfg& cfg, const WaveView&
   wv.uCount[sent] = (u8)U;
 }
 
+// Item of the W4 kernel: one (selected right node, left context) pair, ids resolved by W3 so
+// that the item thread starts gathering after a single 16-byte load.
+//   bigram item:  a = right node, b = unique t1 node,            slot = pos * G + u
+//   trigram item: a = right node, b = t1 node,  c = t2 node,     slot = pos * G + g
+// bit 31 of `slot` = the row is the last one of its loop (goes through Unrolled4).
+struct alignas(16) WaveItem {
+  u32 a, b, c, slot;
+};
+constexpr u32 ITEM_LAST = 0x80000000u;
+constexpr u32 NOT_SELECTED = 0xFFFFFFFFu;
+
+// first unique-t1 index that needs a bigram item: with the right check on, W2 has already
+// gathered the bigram weights of (node, t1 of the head element) -- unique t1 number 0
+JPP_HD u32 first_bigram_item(const ScoreCfg& cfg) { return cfg.rcheck > 0 ? 1u : 0u; }
+
+// Three sums over ONE pass of gathers: NV accumulators (generated applyBiStep2 rows),
+// the r1/r2 pair of applyBiTriFullKernel, and computeUnrolled4RawPerceptron.
+template <int NV, typename WL, typename IdxFn>
+JPP_HD void gsum_triple(const WL& wl, u32 n, IdxFn idxOf, float& sumNV, float& sumPair, float& sum4) {
+  constexpr int LB = 8;
+  float a[NV], c[2], b[4];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) a[j] = 0.0f;
+  c[0] = c[1] = 0.0f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) b[j] = 0.0f;
+  for (u32 f = 0; f < n; f += LB) {
+    u32 id[LB];
+    float x[LB];
+#pragma unroll
+    for (int j = 0; j < LB; ++j) id[j] = idxOf(f + j < n ? f + j : n - 1);
+    wl.get(id, x);
+#pragma unroll
+    for (int j = 0; j < LB; ++j) {
+      if (f + j < n) {  // f is a multiple of 8: accumulator of feature f + j is j % NV / j % 2 / j % 4
+        a[j % NV] += x[j];
+        c[j % 2] += x[j];
+        b[j % 4] += x[j];
+      }
+    }
+  }
+  sumNV = a[0];
+#pragma unroll
+  for (int j = 1; j < NV; ++j) sumNV += a[j];
+  sumPair = c[0] + c[1];
+  sum4 = ((b[0] + b[1]) + b[2]) + b[3];
+}
+
 // W2: computeT0Prescores (score_processor.cc:497-511) for one right node:
 // T0 + bigrams against t1 of head element i + trigrams (generated applyBiStep2 /
 // applyTriStep3: biVars / triVars accumulators, last row of the boundary through
-// computeUnrolled4RawPerceptron; partial_ngram_feature_codegen.cc:13-153)
+// computeUnrolled4RawPerceptron; partial_ngram_feature_codegen.cc:13-153).
+// The bigram weights of (node, t1 of head element 0) are the ones applyBiTri needs again for
+// unique t1 number 0, only summed in another order: that sum is produced from the same
+// gathers and kept in bi0[node], so W4 has no item for it.
 template <typename WL>
 JPP_HD void wave_prescore(const FeatTables& ft, const BatchView& bv, const ScoreCfg& cfg, const WaveView& wv,
                           const WL& wl, u32 node) {
   const u32 gB = bv.nodeBnd[node];
   const u32 sent = bv.bndSent[gB];
-  const u32 G = wv.gCount[sent];
+  const u32 G = wv.gCount[sent], U = wv.uCount[sent];
   const u32 theMax = (u32)cfg.rcheck < G ? (u32)cfg.rcheck : G;
   if (theMax == 0) return;
-  const u32 GMAX = (u32)cfg.gbeam, SP = ft.nStored, mask = ft.mask;
+  const u32 GMAX = (u32)cfg.gbeam, mask = ft.mask;
   const bool lastRow = (node + 1 == bv.bndNodeOff[gB + 1]);
   const PatRow P = pat_row(bv, node);
   const float t0 = bv.t0[node];
@@ -921,15 +977,85 @@ JPP_HD void wave_prescore(const FeatTables& ft, const BatchView& bv, const Score
       return (u32)mix(mix(mix(ft.triState[f], P[ft.triT0[f]]), t1[ft.triT1[f]]), t2[ft.triT2[f]]) & mask;
     };
     float sc = t0;
-    sc += gsum_row(wl, ft.nBi, ft.biVars, biIdx, lastRow);
+    if (i == 0) {
+      float sNV, sPair, s4;
+      switch (ft.biVars) {
+        case 8: gsum_triple<8>(wl, ft.nBi, biIdx, sNV, sPair, s4); break;
+        case 4: gsum_triple<4>(wl, ft.nBi, biIdx, sNV, sPair, s4); break;
+        case 2: gsum_triple<2>(wl, ft.nBi, biIdx, sNV, sPair, s4); break;
+        default: gsum_triple<1>(wl, ft.nBi, biIdx, sNV, sPair, s4); break;
+      }
+      sc += lastRow ? s4 : sNV;
+      bv.bi0[node] = (U == 1) ? s4 : sPair;  // applyBiTriFullKernel row of unique t1 0
+    } else {
+      sc += gsum_row(wl, ft.nBi, ft.biVars, biIdx, lastRow);
+    }
     sc += gsum_row(wl, ft.nTri, ft.triVars, triIdx, lastRow);
     bv.pre[(size_t)i * bv.totalNodes + node] = sc;
   }
 }
 
-// W3: makeT0cutoffBeam (score_processor.cc:471-495) -- exact std::nth_element
-// replay -- and the work counters of the boundary.  Selected nodes are appended
-// to the wave's list.
+// Sizes of one boundary step (fullBeamApplySize, score_processor.cc:299-301, and makeT0cutoffBeam)
+struct StepSizes {
+  u32 full, toKeep, remaining, theMax;
+};
+JPP_HD StepSizes step_sizes(const ScoreCfg& cfg, u32 R, u32 G) {
+  StepSizes z;
+  z.full = 0; z.toKeep = R; z.remaining = G; z.theMax = 0;
+  if (cfg.rcheck > 0) {
+    z.full = (u32)cfg.rcheck;
+    if (R < z.full) z.full = R;
+    if (G < z.full) z.full = G;
+    z.toKeep = (u32)cfg.rbeam < R ? (u32)cfg.rbeam : R;
+    z.remaining = G - z.full;
+    z.theMax = (u32)cfg.rcheck < G ? (u32)cfg.rcheck : G;
+  }
+  return z;
+}
+
+// work counters of one boundary step (DESIGN.md "roofline accounting"): `gathers` is the
+// reference algorithm's figure, `issued` what the kernels really read
+JPP_HD void step_counters(const FeatTables& ft, const ScoreCfg& cfg, const StepSizes& z, u32 R, u32 L, u32 G, u32 U, u32 nsel,
+                          unsigned long long& gathers, unsigned long long& streamBytes, unsigned long long& issued) {
+  const bool scoreTail = z.remaining > 0 && G > 0;
+  gathers = (unsigned long long)z.theMax * R * (ft.nBi + ft.nTri);
+  issued = gathers;
+  if (scoreTail) {
+    const u32 biRows = U - (first_bigram_item(cfg) < U ? first_bigram_item(cfg) : U);
+    gathers += (unsigned long long)nsel * ((unsigned long long)U * ft.nBi + (unsigned long long)z.remaining * ft.nTri);
+    issued += (unsigned long long)nsel * ((unsigned long long)biRows * ft.nBi + (unsigned long long)z.remaining * ft.nTri);
+  }
+  streamBytes = 8ull * L * (u32)cfg.beam + 8ull * ft.nStored * ((unsigned long long)R + U + G) + 4ull * L +
+                (8ull + 4ull * cfg.S) * R * (u32)cfg.beam;
+}
+
+// items of one selected node (position `pos` in the wave's list)
+JPP_HD void emit_items(const BatchView& bv, const ScoreCfg& cfg, const WaveView& wv, u32 sent, const StepSizes& z, u32 G, u32 U,
+                       u32 node, u32 pos, WaveItem* bi, WaveItem* tri) {
+  const u32 GMAX = (u32)cfg.gbeam;
+  const u32* t1node = wv.t1node + (size_t)sent * GMAX;
+  const u8* t1idx = wv.gbT1idx + (size_t)sent * GMAX;
+  const u32* gbT2 = wv.gbT2node + (size_t)sent * GMAX;
+  const u32 u0 = first_bigram_item(cfg);
+  for (u32 u = u0; u < U; ++u) {
+    WaveItem it;
+    it.a = node; it.b = t1node[u]; it.c = 0;
+    it.slot = (pos * GMAX + u) | (u + 1 == U ? ITEM_LAST : 0u);
+    bi[u - u0] = it;
+  }
+  for (u32 g = z.full; g < G; ++g) {
+    WaveItem it;
+    it.a = node; it.b = t1node[t1idx[g]]; it.c = gbT2[g];
+    it.slot = (pos * GMAX + g) | (g + 1 == G ? ITEM_LAST : 0u);
+    tri[g - z.full] = it;
+  }
+  (void)bv;
+}
+
+// W3 (serial statement; the GPU runs k_w_cutoff_group, 8 lanes per sentence, which must
+// produce the same selection): makeT0cutoffBeam (score_processor.cc:471-495) -- exact
+// std::nth_element replay -- the work counters of the boundary, the list of selected nodes
+// and their W4 items.
 JPP_HD void wave_cutoff(const FeatTables& ft, const BatchView& bv, const ScoreCfg& cfg, const WaveView& wv, u32 sent, u32 bnd) {
   const u32 b0 = bv.sentBndOff[sent];
   const u32 nb = bv.sentBndOff[sent + 1] - b0;
@@ -939,290 +1065,184 @@ JPP_HD void wave_cutoff(const FeatTables& ft, const BatchView& bv, const ScoreCf
   const u32 R = bv.bndNodeOff[gB + 1] - n0;
   if (R == 0) return;
   const u32 G = wv.gCount[sent], U = wv.uCount[sent];
-  const u32 B = (u32)cfg.beam, SP = ft.nStored;
   const u32 L = bv.bndEndOff[gB + 1] - bv.bndEndOff[gB];
-  u32 full = 0, toKeep = R, remaining = G, theMax = 0;
-  if (cfg.rcheck > 0) {
-    full = (u32)cfg.rcheck;
-    if (R < full) full = R;
-    if (G < full) full = G;  // fullBeamApplySize, :299-301
-    toKeep = (u32)cfg.rbeam < R ? (u32)cfg.rbeam : R;
-    remaining = G - full;
-    theMax = (u32)cfg.rcheck < G ? (u32)cfg.rcheck : G;
-  }
-  if (cfg.rcheck > 0 && R > toKeep) {
+  const StepSizes z = step_sizes(cfg, R, G);
+  if (cfg.rcheck > 0 && R > z.toKeep) {
     u32* idx = bv.cutIdx + n0;
     float* cut = bv.cut + n0;
     for (u32 r = 0; r < R; ++r) {
       float v = 0;
-      for (u32 j = 0; j < full; ++j) v += bv.pre[(size_t)j * bv.totalNodes + n0 + r];
+      for (u32 j = 0; j < z.full; ++j) v += bv.pre[(size_t)j * bv.totalNodes + n0 + r];
       cut[r] = v;
       idx[r] = r;
-      bv.selK[n0 + r] = 0xFFFFu;
+      bv.selPos[n0 + r] = NOT_SELECTED;
     }
-    em_std_nth_element(idx, (long)toKeep, (long)R, ScoreCmp{cut});
-    for (u32 k = 0; k < toKeep; ++k) bv.selK[n0 + idx[k]] = 1;
+    em_std_nth_element(idx, (long)z.toKeep, (long)R, ScoreCmp{cut});
+    for (u32 k = 0; k < z.toKeep; ++k) bv.selPos[n0 + idx[k]] = 0;
   } else {
-    for (u32 r = 0; r < R; ++r) bv.selK[n0 + r] = 1;
+    for (u32 r = 0; r < R; ++r) bv.selPos[n0 + r] = 0;
   }
-  // append the selected nodes (in node order) to the wave list; one atomic per
-  // warp (the lanes of a warp are different sentences)
   u32 nsel = 0;
-  for (u32 r = 0; r < R; ++r) nsel += (bv.selK[n0 + r] != 0xFFFFu);
-  unsigned long long g = 0, sb = 0;
-  if (bv.counters) {
-    const bool scoreTail = remaining > 0 && G > 0;
-    g = (unsigned long long)theMax * R * (ft.nBi + ft.nTri);
-    if (scoreTail) g += (unsigned long long)nsel * ((unsigned long long)U * ft.nBi + (unsigned long long)remaining * ft.nTri);
-    // streaming bytes of the boundary (DESIGN.md "roofline accounting")
-    sb = 8ull * L * B + 8ull * SP * ((unsigned long long)R + U + G) + 4ull * L + (8ull + 4ull * cfg.S) * R * B;
-  }
-  const u32 nitems = (remaining > 0 && G > 0) ? nsel * U : 0u;
-  u32 base, ibase;
-#if defined(__CUDA_ARCH__)
-  {
-    const unsigned m = __activemask();
-    const int lane = (int)(threadIdx.x & 31u);
-    const int leader = __ffs(m) - 1;
-    // the mask may have holes (threads that returned early or diverged): plain broadcast reduction
-    u32 total = 0, excl = 0, itotal = 0, iexcl = 0;
-    unsigned long long gt = 0, st = 0;
-    for (int l = 0; l < 32; ++l) {
-      if (!((m >> l) & 1u)) continue;
-      const u32 v = __shfl_sync(m, nsel, l);
-      const u32 vi = __shfl_sync(m, nitems, l);
-      if (l < lane) { excl += v; iexcl += vi; }
-      total += v;
-      itotal += vi;
-      if (bv.counters) {
-        gt += __shfl_sync(m, g, l);
-        st += __shfl_sync(m, sb, l);
-      }
-    }
-    u32 wbase = 0, wibase = 0;
-    if (lane == leader) {
-      wbase = atomicAdd(wv.selCount, total);
-      wibase = atomicAdd(wv.selCount + 1, itotal);
-      if (bv.counters) { atomicAdd(bv.counters + 0, gt); atomicAdd(bv.counters + 1, st); }
-    }
-    base = __shfl_sync(m, wbase, leader) + excl;
-    ibase = __shfl_sync(m, wibase, leader) + iexcl;
-  }
-#else
-  base = wv.selCount[0];
-  ibase = wv.selCount[1];
+  for (u32 r = 0; r < R; ++r) nsel += (bv.selPos[n0 + r] != NOT_SELECTED);
+  const bool scoreTail = z.remaining > 0 && G > 0;
+  const u32 u0 = first_bigram_item(cfg);
+  const u32 biPer = scoreTail && U > u0 ? U - u0 : 0u;
+  const u32 triPer = scoreTail ? z.remaining : 0u;
+  unsigned long long g = 0, sb = 0, gi = 0;
+  step_counters(ft, cfg, z, R, L, G, U, nsel, g, sb, gi);
+  if (bv.counters) { bv.counters[0] += g; bv.counters[1] += sb; bv.counters[2] += gi; }
+  const u32 base = wv.selCount[0], biBase = wv.selCount[1], triBase = wv.selCount[2];
   wv.selCount[0] += nsel;
-  wv.selCount[1] += nitems;
-  if (bv.counters) { bv.counters[0] += g; bv.counters[1] += sb; }
-#endif
+  wv.selCount[1] += nsel * biPer;
+  wv.selCount[2] += nsel * triPer;
   for (u32 r = 0, k = 0; r < R; ++r) {
-    if (bv.selK[n0 + r] == 0xFFFFu) continue;
-    wv.selList[base + k] = n0 + r;
-    if (nitems)
-      for (u32 u = 0; u < U; ++u) wv.itemList[ibase + k * U + u] = ((base + k) << 5) | u;
+    if (bv.selPos[n0 + r] == NOT_SELECTED) continue;
+    const u32 pos = base + k;
+    bv.selPos[n0 + r] = pos;
+    if (scoreTail)
+      emit_items(bv, cfg, wv, sent, z, G, U, n0 + r, pos, wv.biItems + biBase + (size_t)k * biPer,
+                 wv.triItems + triBase + (size_t)k * triPer);
     ++k;
   }
 }
 
-// W4a: bigram part of applyBiTri for one (selected right node, unique t1) pair
-// (applyBiTriFullKernel, feature_impl_ngram_partial_kernels.h:19-110: the r1/r2 accumulator
-// pair; the last t1 row goes through Unrolled4).  Every item is exactly nBi gathers, so the
-// lanes of a warp stay converged whatever the number of unique t1 nodes of their sentences.
+// W4, bigram item: applyBiTriFullKernel (feature_impl_ngram_partial_kernels.h:19-110) row of one
+// (selected right node, unique t1): the r1/r2 accumulator pair, the last t1 row through
+// Unrolled4.  Every item is exactly nBi gathers, so the lanes of a warp stay converged
+// whatever the number of unique t1 nodes of their sentences.
 template <typename WL>
-JPP_HD void wave_score_bigram(const FeatTables& ft, const BatchView& bv, const ScoreCfg& cfg, const WaveView& wv,
-                              const WL& wl, u32 item) {
-  const u32 pos = item >> 5, u = item & 31u;
-  const u32 node = wv.selList[pos];
-  const u32 sent = bv.bndSent[bv.nodeBnd[node]];
-  const u32 U = wv.uCount[sent], mask = ft.mask;
-  const PatRow P = pat_row(bv, node);
-  const PatRow t1 = pat_row(bv, wv.t1node[(size_t)sent * (u32)cfg.gbeam + u]);
+JPP_HD void wave_item_bigram(const FeatTables& ft, const BatchView& bv, const WaveView& wv, const WL& wl, const WaveItem& it) {
+  const u32 mask = ft.mask;
+  const PatRow P = pat_row(bv, it.a);
+  const PatRow t1 = pat_row(bv, it.b);
   auto biIdx = [&](u32 f) -> u32 { return (u32)mix(mix(ft.biState[f], P[ft.biT0[f]]), t1[ft.biT1[f]]) & mask; };
   float a[2], s4;
   gsum_dual<2, 8>(wl, ft.nBi, biIdx, a, s4);
-  wv.scb[(size_t)pos * (u32)cfg.gbeam + u] = (u + 1 == U) ? s4 : a[0] + a[1];
+  wv.scb[it.slot & ~ITEM_LAST] = (it.slot & ITEM_LAST) ? s4 : a[0] + a[1];
 }
 
-// W4b: one selected right node against the whole global beam: trigram part of applyBiTri
-// on top of the W4a bigram sums, copyT0Scores (score_processor.cc:411-424), makeT0Beam (:426-469).
+// W4, trigram item: the trigram part of the same kernel for one (selected right node, global
+// beam element); the two accumulators are kept apart because the reference adds them to the
+// bigram sum one after the other (scbuf + r1 + r2).
 template <typename WL>
-JPP_HD void wave_score_node(const FeatTables& ft, const BatchView& bv, const ScoreCfg& cfg, const WaveView& wv,
-                            const WL& wl, u32 pos) {
-  const u32 node = wv.selList[pos];
-  const u32 gB = bv.nodeBnd[node];
-  const u32 sent = bv.bndSent[gB];
-  const u32 G = wv.gCount[sent], U = wv.uCount[sent];
-  const u32 GMAX = (u32)cfg.gbeam, SP = ft.nStored, mask = ft.mask, nB = ft.nBi, nT = ft.nTri;
-  const u32 R = bv.bndNodeOff[gB + 1] - bv.bndNodeOff[gB];
-  u32 full = 0, remaining = G;
-  if (cfg.rcheck > 0) {
-    full = (u32)cfg.rcheck;
-    if (R < full) full = R;
-    if (G < full) full = G;
-    remaining = G - full;
-  }
-  const u64* gbKey = wv.gbKey + (size_t)sent * GMAX;
-  const u32* t1node = wv.t1node + (size_t)sent * GMAX;
-  const u8* t1idx = wv.gbT1idx + (size_t)sent * GMAX;
-  const u32* gbT2 = wv.gbT2node + (size_t)sent * GMAX;
-  const PatRow P = pat_row(bv, node);
-  float tot[MAX_BEAM], loc[MAX_BEAM];
-  const float* scbuf = wv.scb + (size_t)pos * GMAX;
-  for (u32 i = 0; i < full; ++i) {
-    float v = bv.pre[(size_t)i * bv.totalNodes + node];
-    v += 0.0f;  // copyT0Scores(head, 0)
-    loc[i] = v;
-    v += cand_score(gbKey[i]);
-    tot[i] = v;
-  }
-  if (remaining > 0 && G > 0) {
-    const float t0 = bv.t0[node];
-    for (u32 j = 0; j < remaining; ++j) {
-      const u32 gi = full + j;
-      const PatRow t1 = pat_row(bv, t1node[t1idx[gi]]);
-      const PatRow t2 = pat_row(bv, gbT2[gi]);
-      auto triIdx = [&](u32 f) -> u32 {
-        return (u32)mix(mix(mix(ft.triState[f], P[ft.triT0[f]]), t1[ft.triT1[f]]), t2[ft.triT2[f]]) & mask;
-      };
-      float a[2], s4;
-      gsum_dual<2, 4>(wl, nT, triIdx, a, s4);
-      const float sc = scbuf[t1idx[gi]];
-      float v = (j + 1 == remaining) ? sc + s4 : sc + a[0] + a[1];
-      v += t0;  // copyT0Scores(tail, t0Score)
-      loc[gi] = v;
-      v += cand_score(gbKey[gi]);
-      tot[gi] = v;
-    }
-  }
-  write_beam(bv, cfg, node, gbKey, (int)G, tot, loc);
-  const u32 b0 = bv.sentBndOff[sent];
-  if (gB + 1 == bv.sentBndOff[sent + 1]) {  // EOS boundary: keep every connection for the re-rank
-    for (u32 g = 0; g < G; ++g) {
-      bv.eosGbeam[(size_t)sent * GMAX + g] = gbKey[g];
-      bv.eosLocal[(size_t)sent * GMAX + g] = loc[g];
-    }
-  }
-  (void)b0;
+JPP_HD void wave_item_trigram(const FeatTables& ft, const BatchView& bv, const WaveView& wv, const WL& wl, const WaveItem& it) {
+  const u32 mask = ft.mask;
+  const PatRow P = pat_row(bv, it.a);
+  const PatRow t1 = pat_row(bv, it.b);
+  const PatRow t2 = pat_row(bv, it.c);
+  auto triIdx = [&](u32 f) -> u32 {
+    return (u32)mix(mix(mix(ft.triState[f], P[ft.triT0[f]]), t1[ft.triT1[f]]), t2[ft.triT2[f]]) & mask;
+  };
+  float a[2], s4;
+  gsum_dual<2, 4>(wl, ft.nTri, triIdx, a, s4);
+  float* out = wv.tri + 2 * (size_t)(it.slot & ~ITEM_LAST);
+  if (it.slot & ITEM_LAST) { out[0] = s4; out[1] = 0.0f; }
+  else { out[0] = a[0]; out[1] = a[1]; }
 }
 
-// W4b for small global beams (G <= 8 and G <= beam*4/3, the CLI default 6 / 5): the same
-// result as wave_score_node with everything in registers.  With at most 16 candidates and
-// no partition step makeT0Beam's std::sort is libstdc++'s insertion sort, i.e. a stable
-// descending sort, so the slot of candidate i is the number of candidates that are larger
-// or equal-and-earlier (tests/test_sort_emulation.py checks exactly this equivalence).
+// connection score of (selected node at `pos`, global beam element gi): head elements come
+// from the prescores, the others from the W4 sums; copyT0Scores (score_processor.cc:411-424)
+JPP_HD float step_local_score(const BatchView& bv, const ScoreCfg& cfg, const WaveView& wv, const StepSizes& z, u32 G, u32 node,
+                              u32 pos, u32 gi, const u8* t1idx, float t0) {
+  const u32 GMAX = (u32)cfg.gbeam;
+  if (gi < z.full) {
+    float v = bv.pre[(size_t)gi * bv.totalNodes + node];
+    v += 0.0f;  // copyT0Scores(head, 0)
+    return v;
+  }
+  const u32 ti = t1idx[gi];
+  const float sc = (ti < first_bigram_item(cfg)) ? bv.bi0[node] : wv.scb[(size_t)pos * GMAX + ti];
+  const float* tr = wv.tri + 2 * ((size_t)pos * GMAX + gi);
+  float v = (gi + 1 == G) ? sc + tr[0] : sc + tr[0] + tr[1];
+  v += t0;  // copyT0Scores(tail, t0Score)
+  return v;
+}
+
+// With at most 16 candidates and no partition step makeT0Beam's std::sort is libstdc++'s
+// insertion sort, i.e. a stable descending sort, so for global beams of up to 8 elements
+// (G <= beam*4/3; the CLI default is 6 / 5) the slot of candidate i is the number of
+// candidates that are larger or equal-and-earlier: everything stays in registers
+// (tests/test_sort_emulation.py checks this equivalence against std::sort).
 constexpr int SMALL_G = 8;
 JPP_HD bool small_gbeam_ok(const ScoreCfg& cfg) {
-  return cfg.gbeam <= SMALL_G && cfg.gbeam <= 16 && (long)cfg.gbeam <= (long)cfg.beam * 4 / 3;
+  return cfg.gbeam <= SMALL_G && (long)cfg.gbeam <= (long)cfg.beam * 4 / 3;
 }
 
-template <typename WL>
-JPP_HD void wave_score_node_small(const FeatTables& ft, const BatchView& bv, const ScoreCfg& cfg, const WaveView& wv,
-                                  const WL& wl, u32 pos) {
-  const u32 node = wv.selList[pos];
+// W5: beam row of one right node of the wave (makeT0Beam, score_processor.cc:426-469).
+// Selected nodes see the whole global beam; the others keep a beam of the head elements only
+// (:336-346).
+template <bool SMALL>
+JPP_HD void wave_final_node(const BatchView& bv, const ScoreCfg& cfg, const WaveView& wv, u32 node) {
   const u32 gB = bv.nodeBnd[node];
   const u32 sent = bv.bndSent[gB];
   const u32 G = wv.gCount[sent];
-  const u32 GMAX = (u32)cfg.gbeam, mask = ft.mask, nT = ft.nTri, B = (u32)cfg.beam;
+  const u32 GMAX = (u32)cfg.gbeam, B = (u32)cfg.beam;
   const u32 R = bv.bndNodeOff[gB + 1] - bv.bndNodeOff[gB];
-  u32 full = 0;
-  if (cfg.rcheck > 0) {
-    full = (u32)cfg.rcheck;
-    if (R < full) full = R;
-    if (G < full) full = G;
-  }
+  const StepSizes z = step_sizes(cfg, R, G);
+  const u32 pos = bv.selPos[node];
+  const u32 n = (pos != NOT_SELECTED) ? G : z.full;  // candidates of this node
   const u64* gbKey = wv.gbKey + (size_t)sent * GMAX;
-  const u32* t1node = wv.t1node + (size_t)sent * GMAX;
   const u8* t1idx = wv.gbT1idx + (size_t)sent * GMAX;
-  const u32* gbT2 = wv.gbT2node + (size_t)sent * GMAX;
-  const float* scbuf = wv.scb + (size_t)pos * GMAX;
-  const PatRow P = pat_row(bv, node);
   const float t0 = bv.t0[node];
-  float tot[SMALL_G], loc[SMALL_G];
-  u64 key[SMALL_G];
+  const bool eos = (pos != NOT_SELECTED) && gB + 1 == bv.sentBndOff[sent + 1];
+  if (SMALL) {
+    float tot[SMALL_G], loc[SMALL_G];
+    u64 key[SMALL_G];
 #pragma unroll
-  for (int gi = 0; gi < SMALL_G; ++gi) {
-    tot[gi] = 0.0f;
-    loc[gi] = 0.0f;
-    key[gi] = 0;
-    if ((u32)gi >= G) continue;
-    key[gi] = gbKey[gi];
-    float v;
-    if ((u32)gi < full) {
-      v = bv.pre[(size_t)gi * bv.totalNodes + node];
-      v += 0.0f;  // copyT0Scores(head, 0)
-    } else {
-      const u32 ti = t1idx[gi];
-      const PatRow t1 = pat_row(bv, t1node[ti]);
-      const PatRow t2 = pat_row(bv, gbT2[gi]);
-      auto triIdx = [&](u32 f) -> u32 {
-        return (u32)mix(mix(mix(ft.triState[f], P[ft.triT0[f]]), t1[ft.triT1[f]]), t2[ft.triT2[f]]) & mask;
-      };
-      float a[2], s4;
-      gsum_dual<2, 4>(wl, nT, triIdx, a, s4);
-      const float sc = scbuf[ti];
-      v = ((u32)gi + 1 == G) ? sc + s4 : sc + a[0] + a[1];
-      v += t0;  // copyT0Scores(tail, t0Score)
+    for (int gi = 0; gi < SMALL_G; ++gi) {
+      tot[gi] = 0.0f; loc[gi] = 0.0f; key[gi] = 0;
+      if ((u32)gi >= n) continue;
+      key[gi] = gbKey[gi];
+      loc[gi] = step_local_score(bv, cfg, wv, z, G, node, pos, (u32)gi, t1idx, t0);
+      tot[gi] = loc[gi] + cand_score(key[gi]);
     }
-    loc[gi] = v;
-    tot[gi] = v + cand_score(key[gi]);
-  }
-  jpp_b200_beam_element* row = bv.beam + (size_t)node * B;
-  float* srow = bv.beamScores + (size_t)node * B * cfg.S;
+    jpp_b200_beam_element* row = bv.beam + (size_t)node * B;
+    float* srow = bv.beamScores + (size_t)node * B * cfg.S;
 #pragma unroll
-  for (int i = 0; i < SMALL_G; ++i) {
-    if ((u32)i >= G) continue;
-    u32 rank = 0;
+    for (int i = 0; i < SMALL_G; ++i) {
+      if ((u32)i >= n) continue;
+      u32 rank = 0;
 #pragma unroll
-    for (int j = 0; j < SMALL_G; ++j) {
-      if ((u32)j >= G || j == i) continue;
-      const bool before = (tot[j] > tot[i]) || (j < i && !(tot[i] > tot[j]));
-      rank += before ? 1u : 0u;
+      for (int j = 0; j < SMALL_G; ++j) {
+        if ((u32)j >= n || j == i) continue;
+        rank += ((tot[j] > tot[i]) || (j < i && !(tot[i] > tot[j]))) ? 1u : 0u;
+      }
+      if (rank < B) {
+        jpp_b200_beam_element e;
+        e.left = (u16)(key[i] >> 16);
+        e.prev_beam = (u16)key[i];
+        e.total_score = tot[i];
+        row[rank] = e;
+        srow[(size_t)rank * cfg.S] = loc[i];
+        for (u32 q = 1; q < cfg.S; ++q) srow[(size_t)rank * cfg.S + q] = 0.0f;
+      }
     }
-    if (rank < B) {
-      jpp_b200_beam_element e;
-      e.left = (u16)(key[i] >> 16);
-      e.prev_beam = (u16)key[i];
-      e.total_score = tot[i];
-      row[rank] = e;
-      srow[(size_t)rank * cfg.S] = loc[i];
-      for (u32 q = 1; q < cfg.S; ++q) srow[(size_t)rank * cfg.S + q] = 0.0f;
+    for (u32 k = n; k < B; ++k) {
+      row[k] = fake_elem();
+      for (u32 q = 0; q < cfg.S; ++q) srow[(size_t)k * cfg.S + q] = 0.0f;
     }
-  }
-  for (u32 k = G; k < B; ++k) {
-    row[k] = fake_elem();
-    for (u32 q = 0; q < cfg.S; ++q) srow[(size_t)k * cfg.S + q] = 0.0f;
-  }
-  if (gB + 1 == bv.sentBndOff[sent + 1]) {  // EOS boundary: keep every connection for the re-rank
+    if (eos) {  // EOS boundary: keep every connection for the re-rank
 #pragma unroll
-    for (int g = 0; g < SMALL_G; ++g) {
-      if ((u32)g >= G) continue;
-      bv.eosGbeam[(size_t)sent * GMAX + g] = key[g];
-      bv.eosLocal[(size_t)sent * GMAX + g] = loc[g];
+      for (int g = 0; g < SMALL_G; ++g) {
+        if ((u32)g >= G) continue;
+        bv.eosGbeam[(size_t)sent * GMAX + g] = key[g];
+        bv.eosLocal[(size_t)sent * GMAX + g] = loc[g];
+      }
+    }
+  } else {
+    float tot[MAX_BEAM], loc[MAX_BEAM];
+    for (u32 gi = 0; gi < n; ++gi) {
+      loc[gi] = step_local_score(bv, cfg, wv, z, G, node, pos, gi, t1idx, t0);
+      tot[gi] = loc[gi] + cand_score(gbKey[gi]);
+    }
+    write_beam(bv, cfg, node, gbKey, (int)n, tot, loc);
+    if (eos) {
+      for (u32 g = 0; g < G; ++g) {
+        bv.eosGbeam[(size_t)sent * GMAX + g] = gbKey[g];
+        bv.eosLocal[(size_t)sent * GMAX + g] = loc[g];
+      }
     }
   }
-}
-
-// W5: right nodes outside the cutoff keep a beam of the head elements only
-// (score_processor.cc:336-346)
-JPP_HD void wave_rest_node(const BatchView& bv, const ScoreCfg& cfg, const WaveView& wv, u32 node) {
-  if (bv.selK[node] != 0xFFFFu) return;
-  const u32 gB = bv.nodeBnd[node];
-  const u32 sent = bv.bndSent[gB];
-  const u32 G = wv.gCount[sent];
-  const u32 R = bv.bndNodeOff[gB + 1] - bv.bndNodeOff[gB];
-  u32 full = (u32)cfg.rcheck;
-  if (R < full) full = R;
-  if (G < full) full = G;
-  const u64* gbKey = wv.gbKey + (size_t)sent * (u32)cfg.gbeam;
-  float tot[MAX_BEAM], loc[MAX_BEAM];
-  for (u32 i = 0; i < full; ++i) {
-    float v = bv.pre[(size_t)i * bv.totalNodes + node];
-    v += 0.0f;
-    loc[i] = v;
-    v += cand_score(gbKey[i]);
-    tot[i] = v;
-  }
-  write_beam(bv, cfg, node, gbKey, (int)full, tot, loc);
 }
 
 // Full-beam scoring (computeScoresFull, analyzer_impl.cc:197-248; selected when the global

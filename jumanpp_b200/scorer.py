@@ -141,6 +141,7 @@ class LatticeScorer:
         return {"sentences": c.sentences, "boundaries": c.boundaries, "nodes": c.nodes, "gathers": c.gathers,
                 "algorithmic_bytes": c.algorithmic_bytes, "rnn_nodes": c.rnn_nodes,
                 "walk_gathers": c.walk_gathers, "walk_bytes": c.walk_bytes, "launches": c.launches,
+                "walk_gathers_issued": c.walk_gathers_issued,
                 "kernel_ms": {n: float(c.kernel_ms[i]) for i, n in enumerate(names)}}
 
     def close(self) -> None:

@@ -36,7 +36,9 @@ extern "C" int jpp_b200_emul_score_batch(const jpp_b200_model* model, const jpp_
   const u32 B = (u32)cfg.beam, G = (u32)std::max(1, cfg.gbeam), S = cfg.S, SP = ft.nStored;
   const u32 RC = cfg.rcheck > 0 ? (u32)cfg.rcheck : 1u;
   std::vector<u32> nodeBnd(NN), bndSent(NB), endNode(NE), cutIdx(NN), gbNode((size_t)NB * G);
-  std::vector<u16> selK(NN), gbSlot((size_t)NB * G), gbLeftBnd((size_t)NB * G);
+  std::vector<u32> selPos(NN);
+  std::vector<float> bi0(NN);
+  std::vector<u16> gbSlot((size_t)NB * G), gbLeftBnd((size_t)NB * G);
   std::vector<u8> gbCount(NB);
   std::vector<float> pre((size_t)NN * RC), cut(NN), eosLocal((size_t)NS * G), eosRnn((size_t)NS * G);
   std::vector<u64> eosGbeam((size_t)NS * G);
@@ -59,7 +61,7 @@ extern "C" int jpp_b200_emul_score_batch(const jpp_b200_model* model, const jpp_
   bv.nodeBnd = nodeBnd.data(); bv.bndSent = bndSent.data(); bv.endNode = endNode.data(); bv.sentOrder = nullptr;
   bv.beam = r->node_beam; bv.beamScores = r->node_beam_scores; bv.patterns = r->node_patterns; bv.patNodeStride = SP; bv.patPStride = 1;
   bv.t0 = r->node_t0_score ? r->node_t0_score : t0tmp.data();
-  bv.pre = pre.data(); bv.cut = cut.data(); bv.cutIdx = cutIdx.data(); bv.selK = selK.data();
+  bv.pre = pre.data(); bv.cut = cut.data(); bv.cutIdx = cutIdx.data(); bv.selPos = selPos.data(); bv.bi0 = bi0.data();
   bv.gbNode = gbNode.data(); bv.gbSlot = gbSlot.data(); bv.gbLeftBnd = gbLeftBnd.data(); bv.gbCount = gbCount.data();
   bv.eosGbeam = eosGbeam.data(); bv.eosLocal = eosLocal.data(); bv.eosRnn = eosRnn.data(); bv.counters = counters;
   const WLoadDirect wl{weights};
@@ -75,31 +77,30 @@ extern "C" int jpp_b200_emul_score_batch(const jpp_b200_model* model, const jpp_
     for (u32 n = 0; n < NN; ++n) waveNodes[cur[nodeBnd[n] - b->sent_boundary_off[bndSent[nodeBnd[n]]]]++] = n;
   }
   std::vector<u64> gbKey((size_t)NS * G);
-  std::vector<u32> gbLnode((size_t)NS * G), gbT2node((size_t)NS * G), t1node((size_t)NS * G), selList(NN + 1);
+  std::vector<u32> gbLnode((size_t)NS * G), gbT2node((size_t)NS * G), t1node((size_t)NS * G);
   std::vector<u8> gbT1idx((size_t)NS * G), gCount(NS), uCount(NS);
-  u32 selCount[2] = {0, 0};
-  std::vector<u32> itemList((size_t)(NN + 1) * G);
-  std::vector<float> scb((size_t)(NN + 1) * G);
+  u32 selCount[3] = {0, 0, 0};
+  std::vector<WaveItem> biItems((size_t)(NN + 1) * G), triItems((size_t)(NN + 1) * G);
+  std::vector<float> scb((size_t)(NN + 1) * G), tri((size_t)(NN + 1) * G * 2);
   WaveView wv{};
   wv.gbKey = gbKey.data(); wv.gbLnode = gbLnode.data(); wv.gbT2node = gbT2node.data(); wv.gbT1idx = gbT1idx.data();
-  wv.t1node = t1node.data(); wv.gCount = gCount.data(); wv.uCount = uCount.data(); wv.selList = selList.data();
-  wv.selCount = selCount; wv.itemList = itemList.data(); wv.scb = scb.data(); wv.waveNodes = waveNodes.data(); wv.waveNodeOff = waveNodeOff.data();
+  wv.t1node = t1node.data(); wv.gCount = gCount.data(); wv.uCount = uCount.data();
+  wv.selCount = selCount; wv.biItems = biItems.data(); wv.triItems = triItems.data(); wv.scb = scb.data(); wv.tri = tri.data(); wv.waveNodes = waveNodes.data(); wv.waveNodeOff = waveNodeOff.data();
   for (u32 s = 0; s < NS; ++s) wave_init_sentence(bv, cfg, s);
   for (u32 bnd = 2; bnd < maxNb && cfg.gbeam <= 0; ++bnd)  // full-beam loop
     for (u32 i = waveNodeOff[bnd]; i < waveNodeOff[bnd + 1]; ++i) counters[0] += wave_full_node(ft, bv, cfg, wl, waveNodes[i]);
   for (u32 bnd = 2; bnd < maxNb && cfg.gbeam > 0; ++bnd) {
-    selCount[0] = selCount[1] = 0;
+    selCount[0] = selCount[1] = selCount[2] = 0;
     for (u32 s = 0; s < NS; ++s) wave_gbeam(bv, cfg, wv, s, bnd);
     if (cfg.rcheck > 0)
       for (u32 i = waveNodeOff[bnd]; i < waveNodeOff[bnd + 1]; ++i) wave_prescore(ft, bv, cfg, wv, wl, waveNodes[i]);
     for (u32 s = 0; s < NS; ++s) wave_cutoff(ft, bv, cfg, wv, s, bnd);
-    for (u32 i = 0; i < selCount[1]; ++i) wave_score_bigram(ft, bv, cfg, wv, wl, itemList[i]);
-    for (u32 i = 0; i < selCount[0]; ++i) {
-      if (small_gbeam_ok(cfg)) wave_score_node_small(ft, bv, cfg, wv, wl, i);
-      else wave_score_node(ft, bv, cfg, wv, wl, i);
+    for (u32 i = 0; i < selCount[1]; ++i) wave_item_bigram(ft, bv, wv, wl, biItems[i]);
+    for (u32 i = 0; i < selCount[2]; ++i) wave_item_trigram(ft, bv, wv, wl, triItems[i]);
+    for (u32 i = waveNodeOff[bnd]; i < waveNodeOff[bnd + 1]; ++i) {
+      if (small_gbeam_ok(cfg)) wave_final_node<true>(bv, cfg, wv, waveNodes[i]);
+      else wave_final_node<false>(bv, cfg, wv, waveNodes[i]);
     }
-    if (cfg.rcheck > 0)
-      for (u32 i = waveNodeOff[bnd]; i < waveNodeOff[bnd + 1]; ++i) wave_rest_node(bv, cfg, wv, waveNodes[i]);
   }
   if (model->num_scorers == 2) {
     const jpp_b200_rnn_model* rm = model->rnn;
