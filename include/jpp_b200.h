@@ -219,6 +219,13 @@ typedef struct jpp_b200_batch {
   const uint32_t* node_entry_row;       /* [total_nodes] or NULL              */
   const int32_t* entry_rows;            /* [num_entry_rows][entry_size]       */
   uint32_t num_entry_rows;
+  /* Everything else that is a function of the entry can ride in the row as well:
+   * providedFeature() is 0 for dictionary words and set by the unk makers for
+   * unknown-word nodes (which own their rows), and RnnIdContainer::resolveId
+   * depends on the entry's fields / the unk node's surface only.  Used, in the
+   * compact form, when the per-node arrays above are NULL. */
+  const int32_t* row_placeholders;      /* [num_entry_rows][num_placeholders] or NULL */
+  const int32_t* row_rnn_id;            /* [num_entry_rows] or NULL                   */
 } jpp_b200_batch;
 
 /* ConnectionBeamElement (lattice_config.h:70-73) without the raw pointer: the

@@ -75,7 +75,8 @@ class Batch(C.Structure):
                 ("boundary_node_off", C.c_void_p), ("boundary_end_off", C.c_void_p),
                 ("node_info", C.c_void_p), ("node_entry", C.c_void_p), ("node_placeholders", C.c_void_p),
                 ("node_rnn_id", C.c_void_p), ("ends", C.c_void_p), ("codepoints", C.c_void_p),
-                ("node_entry_row", C.c_void_p), ("entry_rows", C.c_void_p), ("num_entry_rows", C.c_uint32)]
+                ("node_entry_row", C.c_void_p), ("entry_rows", C.c_void_p), ("num_entry_rows", C.c_uint32),
+                ("row_placeholders", C.c_void_p), ("row_rnn_id", C.c_void_p)]
 
 
 class Result(C.Structure):
@@ -252,6 +253,8 @@ class StagedBatch:
     codepoints: np.ndarray       # CODEPOINT_DT
     node_entry_row: np.ndarray | None = None   # compact form: [nodes] u32 index into entry_rows
     entry_rows: np.ndarray | None = None       # [rows][entry_size] i32
+    row_placeholders: np.ndarray | None = None # [rows][placeholders] i32 (then node_placeholders is None)
+    row_rnn_id: np.ndarray | None = None       # [rows] i32 (then node_rnn_id is None)
 
     @property
     def num_sentences(self) -> int:
@@ -296,6 +299,8 @@ class StagedBatch:
         b.node_entry_row = _ptr(self.node_entry_row)
         b.entry_rows = _ptr(self.entry_rows)
         b.num_entry_rows = 0 if self.entry_rows is None else len(self.entry_rows)
+        b.row_placeholders = _ptr(self.row_placeholders)
+        b.row_rnn_id = _ptr(self.row_rnn_id)
         b.node_placeholders = _ptr(self.node_placeholders)
         b.node_rnn_id = _ptr(self.node_rnn_id)
         b.ends = _ptr(self.ends)
@@ -320,17 +325,21 @@ class StagedBatch:
             arrs = [get(p) for p in parts]
             return None if arrs[0] is None else pin(np.concatenate(arrs))
 
-        rows = row_idx = None
+        rows = row_idx = row_ph = row_rnn = None
         if parts[0].node_entry is None:   # compact parts: stack the row tables, rebase the indices
             bases = np.cumsum([0] + [len(p.entry_rows) for p in parts[:-1]])
             rows = pin(np.concatenate([p.entry_rows for p in parts]))
             row_idx = pin(np.concatenate([(p.node_entry_row.astype(np.uint64) + int(b)).astype(np.uint32)
                                           for p, b in zip(parts, bases)]))
+            if parts[0].row_placeholders is not None:
+                row_ph = pin(np.concatenate([p.row_placeholders for p in parts]))
+            if parts[0].row_rnn_id is not None:
+                row_rnn = pin(np.concatenate([p.row_rnn_id for p in parts]))
         return StagedBatch(
             pin(offs(lambda p: p.sent_boundary_off, None)), pin(offs(lambda p: p.sent_codepoint_off, None)),
             pin(offs(lambda p: p.boundary_node_off, None)), pin(offs(lambda p: p.boundary_end_off, None)),
             cat(lambda p: p.node_info), cat(lambda p: p.node_entry), cat(lambda p: p.node_placeholders),
-            cat(lambda p: p.node_rnn_id), cat(lambda p: p.ends), cat(lambda p: p.codepoints), row_idx, rows)
+            cat(lambda p: p.node_rnn_id), cat(lambda p: p.ends), cat(lambda p: p.codepoints), row_idx, rows, row_ph, row_rnn)
 
     def select(self, lo: int, hi: int) -> "StagedBatch":
         """Sentences [lo, hi) as an independent batch (offsets rebased)."""
@@ -349,19 +358,34 @@ class StagedBatch:
             None if self.node_rnn_id is None else np.ascontiguousarray(self.node_rnn_id[n0:n1]),
             np.ascontiguousarray(self.ends[e0:e1]), np.ascontiguousarray(self.codepoints[c0:c1]),
             None if self.node_entry_row is None else np.ascontiguousarray(self.node_entry_row[n0:n1]),
-            self.entry_rows)
+            self.entry_rows, self.row_placeholders, self.row_rnn_id)
 
-    def compact_entries(self, pin=None) -> "StagedBatch":
-        """The same batch with one entry row per distinct entry buffer (jpp_b200_batch.node_entry_row /
-        entry_rows): what a stager that keys rows by EntryPtr sends.  Rows are matched by content here,
-        through a 64-bit hash whose collisions are checked.  A batch that is already compact (e.g. a
-        concatenation of compact parts) gets its row table de-duplicated once more."""
+    def compact_entries(self, pin=None, fold: bool = True) -> "StagedBatch":
+        """The same batch with one row per distinct entry (jpp_b200_batch.node_entry_row / entry_rows):
+        what a stager that keys rows by EntryPtr sends.  With `fold` the placeholders and the RNN id --
+        functions of the entry too -- ride in the row (row_placeholders / row_rnn_id) and the per-node
+        arrays are dropped.  Rows are matched by content here, through a 64-bit hash whose collisions are
+        checked.  A batch that is already compact (e.g. a concatenation of compact parts) gets its row
+        table de-duplicated once more."""
         pin = pin or (lambda a: a)
-        rows = np.ascontiguousarray(self.node_entry if self.node_entry is not None else self.entry_rows, np.int32)
-        n, es = rows.shape
+        was_inline = self.node_entry is not None
+        cols = [np.ascontiguousarray(self.node_entry if was_inline else self.entry_rows, np.int32)]
+        es = cols[0].shape[1]
+        ph = self.node_placeholders if was_inline or self.row_placeholders is None else self.row_placeholders
+        rid = self.node_rnn_id if was_inline or self.row_rnn_id is None else self.row_rnn_id
+        fold_ph = ph is not None and (self.row_placeholders is not None or (fold and was_inline))
+        fold_rnn = rid is not None and (self.row_rnn_id is not None or (fold and was_inline))
+        nph = 0
+        if fold_ph:
+            nph = ph.shape[1]
+            cols.append(np.ascontiguousarray(ph, np.int32).reshape(len(ph), nph))
+        if fold_rnn:
+            cols.append(np.ascontiguousarray(rid, np.int32).reshape(-1, 1))
+        rows = np.ascontiguousarray(np.concatenate(cols, axis=1)) if len(cols) > 1 else cols[0]
+        n, width = rows.shape
         h = np.full(n, 0x9E3779B97F4A7C15, np.uint64)
         with np.errstate(over="ignore"):
-            for c in range(es):
+            for c in range(width):
                 h ^= (rows[:, c].astype(np.uint32).astype(np.uint64) + np.uint64(0x9E3779B97F4A7C15)
                       + (h << np.uint64(6)) + (h >> np.uint64(2)))
                 h *= np.uint64(0xFF51AFD7ED558CCD)
@@ -371,15 +395,21 @@ class StagedBatch:
         if not np.array_equal(table[inverse], rows):
             raise RuntimeError("entry-row hash collision; use the inline form")
         inverse = inverse.astype(np.uint32)
-        idx = inverse if self.node_entry is not None else inverse[self.node_entry_row]
-        return dataclasses.replace(self, node_entry=None, node_entry_row=pin(np.ascontiguousarray(idx)),
-                                   entry_rows=pin(table))
+        idx = inverse if was_inline else inverse[self.node_entry_row]
+        out = dataclasses.replace(self, node_entry=None, node_entry_row=pin(np.ascontiguousarray(idx)),
+                                  entry_rows=pin(np.ascontiguousarray(table[:, :es])))
+        if fold_ph:
+            out = dataclasses.replace(out, node_placeholders=None,
+                                      row_placeholders=pin(np.ascontiguousarray(table[:, es:es + nph])))
+        if fold_rnn:
+            out = dataclasses.replace(out, node_rnn_id=None, row_rnn_id=pin(np.ascontiguousarray(table[:, -1])))
+        return out
 
     def h2d_bytes(self) -> int:
         """Bytes jpp_b200_upload_batch copies to the device for this batch."""
         arrs = (self.sent_boundary_off, self.sent_codepoint_off, self.boundary_node_off, self.boundary_end_off,
                 self.node_info, self.node_entry, self.node_placeholders, self.node_rnn_id, self.ends, self.codepoints,
-                self.node_entry_row, self.entry_rows)
+                self.node_entry_row, self.entry_rows, self.row_placeholders, self.row_rnn_id)
         return int(sum(a.nbytes for a in arrs if a is not None))
 
 

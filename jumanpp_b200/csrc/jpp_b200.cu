@@ -1033,9 +1033,12 @@ jpp_b200_status jpp_b200_upload_batch(jpp_b200_handle* h, const jpp_b200_batch* 
   if (!b->sent_boundary_off || !b->sent_codepoint_off || !b->boundary_node_off || !b->boundary_end_off || !b->node_info ||
       (!b->node_entry && (!b->node_entry_row || !b->entry_rows || b->num_entry_rows == 0)) || !b->ends || (!b->codepoints && b->sent_codepoint_off[b->num_sentences] > 0))
     return fail(h, JPP_B200_INVALID_PARAMETER, "batch has null arrays");
-  if (h->hm.ft.nPlaceholders > 0 && !b->node_placeholders)
-    return fail(h, JPP_B200_INVALID_PARAMETER, "model has placeholders but batch.node_placeholders is null");
-  if (h->hasRnn && !b->node_rnn_id) return fail(h, JPP_B200_INVALID_PARAMETER, "model has an RNN but batch.node_rnn_id is null");
+  const bool rowPh = !b->node_placeholders && !b->node_entry && b->row_placeholders;
+  const bool rowRnn = !b->node_rnn_id && !b->node_entry && b->row_rnn_id;
+  if (h->hm.ft.nPlaceholders > 0 && !b->node_placeholders && !rowPh)
+    return fail(h, JPP_B200_INVALID_PARAMETER, "model has placeholders but batch.node_placeholders (or row_placeholders) is null");
+  if (h->hasRnn && !b->node_rnn_id && !rowRnn)
+    return fail(h, JPP_B200_INVALID_PARAMETER, "model has an RNN but batch.node_rnn_id (or row_rnn_id) is null");
   const u32 NS = b->num_sentences;
   const u32 NB = b->sent_boundary_off[NS];
   const u32 NN = b->boundary_node_off[NB];
@@ -1071,8 +1074,8 @@ jpp_b200_status jpp_b200_upload_batch(jpp_b200_handle* h, const jpp_b200_batch* 
   const bool compactEntries = b->node_entry == nullptr;
   ENSURE(B_ENTRY, (size_t)(compactEntries ? b->num_entry_rows : NN) * h->hm.ft.entrySize * 4);
   if (compactEntries) ENSURE(B_ENTRYROW, (size_t)NN * 4);
-  ENSURE(B_PH, (size_t)NN * std::max(1u, h->hm.ft.nPlaceholders) * 4);
-  ENSURE(B_RNNID, (size_t)NN * 4);
+  ENSURE(B_PH, (size_t)(rowPh ? b->num_entry_rows : NN) * std::max(1u, h->hm.ft.nPlaceholders) * 4);
+  ENSURE(B_RNNID, (size_t)(rowRnn ? b->num_entry_rows : NN) * 4);
   ENSURE(B_ENDS, (size_t)NE * sizeof(jpp_b200_node_ptr));
   ENSURE(B_CPS, (size_t)std::max(1u, NC) * sizeof(jpp_b200_codepoint));
   ENSURE(B_NODEBND, (size_t)NN * 4); ENSURE(B_BNDSENT, (size_t)NB * 4); ENSURE(B_ENDNODE, (size_t)NE * 4);
@@ -1102,8 +1105,14 @@ jpp_b200_status jpp_b200_upload_batch(jpp_b200_handle* h, const jpp_b200_batch* 
   } else {
     H2D(B_ENTRY, b->node_entry, (size_t)NN * h->hm.ft.entrySize * 4);
   }
-  if (h->hm.ft.nPlaceholders) H2D(B_PH, b->node_placeholders, (size_t)NN * h->hm.ft.nPlaceholders * 4);
-  if (h->hasRnn) H2D(B_RNNID, b->node_rnn_id, (size_t)NN * 4);
+  if (h->hm.ft.nPlaceholders) {
+    if (rowPh) H2D(B_PH, b->row_placeholders, (size_t)b->num_entry_rows * h->hm.ft.nPlaceholders * 4);
+    else H2D(B_PH, b->node_placeholders, (size_t)NN * h->hm.ft.nPlaceholders * 4);
+  }
+  if (h->hasRnn) {
+    if (rowRnn) H2D(B_RNNID, b->row_rnn_id, (size_t)b->num_entry_rows * 4);
+    else H2D(B_RNNID, b->node_rnn_id, (size_t)NN * 4);
+  }
   H2D(B_ENDS, b->ends, (size_t)NE * sizeof(jpp_b200_node_ptr));
   if (NC) H2D(B_CPS, b->codepoints, (size_t)NC * sizeof(jpp_b200_codepoint));
   H2D(B_ORDER, order.data(), (size_t)NS * 4);
@@ -1115,8 +1124,10 @@ jpp_b200_status jpp_b200_upload_batch(jpp_b200_handle* h, const jpp_b200_batch* 
   bv.nodeInfo = P(B_INFO, jpp_b200_node_info); bv.nodeEntry = compactEntries ? nullptr : P(B_ENTRY, i32);
   bv.nodeEntryRow = compactEntries ? P(B_ENTRYROW, u32) : nullptr; bv.entryRows = compactEntries ? P(B_ENTRY, i32) : nullptr;
   bv.numEntryRows = compactEntries ? b->num_entry_rows : 0;
-  bv.nodePlaceholders = h->hm.ft.nPlaceholders ? P(B_PH, i32) : nullptr;
-  bv.nodeRnnId = h->hasRnn ? P(B_RNNID, i32) : nullptr;
+  bv.nodePlaceholders = (h->hm.ft.nPlaceholders && !rowPh) ? P(B_PH, i32) : nullptr;
+  bv.rowPlaceholders = (h->hm.ft.nPlaceholders && rowPh) ? P(B_PH, i32) : nullptr;
+  bv.nodeRnnId = (h->hasRnn && !rowRnn) ? P(B_RNNID, i32) : nullptr;
+  bv.rowRnnId = (h->hasRnn && rowRnn) ? P(B_RNNID, i32) : nullptr;
   bv.ends = P(B_ENDS, jpp_b200_node_ptr); bv.cps = P(B_CPS, jpp_b200_codepoint);
   bv.nodeBnd = P(B_NODEBND, u32); bv.bndSent = P(B_BNDSENT, u32); bv.endNode = P(B_ENDNODE, u32); bv.sentOrder = P(B_ORDER, u32);
   bv.beam = P(B_BEAM, jpp_b200_beam_element); bv.beamScores = P(B_BSCORES, float); bv.patterns = P(B_PATS, u64);

@@ -108,6 +108,8 @@ struct BatchView {
   const u32* nodeEntryRow;
   const i32* entryRows;
   u32 numEntryRows;
+  const i32* rowPlaceholders;   // compact form, when nodePlaceholders is null
+  const i32* rowRnnId;          // compact form, when nodeRnnId is null
   const i32* nodePlaceholders;  // may be null
   const i32* nodeRnnId;         // may be null
   const jpp_b200_node_ptr* ends;
@@ -299,6 +301,7 @@ JPP_HD void t0_node(const FeatTables& ft, const BatchView& bv, const WL& wl, u32
   const u32 ncp = bv.sentCpOff[sent + 1] - cp0;
   const jpp_b200_codepoint* cps = bv.cps + cp0;
   const i32* entry;
+  const i32* ph = bv.nodePlaceholders ? bv.nodePlaceholders + (size_t)node * ft.nPlaceholders : nullptr;
   if (bv.nodeEntry) {
     entry = bv.nodeEntry + (size_t)node * ft.entrySize;
   } else {
@@ -308,8 +311,8 @@ JPP_HD void t0_node(const FeatTables& ft, const BatchView& bv, const WL& wl, u32
       if (bv.counters) bv.counters[7] = 1;
     }
     entry = bv.entryRows + (size_t)row * ft.entrySize;
+    if (!ph && bv.rowPlaceholders) ph = bv.rowPlaceholders + (size_t)row * ft.nPlaceholders;
   }
-  const i32* ph = bv.nodePlaceholders ? bv.nodePlaceholders + (size_t)node * ft.nPlaceholders : nullptr;
   u64 prim[MAX_PRIM];
   for (u32 i = 0; i < ft.nPrim; ++i) prim[i] = prim_value(ft, i, entry, ph, ni, cps, ncp);
   u64 pat[MAX_PAT];

@@ -118,7 +118,12 @@ JPP_HD void rnn_build_tree(const BatchView& bv, const ScoreCfg& cfg, const RnnWo
       i32 id, length;
       if (k >= 0) {
         cNode = rw.chainNode[base0 + k]; cSlot = rw.chainSlot[base0 + k]; cb = rw.chainBnd[base0 + k];
-        id = bv.nodeRnnId[cNode];
+        if (bv.nodeRnnId) {
+          id = bv.nodeRnnId[cNode];
+        } else {
+          const u32 row = bv.nodeEntryRow[cNode];
+          id = bv.rowRnnId[row < bv.numEntryRows ? row : 0u];  // a bad row fails the call (t0_node flags it)
+        }
         length = (i32)bv.nodeInfo[cNode].end - (i32)bv.nodeInfo[cNode].start;
       } else {
         id = 0; length = 0; cb = eosBnd;  // nodeCache_[{eos,0}] = {eos,0,0} (:306-308)

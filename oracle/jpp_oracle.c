@@ -745,7 +745,8 @@ static int score_sentence(const Ctx* c, Scratch* s, u32 sent) {
       u64* P = s->pats + (size_t)r * NP;
       node_patterns(cm, B->node_entry ? B->node_entry + (size_t)node * m->entry_size
                                       : B->entry_rows + (size_t)B->node_entry_row[node] * m->entry_size,
-                    B->node_placeholders ? B->node_placeholders + (size_t)node * m->num_placeholders : NULL,
+                    B->node_placeholders ? B->node_placeholders + (size_t)node * m->num_placeholders
+                    : (B->row_placeholders && !B->node_entry ? B->row_placeholders + (size_t)B->node_entry_row[node] * m->num_placeholders : NULL),
                     &B->node_info[node], cps, ncp, P);
       for (u32 p = 0; p < SP; ++p) patsOut[(size_t)node * SP + p] = P[p];
       u32 idx[256];
@@ -1056,7 +1057,7 @@ static int score_sentence(const Ctx* c, Scratch* s, u32 sent) {
       for (i32 k = (i32)len - 1; k >= -1; --k) {
         i32 id, length; u32 cb;
         if (k >= 0) {
-          id = B->node_rnn_id[chainp[k].node];
+          id = B->node_rnn_id ? B->node_rnn_id[chainp[k].node] : B->row_rnn_id[B->node_entry_row[chainp[k].node]];
           length = (i32)B->node_info[chainp[k].node].end - (i32)B->node_info[chainp[k].node].start;
           cb = chainBnd[k];
         } else {

@@ -57,6 +57,7 @@ extern "C" int jpp_b200_emul_score_batch(const jpp_b200_model* model, const jpp_
   bv.sentBndOff = b->sent_boundary_off; bv.sentCpOff = b->sent_codepoint_off; bv.bndNodeOff = b->boundary_node_off;
   bv.bndEndOff = b->boundary_end_off; bv.nodeInfo = b->node_info; bv.nodeEntry = b->node_entry; bv.nodeEntryRow = b->node_entry_row; bv.entryRows = b->entry_rows; bv.numEntryRows = b->num_entry_rows;
   bv.nodePlaceholders = ft.nPlaceholders ? b->node_placeholders : nullptr; bv.nodeRnnId = b->node_rnn_id;
+  bv.rowPlaceholders = ft.nPlaceholders ? b->row_placeholders : nullptr; bv.rowRnnId = b->row_rnn_id;
   bv.ends = b->ends; bv.cps = b->codepoints;
   bv.nodeBnd = nodeBnd.data(); bv.bndSent = bndSent.data(); bv.endNode = endNode.data(); bv.sentOrder = nullptr;
   bv.beam = r->node_beam; bv.beamScores = r->node_beam_scores; bv.patterns = r->node_patterns; bv.patNodeStride = SP; bv.patPStride = 1;

@@ -85,3 +85,21 @@ def test_compact_entry_rows_give_the_same_result(emul):
     assert got3.node_beam.tobytes() == ref3.node_beam.tobytes()
     ora, _ = oracle_lib.oracle_score(model, cfg, compact)
     assert ora.node_beam.tobytes() == inline.node_beam.tobytes()
+
+
+def test_compact_rows_carry_placeholders_and_rnn_ids(emul, rnn_dir):
+    d, model, cfg, batch = load_golden("rnn_default", rnn_dir)
+    inline = run_emul(emul, model, cfg, batch)
+    compact = batch.compact_entries()
+    assert compact.node_placeholders is None and compact.node_rnn_id is None
+    assert compact.row_rnn_id is not None and compact.row_placeholders is not None
+    got = run_emul(emul, model, cfg, compact)
+    assert got.node_beam.tobytes() == inline.node_beam.tobytes()
+    assert got.node_beam_scores.tobytes() == inline.node_beam_scores.tobytes()
+    kept = batch.compact_entries(fold=False)      # rows = entry buffers only, per-node arrays kept
+    assert kept.node_rnn_id is not None and kept.row_rnn_id is None
+    got2 = run_emul(emul, model, cfg, kept)
+    assert got2.node_beam.tobytes() == inline.node_beam.tobytes()
+    ora, _ = oracle_lib.oracle_score(model, cfg, compact)
+    ora0, _ = oracle_lib.oracle_score(model, cfg, batch)
+    assert ora.node_beam.tobytes() == ora0.node_beam.tobytes()

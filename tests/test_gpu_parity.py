@@ -110,6 +110,16 @@ def test_compact_entry_rows():
         sc.close()
 
 
+def test_compact_rows_with_rnn(rnn_dir):
+    d, model, cfg, batch = load_golden("rnn_h128", rnn_dir)
+    inline, _ = gpu_score(model, cfg, batch)
+    compact = batch.compact_entries()
+    assert compact.node_rnn_id is None and compact.row_rnn_id is not None
+    got, _ = gpu_score(model, cfg, compact)
+    assert got.node_beam.tobytes() == inline.node_beam.tobytes()
+    assert got.node_beam_scores.tobytes() == inline.node_beam_scores.tobytes()
+
+
 def abi_mod():
     from jumanpp_b200 import abi
     return abi
