@@ -40,7 +40,7 @@ def _compile(verbose: bool, defines: list[str]) -> Path:
     cmd = [nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
            "-fmad=false", "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v" if verbose else "-O3",
            *[f"-D{d}" for d in defines],
-           f"-I{ROOT / 'include'}", f"-I{PKG / 'csrc'}", *map(str, SOURCES), "-o", str(LIB), "-lcudart"]
+           f"-I{ROOT / 'include'}", f"-I{PKG / 'csrc'}", *map(str, SOURCES), "-o", str(LIB), "-lcudart", "-lpthread"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + r.stdout[-3000:] + r.stderr[-6000:])

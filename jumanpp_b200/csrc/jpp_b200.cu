@@ -11,6 +11,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "jpp_b200.h"
@@ -439,6 +440,11 @@ __global__ void __launch_bounds__(128) k_w_full(const __grid_constant__ FeatTabl
   }
 }
 
+__global__ void k_rebase(u32* p, u32 n, u32 base) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] -= base;
+}
+
 __global__ void k_fill_i32(i32* p, size_t n, i32 v) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
 }
@@ -755,9 +761,9 @@ __global__ void __launch_bounds__(128) k_rnn_scores(BatchView bv, ScoreCfg cfg, 
   }
 }
 
-__global__ void k_best_path(BatchView bv, ScoreCfg cfg, u32* pathLen, u32* pathNodes) {
+__global__ void k_best_path(BatchView bv, ScoreCfg cfg, u32* pathLen, u32* pathNodes, u32 nodeBase) {
   const u32 s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s < bv.numSentences) best_path_sentence(bv, cfg, pathLen, pathNodes, s);
+  if (s < bv.numSentences) best_path_sentence(bv, cfg, pathLen, pathNodes, s, nodeBase);
 }
 
 __global__ void k_rerank(BatchView bv, ScoreCfg cfg, float w0, float w1) {
@@ -790,6 +796,8 @@ struct DevBuf {
 
 }  // namespace
 
+namespace { struct WaveProfile; }
+
 struct jpp_b200_handle {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -803,6 +811,13 @@ struct jpp_b200_handle {
   bool hasRnn = false;
   float* dRnnBlocks[4] = {nullptr, nullptr, nullptr, nullptr};
   float* dRnnWt = nullptr;  // transposed recurrent matrix
+  // window of the caller's batch that is resident (upload_window): offsets of its first sentence /
+  // boundary / node; results go to the matching slices of the caller's arrays
+  u32 windowSentBase = 0, windowBndBase = 0, windowNodeBase = 0;
+  // second lane of jpp_b200_score_batch: own stream and buffers, the model memory of this handle
+  jpp_b200_handle* lane = nullptr;
+  bool ownsModel = true;
+  WaveProfile* prof = nullptr;
   float scoreW[2] = {1.0f, 0.0f};
   int smCount = 148;
   // batch buffers
@@ -1009,27 +1024,34 @@ jpp_b200_status jpp_b200_set_config(jpp_b200_handle* h, const jpp_b200_config* c
   h->cfg.rcheck = config->right_gbeam_check;
   h->cfg.rbeam = config->right_gbeam_size;
   h->resident = false;  // result / scratch shapes depend on the configuration
+  if (h->lane) { h->lane->pubCfg = h->pubCfg; h->lane->cfg = h->cfg; h->lane->resident = false; }
   return JPP_B200_OK;
 }
 
 void jpp_b200_destroy(jpp_b200_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
+  if (h->lane) jpp_b200_destroy(h->lane);
+  delete h->prof;
   for (auto& b : h->buf) b.release();
-  if (h->dFt) cudaFree(h->dFt);
-  if (h->dWeights) cudaFree(h->dWeights);
-  for (auto& p : h->dRnnBlocks) if (p) cudaFree(p);
-  if (h->dRnnWt) cudaFree(h->dRnnWt);
+  if (h->ownsModel) {
+    if (h->dFt) cudaFree(h->dFt);
+    if (h->dWeights) cudaFree(h->dWeights);
+    for (auto& p : h->dRnnBlocks) if (p) cudaFree(p);
+    if (h->dRnnWt) cudaFree(h->dRnnWt);
+  }
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
 
-jpp_b200_status jpp_b200_upload_batch(jpp_b200_handle* h, const jpp_b200_batch* b) {
+// Uploads sentences [lo, hi) of `b`.  The CSR offset arrays are copied as they are and rebased on
+// the device, so a window of a larger batch costs the host nothing.
+static jpp_b200_status upload_window(jpp_b200_handle* h, const jpp_b200_batch* b, u32 lo, u32 hi) {
   if (!h || !b) return JPP_B200_INVALID_PARAMETER;
   h->resident = false;
   CU_CHECK(h, cudaSetDevice(h->device));
-  if (b->num_sentences == 0) return fail(h, JPP_B200_INVALID_PARAMETER, "empty batch");
+  if (b->num_sentences == 0 || lo >= hi || hi > b->num_sentences) return fail(h, JPP_B200_INVALID_PARAMETER, "empty batch");
   if (!b->sent_boundary_off || !b->sent_codepoint_off || !b->boundary_node_off || !b->boundary_end_off || !b->node_info ||
       (!b->node_entry && (!b->node_entry_row || !b->entry_rows || b->num_entry_rows == 0)) || !b->ends || (!b->codepoints && b->sent_codepoint_off[b->num_sentences] > 0))
     return fail(h, JPP_B200_INVALID_PARAMETER, "batch has null arrays");
@@ -1039,11 +1061,18 @@ jpp_b200_status jpp_b200_upload_batch(jpp_b200_handle* h, const jpp_b200_batch* 
     return fail(h, JPP_B200_INVALID_PARAMETER, "model has placeholders but batch.node_placeholders (or row_placeholders) is null");
   if (h->hasRnn && !b->node_rnn_id && !rowRnn)
     return fail(h, JPP_B200_INVALID_PARAMETER, "model has an RNN but batch.node_rnn_id (or row_rnn_id) is null");
-  const u32 NS = b->num_sentences;
-  const u32 NB = b->sent_boundary_off[NS];
-  const u32 NN = b->boundary_node_off[NB];
-  const u32 NE = b->boundary_end_off[NB];
-  const u32 NC = b->sent_codepoint_off[NS];
+  const u32 NS = hi - lo;
+  const u32* sbo = b->sent_boundary_off + lo;
+  const u32* sco = b->sent_codepoint_off + lo;
+  const u32 bBase = sbo[0], cBase = sco[0];
+  const u32 NB = sbo[NS] - bBase;
+  const u32* bno = b->boundary_node_off + bBase;
+  const u32* beo = b->boundary_end_off + bBase;
+  const u32 nBase = bno[0], eBase = beo[0];
+  const u32 NN = bno[NB] - nBase;
+  const u32 NE = beo[NB] - eBase;
+  const u32 NC = sco[NS] - cBase;
+  h->windowSentBase = lo; h->windowBndBase = bBase; h->windowNodeBase = nBase;
   const u32 B = (u32)h->cfg.beam, G = (u32)std::max(1, h->cfg.gbeam), S = h->cfg.S, SP = h->hm.ft.nStored;
   const u32 RC = h->cfg.rcheck > 0 ? (u32)h->cfg.rcheck : 1u;
   // work order: longest sentence first; validate shapes on the way
@@ -1053,7 +1082,7 @@ jpp_b200_status jpp_b200_upload_batch(jpp_b200_handle* h, const jpp_b200_batch* 
   std::vector<u32> rnOff(NS + 1);
   for (u32 s = 0; s < NS; ++s) {
     order[s] = s;
-    const u32 nb = b->sent_boundary_off[s + 1] - b->sent_boundary_off[s];
+    const u32 nb = sbo[s + 1] - sbo[s];
     if (nb < 3 || nb > 65535u) return fail(h, JPP_B200_INVALID_PARAMETER, "sentence with fewer than 3 or more than 65535 boundaries");
     maxNb = std::max(maxNb, nb);
     rnOff[s] = (u32)rnTotal;
@@ -1062,7 +1091,7 @@ jpp_b200_status jpp_b200_upload_batch(jpp_b200_handle* h, const jpp_b200_batch* 
   rnOff[NS] = (u32)rnTotal;
   if (rnTotal > 0xFFFFFFF0ull) return fail(h, JPP_B200_INVALID_PARAMETER, "batch too large for the RNN workspace; split it");
   std::stable_sort(order.begin(), order.end(), [&](u32 a, u32 c) {
-    return (b->sent_boundary_off[a + 1] - b->sent_boundary_off[a]) > (b->sent_boundary_off[c + 1] - b->sent_boundary_off[c]);
+    return (sbo[a + 1] - sbo[a]) > (sbo[c + 1] - sbo[c]);
   });
   h->maxNb = maxNb;
   h->rnTotal = rnTotal;
@@ -1094,27 +1123,33 @@ jpp_b200_status jpp_b200_upload_batch(jpp_b200_handle* h, const jpp_b200_batch* 
   cudaStream_t st = h->stream;
 #define H2D(idx, src, bytes) CU_CHECK(h, cudaMemcpyAsync(bf[jpp_b200_handle::idx].p, src, bytes, cudaMemcpyHostToDevice, st))
   CU_CHECK(h, cudaEventRecord(h->ev[0], st));
-  H2D(B_SBO, b->sent_boundary_off, (size_t)(NS + 1) * 4);
-  H2D(B_SCO, b->sent_codepoint_off, (size_t)(NS + 1) * 4);
-  H2D(B_BNO, b->boundary_node_off, (size_t)(NB + 1) * 4);
-  H2D(B_BEO, b->boundary_end_off, (size_t)(NB + 1) * 4);
-  H2D(B_INFO, b->node_info, (size_t)NN * sizeof(jpp_b200_node_info));
+  H2D(B_SBO, sbo, (size_t)(NS + 1) * 4);
+  H2D(B_SCO, sco, (size_t)(NS + 1) * 4);
+  H2D(B_BNO, bno, (size_t)(NB + 1) * 4);
+  H2D(B_BEO, beo, (size_t)(NB + 1) * 4);
+  if (bBase | cBase | nBase | eBase) {
+    k_rebase<<<(NS + 256) / 256, 256, 0, st>>>(bf[jpp_b200_handle::B_SBO].as<u32>(), NS + 1, bBase);
+    k_rebase<<<(NS + 256) / 256, 256, 0, st>>>(bf[jpp_b200_handle::B_SCO].as<u32>(), NS + 1, cBase);
+    k_rebase<<<(NB + 256) / 256, 256, 0, st>>>(bf[jpp_b200_handle::B_BNO].as<u32>(), NB + 1, nBase);
+    k_rebase<<<(NB + 256) / 256, 256, 0, st>>>(bf[jpp_b200_handle::B_BEO].as<u32>(), NB + 1, eBase);
+  }
+  H2D(B_INFO, b->node_info + nBase, (size_t)NN * sizeof(jpp_b200_node_info));
   if (compactEntries) {
     H2D(B_ENTRY, b->entry_rows, (size_t)b->num_entry_rows * h->hm.ft.entrySize * 4);
-    H2D(B_ENTRYROW, b->node_entry_row, (size_t)NN * 4);
+    H2D(B_ENTRYROW, b->node_entry_row + nBase, (size_t)NN * 4);
   } else {
-    H2D(B_ENTRY, b->node_entry, (size_t)NN * h->hm.ft.entrySize * 4);
+    H2D(B_ENTRY, b->node_entry + (size_t)nBase * h->hm.ft.entrySize, (size_t)NN * h->hm.ft.entrySize * 4);
   }
   if (h->hm.ft.nPlaceholders) {
     if (rowPh) H2D(B_PH, b->row_placeholders, (size_t)b->num_entry_rows * h->hm.ft.nPlaceholders * 4);
-    else H2D(B_PH, b->node_placeholders, (size_t)NN * h->hm.ft.nPlaceholders * 4);
+    else H2D(B_PH, b->node_placeholders + (size_t)nBase * h->hm.ft.nPlaceholders, (size_t)NN * h->hm.ft.nPlaceholders * 4);
   }
   if (h->hasRnn) {
     if (rowRnn) H2D(B_RNNID, b->row_rnn_id, (size_t)b->num_entry_rows * 4);
-    else H2D(B_RNNID, b->node_rnn_id, (size_t)NN * 4);
+    else H2D(B_RNNID, b->node_rnn_id + nBase, (size_t)NN * 4);
   }
-  H2D(B_ENDS, b->ends, (size_t)NE * sizeof(jpp_b200_node_ptr));
-  if (NC) H2D(B_CPS, b->codepoints, (size_t)NC * sizeof(jpp_b200_codepoint));
+  H2D(B_ENDS, b->ends + eBase, (size_t)NE * sizeof(jpp_b200_node_ptr));
+  if (NC) H2D(B_CPS, b->codepoints + cBase, (size_t)NC * sizeof(jpp_b200_codepoint));
   H2D(B_ORDER, order.data(), (size_t)NS * 4);
   BatchView& bv = h->bv;
   bv = BatchView{};
@@ -1169,7 +1204,7 @@ jpp_b200_status jpp_b200_upload_batch(jpp_b200_handle* h, const jpp_b200_batch* 
     CU_CHECK(h, cudaMemcpyAsync(h->waveNodeOff.data(), P(W_OFF, u32), (size_t)(maxNb + 2) * 4, cudaMemcpyDeviceToHost, st));
     h->waveActive.assign(maxNb + 1, 0);
     for (u32 s = 0; s < NS; ++s) {
-      const u32 nb = b->sent_boundary_off[s + 1] - b->sent_boundary_off[s];
+      const u32 nb = sbo[s + 1] - sbo[s];
       h->waveActive[0] += 1;               // difference array: active for b < nb
       if (nb <= maxNb) h->waveActive[nb] -= 1;
     }
@@ -1210,6 +1245,12 @@ jpp_b200_status jpp_b200_upload_batch(jpp_b200_handle* h, const jpp_b200_batch* 
 #undef ENSURE
 }
 
+
+jpp_b200_status jpp_b200_upload_batch(jpp_b200_handle* h, const jpp_b200_batch* b) {
+  if (!h || !b) return JPP_B200_INVALID_PARAMETER;
+  return upload_window(h, b, 0, b->num_sentences);
+}
+
 jpp_b200_status jpp_b200_score_resident(jpp_b200_handle* h) {
   if (!h) return JPP_B200_INVALID_PARAMETER;
   if (!h->resident) return fail(h, JPP_B200_INVALID_STATE, "no batch resident: call jpp_b200_upload_batch first");
@@ -1230,7 +1271,8 @@ jpp_b200_status jpp_b200_score_resident(jpp_b200_handle* h) {
     const WaveView& wv = h->wv;
     static const bool profileOn = getenv("JPP_B200_PROFILE") != nullptr;
     static const bool serialGbeam = getenv("JPP_B200_SERIAL_GBEAM") != nullptr;  // A/B switch for W1
-    static WaveProfile prof;
+    if (!h->prof) h->prof = new WaveProfile();
+    WaveProfile& prof = *h->prof;
     prof.on = profileOn;
     enum { K_GBEAM, K_PRESCORE, K_CUTOFF, K_ITEMS, K_FINAL, K_FULL, K_KINDS };
     static const char* const kindNames[K_KINDS] = {"k_w_gbeam", "k_w_prescore", "k_w_cutoff", "k_w_items", "k_w_final", "k_w_full"};
@@ -1347,7 +1389,7 @@ jpp_b200_status jpp_b200_score_resident(jpp_b200_handle* h) {
     // counters: tree nodes and scores
     h->counters.rnn_nodes = rows;
   }
-  k_best_path<<<(NS + 127) / 128, 128, 0, st>>>(bv, h->cfg, bf[jpp_b200_handle::B_PATHLEN].as<u32>(), bf[jpp_b200_handle::B_PATHNODES].as<u32>());
+  k_best_path<<<(NS + 127) / 128, 128, 0, st>>>(bv, h->cfg, bf[jpp_b200_handle::B_PATHLEN].as<u32>(), bf[jpp_b200_handle::B_PATHNODES].as<u32>(), h->windowNodeBase);
   CU_CHECK(h, cudaGetLastError());
   CU_CHECK(h, cudaEventRecord(h->ev[8], st));
   CU_CHECK(h, cudaStreamSynchronize(st));
@@ -1392,23 +1434,93 @@ jpp_b200_status jpp_b200_download_result(jpp_b200_handle* h, jpp_b200_result* r)
   cudaStream_t st = h->stream;
   const BatchView& bv = h->bv;
   const size_t NN = bv.totalNodes, B = (size_t)h->cfg.beam, S = h->cfg.S, SP = h->hm.ft.nStored;
-  if (r->node_beam) CU_CHECK(h, cudaMemcpyAsync(r->node_beam, bv.beam, NN * B * sizeof(jpp_b200_beam_element), cudaMemcpyDeviceToHost, st));
-  if (r->node_beam_scores) CU_CHECK(h, cudaMemcpyAsync(r->node_beam_scores, bv.beamScores, NN * B * S * 4, cudaMemcpyDeviceToHost, st));
-  if (r->node_patterns) CU_CHECK(h, cudaMemcpyAsync(r->node_patterns, bv.patterns, NN * SP * 8, cudaMemcpyDeviceToHost, st));
-  if (r->node_t0_score) CU_CHECK(h, cudaMemcpyAsync(r->node_t0_score, bv.t0, NN * 4, cudaMemcpyDeviceToHost, st));
-  if (r->best_path_len) CU_CHECK(h, cudaMemcpyAsync(r->best_path_len, h->buf[jpp_b200_handle::B_PATHLEN].p, (size_t)bv.numSentences * 4, cudaMemcpyDeviceToHost, st));
-  if (r->best_path_nodes) CU_CHECK(h, cudaMemcpyAsync(r->best_path_nodes, h->buf[jpp_b200_handle::B_PATHNODES].p, (size_t)bv.totalBoundaries * 4, cudaMemcpyDeviceToHost, st));
+  // the resident window's slices of the caller's arrays (whole arrays for a plain upload)
+  const size_t n0 = h->windowNodeBase, s0 = h->windowSentBase, b0 = h->windowBndBase;
+  if (r->node_beam) CU_CHECK(h, cudaMemcpyAsync(r->node_beam + n0 * B, bv.beam, NN * B * sizeof(jpp_b200_beam_element), cudaMemcpyDeviceToHost, st));
+  if (r->node_beam_scores) CU_CHECK(h, cudaMemcpyAsync(r->node_beam_scores + n0 * B * S, bv.beamScores, NN * B * S * 4, cudaMemcpyDeviceToHost, st));
+  if (r->node_patterns) CU_CHECK(h, cudaMemcpyAsync(r->node_patterns + n0 * SP, bv.patterns, NN * SP * 8, cudaMemcpyDeviceToHost, st));
+  if (r->node_t0_score) CU_CHECK(h, cudaMemcpyAsync(r->node_t0_score + n0, bv.t0, NN * 4, cudaMemcpyDeviceToHost, st));
+  if (r->best_path_len) CU_CHECK(h, cudaMemcpyAsync(r->best_path_len + s0, h->buf[jpp_b200_handle::B_PATHLEN].p, (size_t)bv.numSentences * 4, cudaMemcpyDeviceToHost, st));
+  if (r->best_path_nodes) CU_CHECK(h, cudaMemcpyAsync(r->best_path_nodes + b0, h->buf[jpp_b200_handle::B_PATHNODES].p, (size_t)bv.totalBoundaries * 4, cudaMemcpyDeviceToHost, st));
   CU_CHECK(h, cudaStreamSynchronize(st));
   return JPP_B200_OK;
 }
 
-jpp_b200_status jpp_b200_score_batch(jpp_b200_handle* h, const jpp_b200_batch* batch, jpp_b200_result* result) {
-  if (!h || !batch || !result) return JPP_B200_INVALID_PARAMETER;
-  jpp_b200_status st = jpp_b200_upload_batch(h, batch);
+namespace {
+
+// second lane: own stream, events and buffers; the model memory of `h`
+jpp_b200_status make_lane(jpp_b200_handle* h) {
+  if (h->lane) return JPP_B200_OK;
+  jpp_b200_handle* l = new (std::nothrow) jpp_b200_handle();
+  if (!l) return fail(h, JPP_B200_INVALID_STATE, "out of host memory");
+  l->device = h->device; l->hm = h->hm; l->cfg = h->cfg; l->pubCfg = h->pubCfg;
+  l->dFt = h->dFt; l->dWeights = h->dWeights; l->rt = h->rt; l->hasRnn = h->hasRnn;
+  for (int i = 0; i < 4; ++i) l->dRnnBlocks[i] = h->dRnnBlocks[i];
+  l->dRnnWt = h->dRnnWt; l->scoreW[0] = h->scoreW[0]; l->scoreW[1] = h->scoreW[1]; l->smCount = h->smCount;
+  l->ownsModel = false;
+  cudaError_t e = cudaStreamCreateWithFlags(&l->stream, cudaStreamNonBlocking);
+  for (auto& ev : l->ev) if (e == cudaSuccess) e = cudaEventCreate(&ev);
+  if (e != cudaSuccess) {
+    jpp_b200_destroy(l);
+    return fail(h, JPP_B200_CUDA_ERROR, std::string("second lane: ") + cudaGetErrorString(e));
+  }
+  h->lane = l;
+  return JPP_B200_OK;
+}
+
+jpp_b200_status run_window(jpp_b200_handle* h, const jpp_b200_batch* batch, u32 lo, u32 hi, jpp_b200_result* result) {
+  jpp_b200_status st = upload_window(h, batch, lo, hi);
   if (st != JPP_B200_OK) return st;
   st = jpp_b200_score_resident(h);
   if (st != JPP_B200_OK) return st;
   return jpp_b200_download_result(h, result);
+}
+
+}  // namespace
+
+// One call = H2D + all kernels + D2H.  Batches of more than a few thousand sentences are cut
+// in two halves of equal node count that run as two lanes (two host threads, two streams, two
+// sets of buffers, one model): the second half's upload hides behind the first half's kernels
+// and the latency-bound kernels of one lane fill the gaps of the other.  Sentences are
+// independent, so the result is the same as scoring the batch in one piece.
+// JPP_B200_LANES=1 turns this off.  The handle holds no resident batch afterwards.
+jpp_b200_status jpp_b200_score_batch(jpp_b200_handle* h, const jpp_b200_batch* batch, jpp_b200_result* result) {
+  if (!h || !batch || !result) return JPP_B200_INVALID_PARAMETER;
+  const char* lanesEnv = getenv("JPP_B200_LANES");
+  const char* minEnv = getenv("JPP_B200_LANE_MIN_SENTENCES");  // tests lower it to reach the two-lane path
+  const bool oneLane = lanesEnv && atoi(lanesEnv) == 1;
+  const u32 minSentences = minEnv ? (u32)std::max(2, atoi(minEnv)) : 4096u;
+  const u32 NS = batch->num_sentences;
+  if (oneLane || NS < minSentences || !batch->sent_boundary_off || !batch->boundary_node_off) return run_window(h, batch, 0, NS, result);
+  // split where half of the nodes lie
+  const u32* sbo = batch->sent_boundary_off;
+  const u32* bno = batch->boundary_node_off;
+  const u64 half = (u64)bno[sbo[NS]] / 2;
+  u32 a = 0, b = NS;
+  while (a < b) {
+    const u32 m = a + (b - a) / 2;
+    if ((u64)bno[sbo[m]] < half) a = m + 1; else b = m;
+  }
+  const u32 mid = std::min(std::max(a, 1u), NS - 1);
+  jpp_b200_status st = make_lane(h);
+  if (st != JPP_B200_OK) return st;
+  jpp_b200_status stB = JPP_B200_OK;
+  std::thread second([&] { stB = run_window(h->lane, batch, mid, NS, result); });
+  const jpp_b200_status stA = run_window(h, batch, 0, mid, result);
+  second.join();
+  h->resident = false;
+  h->lane->resident = false;
+  if (stA != JPP_B200_OK) return stA;
+  if (stB != JPP_B200_OK) { h->error = h->lane->error; return stB; }
+  // counters of the call = both lanes (times: the longer lane)
+  jpp_b200_counters& c = h->counters;
+  const jpp_b200_counters& d = h->lane->counters;
+  c.sentences += d.sentences; c.boundaries += d.boundaries; c.nodes += d.nodes; c.gathers += d.gathers;
+  c.algorithmic_bytes += d.algorithmic_bytes; c.rnn_nodes += d.rnn_nodes; c.rnn_scores += d.rnn_scores;
+  c.walk_gathers += d.walk_gathers; c.walk_bytes += d.walk_bytes; c.launches += d.launches;
+  c.walk_gathers_issued += d.walk_gathers_issued;
+  for (int i = 0; i < 8; ++i) c.kernel_ms[i] = std::max(c.kernel_ms[i], d.kernel_ms[i]);
+  return JPP_B200_OK;
 }
 
 jpp_b200_status jpp_b200_get_counters(const jpp_b200_handle* h, jpp_b200_counters* out) {

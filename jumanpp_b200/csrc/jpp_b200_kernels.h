@@ -1315,7 +1315,8 @@ JPP_HD u32 wave_full_node(const FeatTables& ft, const BatchView& bv, const Score
 
 // 1-best path of a sentence: walk EOS beam[0] back through the (left, prev_beam)
 // links (analysis_result.cc:25-76) and store the node indices in sentence order.
-JPP_HD void best_path_sentence(const BatchView& bv, const ScoreCfg& cfg, u32* pathLen, u32* pathNodes, u32 sent) {
+JPP_HD void best_path_sentence(const BatchView& bv, const ScoreCfg& cfg, u32* pathLen, u32* pathNodes, u32 sent,
+                                u32 nodeBase = 0) {
   const u32 b0 = bv.sentBndOff[sent];
   const u32 nb = bv.sentBndOff[sent + 1] - b0;
   const u32 B = (u32)cfg.beam;
@@ -1332,7 +1333,7 @@ JPP_HD void best_path_sentence(const BatchView& bv, const ScoreCfg& cfg, u32* pa
       bnd = bv.ends[e].boundary;
       node = bv.endNode[e];
       if (bnd < 2) break;
-      if (pass == 1) pathNodes[b0 + (len - 1 - i)] = node;
+      if (pass == 1) pathNodes[b0 + (len - 1 - i)] = node + nodeBase;
       ++i;
     }
     if (pass == 0) len = i;

@@ -107,9 +107,17 @@ class LatticeScorer:
                                         self.model.num_stored_patterns, batch.num_sentences, batch.num_boundaries)
 
     # -- reference: AnalyzerImpl::computeScores for every sentence of the batch
-    def compute_scores(self, batch: abi.StagedBatch, result: abi.ScoreResult | None = None) -> abi.ScoreResult:
+    def compute_scores(self, batch: abi.StagedBatch, result: abi.ScoreResult | None = None,
+                       paths_only: bool = False) -> abi.ScoreResult:
+        """jpp_b200_score_batch: host buffers in, host buffers out.  `paths_only` asks for the
+        device-resolved 1-best paths alone (what the CLI's default output needs)."""
         res = result or self.allocate_result(batch)
         bs, rs = batch.as_struct(), res.as_struct()
+        if paths_only:
+            rs.node_beam = None
+            rs.node_beam_scores = None
+            rs.node_patterns = None
+            rs.node_t0_score = None
         self._check(self._lib.jpp_b200_score_batch(self._h, C.byref(bs), C.byref(rs)))
         return res
 

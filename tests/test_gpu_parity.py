@@ -120,6 +120,25 @@ def test_compact_rows_with_rnn(rnn_dir):
     assert got.node_beam_scores.tobytes() == inline.node_beam_scores.tobytes()
 
 
+@pytest.mark.parametrize("name", ["default", "rnn_h128"])
+def test_two_lanes_give_the_same_result(name, rnn_dir, monkeypatch):
+    """jpp_b200_score_batch cuts large batches in two halves that run concurrently (two streams, two
+    sets of buffers); forced here on a small batch, compact and inline entry forms."""
+    d, model, cfg, batch = load_golden(name, rnn_dir if name.startswith("rnn") else None)
+    monkeypatch.setenv("JPP_B200_LANES", "1")
+    one, _ = gpu_score(model, cfg, batch)
+    monkeypatch.delenv("JPP_B200_LANES")
+    monkeypatch.setenv("JPP_B200_LANE_MIN_SENTENCES", "2")
+    for b in (batch, batch.compact_entries()):
+        two, cnt = gpu_score(model, cfg, b)
+        assert two.node_beam.tobytes() == one.node_beam.tobytes()
+        assert two.node_beam_scores.tobytes() == one.node_beam_scores.tobytes()
+        assert np.array_equal(two.node_patterns, one.node_patterns)
+        assert two.node_t0_score.tobytes() == one.node_t0_score.tobytes()
+        assert two.paths(batch) == one.paths(batch)
+        assert cnt["sentences"] == batch.num_sentences and cnt["nodes"] == batch.num_nodes
+
+
 def abi_mod():
     from jumanpp_b200 import abi
     return abi
