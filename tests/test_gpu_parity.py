@@ -121,15 +121,15 @@ def test_compact_rows_with_rnn(rnn_dir):
 
 
 @pytest.mark.parametrize("name", ["default", "rnn_h128"])
-def test_two_lanes_give_the_same_result(name, rnn_dir, monkeypatch):
+def test_lanes_give_the_same_result(name, rnn_dir, monkeypatch):
     """jpp_b200_score_batch cuts large batches in two halves that run concurrently (two streams, two
     sets of buffers); forced here on a small batch, compact and inline entry forms."""
     d, model, cfg, batch = load_golden(name, rnn_dir if name.startswith("rnn") else None)
     monkeypatch.setenv("JPP_B200_LANES", "1")
     one, _ = gpu_score(model, cfg, batch)
-    monkeypatch.delenv("JPP_B200_LANES")
     monkeypatch.setenv("JPP_B200_LANE_MIN_SENTENCES", "2")
-    for b in (batch, batch.compact_entries()):
+    for lanes, b in (("2", batch), ("2", batch.compact_entries()), ("3", batch), ("4", batch.compact_entries())):
+        monkeypatch.setenv("JPP_B200_LANES", lanes)
         two, cnt = gpu_score(model, cfg, b)
         assert two.node_beam.tobytes() == one.node_beam.tobytes()
         assert two.node_beam_scores.tobytes() == one.node_beam_scores.tobytes()
