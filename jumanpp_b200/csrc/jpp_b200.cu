@@ -896,6 +896,29 @@ struct WaveProfile {
   }
 };
 
+// The perceptron table (256 MiB on the bench model) does not fit the 126 MB L2 and competes there
+// with gigabytes of streamed lattice data.  JPP_B200_L2_PERSIST=<MiB> sets aside that much L2 for
+// persisting lines and marks a matching fraction of the table's lines persisting on the scoring
+// stream (cudaAccessPolicyWindow); everything else on the stream stays normal.  Off by default.
+void apply_l2_policy(jpp_b200_handle* h, cudaStream_t st, size_t tableBytes, const cudaDeviceProp* prop) {
+  const char* e = getenv("JPP_B200_L2_PERSIST");
+  if (!e || atoi(e) <= 0) return;
+  size_t want = (size_t)atoi(e) << 20;
+  want = std::min(want, (size_t)prop->persistingL2CacheMaxSize);
+  if (want == 0 || cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) { cudaGetLastError(); return; }
+  cudaStreamAttrValue attr{};
+  const size_t window = std::min(tableBytes, (size_t)prop->accessPolicyMaxWindowSize);
+  attr.accessPolicyWindow.base_ptr = h->dWeights;
+  attr.accessPolicyWindow.num_bytes = window;
+  attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)want / (double)window);
+  attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+  attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+  if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
+  fprintf(stderr, "[jpp_b200] L2 persisting: %zu MiB set aside (max %d MiB), window %zu MiB (max %d MiB), hit ratio %.2f\n",
+          want >> 20, prop->persistingL2CacheMaxSize >> 20, window >> 20, prop->accessPolicyMaxWindowSize >> 20,
+          attr.accessPolicyWindow.hitRatio);
+}
+
 jpp_b200_status check_config(jpp_b200_handle* h, const jpp_b200_config* c, u32 numScorers) {
   if (c->beam_size <= 0) return fail(h, JPP_B200_INVALID_PARAMETER, "beam size can not be zero for scoring");  // analyzer_impl.cc:53-56
   if (c->right_gbeam_check > 0 && c->right_gbeam_size <= 0)
@@ -1010,6 +1033,7 @@ jpp_b200_status jpp_b200_create(const jpp_b200_model* model, const jpp_b200_conf
   }
   CREATE_CHECK(cudaStreamSynchronize(h->stream));
 #undef CREATE_CHECK
+  apply_l2_policy(h, h->stream, nw * sizeof(float), &prop);
   *out = h;
   return JPP_B200_OK;
 }
@@ -1449,6 +1473,7 @@ jpp_b200_status jpp_b200_download_result(jpp_b200_handle* h, jpp_b200_result* r)
 namespace {
 
 // another lane: own stream, events and buffers; the model memory of `owner`
+// (defined below) L2 residency policy of the weight table on a stream
 jpp_b200_status make_lane(jpp_b200_handle* owner, jpp_b200_handle* prev) {
   if (prev->lane) return JPP_B200_OK;
   jpp_b200_handle* h = owner;
