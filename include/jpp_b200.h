@@ -261,7 +261,8 @@ typedef struct jpp_b200_result {
    * node index into the batch, BOS and EOS excluded, in sentence order) stored
    * at best_path_nodes[sent_boundary_off[s] ...].  A caller that only prints the
    * 1-best analysis (the CLI default) downloads these few MB instead of every
-   * beam.  best_path_len: [num_sentences]; best_path_nodes: [total_boundaries]. */
+   * beam.  best_path_len: [num_sentences]; best_path_nodes: [total_boundaries],
+   * unused slots of a sentence hold 0xFFFFFFFF. */
   uint32_t* best_path_len;
   uint32_t* best_path_nodes;
 } jpp_b200_result;

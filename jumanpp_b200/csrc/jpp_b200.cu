@@ -592,7 +592,15 @@ __global__ void __launch_bounds__(128) k_rnn_level(RnnWork rw, RnnTables rt, con
   }
 }
 
-// Level kernel, layer sizes that are a multiple of 32 (KI = H / 32 <= 6): the same sums as
+// how many blocks share the outputs of one tile of tree nodes: the block's rows of the recurrent
+// matrix (H / split rows of H floats) must fit shared memory; H / split stays a multiple of 4
+__host__ __device__ inline u32 rnn_level_split(u32 H) {
+  u32 split = 1;
+  while ((size_t)H * H * 4 / split > 160 * 1024 && (H / (split * 2)) % 4 == 0) split *= 2;
+  return split;
+}
+
+// Level kernel, layer sizes that are a multiple of 32 (KI = H / 32 <= 8): the same sums as
 // k_rnn_level, arranged so that the additions of the 16/8/4/2/1 tree happen ACROSS lanes.
 // Lane l owns residue l of every dot product: p_l = fma chain over k = l, l+32, ... (KI terms).
 // A warp takes 8 tree nodes (their previous contexts sit in registers, lane l holding elements
@@ -605,16 +613,18 @@ __global__ void __launch_bounds__(128) k_rnn_level(RnnWork rw, RnnTables rt, con
 template <int KI>
 __global__ void __launch_bounds__(256) k_rnn_level_x(RnnWork rw, RnnTables rt, const u32* ctxOff, const u32* rnSent, u32 level) {
   constexpr int TN = 8, TO = 4;
-  extern __shared__ __align__(16) float Ws[];  // recurrent matrix as stored: Ws[o * H + k]
+  extern __shared__ __align__(16) float Ws[];  // this block's rows of the recurrent matrix as stored: Ws[o * H + k]
   const u32 cnt = rw.levelCount[level];
   const u32 tiles = (cnt + TN - 1) / TN;
   const u32 warpsPerBlock = blockDim.x >> 5;
   if (blockIdx.x * warpsPerBlock >= tiles) return;
   constexpr u32 H = 32u * KI;
+  // large layers: the outputs are split over blockIdx.y so that a block's rows fit shared memory
+  const u32 oCount = H / gridDim.y, oBase = blockIdx.y * oCount;
   {
-    const float4* src = reinterpret_cast<const float4*>(rt.matrix);
+    const float4* src = reinterpret_cast<const float4*>(rt.matrix + (size_t)oBase * H);
     float4* dst = reinterpret_cast<float4*>(Ws);
-    for (u32 i = threadIdx.x; i < H * H / 4; i += blockDim.x) dst[i] = src[i];
+    for (u32 i = threadIdx.x; i < oCount * H / 4; i += blockDim.x) dst[i] = src[i];
   }
   __syncthreads();
   const u32 off = rw.levelOff[level];
@@ -646,7 +656,7 @@ __global__ void __launch_bounds__(256) k_rnn_level_x(RnnWork rw, RnnTables rt, c
     const u32 myJ = lane >> 2, myT = lane & 3u;
     const float* myEmb = rt.emb + (size_t)__shfl_sync(full, embRow, myJ) * H;
     float* myOut = rw.ctx + (size_t)__shfl_sync(full, outRow, myJ) * H;
-    for (u32 o0 = 0; o0 < H; o0 += TO) {
+    for (u32 o0 = 0; o0 < oCount; o0 += TO) {
       float P[TN * TO];
 #pragma unroll
       for (int x = 0; x < TN * TO; ++x) P[x] = 0.0f;
@@ -697,7 +707,7 @@ __global__ void __launch_bounds__(256) k_rnn_level_x(RnnWork rw, RnnTables rt, c
         const float a = v2[0], b = v2[1];
         v1 = __fadd_rn(up ? b : a, __shfl_xor_sync(full, up ? a : b, 1));
       }
-      const u32 o = o0 + myT;
+      const u32 o = oBase + o0 + myT;
       const float v = __fadd_rn(v1, myEmb[o]);
       const float r = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-v)));
       if (myJ < nvalid) myOut[o] = r;
@@ -1017,14 +1027,16 @@ jpp_b200_status jpp_b200_create(const jpp_b200_model* model, const jpp_b200_conf
         return JPP_B200_NOT_IMPLEMENTED;
       }
       CREATE_CHECK(cudaFuncSetAttribute(k_rnn_level<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(32 * H * sizeof(float))));
-      if (H % 32 == 0 && H / 32 <= 6) {
-        const int wsBytes = (int)(H * H * sizeof(float));
+      if (H % 32 == 0 && H / 32 <= 8) {
+        const int wsBytes = (int)(H * H * sizeof(float) / rnn_level_split(H));
         CREATE_CHECK(cudaFuncSetAttribute(k_rnn_level_x<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, wsBytes));
         CREATE_CHECK(cudaFuncSetAttribute(k_rnn_level_x<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, wsBytes));
         CREATE_CHECK(cudaFuncSetAttribute(k_rnn_level_x<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, wsBytes));
         CREATE_CHECK(cudaFuncSetAttribute(k_rnn_level_x<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, wsBytes));
         CREATE_CHECK(cudaFuncSetAttribute(k_rnn_level_x<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, wsBytes));
         CREATE_CHECK(cudaFuncSetAttribute(k_rnn_level_x<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, wsBytes));
+        CREATE_CHECK(cudaFuncSetAttribute(k_rnn_level_x<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, wsBytes));
+        CREATE_CHECK(cudaFuncSetAttribute(k_rnn_level_x<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, wsBytes));
       }
     }
     h->rt = RnnTables{r->layer_size, r->maxent_order, r->maxent_size, r->vocab_size, r->nce_constant, r->unk_constant,
@@ -1385,9 +1397,10 @@ jpp_b200_status jpp_b200_score_resident(jpp_b200_handle* h) {
     CU_CHECK(h, cudaEventRecord(h->ev[5], st));
     {
       const u32 H = h->rt.H;
-      const bool crossLane = (H % 32 == 0) && H / 32 <= 6 && !getenv("JPP_B200_RNN_LEVEL_V1");
-      const u32 grid = (u32)h->smCount * 2;
-      const size_t wsBytes = (size_t)H * H * sizeof(float);
+      const bool crossLane = (H % 32 == 0) && H / 32 <= 8 && !getenv("JPP_B200_RNN_LEVEL_V1");
+      const u32 split = rnn_level_split(H);
+      const dim3 grid((u32)h->smCount * 2 / split, split);
+      const size_t wsBytes = (size_t)H * H * sizeof(float) / split;
       for (u32 level = 1; level <= h->maxNb; ++level) {
         if (!crossLane) {
           k_rnn_level<8><<<h->smCount * 4, 128, 4 * 8 * H * sizeof(float), st>>>(rw, h->rt, h->dRnnWt, ctxOff, rnSent, level);
@@ -1399,7 +1412,9 @@ jpp_b200_status jpp_b200_score_resident(jpp_b200_handle* h) {
           case 3: k_rnn_level_x<3><<<grid, 256, wsBytes, st>>>(rw, h->rt, ctxOff, rnSent, level); break;
           case 4: k_rnn_level_x<4><<<grid, 256, wsBytes, st>>>(rw, h->rt, ctxOff, rnSent, level); break;
           case 5: k_rnn_level_x<5><<<grid, 256, wsBytes, st>>>(rw, h->rt, ctxOff, rnSent, level); break;
-          default: k_rnn_level_x<6><<<grid, 256, wsBytes, st>>>(rw, h->rt, ctxOff, rnSent, level); break;
+          case 6: k_rnn_level_x<6><<<grid, 256, wsBytes, st>>>(rw, h->rt, ctxOff, rnSent, level); break;
+          case 7: k_rnn_level_x<7><<<grid, 256, wsBytes, st>>>(rw, h->rt, ctxOff, rnSent, level); break;
+          default: k_rnn_level_x<8><<<grid, 256, wsBytes, st>>>(rw, h->rt, ctxOff, rnSent, level); break;
         }
       }
     }

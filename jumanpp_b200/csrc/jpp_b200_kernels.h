@@ -1321,9 +1321,8 @@ JPP_HD void best_path_sentence(const BatchView& bv, const ScoreCfg& cfg, u32* pa
   const u32 nb = bv.sentBndOff[sent + 1] - b0;
   const u32 B = (u32)cfg.beam;
   pathLen[sent] = 0;
-  if (nb <= 3) return;
   u32 len = 0;
-  for (int pass = 0; pass < 2; ++pass) {
+  for (int pass = 0; pass < 2 && nb > 3; ++pass) {
     u32 node = bv.bndNodeOff[b0 + nb - 1], bnd = nb - 1, slot = 0, i = 0;
     for (;;) {
       const jpp_b200_beam_element el = bv.beam[(size_t)node * B + slot];
@@ -1340,6 +1339,7 @@ JPP_HD void best_path_sentence(const BatchView& bv, const ScoreCfg& cfg, u32* pa
     if (len == 0) break;
   }
   pathLen[sent] = len;
+  for (u32 i = len; i < nb; ++i) pathNodes[b0 + i] = 0xFFFFFFFFu;  // unused slots of the sentence: defined
 }
 
 }  // namespace jppb200

@@ -31,6 +31,7 @@ REF = Path("/root/reference")
 RNN_PARAMS = dict(layer_size=32, maxent_order=3, maxent_size=1 << 16, nce_lnz=9.0, seed=2, vocab=5000)
 RNN2_PARAMS = dict(layer_size=64, maxent_order=4, maxent_size=1 << 15, nce_lnz=7.5, seed=5, vocab=3000)
 RNN3_PARAMS = dict(layer_size=128, maxent_order=3, maxent_size=1 << 16, nce_lnz=9.0, seed=11, vocab=4000)  # bench size
+RNN5_PARAMS = dict(layer_size=256, maxent_order=3, maxent_size=1 << 15, nce_lnz=9.0, seed=17, vocab=2000)  # output split over 2 blocks
 RNN4_PARAMS = dict(layer_size=48, maxent_order=2, maxent_size=1 << 14, nce_lnz=8.0, seed=13, vocab=2000)   # not a multiple of 32
 
 CONFIGS = {
@@ -46,6 +47,7 @@ CONFIGS = {
     "rnn_beam20": ("beam=20 gbeam=20 rcheck=1 rbeam=5 log2w=16 wseed=7 rnn=RNN2 rnn_weight=0.05 nce_bias=3.5", 10),
     "rnn_h128": ("beam=5 gbeam=6 rcheck=1 rbeam=5 log2w=18 wseed=5 rnn=RNN3", 12),
     "rnn_h48": ("beam=4 gbeam=5 rcheck=1 rbeam=4 log2w=16 wseed=6 rnn=RNN4", 10),
+    "rnn_h256": ("beam=20 gbeam=20 rcheck=1 rbeam=5 log2w=16 wseed=8 rnn=RNN5", 8),
 }
 
 
@@ -70,7 +72,8 @@ def main() -> None:
     sents[0] = sents[0][:1]                 # one-codepoint sentence
     sents[1] = "abc12３４" + sents[1][:6]     # ascii / digit unk makers
     sents[2] = sents[2][:3] + "ゴロゴロ" + "ドキドキ"  # onomatopoeia maker
-    for name, prm in (("RNN1", RNN_PARAMS), ("RNN2", RNN2_PARAMS), ("RNN3", RNN3_PARAMS), ("RNN4", RNN4_PARAMS)):
+    for name, prm in (("RNN1", RNN_PARAMS), ("RNN2", RNN2_PARAMS), ("RNN3", RNN3_PARAMS), ("RNN4", RNN4_PARAMS),
+                      ("RNN5", RNN5_PARAMS)):
         words = synth.rnn_vocabulary(dic, prm["vocab"])
         synth.write_rnn_model(tmp / name, words, prm["layer_size"], prm["maxent_order"], prm["maxent_size"],
                               prm["nce_lnz"], prm["seed"])
