@@ -125,15 +125,12 @@ __global__ void __launch_bounds__(128) k_w_gbeam(BatchView bv, ScoreCfg cfg, Wav
 // before it) and the first-seen numbering of the unique left nodes (dedupT1,
 // score_processor.cc:363-385).  GW = 8 (four sentences per warp) when the global beam has at
 // most 8 elements -- a boundary has ~7 left nodes, so a full warp per sentence idles -- else 32.
+// the group's work for sentence `sent` at local boundary `bnd`; every lane of the group calls it
 template <int KB, int GW>
-__global__ void __launch_bounds__(128) k_w_gbeam_warp(BatchView bv, ScoreCfg cfg, WaveView wv, u32 nActive, u32 bnd) {
-  const u32 tid = blockIdx.x * blockDim.x + threadIdx.x;
-  if (tid == 0) wv.selCount[0] = wv.selCount[1] = wv.selCount[2] = 0;
-  const u32 w = tid / GW, lane = threadIdx.x & 31u, sub = lane % GW;
-  if (w >= nActive) return;
+__device__ __forceinline__ void gbeam_group(const BatchView& bv, const ScoreCfg& cfg, const WaveView& wv, u32 sent, u32 bnd) {
+  const u32 lane = threadIdx.x & 31u, sub = lane % GW;
   const unsigned gshift = lane - sub;
   const unsigned gmask = (GW == 32 ? 0xffffffffu : ((1u << GW) - 1u)) << gshift;
-  const u32 sent = bv.sentOrder[w];
   const u32 b0 = bv.sentBndOff[sent];
   const u32 nb = bv.sentBndOff[sent + 1] - b0;
   if (bnd >= nb || nb <= 3) return;
@@ -220,6 +217,15 @@ __global__ void __launch_bounds__(128) k_w_gbeam_warp(BatchView bv, ScoreCfg cfg
   }
 }
 
+template <int KB, int GW>
+__global__ void __launch_bounds__(128) k_w_gbeam_warp(BatchView bv, ScoreCfg cfg, WaveView wv, u32 nActive, u32 bnd) {
+  const u32 tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid == 0) wv.selCount[0] = wv.selCount[1] = wv.selCount[2] = 0;
+  const u32 w = tid / GW;
+  if (w >= nActive) return;
+  gbeam_group<KB, GW>(bv, cfg, wv, bv.sentOrder[w], bnd);
+}
+
 __global__ void __launch_bounds__(kCacheThreads) k_w_prescore(const __grid_constant__ FeatTables ft, BatchView bv, ScoreCfg cfg,
                                                            WaveView wv, const float* __restrict__ w, u32 first, u32 count) {
   extern __shared__ __align__(16) unsigned long long cacheSlots[];
@@ -234,8 +240,11 @@ __global__ void __launch_bounds__(kCacheThreads) k_w_prescore(const __grid_const
 // nth_element selection.  When it does (or with more than 8 right nodes) lane 0 replays
 // std::nth_element exactly as the serial code.  List positions come from a block-wide prefix
 // over the 32 sentences and one atomic per block and list.
-__global__ void __launch_bounds__(256) k_w_cutoff_group(const __grid_constant__ FeatTables ft, BatchView bv, ScoreCfg cfg,
-                                                       WaveView wv, u32 nActive, u32 bnd) {
+// body for a block of 256 threads = 32 sentences: `firstSent` is the block's first index into the
+// longest-first sentence order; the three list counters wv.selCount may live in global memory
+// (wavefront kernels: one atomic per block and list) or in the block's shared memory (fused walk)
+__device__ __forceinline__ void cutoff_group_block(const FeatTables& ft, const BatchView& bv, const ScoreCfg& cfg,
+                                                   const WaveView& wv, u32 nActive, u32 bnd, u32 firstSent) {
   constexpr u32 GW = 8, SPB = 256 / GW;
   static_assert(SPB == 32, "the block prefix below is one warp wide");
   __shared__ u32 sSel[SPB], sBi[SPB], sTri[SPB], sBase[3];
@@ -243,7 +252,7 @@ __global__ void __launch_bounds__(256) k_w_cutoff_group(const __grid_constant__ 
   const u32 lane = threadIdx.x & 31u, sub = lane % GW, grp = threadIdx.x / GW;
   const unsigned gshift = lane - sub;
   const unsigned gmask = ((1u << GW) - 1u) << gshift;
-  const u32 sentIdx = blockIdx.x * SPB + grp;
+  const u32 sentIdx = firstSent + grp;
   if (threadIdx.x < 3) sCnt[threadIdx.x] = 0;
   __syncthreads();
   bool active = sentIdx < nActive;
@@ -408,6 +417,11 @@ __global__ void __launch_bounds__(256) k_w_cutoff_group(const __grid_constant__ 
   }
 }
 
+__global__ void __launch_bounds__(256) k_w_cutoff_group(const __grid_constant__ FeatTables ft, BatchView bv, ScoreCfg cfg,
+                                                       WaveView wv, u32 nActive, u32 bnd) {
+  cutoff_group_block(ft, bv, cfg, wv, nActive, bnd, blockIdx.x * 32u);
+}
+
 // W4: bigram items first, trigram items after them; one 16-byte item per thread
 __global__ void __launch_bounds__(kCacheThreads) k_w_items(const __grid_constant__ FeatTables ft, BatchView bv, WaveView wv,
                                                         const float* __restrict__ w) {
@@ -425,6 +439,113 @@ template <bool SMALL>
 __global__ void __launch_bounds__(128) k_w_final(BatchView bv, ScoreCfg cfg, WaveView wv, u32 first, u32 count) {
   const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < count) wave_final_node<SMALL>(bv, cfg, wv, wv.waveNodes[first + i]);
+}
+
+// ------------------------------------------------------------ fused walk -----
+// The five phases of a wave need each other's results only within a sentence.  A block of 256
+// threads therefore owns 32 sentences (neighbours in the longest-first order, so of similar
+// length) and walks them through ALL their boundaries on its own: the same device functions as
+// the wavefront kernels, __syncthreads() where those have a kernel boundary, the lists of
+// selected nodes / items private to the block (counters in shared memory, no global atomics).
+// Blocks drift apart in phase, so while one block chases the dependent loads of its global
+// beams another one keeps the gather pipe busy -- across kernels that overlap does not exist.
+// Used when the right check is on (a selected-node bound per sentence exists) and beam / global
+// beam fit the 8-lane groups; other configurations take the wavefront kernels.
+constexpr u32 kFusedSent = 32;     // sentences per block
+constexpr u32 kFusedThreads = 256;
+
+inline bool fused_walk_ok(const ScoreCfg& cfg) {
+  static const bool off = getenv("JPP_B200_WAVEFRONT") != nullptr;  // A/B and per-kernel profiling
+  return !off && cfg.rcheck > 0 && cfg.gbeam > 0 && cfg.gbeam <= 8 && cfg.beam <= 8;
+}
+
+template <bool SMALL>
+__global__ void __launch_bounds__(kFusedThreads, 3) k_walk_fused(const __grid_constant__ FeatTables ft, BatchView bv, ScoreCfg cfg,
+                                                               WaveView wv, const float* __restrict__ w, u32 itemCap) {
+  __shared__ u32 sCount[4];                 // selected nodes, bigram items, trigram items of the current wave
+  __shared__ u32 sNodeOff[kFusedSent + 1];  // right nodes of the block's sentences at the current boundary (prefix)
+  __shared__ u32 sNode0[kFusedSent];
+  const u32 NS = bv.numSentences;
+  const u32 firstSent = blockIdx.x * kFusedSent;
+  if (firstSent >= NS) return;
+  const u32 nHere = NS - firstSent < kFusedSent ? NS - firstSent : kFusedSent;
+  const u32 grp = threadIdx.x / 8u, sub = threadIdx.x % 8u;
+  // the block's private lists
+  WaveView lw = wv;
+  lw.selCount = sCount;
+  lw.biItems = wv.biItems + (size_t)blockIdx.x * itemCap;
+  lw.triItems = wv.triItems + (size_t)blockIdx.x * itemCap;
+  lw.scb = wv.scb + (size_t)blockIdx.x * itemCap;
+  lw.tri = wv.tri + 2 * (size_t)blockIdx.x * itemCap;
+  const WLoadDirect wl{w};
+  // longest sentence of the block = its first one
+  u32 maxNb;
+  {
+    const u32 s0 = bv.sentOrder[firstSent];
+    maxNb = bv.sentBndOff[s0 + 1] - bv.sentBndOff[s0];
+  }
+  const u32 mySent = grp < nHere ? bv.sentOrder[firstSent + grp] : 0xFFFFFFFFu;
+  u32 myB0 = 0, myNb = 0;
+  if (mySent != 0xFFFFFFFFu) {
+    myB0 = bv.sentBndOff[mySent];
+    myNb = bv.sentBndOff[mySent + 1] - myB0;
+  }
+  for (u32 bnd = 2; bnd < maxNb; ++bnd) {
+    // W1 + the block's node list of this wave
+    if (threadIdx.x < 3) sCount[threadIdx.x] = 0;
+    u32 R = 0, n0 = 0;
+    if (mySent != 0xFFFFFFFFu && bnd < myNb && myNb > 3) {
+      n0 = bv.bndNodeOff[myB0 + bnd];
+      R = bv.bndNodeOff[myB0 + bnd + 1] - n0;
+      gbeam_group<8, 8>(bv, cfg, lw, mySent, bnd);
+    }
+    if (sub == 0) { sNodeOff[grp + 1] = R; sNode0[grp] = n0; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      u32 v = sNodeOff[threadIdx.x + 1];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const u32 t = __shfl_up_sync(0xffffffffu, v, d);
+        if ((int)threadIdx.x >= d) v += t;
+      }
+      sNodeOff[threadIdx.x + 1] = v;
+      if (threadIdx.x == 0) sNodeOff[0] = 0;
+    }
+    __syncthreads();
+    const u32 T = sNodeOff[kFusedSent];
+    // W2
+    for (u32 i = threadIdx.x; i < T; i += kFusedThreads) {
+      u32 lo = 0, hi = kFusedSent;  // sentence j with sNodeOff[j] <= i < sNodeOff[j + 1]
+      while (hi - lo > 1) {
+        const u32 m = (lo + hi) >> 1;
+        if (sNodeOff[m] <= i) lo = m; else hi = m;
+      }
+      wave_prescore(ft, bv, cfg, lw, wl, sNode0[lo] + (i - sNodeOff[lo]));
+    }
+    __syncthreads();
+    // W3 (positions and items are private to the block: counters in shared memory)
+    cutoff_group_block(ft, bv, cfg, lw, firstSent + nHere, bnd, firstSent);
+    __syncthreads();
+    // W4
+    {
+      const u32 n1 = sCount[1], n2 = sCount[2];
+      for (u32 i = threadIdx.x; i < n1 + n2; i += kFusedThreads) {
+        if (i < n1) wave_item_bigram(ft, bv, lw, wl, lw.biItems[i]);
+        else wave_item_trigram(ft, bv, lw, wl, lw.triItems[i - n1]);
+      }
+    }
+    __syncthreads();
+    // W5
+    for (u32 i = threadIdx.x; i < T; i += kFusedThreads) {
+      u32 lo = 0, hi = kFusedSent;
+      while (hi - lo > 1) {
+        const u32 m = (lo + hi) >> 1;
+        if (sNodeOff[m] <= i) lo = m; else hi = m;
+      }
+      wave_final_node<SMALL>(bv, cfg, lw, sNode0[lo] + (i - sNodeOff[lo]));
+    }
+    __syncthreads();
+  }
 }
 
 // full-beam mode: the whole boundary step of a right node in one thread
@@ -1221,6 +1342,8 @@ static jpp_b200_status upload_window(jpp_b200_handle* h, const jpp_b200_batch* b
       // selected right nodes of one wave: at most right_gbeam_size per active sentence (makeT0cutoffBeam)
       size_t selCap = NN;
       if (h->cfg.rcheck > 0) selCap = std::min<size_t>(NN, (size_t)NS * (u32)h->cfg.rbeam);
+      // the fused walk gives every block of 32 sentences a fixed slice
+      if (fused_walk_ok(h->cfg)) selCap = (size_t)((NS + kFusedSent - 1) / kFusedSent) * kFusedSent * (u32)h->cfg.rbeam;
       if (selCap * G >= 0x7FFFFFFFull) return fail(h, JPP_B200_INVALID_PARAMETER, "batch too large for the item lists; split it");
       ENSURE(W_BIITEMS, (selCap * G + 4) * sizeof(WaveItem)); ENSURE(W_TRIITEMS, (selCap * G + 4) * sizeof(WaveItem));
       ENSURE(W_SCB, (selCap * G + 4) * 4); ENSURE(W_TRI, (selCap * G + 4) * 8);
@@ -1314,7 +1437,15 @@ jpp_b200_status jpp_b200_score_resident(jpp_b200_handle* h) {
     static const char* const kindNames[K_KINDS] = {"k_w_gbeam", "k_w_prescore", "k_w_cutoff", "k_w_items", "k_w_final", "k_w_full"};
     k_w_init<<<(NS + 127) / 128, 128, 0, st>>>(bv, cfg);
     u32 launches = 1;
-    for (u32 bnd = 2; bnd < h->maxNb; ++bnd) {
+    const bool fused = fused_walk_ok(cfg) && !profileOn;
+    if (fused) {
+      const u32 itemCap = kFusedSent * (u32)cfg.rbeam * (u32)cfg.gbeam;
+      const u32 blocks = (NS + kFusedSent - 1) / kFusedSent;
+      if (small_gbeam_ok(cfg)) k_walk_fused<true><<<blocks, kFusedThreads, 0, st>>>(ft, bv, cfg, wv, h->dWeights, itemCap);
+      else k_walk_fused<false><<<blocks, kFusedThreads, 0, st>>>(ft, bv, cfg, wv, h->dWeights, itemCap);
+      ++launches;
+    }
+    for (u32 bnd = 2; bnd < h->maxNb && !fused; ++bnd) {
       const u32 nAct = h->waveActive[bnd];
       if (nAct == 0) break;
       const u32 first = h->waveNodeOff[bnd], count = h->waveNodeOff[bnd + 1] - first;
