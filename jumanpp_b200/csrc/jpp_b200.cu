@@ -575,14 +575,15 @@ __global__ void k_rnn_tree(BatchView bv, ScoreCfg cfg, RnnWork rw) {
   if (s < bv.numSentences) rnn_build_tree(bv, cfg, rw, s);
 }
 
-// level lists (the histogram is accumulated by k_rnn_tree)
+// level lists (the histogram is accumulated by k_rnn_tree); 8 lanes share a sentence's nodes
 __global__ void k_rnn_level_fill(BatchView bv, RnnWork rw, u32* cursor) {
-  const u32 s = blockIdx.x * blockDim.x + threadIdx.x;
+  const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+  const u32 s = t >> 3, sub = t & 7u;
   if (s >= bv.numSentences) return;
   const u32 base0 = rw.rnOff[s];
   const u32 n = rw.rnCount[s];
   const u32 nb = bv.sentBndOff[s + 1] - bv.sentBndOff[s];
-  for (u32 i = 2; i < n; ++i) {
+  for (u32 i = 2 + sub; i < n; i += 8) {
     const u32 q = base0 + i;
     if ((u32)rw.bnd[q] + 1 < nb) {
       const u32 d = (u32)rw.depth[q];
@@ -765,31 +766,47 @@ __global__ void __launch_bounds__(256) k_rnn_level_x(RnnWork rw, RnnTables rt, c
       if (id == -1) id = 0;  // rnn_scorer_gbeam.cc:126-129
       embRow = (u32)id;
     }
-    float c[TN][KI];
+    // contexts of node pairs side by side: one packed FMA (fma.rn.f32x2, two IEEE single-precision
+    // FMAs in one issue slot) advances the same residue of two nodes
+    float2 c2[TN / 2][KI];
 #pragma unroll
     for (int j = 0; j < TN; ++j) {
       const u32 r = __shfl_sync(full, inRow, j);
       const float* cin = rw.ctx + (size_t)r * H;
 #pragma unroll
-      for (int i = 0; i < KI; ++i) c[j][i] = cin[lane + 32u * i];
+      for (int i = 0; i < KI; ++i) {
+        const float v = cin[lane + 32u * i];
+        if (j & 1) c2[j / 2][i].y = v; else c2[j / 2][i].x = v;
+      }
     }
     // lane L finishes pair L = j * TO + t: node j = L / 4, output o0 + (L % 4)
     const u32 myJ = lane >> 2, myT = lane & 3u;
     const float* myEmb = rt.emb + (size_t)__shfl_sync(full, embRow, myJ) * H;
     float* myOut = rw.ctx + (size_t)__shfl_sync(full, outRow, myJ) * H;
     for (u32 o0 = 0; o0 < oCount; o0 += TO) {
-      float P[TN * TO];
+      float2 P2[TN / 2][TO];
 #pragma unroll
-      for (int x = 0; x < TN * TO; ++x) P[x] = 0.0f;
+      for (int jj = 0; jj < TN / 2; ++jj)
+#pragma unroll
+        for (int t = 0; t < TO; ++t) P2[jj][t] = make_float2(0.0f, 0.0f);
 #pragma unroll
       for (int t = 0; t < TO; ++t) {
 #pragma unroll
         for (int i = 0; i < KI; ++i) {
           const float w = Ws[(o0 + t) * H + 32u * i + lane];
+          const float2 ww = make_float2(w, w);
 #pragma unroll
-          for (int j = 0; j < TN; ++j) P[j * TO + t] = __fmaf_rn(w, c[j][i], P[j * TO + t]);
+          for (int jj = 0; jj < TN / 2; ++jj) P2[jj][t] = __ffma2_rn(ww, c2[jj][i], P2[jj][t]);
         }
       }
+      float P[TN * TO];
+#pragma unroll
+      for (int jj = 0; jj < TN / 2; ++jj)
+#pragma unroll
+        for (int t = 0; t < TO; ++t) {
+          P[(2 * jj) * TO + t] = P2[jj][t].x;
+          P[(2 * jj + 1) * TO + t] = P2[jj][t].y;
+        }
       float v16[16], v8[8], v4[4], v2[2], v1;
       {
         const bool up = (lane & 16u) != 0;
@@ -897,9 +914,38 @@ __global__ void k_best_path(BatchView bv, ScoreCfg cfg, u32* pathLen, u32* pathN
   if (s < bv.numSentences) best_path_sentence(bv, cfg, pathLen, pathNodes, s, nodeBase);
 }
 
-__global__ void k_rerank(BatchView bv, ScoreCfg cfg, float w0, float w1) {
-  const u32 s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s < bv.numSentences) rerank_sentence(bv, cfg, w0, w1, s);
+// adjustBeamScores + remakeEosBeam (analyzer_impl.cc:286-294; serial statement: rerank_sentence).
+// Totals of a boundary's global-beam elements depend on totals of EARLIER boundaries only, so
+// the 8 lanes of a group take the elements of one boundary side by side and the group walks
+// the boundaries in order; lane 0 then rebuilds the EOS beam.
+__global__ void __launch_bounds__(256) k_rerank(BatchView bv, ScoreCfg cfg, float w0, float w1) {
+  const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+  const u32 sent = t >> 3, sub = threadIdx.x & 7u;
+  if (sent >= bv.numSentences) return;
+  const unsigned gmask = 0xFFu << ((threadIdx.x & 31u) - sub);
+  const u32 b0 = bv.sentBndOff[sent];
+  const u32 nb = bv.sentBndOff[sent + 1] - b0;
+  if (nb <= 3) return;
+  const u32 B = (u32)cfg.beam, GMAX = (u32)cfg.gbeam, S = cfg.S;
+  for (u32 bnd = 3; bnd < nb; ++bnd) {
+    const u32 gB = b0 + bnd;
+    const u32 G = (bv.bndNodeOff[gB + 1] == bv.bndNodeOff[gB]) ? 0u : bv.gbCount[gB];
+    for (u32 i = sub; i < G; i += 8) {
+      const u32 node = bv.gbNode[(size_t)gB * GMAX + i];
+      const u32 slot = bv.gbSlot[(size_t)gB * GMAX + i];
+      const u32 nbnd = bv.gbLeftBnd[(size_t)gB * GMAX + i];
+      jpp_b200_beam_element* el = bv.beam + (size_t)node * B + slot;
+      const float* sc = bv.beamScores + ((size_t)node * B + slot) * S;
+      float localScore = 0.0f;
+      localScore += sc[0] * w0;
+      localScore += sc[1] * w1;
+      const u32 pnode = bv.endNode[bv.bndEndOff[b0 + nbnd] + el->left];
+      localScore += bv.beam[(size_t)pnode * B + el->prev_beam].total_score;
+      el->total_score = localScore;
+    }
+    __syncwarp(gmask);  // the next boundary reads these totals
+  }
+  if (sub == 0) rerank_eos(bv, cfg, w0, w1, sent);
 }
 
 // ------------------------------------------------------------- helpers ------
@@ -958,7 +1004,7 @@ struct jpp_b200_handle {
          B_PATHLEN, B_PATHNODES,
          W_GBKEY, W_GBLNODE, W_GBT2, W_GBT1IDX, W_T1NODE, W_GCNT, W_UCNT, W_SELCNT, W_BIITEMS, W_TRIITEMS, W_SCB, W_TRI, W_NODES, W_OFF, W_CURSOR,
          R_OFF, R_ID, R_PREV, R_NEXT, R_BND, R_LEN, R_DEPTH, R_HASH, R_RNCNT, R_RSNODE, R_RSSLOT, R_RSEOSG, R_RSRNODE,
-         R_RSCNT, R_CONN, R_BNDHEAD, R_CTX, R_CHNODE, R_CHSLOT, R_CHBND, R_SCLIST, R_SCTOTAL, R_LVLCNT, R_LVLOFF, R_LVLLIST, R_CTXOFF, R_RNSENT, R_CURSOR, R_CUBTMP,
+         R_RSCNT, R_CONN, R_BNDHEAD, R_CTX, R_CHNODE, R_CHSLOT, R_CHBND, R_CHID, R_CHLEN, R_SCLIST, R_SCTOTAL, R_LVLCNT, R_LVLOFF, R_LVLLIST, R_CTXOFF, R_RNSENT, R_CURSOR, R_CUBTMP,
          NUM_BUFS };
   DevBuf buf[NUM_BUFS];
   BatchView bv{};
@@ -1383,7 +1429,7 @@ static jpp_b200_status upload_window(jpp_b200_handle* h, const jpp_b200_batch* b
     ENSURE(R_RSCNT, (size_t)NS * 4); ENSURE(R_CONN, (size_t)NN * B * 4); ENSURE(R_BNDHEAD, (size_t)NB * 4);
     ENSURE(R_LVLCNT, (size_t)(maxNb + 4) * 4); ENSURE(R_LVLOFF, (size_t)(maxNb + 4) * 4); ENSURE(R_CURSOR, (size_t)(maxNb + 4) * 4);
     ENSURE(R_LVLLIST, rnTotal * 4); ENSURE(R_CTXOFF, (size_t)(NS + 1) * 4); ENSURE(R_RNSENT, rnTotal * 4);
-    ENSURE(R_CHNODE, rnTotal * 4); ENSURE(R_CHSLOT, rnTotal * 2); ENSURE(R_CHBND, rnTotal * 2); ENSURE(R_SCLIST, rnTotal * 4);
+    ENSURE(R_CHNODE, rnTotal * 4); ENSURE(R_CHSLOT, rnTotal * 2); ENSURE(R_CHBND, rnTotal * 2); ENSURE(R_CHID, rnTotal * 4); ENSURE(R_CHLEN, rnTotal * 4); ENSURE(R_SCLIST, rnTotal * 4);
     ENSURE(R_SCTOTAL, 16);
     RnnWork& rw = h->rw;
     rw = RnnWork{};
@@ -1393,6 +1439,7 @@ static jpp_b200_status upload_window(jpp_b200_handle* h, const jpp_b200_batch* b
     rw.rsCount = P(R_RSCNT, u32); rw.connNode = P(R_CONN, i32); rw.bndHead = P(R_BNDHEAD, i32);
     rw.levelCount = P(R_LVLCNT, u32); rw.levelOff = P(R_LVLOFF, u32); rw.levelList = P(R_LVLLIST, u32);
     rw.chainNode = P(R_CHNODE, u32); rw.chainSlot = P(R_CHSLOT, u16); rw.chainBnd = P(R_CHBND, u16);
+    rw.chainId = P(R_CHID, i32); rw.chainLen = P(R_CHLEN, i32);
     rw.scoreList = P(R_SCLIST, u32); rw.scoreTotal = P(R_SCTOTAL, u32);
     rw.maxDepth = maxNb + 1;
   }
@@ -1522,7 +1569,7 @@ jpp_b200_status jpp_b200_score_resident(jpp_b200_handle* h) {
     cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, rw.levelCount, rw.levelOff, (int)(h->maxNb + 2), st);
     CU_CHECK(h, bf[jpp_b200_handle::R_CUBTMP].ensure(tmpBytes + 16));
     cub::DeviceScan::ExclusiveSum(bf[jpp_b200_handle::R_CUBTMP].p, tmpBytes, rw.levelCount, rw.levelOff, (int)(h->maxNb + 2), st);
-    k_rnn_level_fill<<<(NS + 127) / 128, 128, 0, st>>>(bv, rw, bf[jpp_b200_handle::R_CURSOR].as<u32>());
+    k_rnn_level_fill<<<(NS * 8 + 255) / 256, 256, 0, st>>>(bv, rw, bf[jpp_b200_handle::R_CURSOR].as<u32>());
     k_rnn_bos<<<NS, 64, 0, st>>>(bv, rw, h->rt, ctxOff);
     CU_CHECK(h, cudaGetLastError());
     CU_CHECK(h, cudaEventRecord(h->ev[5], st));
@@ -1554,7 +1601,7 @@ jpp_b200_status jpp_b200_score_resident(jpp_b200_handle* h) {
     k_rnn_scores<<<h->smCount * 16, 128, 0, st>>>(bv, h->cfg, rw, h->rt, ctxOff, rnSent);
     CU_CHECK(h, cudaGetLastError());
     CU_CHECK(h, cudaEventRecord(h->ev[7], st));
-    k_rerank<<<(NS + 63) / 64, 64, 0, st>>>(bv, h->cfg, h->scoreW[0], h->scoreW[1]);
+    k_rerank<<<(NS * 8 + 255) / 256, 256, 0, st>>>(bv, h->cfg, h->scoreW[0], h->scoreW[1]);
     CU_CHECK(h, cudaGetLastError());
     // counters: tree nodes and scores
     h->counters.rnn_nodes = rows;

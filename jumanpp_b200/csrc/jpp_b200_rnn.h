@@ -49,6 +49,8 @@ struct RnnWork {
   u32* chainNode;     // [rnode capacity] scratch: connections of the path being added
   u16* chainSlot;
   u16* chainBnd;
+  i32* chainId;   // RNN id and surface length of the chain's nodes, fetched while walking back
+  i32* chainLen;
   u32* scoreList;     // [rnode capacity] flat list of score entries of the whole batch
   u32* scoreTotal;    // [1]
   float* ctx;         // [total rnodes][H]
@@ -98,13 +100,29 @@ JPP_HD void rnn_build_tree(const BatchView& bv, const ScoreCfg& cfg, const RnnWo
       u32 curNode = bv.endNode[eosE0 + left0];
       u32 curBnd = bv.ends[eosE0 + left0].boundary;
       u32 curSlot = (u32)key & 0xFFFFu;
+      // the connection's own record and its cache entry are independent loads: issue both, then
+      // decide (one round trip per step of the walk back instead of two)
       i32 known;
-      while ((known = rw.connNode[(size_t)curNode * B + curSlot]) == -1) {
+      for (;;) {
+        known = rw.connNode[(size_t)curNode * B + curSlot];
+        const jpp_b200_beam_element el = bv.beam[(size_t)curNode * B + curSlot];
+        if (known != -1) break;
         rw.chainNode[base0 + len] = curNode;
         rw.chainSlot[base0 + len] = (u16)curSlot;
         rw.chainBnd[base0 + len] = (u16)curBnd;
+        {  // id / length of this node: off the critical path here, ready when the chain is unwound
+          i32 nid;
+          if (bv.nodeRnnId) {
+            nid = bv.nodeRnnId[curNode];
+          } else {
+            const u32 row = bv.nodeEntryRow[curNode];
+            nid = bv.rowRnnId[row < bv.numEntryRows ? row : 0u];  // a bad row fails the call (t0_node flags it)
+          }
+          const jpp_b200_node_info ni = bv.nodeInfo[curNode];
+          rw.chainId[base0 + len] = nid;
+          rw.chainLen[base0 + len] = (i32)ni.end - (i32)ni.start;
+        }
         ++len;
-        const jpp_b200_beam_element el = bv.beam[(size_t)curNode * B + curSlot];
         const u32 e = bv.bndEndOff[b0 + curBnd] + el.left;
         curSlot = el.prev_beam;
         curBnd = bv.ends[e].boundary;
@@ -112,24 +130,22 @@ JPP_HD void rnn_build_tree(const BatchView& bv, const ScoreCfg& cfg, const RnnWo
       }
       first = prev = known;
     }
-    // unwind: deepest new connection first, the EOS fake connection (k == -1) last
+    // unwind: deepest new connection first, the EOS fake connection (k == -1) last; hash and
+    // depth of `prev` travel in registers (they were just computed unless the step collapsed)
+    u64 prevHash = rw.hash[prev];
+    i32 prevDepth = rw.depth[prev];
     for (i32 k = (i32)len - 1; k >= -1; --k) {
       u32 cNode = 0, cSlot = 0, cb;
       i32 id, length;
       if (k >= 0) {
         cNode = rw.chainNode[base0 + k]; cSlot = rw.chainSlot[base0 + k]; cb = rw.chainBnd[base0 + k];
-        if (bv.nodeRnnId) {
-          id = bv.nodeRnnId[cNode];
-        } else {
-          const u32 row = bv.nodeEntryRow[cNode];
-          id = bv.rowRnnId[row < bv.numEntryRows ? row : 0u];  // a bad row fails the call (t0_node flags it)
-        }
-        length = (i32)bv.nodeInfo[cNode].end - (i32)bv.nodeInfo[cNode].start;
+        id = rw.chainId[base0 + k];
+        length = rw.chainLen[base0 + k];
       } else {
         id = 0; length = 0; cb = eosBnd;  // nodeCache_[{eos,0}] = {eos,0,0} (:306-308)
       }
       const u64 data = (u64)(u32)id | ((u64)(u16)length << 32);
-      const u64 hv = fast_hash1_mix(rw.hash[prev], data);
+      const u64 hv = fast_hash1_mix(prevHash, data);
       // crdCache_.find(coord): newest published node with this (boundary, length, id)
       i32 it = -1;
       for (i32 q = rw.bndHead[b0 + cb]; q != -1; q = rw.next[q])
@@ -145,15 +161,19 @@ JPP_HD void rnn_build_tree(const BatchView& bv, const ScoreCfg& cfg, const RnnWo
         rw.rsNode[si] = cNode; rw.rsSlot[si] = (u16)cSlot; rw.rsEosG[si] = k < 0 ? (u16)g : (u16)0xFFFFu;
         rw.rsRnode[si] = mine;
         first = mine;
+        prevHash = rw.hash[mine];
+        prevDepth = rw.depth[mine];
       } else {
         mine = (i32)(base0 + nrn++);
         rw.id[mine] = id; rw.prev[mine] = prev; rw.next[mine] = -1; rw.bnd[mine] = (i32)cb;
-        rw.length[mine] = length; rw.hash[mine] = hv; rw.depth[mine] = rw.depth[prev] + 1;
+        rw.length[mine] = length; rw.hash[mine] = hv; rw.depth[mine] = prevDepth + 1;
+        prevHash = hv;
+        prevDepth = prevDepth + 1;
         if (cb + 1 < nb && rw.levelCount) {  // a context is needed for every node before EOS
 #if defined(__CUDA_ARCH__)
-          atomicAdd(rw.levelCount + rw.depth[mine], 1u);
+          atomicAdd(rw.levelCount + prevDepth, 1u);
 #else
-          rw.levelCount[rw.depth[mine]] += 1;
+          rw.levelCount[prevDepth] += 1;
 #endif
         }
       }
@@ -238,30 +258,11 @@ JPP_HD float rnn_finish_score(const RnnTables& rt, float dot, i32 prevId, i32 id
   return s - rt.nceConstant;
 }
 
-// R4: adjustBeamScores + remakeEosBeam, one thread per sentence
-JPP_HD void rerank_sentence(const BatchView& bv, const ScoreCfg& cfg, float w0, float w1, u32 sent) {
+// remakeEosBeam (analyzer_impl.cc:286-294): the EOS row from the re-scored global beam
+JPP_HD void rerank_eos(const BatchView& bv, const ScoreCfg& cfg, float w0, float w1, u32 sent) {
   const u32 b0 = bv.sentBndOff[sent];
   const u32 nb = bv.sentBndOff[sent + 1] - b0;
-  if (nb <= 3) return;
   const u32 B = (u32)cfg.beam, GMAX = (u32)cfg.gbeam, S = cfg.S;
-  for (u32 bnd = 3; bnd < nb; ++bnd) {
-    const u32 gB = b0 + bnd;
-    if (bv.bndNodeOff[gB + 1] == bv.bndNodeOff[gB]) continue;
-    const u32 G = bv.gbCount[gB];
-    for (u32 i = 0; i < G; ++i) {
-      const u32 node = bv.gbNode[(size_t)gB * GMAX + i];
-      const u32 slot = bv.gbSlot[(size_t)gB * GMAX + i];
-      const u32 nbnd = bv.gbLeftBnd[(size_t)gB * GMAX + i];
-      jpp_b200_beam_element* el = bv.beam + (size_t)node * B + slot;
-      const float* sc = bv.beamScores + ((size_t)node * B + slot) * S;
-      float localScore = 0.0f;
-      localScore += sc[0] * w0;
-      localScore += sc[1] * w1;
-      const u32 pnode = bv.endNode[bv.bndEndOff[b0 + nbnd] + el->left];
-      localScore += bv.beam[(size_t)pnode * B + el->prev_beam].total_score;
-      el->total_score = localScore;
-    }
-  }
   const u32 eosB = b0 + nb - 1;
   const u32 eosNode = bv.bndNodeOff[eosB];
   const u32 eosE0 = bv.bndEndOff[eosB];
@@ -303,6 +304,33 @@ JPP_HD void rerank_sentence(const BatchView& bv, const ScoreCfg& cfg, float w0, 
     srow[(size_t)k * S] = 0.0f;
     srow[(size_t)k * S + 1] = 0.0f;
   }
+}
+
+// R4: adjustBeamScores + remakeEosBeam, one thread per sentence
+JPP_HD void rerank_sentence(const BatchView& bv, const ScoreCfg& cfg, float w0, float w1, u32 sent) {
+  const u32 b0 = bv.sentBndOff[sent];
+  const u32 nb = bv.sentBndOff[sent + 1] - b0;
+  if (nb <= 3) return;
+  const u32 B = (u32)cfg.beam, GMAX = (u32)cfg.gbeam, S = cfg.S;
+  for (u32 bnd = 3; bnd < nb; ++bnd) {
+    const u32 gB = b0 + bnd;
+    if (bv.bndNodeOff[gB + 1] == bv.bndNodeOff[gB]) continue;
+    const u32 G = bv.gbCount[gB];
+    for (u32 i = 0; i < G; ++i) {
+      const u32 node = bv.gbNode[(size_t)gB * GMAX + i];
+      const u32 slot = bv.gbSlot[(size_t)gB * GMAX + i];
+      const u32 nbnd = bv.gbLeftBnd[(size_t)gB * GMAX + i];
+      jpp_b200_beam_element* el = bv.beam + (size_t)node * B + slot;
+      const float* sc = bv.beamScores + ((size_t)node * B + slot) * S;
+      float localScore = 0.0f;
+      localScore += sc[0] * w0;
+      localScore += sc[1] * w1;
+      const u32 pnode = bv.endNode[bv.bndEndOff[b0 + nbnd] + el->left];
+      localScore += bv.beam[(size_t)pnode * B + el->prev_beam].total_score;
+      el->total_score = localScore;
+    }
+  }
+  rerank_eos(bv, cfg, w0, w1, sent);
 }
 
 }  // namespace jppb200

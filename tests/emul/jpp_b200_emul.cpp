@@ -125,7 +125,9 @@ extern "C" int jpp_b200_emul_score_batch(const jpp_b200_model* model, const jpp_
     rw.rsNode = rsNode.data(); rw.rsSlot = rsSlot.data(); rw.rsEosG = rsEosG.data(); rw.rsRnode = rsRnode.data();
     rw.rsCount = rsCount.data(); rw.connNode = conn.data(); rw.bndHead = bndHead.data();
     std::vector<u32> chainNode(tot); std::vector<u16> chainSlot(tot), chainBnd(tot);
+    std::vector<i32> chainId(tot), chainLen(tot);
     rw.chainNode = chainNode.data(); rw.chainSlot = chainSlot.data(); rw.chainBnd = chainBnd.data();
+    rw.chainId = chainId.data(); rw.chainLen = chainLen.data();
     const u32 H = rt.H;
     for (u32 s = 0; s < NS; ++s) {
       rnn_build_tree(bv, cfg, rw, s);
