@@ -351,7 +351,7 @@ def product_arm(args, rank: int, world: int, local_rank: int) -> None:
             "e2e": {"value": e2e_value, "unit": "sentences/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": 1000.0 * e2e_s / args.steps,
                     "entry_rows": (None if batch.entry_rows is None else int(len(batch.entry_rows))),
-                    "how": "one jpp_b200_score_batch call per step from pinned host buffers, three internal lanes (JPP_B200_LANES) "
+                    "how": "one jpp_b200_score_batch call per step from pinned host buffers, six internal lanes (JPP_B200_LANES) "
                            "(entry buffers sent " + ("inline, one per node" if batch.entry_rows is None else "as one row per distinct entry + a row index per node") + "); "
                            "D2H = device-resolved 1-best paths (jpp_b200_result.best_path_*)",
                     "paths_equal_to_one_lane_run": lanes_agree, "pipelined_two_handles": pipelined},

@@ -11,6 +11,8 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <atomic>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -993,6 +995,7 @@ struct jpp_b200_handle {
   u32 windowSentBase = 0, windowBndBase = 0, windowNodeBase = 0;
   // second lane of jpp_b200_score_batch: own stream and buffers, the model memory of this handle
   jpp_b200_handle* lane = nullptr;   // next lane (a chain: at most kMaxLanes - 1 of them)
+  std::mutex* computeToken = nullptr;  // lanes of one handle take turns on the GPU's compute (see jpp_b200_score_batch)
   bool ownsModel = true;
   WaveProfile* prof = nullptr;
   float scoreW[2] = {1.0f, 0.0f};
@@ -1236,6 +1239,7 @@ void jpp_b200_destroy(jpp_b200_handle* h) {
   cudaSetDevice(h->device);
   if (h->lane) jpp_b200_destroy(h->lane);
   delete h->prof;
+  delete h->computeToken;
   for (auto& b : h->buf) b.release();
   if (h->ownsModel) {
     if (h->dFt) cudaFree(h->dFt);
@@ -1687,15 +1691,23 @@ jpp_b200_status make_lane(jpp_b200_handle* owner, jpp_b200_handle* prev) {
   return JPP_B200_OK;
 }
 
-jpp_b200_status run_window(jpp_b200_handle* h, const jpp_b200_batch* batch, u32 lo, u32 hi, jpp_b200_result* result) {
+jpp_b200_status run_window(jpp_b200_handle* h, const jpp_b200_batch* batch, u32 lo, u32 hi, jpp_b200_result* result,
+                           std::mutex* token = nullptr) {
   jpp_b200_status st = upload_window(h, batch, lo, hi);
   if (st != JPP_B200_OK) return st;
-  st = jpp_b200_score_resident(h);
+  if (token) {
+    // one window computes at a time (kernels of two windows side by side slow each other down
+    // more than they overlap); the other lanes' uploads run meanwhile
+    std::lock_guard<std::mutex> turn(*token);
+    st = jpp_b200_score_resident(h);
+  } else {
+    st = jpp_b200_score_resident(h);
+  }
   if (st != JPP_B200_OK) return st;
   return jpp_b200_download_result(h, result);
 }
 
-constexpr int kMaxLanes = 4;
+constexpr int kMaxLanes = 8;
 
 }  // namespace
 
@@ -1704,13 +1716,16 @@ constexpr int kMaxLanes = 4;
 // set of buffers each, one model): the upload of one window hides behind the kernels of
 // another and the latency-bound kernels of one lane fill the gaps of the others.  Sentences are
 // independent, so the result is the same as scoring the batch in one piece.
-// JPP_B200_LANES=n (1..4, default 3: measured 111 / 108.5 / 108.5 ms for 2 / 3 / 4 on the bench
-// batch).  The handle holds no resident batch afterwards.
+// The lanes upload one after the other (PCIe is one pipe: window 0 complete after a sixth of the
+// transfer beats six windows complete at the end) and compute side by side.
+// JPP_B200_LANES=n (1..8, default 6: 108.8 / 86.7 / 84.6 / 82.3 / 82.9 ms per 100 000 sentences for
+// 1 / 3 / 4 / 6 / 8 lanes, 80 ms with the batch already resident).  The handle holds no resident
+// batch afterwards.
 jpp_b200_status jpp_b200_score_batch(jpp_b200_handle* h, const jpp_b200_batch* batch, jpp_b200_result* result) {
   if (!h || !batch || !result) return JPP_B200_INVALID_PARAMETER;
   const char* lanesEnv = getenv("JPP_B200_LANES");
   const char* minEnv = getenv("JPP_B200_LANE_MIN_SENTENCES");  // tests lower it to reach the multi-lane path
-  int nLanes = lanesEnv ? atoi(lanesEnv) : 3;
+  int nLanes = lanesEnv ? atoi(lanesEnv) : 6;
   nLanes = std::max(1, std::min(nLanes, kMaxLanes));
   const u32 minSentences = minEnv ? (u32)std::max(1, atoi(minEnv)) : 2048u;  // per lane
   const u32 NS = batch->num_sentences;
@@ -1735,7 +1750,7 @@ jpp_b200_status jpp_b200_score_batch(jpp_b200_handle* h, const jpp_b200_batch* b
     cut[k] = a;
   }
   cut[nLanes] = NS;
-  jpp_b200_handle* lanes[kMaxLanes] = {h, nullptr, nullptr, nullptr};
+  jpp_b200_handle* lanes[kMaxLanes] = {h};
   for (int k = 1; k < nLanes; ++k) {
     const jpp_b200_status st = make_lane(h, lanes[k - 1]);
     if (st != JPP_B200_OK) return st;
@@ -1743,11 +1758,31 @@ jpp_b200_status jpp_b200_score_batch(jpp_b200_handle* h, const jpp_b200_batch* b
     lanes[k]->cfg = h->cfg;
     lanes[k]->pubCfg = h->pubCfg;
   }
-  jpp_b200_status sts[kMaxLanes] = {JPP_B200_OK, JPP_B200_OK, JPP_B200_OK, JPP_B200_OK};
+  jpp_b200_status sts[kMaxLanes];
+  for (auto& x : sts) x = JPP_B200_OK;
   std::thread workers[kMaxLanes];
-  for (int k = 1; k < nLanes; ++k)
-    workers[k] = std::thread([&, k] { sts[k] = run_window(lanes[k], batch, cut[k], cut[k + 1], result); });
-  sts[0] = run_window(h, batch, cut[0], cut[1], result);
+  if (!h->computeToken) h->computeToken = new std::mutex();
+  const char* serialEnv = getenv("JPP_B200_LANE_TURNS");
+  // JPP_B200_LANE_TURNS=1: one window computes at a time.  Measured slower (100 ms against 85 ms
+  // per 100 000 sentences with the kernels of the windows side by side), so it is off.
+  std::mutex* token = (serialEnv && atoi(serialEnv) == 1) ? h->computeToken : nullptr;
+  // windows start in order: a lane begins its upload when the previous one has finished its own
+  // (PCIe is one pipe; finishing window 0 early matters more than starting all at once)
+  std::atomic<int> uploaded{0};
+  auto work = [&](int k) {
+    jpp_b200_status st = JPP_B200_OK;
+    while (uploaded.load(std::memory_order_acquire) < k) std::this_thread::yield();
+    st = upload_window(lanes[k], batch, cut[k], cut[k + 1]);
+    uploaded.store(k + 1, std::memory_order_release);
+    if (st == JPP_B200_OK) {
+      if (token) { std::lock_guard<std::mutex> turn(*token); st = jpp_b200_score_resident(lanes[k]); }
+      else st = jpp_b200_score_resident(lanes[k]);
+    }
+    if (st == JPP_B200_OK) st = jpp_b200_download_result(lanes[k], result);
+    sts[k] = st;
+  };
+  for (int k = 1; k < nLanes; ++k) workers[k] = std::thread(work, k);
+  work(0);
   for (int k = 1; k < nLanes; ++k) workers[k].join();
   for (int k = 0; k < nLanes; ++k) lanes[k]->resident = false;
   for (int k = 0; k < nLanes; ++k)

@@ -128,7 +128,8 @@ def test_lanes_give_the_same_result(name, rnn_dir, monkeypatch):
     monkeypatch.setenv("JPP_B200_LANES", "1")
     one, _ = gpu_score(model, cfg, batch)
     monkeypatch.setenv("JPP_B200_LANE_MIN_SENTENCES", "2")
-    for lanes, b in (("2", batch), ("2", batch.compact_entries()), ("3", batch), ("4", batch.compact_entries())):
+    for lanes, b in (("2", batch), ("2", batch.compact_entries()), ("3", batch), ("4", batch.compact_entries()),
+                     ("7", batch)):
         monkeypatch.setenv("JPP_B200_LANES", lanes)
         two, cnt = gpu_score(model, cfg, b)
         assert two.node_beam.tobytes() == one.node_beam.tobytes()
