@@ -1387,7 +1387,9 @@ static jpp_b200_status upload_window(jpp_b200_handle* h, const jpp_b200_batch* b
     // wave index (nodes grouped by local boundary) + per-sentence wave state
     ENSURE(W_GBKEY, (size_t)NS * G * 8); ENSURE(W_GBLNODE, (size_t)NS * G * 4); ENSURE(W_GBT2, (size_t)NS * G * 4);
     ENSURE(W_GBT1IDX, (size_t)NS * G); ENSURE(W_T1NODE, (size_t)NS * G * 4); ENSURE(W_GCNT, NS); ENSURE(W_UCNT, NS);
-    ENSURE(W_SELCNT, 16); ENSURE(W_NODES, (size_t)NN * 4 + 16);
+    // the node list per boundary number is only read by the wavefront kernels (and full-beam mode)
+    const bool needWaveIndex = !fused_walk_ok(h->cfg) || getenv("JPP_B200_PROFILE") != nullptr;
+    ENSURE(W_SELCNT, 16); ENSURE(W_NODES, needWaveIndex ? (size_t)NN * 4 + 16 : 16);
     {
       // selected right nodes of one wave: at most right_gbeam_size per active sentence (makeT0cutoffBeam)
       size_t selCap = NN;
@@ -1399,18 +1401,20 @@ static jpp_b200_status upload_window(jpp_b200_handle* h, const jpp_b200_batch* b
       ENSURE(W_SCB, (selCap * G + 4) * 4); ENSURE(W_TRI, (selCap * G + 4) * 8);
     }
     ENSURE(W_OFF, (size_t)(maxNb + 4) * 4); ENSURE(W_CURSOR, (size_t)(maxNb + 4) * 4 * 2);
-    u32* cnt = P(W_CURSOR, u32);
-    u32* cursor = cnt + (maxNb + 4);
-    CU_CHECK(h, cudaMemsetAsync(cnt, 0, (size_t)(maxNb + 4) * 4 * 2, st));
-    k_wave_count<<<(NB + 255) / 256, 256, 0, st>>>(bv, cnt);
-    size_t tmpBytes = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, cnt, P(W_OFF, u32), (int)(maxNb + 2), st);
-    CU_CHECK(h, bf[jpp_b200_handle::R_CUBTMP].ensure(tmpBytes + 16));
-    cub::DeviceScan::ExclusiveSum(bf[jpp_b200_handle::R_CUBTMP].p, tmpBytes, cnt, P(W_OFF, u32), (int)(maxNb + 2), st);
-    k_wave_fill<<<(NB + 255) / 256, 256, 0, st>>>(bv, P(W_OFF, u32), cursor, P(W_NODES, u32));
-    CU_CHECK(h, cudaGetLastError());
     h->waveNodeOff.assign(maxNb + 2, 0);
-    CU_CHECK(h, cudaMemcpyAsync(h->waveNodeOff.data(), P(W_OFF, u32), (size_t)(maxNb + 2) * 4, cudaMemcpyDeviceToHost, st));
+    if (needWaveIndex) {
+      u32* cnt = P(W_CURSOR, u32);
+      u32* cursor = cnt + (maxNb + 4);
+      CU_CHECK(h, cudaMemsetAsync(cnt, 0, (size_t)(maxNb + 4) * 4 * 2, st));
+      k_wave_count<<<(NB + 255) / 256, 256, 0, st>>>(bv, cnt);
+      size_t tmpBytes = 0;
+      cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, cnt, P(W_OFF, u32), (int)(maxNb + 2), st);
+      CU_CHECK(h, bf[jpp_b200_handle::R_CUBTMP].ensure(tmpBytes + 16));
+      cub::DeviceScan::ExclusiveSum(bf[jpp_b200_handle::R_CUBTMP].p, tmpBytes, cnt, P(W_OFF, u32), (int)(maxNb + 2), st);
+      k_wave_fill<<<(NB + 255) / 256, 256, 0, st>>>(bv, P(W_OFF, u32), cursor, P(W_NODES, u32));
+      CU_CHECK(h, cudaGetLastError());
+      CU_CHECK(h, cudaMemcpyAsync(h->waveNodeOff.data(), P(W_OFF, u32), (size_t)(maxNb + 2) * 4, cudaMemcpyDeviceToHost, st));
+    }
     h->waveActive.assign(maxNb + 1, 0);
     for (u32 s = 0; s < NS; ++s) {
       const u32 nb = sbo[s + 1] - sbo[s];
