@@ -74,6 +74,7 @@ __device__ __forceinline__ WLoadCached make_cache(const float* w, unsigned long 
 
 // T0: one thread per node.  No hot-weight cache here: measured 13.4 ms without vs 19.9 ms with
 // (profiles/README.md r1h) -- most unigram features are high-cardinality (surface, base form).
+template <bool LEAN>
 __global__ void __launch_bounds__(128) k_t0(const FeatTables* __restrict__ ftg, BatchView bv, const float* __restrict__ w) {
   // per-thread (divergent) table indices here: shared memory, not the constant bank
   __shared__ FeatTables ft;
@@ -85,7 +86,7 @@ __global__ void __launch_bounds__(128) k_t0(const FeatTables* __restrict__ ftg, 
   __syncthreads();
   const WLoadDirect wl{w};
   const u32 node = blockIdx.x * blockDim.x + threadIdx.x;
-  if (node < bv.totalNodes) t0_node(ft, bv, wl, node);
+  if (node < bv.totalNodes) t0_node<WLoadDirect, LEAN>(ft, bv, wl, node);
 }
 
 // ---- wavefront walk kernels (see jpp_b200_kernels.h "wavefront walk") ----
@@ -1476,7 +1477,11 @@ jpp_b200_status jpp_b200_score_resident(jpp_b200_handle* h) {
   CU_CHECK(h, cudaMemsetAsync(bf[jpp_b200_handle::B_COUNTERS].p, 0, 64, st));
   CU_CHECK(h, cudaMemsetAsync(bf[jpp_b200_handle::B_WORK].p, 0, 16, st));
   CU_CHECK(h, cudaEventRecord(h->ev[2], st));
-  k_t0<<<(NN + 127) / 128, 128, 0, st>>>(h->dFt, bv, h->dWeights);
+  {
+    static const bool t0Array = getenv("JPP_B200_T0_ARRAY") != nullptr;  // A/B: all patterns in a local array
+    if (t0Array) k_t0<false><<<(NN + 127) / 128, 128, 0, st>>>(h->dFt, bv, h->dWeights);
+    else k_t0<true><<<(NN + 127) / 128, 128, 0, st>>>(h->dFt, bv, h->dWeights);
+  }
   CU_CHECK(h, cudaGetLastError());
   CU_CHECK(h, cudaEventRecord(h->ev[3], st));
   {

@@ -70,10 +70,12 @@ inline jpp_b200_status compile_host_model(const jpp_b200_model* m, HostModel* ou
     if (rp[i] < 0 || (u32)rp[i] >= m->num_computations) return bad(JPP_B200_INVALID_PARAMETER, "pattern reference out of range");
     ft.patRefPool[i] = (u8)rp[i];
   }
+  for (u32 i = 0; i < MAX_PAT; ++i) ft.patOfSlot[i] = 0xFF;
   for (u32 p = 0; p < m->num_patterns; ++p) {
     const jpp_b200_pattern& pt = m->patterns[p];
     if (pt.index >= m->num_patterns || pt.ref_off + pt.ref_len > m->pattern_ref_pool_size || pt.ref_len > 255)
       return bad(JPP_B200_INVALID_PARAMETER, "pattern feature out of range");
+    ft.patOfSlot[pt.index] = (u8)p;  // a later pattern with the same slot wins, as in the array form
     ft.patIndex[p] = (u8)pt.index; ft.patRefOff[p] = (u16)pt.ref_off; ft.patRefLen[p] = (u8)pt.ref_len;
     ft.patState[p] = mix(mix(mix(kSeed0, pt.index), pt.ref_len), kPatternSeed);
   }

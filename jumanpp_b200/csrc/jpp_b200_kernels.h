@@ -78,6 +78,7 @@ struct FeatTables {
   u8 compTrueLen[MAX_COMP], compFalseLen[MAX_COMP];
   u16 patRefOff[MAX_PAT];
   u8 patRefLen[MAX_PAT], patIndex[MAX_PAT];
+  u8 patOfSlot[MAX_PAT];   // inverse of patIndex (0xFF: no pattern writes the slot)
   u8 uniT0[MAX_UNI];
   u8 biT0[MAX_BI], biT1[MAX_BI];
   u8 triT0[MAX_TRI], triT1[MAX_TRI], triT2[MAX_TRI];
@@ -283,7 +284,29 @@ JPP_HD u64 prim_value(const FeatTables& ft, u32 p, const i32* entry, const i32* 
   }
 }
 
-template <typename WL>
+// hash of pattern p over the primitive values (pattern_feature_codegen.cc:199-313)
+JPP_HD u64 pattern_value(const FeatTables& ft, u32 p, const u64* prim) {
+  u64 h = ft.patState[p];
+  const u32 off = ft.patRefOff[p];
+  for (u32 k = 0; k < ft.patRefLen[p]; ++k) {
+    const u32 c = ft.patRefPool[off + k];
+    const u32 tl = ft.compTrueLen[c], fl = ft.compFalseLen[c];
+    if (tl == 0 && fl == 0) {
+      h = mix(h, prim[ft.compPrim[c]]);
+    } else if (prim[ft.compPrim[c]] != 0) {
+      for (u32 t = 0; t < tl; ++t) h = mix(h, prim[ft.branchPool[ft.compTrueOff[c] + t]]);
+    } else {
+      for (u32 t = 0; t < fl; ++t) h = mix(h, prim[ft.branchPool[ft.compFalseOff[c] + t]]);
+    }
+  }
+  return h;
+}
+
+// LEAN: a pattern is hashed where it is consumed (stored row, unigram feature) instead of
+// keeping all of them in a per-thread array.  With 2 048 threads per SM that array alone was
+// 0.6 MB of local memory per SM, evicted through L2 to HBM: ncu showed 28 GB written by a kernel
+// whose output is 5 GB (profiles/r2_ncu_summary.md).  The primitive values (8 B x nPrim) stay.
+template <typename WL, bool LEAN = true>
 JPP_HD void t0_node(const FeatTables& ft, const BatchView& bv, const WL& wl, u32 node) {
   const u32 gb = bv.nodeBnd[node];
   const u32 sent = bv.bndSent[gb];
@@ -315,24 +338,15 @@ JPP_HD void t0_node(const FeatTables& ft, const BatchView& bv, const WL& wl, u32
   }
   u64 prim[MAX_PRIM];
   for (u32 i = 0; i < ft.nPrim; ++i) prim[i] = prim_value(ft, i, entry, ph, ni, cps, ncp);
-  u64 pat[MAX_PAT];
-  for (u32 p = 0; p < ft.nPat; ++p) {
-    u64 h = ft.patState[p];
-    const u32 off = ft.patRefOff[p];
-    for (u32 k = 0; k < ft.patRefLen[p]; ++k) {
-      const u32 c = ft.patRefPool[off + k];
-      const u32 tl = ft.compTrueLen[c], fl = ft.compFalseLen[c];
-      if (tl == 0 && fl == 0) {
-        h = mix(h, prim[ft.compPrim[c]]);
-      } else if (prim[ft.compPrim[c]] != 0) {
-        for (u32 t = 0; t < tl; ++t) h = mix(h, prim[ft.branchPool[ft.compTrueOff[c] + t]]);
-      } else {
-        for (u32 t = 0; t < fl; ++t) h = mix(h, prim[ft.branchPool[ft.compFalseOff[c] + t]]);
-      }
-    }
-    pat[ft.patIndex[p]] = h;
-  }
-  for (u32 p = 0; p < SP; ++p) pout[p * pstr] = pat[p];
+  u64 pat[LEAN ? 1 : MAX_PAT];
+  auto slot_value = [&](u32 slot) -> u64 {
+    if (!LEAN) return pat[slot];
+    const u32 p = ft.patOfSlot[slot];
+    return p == 0xFFu ? 0ull : pattern_value(ft, p, prim);
+  };
+  if (!LEAN)
+    for (u32 p = 0; p < ft.nPat; ++p) pat[ft.patIndex[p]] = pattern_value(ft, p, prim);
+  for (u32 p = 0; p < SP; ++p) pout[p * pstr] = slot_value(p);
   // unigram score.  Rows 0..R-2 of a boundary: "float score_part_j = w" for the
   // first uniVars terms then "+=" (pattern_feature_codegen.cc:229-236), summed
   // p0 + p1 + ...; the last row goes through computeUnrolled4RawPerceptron
@@ -348,7 +362,7 @@ JPP_HD void t0_node(const FeatTables& ft, const BatchView& bv, const WL& wl, u32
 #pragma unroll
     for (u32 j = 0; j < T0_LB; ++j) {
       const u32 u = u0 + j < nU ? u0 + j : nU - 1;
-      id[j] = (u32)mix(ft.uniState[u], pat[ft.uniT0[u]]) & mask;
+      id[j] = (u32)mix(ft.uniState[u], slot_value(ft.uniT0[u])) & mask;
     }
     wl.get(id, wv);
 #pragma unroll
