@@ -22,7 +22,7 @@ def nvcc() -> str:
 
 
 def build(force: bool = False, verbose: bool = False, defines: list[str] | None = None, out: Path | None = None) -> Path:
-    """`defines`/`out` build tuning variants (tools/tune_walk.py); the default build is the product."""
+    """`defines`/`out` build tuning variants (e.g. JPP_FUSED_MINBLOCKS) beside the product; the default build is the product."""
     newest = max(p.stat().st_mtime for p in SOURCES + HEADERS)
     if out is not None:
         global LIB

@@ -1638,7 +1638,7 @@ jpp_b200_status jpp_b200_score_resident(jpp_b200_handle* h) {
   c.launches = 2 + h->walkLaunches + (h->hasRnn ? (12ull + h->maxNb) : 0ull);
   // BASELINE.md roofline accounting: 4 B per gather + streaming terms
   const u32 B = (u32)h->cfg.beam, SP = h->hm.ft.nStored;
-  // T0 kernel: entry + NodeInfo + placeholders in, pattern row + score out; walk kernel: see walk_sentence
+  // T0 kernel: entry + NodeInfo + placeholders in, pattern row + score out; walk: step_counters()
   c.algorithmic_bytes = c.walk_bytes + 4ull * t0Nodes * h->hm.ft.nUni +
                         (unsigned long long)NN * (h->hm.ft.entrySize * 4 + 8 + 4 * h->hm.ft.nPlaceholders + 8ull * SP + 4);
   (void)B;
@@ -1700,18 +1700,10 @@ jpp_b200_status make_lane(jpp_b200_handle* owner, jpp_b200_handle* prev) {
   return JPP_B200_OK;
 }
 
-jpp_b200_status run_window(jpp_b200_handle* h, const jpp_b200_batch* batch, u32 lo, u32 hi, jpp_b200_result* result,
-                           std::mutex* token = nullptr) {
+jpp_b200_status run_window(jpp_b200_handle* h, const jpp_b200_batch* batch, u32 lo, u32 hi, jpp_b200_result* result) {
   jpp_b200_status st = upload_window(h, batch, lo, hi);
   if (st != JPP_B200_OK) return st;
-  if (token) {
-    // one window computes at a time (kernels of two windows side by side slow each other down
-    // more than they overlap); the other lanes' uploads run meanwhile
-    std::lock_guard<std::mutex> turn(*token);
-    st = jpp_b200_score_resident(h);
-  } else {
-    st = jpp_b200_score_resident(h);
-  }
+  st = jpp_b200_score_resident(h);
   if (st != JPP_B200_OK) return st;
   return jpp_b200_download_result(h, result);
 }

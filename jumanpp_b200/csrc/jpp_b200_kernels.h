@@ -654,7 +654,6 @@ struct WaveView {
   u32* t1node;     // [NS][G]  unique left nodes, first-seen order
   u8* gCount;      // [NS]
   u8* uCount;      // [NS]
-  u32* selList;    // [cap]    selected right nodes of the wave (global node ids)
   u32* selCount;   // [3]      [0] selected nodes, [1] bigram items, [2] trigram items
   struct WaveItem* biItems;   // [cap*G]
   struct WaveItem* triItems;  // [cap*G]

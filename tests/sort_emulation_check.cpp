@@ -52,7 +52,7 @@ int main() {
     ++checked;
   }
   // n <= 16: std::sort is a plain insertion sort, i.e. stable -- the register fast path
-  // (wave_score_node_small) ranks a candidate by "larger, or equal and earlier"
+  // (wave_final_node<true>) ranks a candidate by "larger, or equal and earlier"
   for (int t = 0; t < 40000; ++t) {
     int n = 1 + (int)(rng() % 16);
     int distinct = 1 + (int)(rng() % 5);
