@@ -912,6 +912,98 @@ __global__ void __launch_bounds__(128) k_rnn_scores(BatchView bv, ScoreCfg cfg, 
   }
 }
 
+// The same scores, a warp per 32 entries, for layer sizes that are a multiple of 32 (KI = H / 32):
+// lane l reads elements l + 32 i of every entry's two rows -- coalesced, one line per load
+// instead of 32 -- and keeps residue l of the 32 dot products; the transpose-reduce of
+// k_rnn_level_x then hands entry L's complete sum to lane L, which finishes the score.
+template <int KI>
+__global__ void __launch_bounds__(128) k_rnn_scores_x(BatchView bv, ScoreCfg cfg, RnnWork rw, RnnTables rt, const u32* ctxOff,
+                                                    const u32* rnSent) {
+  constexpr u32 H = 32u * KI;
+  const u32 total = *rw.scoreTotal;
+  const u32 lane = threadIdx.x & 31u;
+  const u32 warpsPerBlock = blockDim.x >> 5;
+  const unsigned full = 0xffffffffu;
+  const u32 tiles = (total + 31) / 32;
+  for (u32 tile = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); tile < tiles; tile += gridDim.x * warpsPerBlock) {
+    const u32 e = tile * 32 + lane;
+    const bool valid = e < total;
+    u32 si = 0, s = 0, aRow = 0, bRow = 0;
+    i32 q = 0, id = 0, p = 0;
+    bool dot = false;
+    if (valid) {
+      si = rw.scoreList[e];
+      s = rnSent[si];
+      q = rw.rsRnode[si];
+      id = rw.id[q];
+      if (id != rt.unkId) {
+        p = rw.prev[q];
+        aRow = (u32)(id == -1 ? 0 : id);
+        bRow = (u32)ctx_row(rw, ctxOff, rnSent, (u32)p);
+        dot = true;
+      }
+    }
+    float P[32];
+#pragma unroll
+    for (int x = 0; x < 32; ++x) {
+      P[x] = 0.0f;
+      const bool need = __shfl_sync(full, dot ? 1 : 0, x) != 0;
+      const u32 ar = __shfl_sync(full, aRow, x), br = __shfl_sync(full, bRow, x);
+      if (need) {
+        const float* a = rt.nce + (size_t)ar * H;
+        const float* b = rw.ctx + (size_t)br * H;
+#pragma unroll
+        for (int i = 0; i < KI; ++i) P[x] = __fmaf_rn(a[lane + 32u * i], b[lane + 32u * i], P[x]);
+      }
+    }
+    float v16[16], v8[8], v4[4], v2[2], v1;
+    {
+      const bool up = (lane & 16u) != 0;
+#pragma unroll
+      for (int x = 0; x < 16; ++x) {
+        const float a = P[x], b = P[x + 16];
+        v16[x] = __fadd_rn(up ? b : a, __shfl_xor_sync(full, up ? a : b, 16));
+      }
+    }
+    {
+      const bool up = (lane & 8u) != 0;
+#pragma unroll
+      for (int x = 0; x < 8; ++x) {
+        const float a = v16[x], b = v16[x + 8];
+        v8[x] = __fadd_rn(up ? b : a, __shfl_xor_sync(full, up ? a : b, 8));
+      }
+    }
+    {
+      const bool up = (lane & 4u) != 0;
+#pragma unroll
+      for (int x = 0; x < 4; ++x) {
+        const float a = v8[x], b = v8[x + 4];
+        v4[x] = __fadd_rn(up ? b : a, __shfl_xor_sync(full, up ? a : b, 4));
+      }
+    }
+    {
+      const bool up = (lane & 2u) != 0;
+#pragma unroll
+      for (int x = 0; x < 2; ++x) {
+        const float a = v4[x], b = v4[x + 2];
+        v2[x] = __fadd_rn(up ? b : a, __shfl_xor_sync(full, up ? a : b, 2));
+      }
+    }
+    {
+      const bool up = (lane & 1u) != 0;
+      const float a = v2[0], b = v2[1];
+      v1 = __fadd_rn(up ? b : a, __shfl_xor_sync(full, up ? a : b, 1));
+    }
+    if (!valid) continue;
+    float sc;
+    if (!dot) sc = __fadd_rn(rt.unkConstant, __fmul_rn(rt.unkLengthPenalty, (float)rw.length[q]));  // rnn_scorer_gbeam.cc:236-240
+    else sc = rnn_finish_score(rt, v1, rw.id[p], id);
+    const u16 g = rw.rsEosG[si];
+    if (g != 0xFFFFu) bv.eosRnn[(size_t)s * cfg.gbeam + g] = sc;
+    else bv.beamScores[((size_t)rw.rsNode[si] * cfg.beam + rw.rsSlot[si]) * cfg.S + 1] = sc;
+  }
+}
+
 __global__ void k_best_path(BatchView bv, ScoreCfg cfg, u32* pathLen, u32* pathNodes, u32 nodeBase) {
   const u32 s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s < bv.numSentences) best_path_sentence(bv, cfg, pathLen, pathNodes, s, nodeBase);
@@ -1611,7 +1703,24 @@ jpp_b200_status jpp_b200_score_resident(jpp_b200_handle* h) {
     }
     CU_CHECK(h, cudaGetLastError());
     CU_CHECK(h, cudaEventRecord(h->ev[6], st));
-    k_rnn_scores<<<h->smCount * 16, 128, 0, st>>>(bv, h->cfg, rw, h->rt, ctxOff, rnSent);
+    {
+      const u32 H = h->rt.H;
+      const bool coop = (H % 32 == 0) && H / 32 <= 8 && !getenv("JPP_B200_RNN_SCORES_V1");
+      const u32 grid = (u32)h->smCount * 16;
+#define JPP_SCORES_X(KI) k_rnn_scores_x<KI><<<grid, 128, 0, st>>>(bv, h->cfg, rw, h->rt, ctxOff, rnSent)
+      if (!coop) k_rnn_scores<<<grid, 128, 0, st>>>(bv, h->cfg, rw, h->rt, ctxOff, rnSent);
+      else switch (H / 32) {
+        case 1: JPP_SCORES_X(1); break;
+        case 2: JPP_SCORES_X(2); break;
+        case 3: JPP_SCORES_X(3); break;
+        case 4: JPP_SCORES_X(4); break;
+        case 5: JPP_SCORES_X(5); break;
+        case 6: JPP_SCORES_X(6); break;
+        case 7: JPP_SCORES_X(7); break;
+        default: JPP_SCORES_X(8); break;
+      }
+#undef JPP_SCORES_X
+    }
     CU_CHECK(h, cudaGetLastError());
     CU_CHECK(h, cudaEventRecord(h->ev[7], st));
     k_rerank<<<(NS * 8 + 255) / 256, 256, 0, st>>>(bv, h->cfg, h->scoreW[0], h->scoreW[1]);

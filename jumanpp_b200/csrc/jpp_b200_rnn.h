@@ -134,13 +134,24 @@ JPP_HD void rnn_build_tree(const BatchView& bv, const ScoreCfg& cfg, const RnnWo
     // depth of `prev` travel in registers (they were just computed unless the step collapsed)
     u64 prevHash = rw.hash[prev];
     i32 prevDepth = rw.depth[prev];
+    // nodes created since the last collapse of this path: exactly the ones addPath publishes
+    u32 sinceCollapse = 0;
+    // record of step k, loaded one step ahead so that its latency hides behind the list scan
+    u32 nNode = 0, nSlot = 0, nBnd = 0;
+    i32 nId = 0, nLen = 0;
+    if (len > 0) {
+      const u32 j = base0 + len - 1;
+      nNode = rw.chainNode[j]; nSlot = rw.chainSlot[j]; nBnd = rw.chainBnd[j]; nId = rw.chainId[j]; nLen = rw.chainLen[j];
+    }
     for (i32 k = (i32)len - 1; k >= -1; --k) {
       u32 cNode = 0, cSlot = 0, cb;
       i32 id, length;
       if (k >= 0) {
-        cNode = rw.chainNode[base0 + k]; cSlot = rw.chainSlot[base0 + k]; cb = rw.chainBnd[base0 + k];
-        id = rw.chainId[base0 + k];
-        length = rw.chainLen[base0 + k];
+        cNode = nNode; cSlot = nSlot; cb = nBnd; id = nId; length = nLen;
+        if (k > 0) {
+          const u32 j = base0 + (u32)k - 1;
+          nNode = rw.chainNode[j]; nSlot = rw.chainSlot[j]; nBnd = rw.chainBnd[j]; nId = rw.chainId[j]; nLen = rw.chainLen[j];
+        }
       } else {
         id = 0; length = 0; cb = eosBnd;  // nodeCache_[{eos,0}] = {eos,0,0} (:306-308)
       }
@@ -163,12 +174,14 @@ JPP_HD void rnn_build_tree(const BatchView& bv, const ScoreCfg& cfg, const RnnWo
         first = mine;
         prevHash = rw.hash[mine];
         prevDepth = rw.depth[mine];
+        sinceCollapse = 0;
       } else {
         mine = (i32)(base0 + nrn++);
         rw.id[mine] = id; rw.prev[mine] = prev; rw.next[mine] = -1; rw.bnd[mine] = (i32)cb;
         rw.length[mine] = length; rw.hash[mine] = hv; rw.depth[mine] = prevDepth + 1;
         prevHash = hv;
         prevDepth = prevDepth + 1;
+        ++sinceCollapse;
         if (cb + 1 < nb && rw.levelCount) {  // a context is needed for every node before EOS
 #if defined(__CUDA_ARCH__)
           atomicAdd(rw.levelCount + prevDepth, 1u);
@@ -180,12 +193,15 @@ JPP_HD void rnn_build_tree(const BatchView& bv, const ScoreCfg& cfg, const RnnWo
       if (k >= 0) rw.connNode[(size_t)cNode * B + cSlot] = mine;
       prev = mine;
     }
-    // publish (addPath :247-266): from the tip back to `first`
+    // publish (addPath :247-266): from the tip back to `first`.  New nodes of a path get
+    // consecutive ids and link to each other, so the walk over rw.prev is a count-down, and the
+    // boundary of the node made in unwind step k is chainBnd[k]: no dependent loads left here.
     {
-      i32 lastN = prev;
-      i32 k = -1;
-      while (lastN != first) {
-        const u32 cb = (u32)rw.bnd[lastN];
+      const i32 tip = (i32)(base0 + nrn) - 1;
+      for (u32 j = 0; j < sinceCollapse; ++j) {
+        const i32 lastN = tip - (i32)j;
+        const i32 k = (i32)j - 1;
+        const u32 cb = k < 0 ? eosBnd : (u32)rw.chainBnd[base0 + k];
         rw.next[lastN] = rw.bndHead[b0 + cb];
         rw.bndHead[b0 + cb] = lastN;
         const u32 si = base0 + nrs++;
@@ -195,9 +211,8 @@ JPP_HD void rnn_build_tree(const BatchView& bv, const ScoreCfg& cfg, const RnnWo
           rw.rsNode[si] = rw.chainNode[base0 + k]; rw.rsSlot[si] = rw.chainSlot[base0 + k]; rw.rsEosG[si] = (u16)0xFFFFu;
         }
         rw.rsRnode[si] = lastN;
-        lastN = rw.prev[lastN];
-        ++k;
       }
+      (void)first;
     }
   }
   rw.rnCount[sent] = nrn;
