@@ -202,6 +202,17 @@ def emit_result(line: dict) -> None:
     out.flush()
 
 
+def walk_kernel_name(wl) -> str:
+    """The dominant kernel of the step as the library will run it for this configuration
+    (jpp_b200.cu fused_walk_ok): the fused walk, or the wavefront kernels."""
+    fused = (wl["rcheck"] > 0 and 0 < wl["gbeam"] <= 8 and wl["beam"] <= 8 and "JPP_B200_WAVEFRONT" not in os.environ)
+    if fused:
+        return ("k_walk_fused: a block of 256 threads walks 32 sentences through all their boundaries "
+                "(global beam, prescore, cutoff, n-gram items, beam rows; n-gram hash + weight gather + beams)")
+    return ("wave loop: k_w_gbeam_warp + k_w_prescore + k_w_cutoff_group + k_w_items + k_w_final per boundary number "
+            "(n-gram hash + weight gather + beams)")
+
+
 def workload_config(args, wl) -> dict:
     return {"workload": wl["desc"], "sentences_per_gpu": args.sentences, "length_codepoints": [args.min_len, args.max_len],
             "dictionary_rows": args.dict_rows, "weights": f"float[2^{args.log2w}] counter-based synthetic",
@@ -358,7 +369,7 @@ def product_arm(args, rank: int, world: int, local_rank: int) -> None:
             "gpu_launches": int(cnt["launches"]) * args.steps,
             "wall_ms_per_step_resident": 1000.0 * wall_s / args.steps,
             "stage_ms": {k: statistics.mean(x[k] for x in kms) for k in kms[0]},
-            "roofline": {"bound": "hbm", "kernel": "wave loop: k_w_gbeam_warp + k_w_prescore + k_w_cutoff_group + k_w_items + k_w_final per boundary number (n-gram hash + weight gather + beams)",
+            "roofline": {"bound": "hbm", "kernel": walk_kernel_name(info["wl"]),
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                          "algorithmic_bytes_per_launch": int(cnt["walk_bytes"]), "kernel_ms": walk_ms,
