@@ -16,14 +16,15 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 
 
-def test_oracle_equals_reference_on_a_fresh_bench_like_sample(tmp_path):
+@pytest.mark.parametrize("workload,seed,n", [("jumandic_beam5", 23, 300), ("jumandic_beam5", 977, 200),
+                                             ("jumandic_beam20", 101, 120), ("jumandic_beam5_linear", 5, 300)])
+def test_oracle_equals_reference_on_a_fresh_bench_like_sample(tmp_path, workload, seed, n):
     import bench
     from jumanpp_b200 import abi, jppb
     if not bench.HARNESS.exists():
         pytest.skip("oracle/_ref/jpp_ref_harness is not built")
-    n = 300
-    args = argparse.Namespace(workload="jumandic_beam5", cache=str(tmp_path), dict_rows=20000, sentences=n, min_len=4,
-                              max_len=96, seed=23, log2w=20, wseed=5, stage_chunk=2048, gpus=1, inline_entries=True)
+    args = argparse.Namespace(workload=workload, cache=str(tmp_path), dict_rows=20000, sentences=n, min_len=4,
+                              max_len=96, seed=seed, log2w=20, wseed=5, stage_chunk=2048, gpus=1, inline_entries=True)
     info = bench.prepare_workload(args, 0)
     model, cfg, batch = bench.load_staged(info, args, pin=lambda a: a)
     out = info["dir"] / "expected.jppb"
@@ -35,6 +36,8 @@ def test_oracle_equals_reference_on_a_fresh_bench_like_sample(tmp_path):
         ora, _ = oracle_lib.oracle_score(model, cfg, b)
         # parity.py: patterns / links / linear scores bit-equal everywhere; totals and RNN scores bit-equal
         # on the elements of the final paths (the reference leaves the RNN slot of the others uninitialised)
-        rep = parity.compare_with_expected(d, b, ora, rnn=True)
-        assert rep.pop("final_path_elements") > 1000
+        rnn = info["wl"]["rnn"]
+        rep = parity.compare_with_expected(d, b, ora, rnn=rnn)
+        if rnn:
+            assert rep.pop("final_path_elements") > 500
         assert all(v == 0 for v in rep.values()), rep
