@@ -210,6 +210,13 @@ def build(verbose: bool = True) -> None:
     if harness.exists():
         o = compile_one(harness, extra=[f"-I{HERE.parent / 'include'}"])
         link(OUT / "jpp_ref_harness", [o], [lib])
+    # independent RNN check: the reference's vendored Eigen-free legacy implementation
+    # (src/rnn/legacy/rnnlmlib_static.cpp, compiled in place) beside MikolovRnn + eigen_shim
+    legacy_check = HERE / "rnn_legacy_check.cc"
+    if legacy_check.exists():
+        o1 = compile_one(legacy_check)
+        o2 = compile_one(REF / "src/rnn/legacy/rnnlmlib_static.cpp")
+        link(OUT / "rnn_legacy_check", [o1, o2], [lib])
     if verbose:
         print("[build_ref] done ->", OUT, flush=True)
 
