@@ -13,8 +13,8 @@
  * that seam needs; each one cites the reference interface it replaces.
  *
  * Conventions
- *   - plain C, no CUDA / torch types in any signature; `stream` arguments are a
- *     `void*` holding a cudaStream_t (NULL = the handle's own stream);
+ *   - plain C, no CUDA / torch types in any signature; every call runs on streams
+ *     the handle owns and returns when its work is complete;
  *   - all buffers are caller-owned host memory (pinned memory makes the copies
  *     asynchronous, pageable memory works too); the handle owns device copies;
  *   - every function returns a jpp_b200_status; text via jpp_b200_last_error();
@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define JPP_B200_ABI_VERSION 2u
+#define JPP_B200_ABI_VERSION 3u
 
 typedef enum jpp_b200_status {
   JPP_B200_OK = 0,
@@ -144,7 +144,22 @@ typedef struct jpp_b200_model {
   uint32_t num_scorers;
   float score_weights[2];
   const jpp_b200_rnn_model* rnn;  /* NULL when num_scorers == 1 */
+  /* Which of the reference's two feature implementations the float sums replay
+   * (jpp_b200_float_order).  The CLI runs the code GENERATED for its spec
+   * (StaticFeatureFactory, core.cc:18-22): per-row accumulator interleavings of
+   * pattern_feature_codegen.cc:199-313 / partial_ngram_feature_codegen.cc:13-153,
+   * last row of a block through computeUnrolled4RawPerceptron.  A model without
+   * generated code runs PartialNgramDynamicFeatureApply
+   * (feature_impl_ngram_partial.h:196-371): every row through
+   * computeUnrolled4RawPerceptron.  The sums differ in the last bits, and with
+   * them which of two near-equal candidates wins. */
+  uint32_t float_order;
 } jpp_b200_model;
+
+typedef enum jpp_b200_float_order {
+  JPP_B200_ORDER_STATIC_CODEGEN = 0,
+  JPP_B200_ORDER_DYNAMIC = 1
+} jpp_b200_float_order;
 
 /* ----------------------------------------------------------------- config -- */
 
@@ -230,8 +245,9 @@ typedef struct jpp_b200_batch {
 
 /* ConnectionBeamElement (lattice_config.h:70-73) without the raw pointer: the
  * `previous` link is (boundary/position of ends[left], beam index `prev_beam`);
- * a fake (padding) element has left == prev_beam == 0xFFFF and the lowest float
- * (score_processor.h:67-79). */
+ * a fake (padding) element has left == prev_beam == 0xFFFF -- test that, not the
+ * score: the reference pads with memset 0xFF (score_processor.cc:466-468, a NaN
+ * bit pattern) in makeT0Beam and with lowest() in EntryBeam::fake(). */
 typedef struct jpp_b200_beam_element {
   uint16_t left;      /* ConnectionPtr::left : index into the boundary's ends  */
   uint16_t prev_beam; /* ConnectionPtr::beam : beam slot of the previous node  */
@@ -265,7 +281,29 @@ typedef struct jpp_b200_result {
    * unused slots of a sentence hold 0xFFFFFFFF. */
   uint32_t* best_path_len;
   uint32_t* best_path_nodes;
+  /* [num_sentences] 0 = scored; otherwise a mask of jpp_b200_sentence_status bits
+   * saying why the sentence was NOT scored.  The reference fails one sentence and
+   * goes on (`# ERROR` + EOS, jumanpp.cc:166-171); so does the batch: a malformed
+   * lattice is found by a validation kernel at upload, skipped by every scoring
+   * kernel, and reported here with best_path_len = 0 (its other outputs are
+   * undefined).  When this pointer is NULL the caller has not asked for
+   * per-sentence status and a batch with a failed sentence returns
+   * JPP_B200_INVALID_PARAMETER (the other sentences' outputs are still written). */
+  uint8_t* sentence_status;
 } jpp_b200_result;
+
+typedef enum jpp_b200_sentence_status {
+  JPP_B200_SENT_OK = 0,
+  JPP_B200_SENT_BAD_OFFSETS = 1,  /* boundary_node_off / boundary_end_off / codepoint offsets not
+                                     monotonic or past the arrays                             */
+  JPP_B200_SENT_BAD_SHAPE = 2,    /* fewer than 3 or more than 65535 boundaries, or not exactly
+                                     one node on the BOS / BOS / EOS boundaries               */
+  JPP_B200_SENT_BAD_ENDS = 4,     /* ends[] entry that names a later boundary or a node the
+                                     boundary does not have                                   */
+  JPP_B200_SENT_BAD_SPAN = 8,     /* node_info.start/end outside the sentence's codepoints     */
+  JPP_B200_SENT_BAD_ENTRY = 16,   /* node_entry_row >= num_entry_rows                          */
+  JPP_B200_SENT_BAD_RNN_ID = 32   /* RNN id outside [-1, vocab_size)                           */
+} jpp_b200_sentence_status;
 
 /* Work counters of the last scored batch (roofline accounting). */
 typedef struct jpp_b200_counters {
@@ -277,7 +315,7 @@ typedef struct jpp_b200_counters {
                               per boundary; 4 B each)                          */
   uint64_t algorithmic_bytes; /* A of BASELINE.md "Roofline accounting"           */
   uint64_t rnn_nodes;      /* prefix-tree contexts computed (2*H*H flop each)   */
-  uint64_t rnn_scores;
+  uint64_t rnn_scores;     /* RNN scores computed (2*H flop + maxent_order reads each) */
   uint64_t walk_gathers;   /* the same for the wave loop alone (without T0)     */
   uint64_t walk_bytes;     /* algorithmic bytes of the beam-walk kernel alone   */
   uint64_t launches;       /* kernels launched by the last score call           */
@@ -287,14 +325,15 @@ typedef struct jpp_b200_counters {
   uint64_t walk_gathers_issued; /* table reads the wave loop really made: the bigram
                               weights of (node, head element's t1) are read once
                               and summed in both orders, so this is smaller   */
+  uint64_t failed_sentences;  /* sentences with a non-zero status                  */
 } jpp_b200_counters;
 
 typedef struct jpp_b200_handle jpp_b200_handle;
 
 /* Replaces: JumanppEnv::loadModel + initFeatures + makeAnalyzer -> AnalyzerImpl
  * ctor + initScorers (env.cc:11-36, analyzer_impl.cc:27-95): uploads the model
- * once, fixes the scoring configuration. `max_*` bound the per-call batch so
- * device buffers are allocated once (0 = grow on demand). */
+ * once, fixes the scoring configuration.  Device buffers for batches grow on
+ * demand and are kept between calls. */
 jpp_b200_status jpp_b200_create(const jpp_b200_model* model,
                                 const jpp_b200_config* config, int device,
                                 jpp_b200_handle** out);
@@ -308,7 +347,8 @@ jpp_b200_status jpp_b200_set_config(jpp_b200_handle* h,
  * computeScores (analyzer_impl.cc:179-195, :299-309) including the
  * ScoreComputer (RNN) pass and adjustBeamScores/remakeEosBeam (:286-294).
  * Host buffers in, host buffers out; H2D/D2H copies are issued on the
- * handle's stream and the call returns after they complete. */
+ * handle's streams and the call returns after they complete.  A batch of zero
+ * sentences is a no-op (JPP_B200_OK). */
 jpp_b200_status jpp_b200_score_batch(jpp_b200_handle* h,
                                      const jpp_b200_batch* batch,
                                      jpp_b200_result* result);

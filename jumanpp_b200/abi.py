@@ -14,10 +14,16 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # jpp_b200_status
 OK, INVALID_PARAMETER, INVALID_STATE, NOT_IMPLEMENTED, CUDA_ERROR = range(5)
+
+# jpp_b200_float_order
+ORDER_STATIC_CODEGEN, ORDER_DYNAMIC = 0, 1
+
+# jpp_b200_sentence_status bits
+SENT_BAD_OFFSETS, SENT_BAD_SHAPE, SENT_BAD_ENDS, SENT_BAD_SPAN, SENT_BAD_ENTRY, SENT_BAD_RNN_ID = 1, 2, 4, 8, 16, 32
 
 # jpp_b200_prim_kind
 PRIM_COPY, PRIM_SHIFT_MASK, PRIM_PROVIDED, PRIM_BYTE_LENGTH, PRIM_CODEPOINT_SIZE = 1, 2, 3, 4, 5
@@ -61,7 +67,7 @@ class Model(C.Structure):
                 ("pattern_ref_pool_size", C.c_uint32), ("pattern_ref_pool", C.c_void_p),
                 ("num_ngrams", C.c_uint32), ("ngrams", C.POINTER(Ngram)),
                 ("num_scorers", C.c_uint32), ("score_weights", C.c_float * 2),
-                ("rnn", C.POINTER(RnnModel))]
+                ("rnn", C.POINTER(RnnModel)), ("float_order", C.c_uint32)]
 
 
 class Config(C.Structure):
@@ -82,7 +88,7 @@ class Batch(C.Structure):
 class Result(C.Structure):
     _fields_ = [("node_beam", C.c_void_p), ("node_beam_scores", C.c_void_p),
                 ("node_patterns", C.c_void_p), ("node_t0_score", C.c_void_p),
-                ("best_path_len", C.c_void_p), ("best_path_nodes", C.c_void_p)]
+                ("best_path_len", C.c_void_p), ("best_path_nodes", C.c_void_p), ("sentence_status", C.c_void_p)]
 
 
 class Counters(C.Structure):
@@ -90,7 +96,7 @@ class Counters(C.Structure):
                 ("gathers", C.c_uint64), ("algorithmic_bytes", C.c_uint64),
                 ("rnn_nodes", C.c_uint64), ("rnn_scores", C.c_uint64), ("walk_gathers", C.c_uint64),
                 ("walk_bytes", C.c_uint64), ("launches", C.c_uint64), ("kernel_ms", C.c_float * 8),
-                ("walk_gathers_issued", C.c_uint64)]
+                ("walk_gathers_issued", C.c_uint64), ("failed_sentences", C.c_uint64)]
 
 
 NODE_INFO_DT = np.dtype([("entry_ptr", "<i4"), ("start", "<u2"), ("end", "<u2")])
@@ -155,6 +161,7 @@ class ModelSpec:
     num_scorers: int = 1
     weights: np.ndarray | None = None   # explicit table, else synthesised from the seed
     rnn: RnnSpec | None = None
+    float_order: int = ORDER_STATIC_CODEGEN
     _keep: list = field(default_factory=list, repr=False)
 
     @staticmethod
@@ -170,7 +177,9 @@ class ModelSpec:
             pattern_ref_pool=np.ascontiguousarray(d["spec_pattern_ref_pool"], np.int32),
             ngrams=np.ascontiguousarray(d["spec_ngrams"], np.int32),
             num_stored_patterns=int(cnt[3]),
-            score_weights=(float(fcfg[1]), float(fcfg[2])), num_scorers=int(cfg[4]))
+            score_weights=(float(fcfg[1]), float(fcfg[2])), num_scorers=int(cfg[4]),
+            # staged from the reference's dynamic feature path (harness dynamic=1): its float order
+            float_order=ORDER_DYNAMIC if len(cfg) > 8 and int(cfg[8]) else ORDER_STATIC_CODEGEN)
         if "weights" in d:
             ms.weights = np.ascontiguousarray(d["weights"], np.float32)
         if ms.num_scorers == 2:
@@ -209,6 +218,7 @@ class ModelSpec:
         m.num_scorers = self.num_scorers
         m.score_weights[0] = self.score_weights[0]
         m.score_weights[1] = self.score_weights[1]
+        m.float_order = self.float_order
         if self.rnn is not None:
             r = RnnModel()
             r.layer_size, r.maxent_order = self.rnn.layer_size, self.rnn.maxent_order
@@ -422,6 +432,7 @@ class ScoreResult:
     node_t0_score: np.ndarray      # [nodes] f32
     best_path_len: np.ndarray | None = None     # [sentences] u32
     best_path_nodes: np.ndarray | None = None   # [boundaries] u32, sentence s at sent_boundary_off[s]
+    sentence_status: np.ndarray | None = None   # [sentences] u8, 0 = scored (jpp_b200_sentence_status bits)
 
     @staticmethod
     def allocate(num_nodes: int, beam: int, num_scorers: int, stored: int, num_sentences: int = 0,
@@ -432,11 +443,13 @@ class ScoreResult:
         if num_sentences:
             r.best_path_len = np.zeros(num_sentences, np.uint32)
             r.best_path_nodes = np.zeros(num_boundaries, np.uint32)
+            r.sentence_status = np.zeros(num_sentences, np.uint8)
         return r
 
     def as_struct(self) -> Result:
         return Result(_ptr(self.node_beam), _ptr(self.node_beam_scores), _ptr(self.node_patterns),
-                      _ptr(self.node_t0_score), _ptr(self.best_path_len), _ptr(self.best_path_nodes))
+                      _ptr(self.node_t0_score), _ptr(self.best_path_len), _ptr(self.best_path_nodes),
+                      _ptr(self.sentence_status))
 
     def paths(self, batch: "StagedBatch") -> list[list[int]]:
         """1-best node indices per sentence from the device-resolved paths."""

@@ -12,6 +12,8 @@
 #include <new>
 #include <string>
 #include <atomic>
+#include <condition_variable>
+#include <exception>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -50,11 +52,64 @@ __global__ void k_boundary_index(BatchView bv) {
   for (u32 b = bv.sentBndOff[s]; b < bv.sentBndOff[s + 1]; ++b) bv.bndSent[b] = s;
 }
 
+// Validation of everything a caller supplies that the scoring kernels index with (one thread per
+// boundary; reads are guarded, the only writes are status bits).  A sentence that fails is skipped
+// by every later kernel -- sent_span() gives it zero boundaries -- so a malformed lattice costs its
+// own sentence, not the batch and not the process (reference: one `# ERROR` and on to the next
+// sentence, jumanpp.cc:166-171).
+struct ValidateArgs {
+  u32 totalCodepoints, vocab, hasRnn;
+  u8* status;  // [sentences], padded to a multiple of 4 bytes
+};
+
+__device__ __forceinline__ void mark_failed(u8* status, u32 sent, u32 bits) {
+  atomicOr(reinterpret_cast<unsigned*>(status + (sent & ~3u)), bits << (8u * (sent & 3u)));
+}
+
+__global__ void k_validate(BatchView bv, ValidateArgs va) {
+  const u32 gB = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gB >= bv.totalBoundaries) return;
+  const u32 s = bv.bndSent[gB];
+  const u32 b0 = bv.sentBndOff[s];
+  const u32 nb = bv.sentBndOff[s + 1] - b0;
+  const u32 lb = gB - b0;
+  u32 bad = 0;
+  const u32 n0 = bv.bndNodeOff[gB], n1 = bv.bndNodeOff[gB + 1];
+  const u32 e0 = bv.bndEndOff[gB], e1 = bv.bndEndOff[gB + 1];
+  const u32 c0 = bv.sentCpOff[s], c1 = bv.sentCpOff[s + 1];
+  if (n0 > n1 || n1 > bv.totalNodes || e0 > e1 || e1 > bv.totalEnds || c0 > c1 || c1 > va.totalCodepoints) bad |= JPP_B200_SENT_BAD_OFFSETS;
+  if (!bad) {
+    const u32 R = n1 - n0, ncp = c1 - c0;
+    if (((lb < 2 || lb + 1 == nb) && R != 1) || R > 65535u) bad |= JPP_B200_SENT_BAD_SHAPE;
+    for (u32 n = n0; n < n1; ++n) {
+      const jpp_b200_node_info ni = bv.nodeInfo[n];
+      if (lb >= 2 && lb + 1 != nb && (ni.start > ni.end || ni.end > ncp)) bad |= JPP_B200_SENT_BAD_SPAN;
+      i32 id = 0;
+      if (!bv.nodeEntry) {
+        const u32 row = bv.nodeEntryRow[n];
+        if (row >= bv.numEntryRows) bad |= JPP_B200_SENT_BAD_ENTRY;
+        else if (bv.rowRnnId) id = bv.rowRnnId[row];
+      }
+      if (bv.nodeRnnId) id = bv.nodeRnnId[n];
+      if (va.hasRnn && (id < -1 || (id >= 0 && (u32)id >= va.vocab))) bad |= JPP_B200_SENT_BAD_RNN_ID;
+    }
+    for (u32 e = e0; e < e1; ++e) {
+      const jpp_b200_node_ptr p = bv.ends[e];
+      if (p.boundary >= lb) { bad |= JPP_B200_SENT_BAD_ENDS; continue; }
+      // the left boundary's own offsets are checked by its thread; only compare here
+      const u32 l0 = bv.bndNodeOff[b0 + p.boundary], l1 = bv.bndNodeOff[b0 + p.boundary + 1];
+      if (l1 < l0 || p.position >= l1 - l0) bad |= JPP_B200_SENT_BAD_ENDS;
+    }
+  }
+  if (bad) mark_failed(va.status, s, bad);
+}
+
 __global__ void k_node_index(BatchView bv) {
   const u32 b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= bv.totalBoundaries) return;
-  for (u32 n = bv.bndNodeOff[b]; n < bv.bndNodeOff[b + 1]; ++n) bv.nodeBnd[n] = b;
   const u32 s = bv.bndSent[b];
+  if (bv.sentStatus[s]) return;  // its nodes keep nodeBnd = 0xFFFFFFFF: no kernel touches them
+  for (u32 n = bv.bndNodeOff[b]; n < bv.bndNodeOff[b + 1]; ++n) bv.nodeBnd[n] = b;
   const u32 b0 = bv.sentBndOff[s];
   for (u32 e = bv.bndEndOff[b]; e < bv.bndEndOff[b + 1]; ++e) {
     const jpp_b200_node_ptr p = bv.ends[e];
@@ -94,6 +149,7 @@ __global__ void __launch_bounds__(128) k_t0(const FeatTables* __restrict__ ftg, 
 __global__ void k_wave_count(BatchView bv, u32* cnt) {
   const u32 gB = blockIdx.x * blockDim.x + threadIdx.x;
   if (gB >= bv.totalBoundaries) return;
+  if (bv.sentStatus[bv.bndSent[gB]]) return;
   const u32 R = bv.bndNodeOff[gB + 1] - bv.bndNodeOff[gB];
   if (R) atomicAdd(cnt + (gB - bv.sentBndOff[bv.bndSent[gB]]), R);
 }
@@ -101,6 +157,7 @@ __global__ void k_wave_count(BatchView bv, u32* cnt) {
 __global__ void k_wave_fill(BatchView bv, const u32* off, u32* cursor, u32* waveNodes) {
   const u32 gB = blockIdx.x * blockDim.x + threadIdx.x;
   if (gB >= bv.totalBoundaries) return;
+  if (bv.sentStatus[bv.bndSent[gB]]) return;
   const u32 n0 = bv.bndNodeOff[gB];
   const u32 R = bv.bndNodeOff[gB + 1] - n0;
   if (!R) return;
@@ -134,8 +191,8 @@ __device__ __forceinline__ void gbeam_group(const BatchView& bv, const ScoreCfg&
   const u32 lane = threadIdx.x & 31u, sub = lane % GW;
   const unsigned gshift = lane - sub;
   const unsigned gmask = (GW == 32 ? 0xffffffffu : ((1u << GW) - 1u)) << gshift;
-  const u32 b0 = bv.sentBndOff[sent];
-  const u32 nb = bv.sentBndOff[sent + 1] - b0;
+  u32 b0;
+  const u32 nb = sent_span(bv, sent, b0);
   if (bnd >= nb || nb <= 3) return;
   const u32 gB = b0 + bnd;
   const u32 R = bv.bndNodeOff[gB + 1] - bv.bndNodeOff[gB];
@@ -262,8 +319,8 @@ __device__ __forceinline__ void cutoff_group_block(const FeatTables& ft, const B
   u32 sent = 0, gB = 0, n0 = 0, R = 0, G = 0, U = 0, L = 0;
   if (active) {
     sent = bv.sentOrder[sentIdx];
-    const u32 b0 = bv.sentBndOff[sent];
-    const u32 nb = bv.sentBndOff[sent + 1] - b0;
+    u32 b0;
+    const u32 nb = sent_span(bv, sent, b0);
     if (bnd >= nb || nb <= 3) {
       active = false;
     } else {
@@ -457,6 +514,18 @@ __global__ void __launch_bounds__(128) k_w_final(BatchView bv, ScoreCfg cfg, Wav
 constexpr u32 kFusedSent = 32;     // sentences per block
 constexpr u32 kFusedThreads = 256;
 
+// block-wide maximum through a 4-word shared scratch (all threads call it)
+__device__ __forceinline__ u32 block_max_u32(u32 v, u32* scratch) {
+  if (threadIdx.x == 0) scratch[3] = 0;
+  __syncthreads();
+  v = __reduce_max_sync(0xffffffffu, v);
+  if ((threadIdx.x & 31u) == 0) atomicMax(scratch + 3, v);
+  __syncthreads();
+  const u32 r = scratch[3];
+  __syncthreads();
+  return r;
+}
+
 inline bool fused_walk_ok(const ScoreCfg& cfg) {
   static const bool off = getenv("JPP_B200_WAVEFRONT") != nullptr;  // A/B and per-kernel profiling
   return !off && cfg.rcheck > 0 && cfg.gbeam > 0 && cfg.gbeam <= 8 && cfg.beam <= 8;
@@ -481,18 +550,12 @@ __global__ void __launch_bounds__(kFusedThreads, 3) k_walk_fused(const __grid_co
   lw.scb = wv.scb + (size_t)blockIdx.x * itemCap;
   lw.tri = wv.tri + 2 * (size_t)blockIdx.x * itemCap;
   const WLoadDirect wl{w};
-  // longest sentence of the block = its first one
-  u32 maxNb;
-  {
-    const u32 s0 = bv.sentOrder[firstSent];
-    maxNb = bv.sentBndOff[s0 + 1] - bv.sentBndOff[s0];
-  }
   const u32 mySent = grp < nHere ? bv.sentOrder[firstSent + grp] : 0xFFFFFFFFu;
   u32 myB0 = 0, myNb = 0;
-  if (mySent != 0xFFFFFFFFu) {
-    myB0 = bv.sentBndOff[mySent];
-    myNb = bv.sentBndOff[mySent + 1] - myB0;
-  }
+  if (mySent != 0xFFFFFFFFu) myNb = sent_span(bv, mySent, myB0);
+  // longest sentence of the block (the first one in the longest-first order, unless that one failed
+  // validation on the device after the order was made)
+  const u32 maxNb = block_max_u32(myNb, sCount);
   for (u32 bnd = 2; bnd < maxNb; ++bnd) {
     // W1 + the block's node list of this wave
     if (threadIdx.x < 3) sCount[threadIdx.x] = 0;
@@ -585,7 +648,8 @@ __global__ void k_rnn_level_fill(BatchView bv, RnnWork rw, u32* cursor) {
   if (s >= bv.numSentences) return;
   const u32 base0 = rw.rnOff[s];
   const u32 n = rw.rnCount[s];
-  const u32 nb = bv.sentBndOff[s + 1] - bv.sentBndOff[s];
+  u32 b0unused;
+  const u32 nb = sent_span(bv, s, b0unused);
   for (u32 i = 2 + sub; i < n; i += 8) {
     const u32 q = base0 + i;
     if ((u32)rw.bnd[q] + 1 < nb) {
@@ -1018,8 +1082,8 @@ __global__ void __launch_bounds__(256) k_rerank(BatchView bv, ScoreCfg cfg, floa
   const u32 sent = t >> 3, sub = threadIdx.x & 7u;
   if (sent >= bv.numSentences) return;
   const unsigned gmask = 0xFFu << ((threadIdx.x & 31u) - sub);
-  const u32 b0 = bv.sentBndOff[sent];
-  const u32 nb = bv.sentBndOff[sent + 1] - b0;
+  u32 b0;
+  const u32 nb = sent_span(bv, sent, b0);
   if (nb <= 3) return;
   const u32 B = (u32)cfg.beam, GMAX = (u32)cfg.gbeam, S = cfg.S;
   for (u32 bnd = 3; bnd < nb; ++bnd) {
@@ -1097,7 +1161,7 @@ struct jpp_b200_handle {
   enum { B_SBO, B_SCO, B_BNO, B_BEO, B_INFO, B_ENTRY, B_ENTRYROW, B_PH, B_RNNID, B_ENDS, B_CPS, B_NODEBND, B_BNDSENT, B_ENDNODE,
          B_ORDER, B_BEAM, B_BSCORES, B_PATS, B_T0, B_PRE, B_CUT, B_CUTIDX, B_SELPOS, B_BI0, B_GBNODE, B_GBSLOT, B_GBLBND, B_GBCNT,
          B_EOSG, B_EOSLOC, B_EOSRNN, B_COUNTERS, B_WORK,
-         B_PATHLEN, B_PATHNODES,
+         B_PATHLEN, B_PATHNODES, B_STATUS,
          W_GBKEY, W_GBLNODE, W_GBT2, W_GBT1IDX, W_T1NODE, W_GCNT, W_UCNT, W_SELCNT, W_BIITEMS, W_TRIITEMS, W_SCB, W_TRI, W_NODES, W_OFF, W_CURSOR,
          R_OFF, R_ID, R_PREV, R_NEXT, R_BND, R_LEN, R_DEPTH, R_HASH, R_RNCNT, R_RSNODE, R_RSSLOT, R_RSEOSG, R_RSRNODE,
          R_RSCNT, R_CONN, R_BNDHEAD, R_CTX, R_CHNODE, R_CHSLOT, R_CHBND, R_CHID, R_CHLEN, R_SCLIST, R_SCTOTAL, R_LVLCNT, R_LVLOFF, R_LVLLIST, R_CTXOFF, R_RNSENT, R_CURSOR, R_CUBTMP,
@@ -1113,6 +1177,8 @@ struct jpp_b200_handle {
   u32 maxNb = 0;
   size_t rnTotal = 0;
   jpp_b200_counters counters{};
+  std::vector<u8> hostStatus;    // [sentences of the resident window] jpp_b200_sentence_status bits
+  u32 failedSentences = 0;
   cudaEvent_t ev[10] = {};
 };
 
@@ -1121,6 +1187,20 @@ namespace {
 jpp_b200_status fail(jpp_b200_handle* h, jpp_b200_status st, const std::string& msg) {
   if (h) h->error = msg; else g_create_error = msg;
   return st;
+}
+
+// no C++ exception crosses the C ABI
+template <typename F>
+jpp_b200_status guarded(jpp_b200_handle* h, F&& f) noexcept {
+  try {
+    return f();
+  } catch (const std::bad_alloc&) {
+    try { return fail(h, JPP_B200_INVALID_STATE, "out of host memory"); } catch (...) { return JPP_B200_INVALID_STATE; }
+  } catch (const std::exception& e) {
+    try { return fail(h, JPP_B200_INVALID_STATE, std::string("unexpected exception: ") + e.what()); } catch (...) { return JPP_B200_INVALID_STATE; }
+  } catch (...) {
+    return JPP_B200_INVALID_STATE;
+  }
 }
 
 #define CU_CHECK(h, expr)                                                                         \
@@ -1215,7 +1295,7 @@ const char* jpp_b200_build_info(void) {
 
 const char* jpp_b200_last_error(const jpp_b200_handle* h) { return h ? h->error.c_str() : g_create_error.c_str(); }
 
-jpp_b200_status jpp_b200_create(const jpp_b200_model* model, const jpp_b200_config* config, int device,
+static jpp_b200_status create_impl(const jpp_b200_model* model, const jpp_b200_config* config, int device,
                                 jpp_b200_handle** out) {
   if (!model || !config || !out) return fail(nullptr, JPP_B200_INVALID_PARAMETER, "null argument");
   *out = nullptr;
@@ -1237,7 +1317,7 @@ jpp_b200_status jpp_b200_create(const jpp_b200_model* model, const jpp_b200_conf
   h->hm = hm;
   h->pubCfg = *config;
   h->cfg = ScoreCfg{config->beam_size, config->global_beam_size, config->right_gbeam_check, config->right_gbeam_size,
-                    model->num_scorers};
+                    model->num_scorers, hm.ft.dynamicOrder};
   h->scoreW[0] = model->score_weights[0];
   h->scoreW[1] = model->score_weights[1];
 #define CREATE_CHECK(expr)                                                                      \
@@ -1314,7 +1394,8 @@ jpp_b200_status jpp_b200_create(const jpp_b200_model* model, const jpp_b200_conf
 }
 
 jpp_b200_status jpp_b200_set_config(jpp_b200_handle* h, const jpp_b200_config* config) {
-  if (!h || !config) return JPP_B200_INVALID_PARAMETER;
+  if (!h) return JPP_B200_INVALID_PARAMETER;
+  if (!config) return fail(h, JPP_B200_INVALID_PARAMETER, "null config");
   jpp_b200_status st = check_config(h, config, h->cfg.S);
   if (st != JPP_B200_OK) return st;
   h->pubCfg = *config;
@@ -1365,10 +1446,16 @@ static jpp_b200_status upload_window(jpp_b200_handle* h, const jpp_b200_batch* b
   const u32* sbo = b->sent_boundary_off + lo;
   const u32* sco = b->sent_codepoint_off + lo;
   const u32 bBase = sbo[0], cBase = sco[0];
+  // the sentence -> boundary offsets size everything else: they must be sound as a whole.  What
+  // hangs off them (node / end / codepoint offsets, indices) is checked per sentence on the device.
+  for (u32 s = 0; s < NS; ++s)
+    if (sbo[s + 1] < sbo[s]) return fail(h, JPP_B200_INVALID_PARAMETER, "sent_boundary_off is not monotonic");
   const u32 NB = sbo[NS] - bBase;
   const u32* bno = b->boundary_node_off + bBase;
   const u32* beo = b->boundary_end_off + bBase;
   const u32 nBase = bno[0], eBase = beo[0];
+  if (bno[NB] < nBase || beo[NB] < eBase || sco[NS] < cBase)
+    return fail(h, JPP_B200_INVALID_PARAMETER, "boundary_node_off / boundary_end_off / sent_codepoint_off end before they start");
   const u32 NN = bno[NB] - nBase;
   const u32 NE = beo[NB] - eBase;
   const u32 NC = sco[NS] - cBase;
@@ -1380,19 +1467,19 @@ static jpp_b200_status upload_window(jpp_b200_handle* h, const jpp_b200_batch* b
   u32 maxNb = 0;
   size_t rnTotal = 0;
   std::vector<u32> rnOff(NS + 1);
+  h->hostStatus.assign(((size_t)NS + 3) & ~(size_t)3, 0);
+  auto effNb = [&](u32 s) -> u32 { return h->hostStatus[s] ? 0u : sbo[s + 1] - sbo[s]; };
   for (u32 s = 0; s < NS; ++s) {
     order[s] = s;
     const u32 nb = sbo[s + 1] - sbo[s];
-    if (nb < 3 || nb > 65535u) return fail(h, JPP_B200_INVALID_PARAMETER, "sentence with fewer than 3 or more than 65535 boundaries");
-    maxNb = std::max(maxNb, nb);
+    if (nb < 3 || nb > 65535u) h->hostStatus[s] = JPP_B200_SENT_BAD_SHAPE;  // this sentence fails, the batch goes on
+    maxNb = std::max(maxNb, effNb(s));
     rnOff[s] = (u32)rnTotal;
-    rnTotal += (size_t)G * (nb + 1) + 4;
+    rnTotal += (size_t)G * (effNb(s) + 1) + 4;
   }
   rnOff[NS] = (u32)rnTotal;
   if (rnTotal > 0xFFFFFFF0ull) return fail(h, JPP_B200_INVALID_PARAMETER, "batch too large for the RNN workspace; split it");
-  std::stable_sort(order.begin(), order.end(), [&](u32 a, u32 c) {
-    return (sbo[a + 1] - sbo[a]) > (sbo[c + 1] - sbo[c]);
-  });
+  std::stable_sort(order.begin(), order.end(), [&](u32 a, u32 c) { return effNb(a) > effNb(c); });
   h->maxNb = maxNb;
   h->rnTotal = rnTotal;
   auto& bf = h->buf;
@@ -1420,6 +1507,7 @@ static jpp_b200_status upload_window(jpp_b200_handle* h, const jpp_b200_batch* b
   ENSURE(B_EOSG, (size_t)NS * G * 8); ENSURE(B_EOSLOC, (size_t)NS * G * 4); ENSURE(B_EOSRNN, (size_t)NS * G * 4);
   ENSURE(B_COUNTERS, 64); ENSURE(B_WORK, 16);
   ENSURE(B_PATHLEN, (size_t)NS * 4); ENSURE(B_PATHNODES, (size_t)NB * 4);
+  ENSURE(B_STATUS, h->hostStatus.size());
   cudaStream_t st = h->stream;
 #define H2D(idx, src, bytes) CU_CHECK(h, cudaMemcpyAsync(bf[jpp_b200_handle::idx].p, src, bytes, cudaMemcpyHostToDevice, st))
   CU_CHECK(h, cudaEventRecord(h->ev[0], st));
@@ -1451,6 +1539,7 @@ static jpp_b200_status upload_window(jpp_b200_handle* h, const jpp_b200_batch* b
   H2D(B_ENDS, b->ends + eBase, (size_t)NE * sizeof(jpp_b200_node_ptr));
   if (NC) H2D(B_CPS, b->codepoints + cBase, (size_t)NC * sizeof(jpp_b200_codepoint));
   H2D(B_ORDER, order.data(), (size_t)NS * 4);
+  H2D(B_STATUS, h->hostStatus.data(), h->hostStatus.size());
   BatchView& bv = h->bv;
   bv = BatchView{};
   bv.numSentences = NS; bv.totalBoundaries = NB; bv.totalNodes = NN; bv.totalEnds = NE;
@@ -1473,7 +1562,11 @@ static jpp_b200_status upload_window(jpp_b200_handle* h, const jpp_b200_batch* b
   bv.selPos = P(B_SELPOS, u32); bv.bi0 = P(B_BI0, float); bv.gbNode = P(B_GBNODE, u32); bv.gbSlot = P(B_GBSLOT, u16); bv.gbLeftBnd = P(B_GBLBND, u16);
   bv.gbCount = P(B_GBCNT, u8); bv.eosGbeam = P(B_EOSG, u64); bv.eosLocal = P(B_EOSLOC, float); bv.eosRnn = P(B_EOSRNN, float);
   bv.counters = P(B_COUNTERS, unsigned long long);
+  bv.sentStatus = P(B_STATUS, u8);
+  CU_CHECK(h, cudaMemsetAsync(bv.nodeBnd, 0xFF, (size_t)NN * 4, st));  // nodes of failed sentences stay unowned
   k_boundary_index<<<(NS + 127) / 128, 128, 0, st>>>(bv);
+  k_validate<<<(NB + 127) / 128, 128, 0, st>>>(bv, ValidateArgs{NC, h->hasRnn ? (u32)h->rt.vocab : 0u, h->hasRnn ? 1u : 0u, P(B_STATUS, u8)});
+  CU_CHECK(h, cudaMemcpyAsync(h->hostStatus.data(), bv.sentStatus, h->hostStatus.size(), cudaMemcpyDeviceToHost, st));
   k_node_index<<<(NB + 127) / 128, 128, 0, st>>>(bv);
   CU_CHECK(h, cudaGetLastError());
   {
@@ -1510,7 +1603,7 @@ static jpp_b200_status upload_window(jpp_b200_handle* h, const jpp_b200_batch* b
     }
     h->waveActive.assign(maxNb + 1, 0);
     for (u32 s = 0; s < NS; ++s) {
-      const u32 nb = sbo[s + 1] - sbo[s];
+      const u32 nb = effNb(s);
       h->waveActive[0] += 1;               // difference array: active for b < nb
       if (nb <= maxNb) h->waveActive[nb] -= 1;
     }
@@ -1546,6 +1639,8 @@ static jpp_b200_status upload_window(jpp_b200_handle* h, const jpp_b200_batch* b
   }
   CU_CHECK(h, cudaEventRecord(h->ev[1], st));
   CU_CHECK(h, cudaStreamSynchronize(st));
+  h->failedSentences = 0;
+  for (u32 s = 0; s < NS; ++s) h->failedSentences += h->hostStatus[s] != 0;
   h->resident = true;
   return JPP_B200_OK;
 #undef H2D
@@ -1553,12 +1648,12 @@ static jpp_b200_status upload_window(jpp_b200_handle* h, const jpp_b200_batch* b
 }
 
 
-jpp_b200_status jpp_b200_upload_batch(jpp_b200_handle* h, const jpp_b200_batch* b) {
+static jpp_b200_status upload_batch_impl(jpp_b200_handle* h, const jpp_b200_batch* b) {
   if (!h || !b) return JPP_B200_INVALID_PARAMETER;
   return upload_window(h, b, 0, b->num_sentences);
 }
 
-jpp_b200_status jpp_b200_score_resident(jpp_b200_handle* h) {
+static jpp_b200_status score_resident_impl(jpp_b200_handle* h) {
   if (!h) return JPP_B200_INVALID_PARAMETER;
   if (!h->resident) return fail(h, JPP_B200_INVALID_STATE, "no batch resident: call jpp_b200_upload_batch first");
   CU_CHECK(h, cudaSetDevice(h->device));
@@ -1727,6 +1822,7 @@ jpp_b200_status jpp_b200_score_resident(jpp_b200_handle* h) {
     CU_CHECK(h, cudaGetLastError());
     // counters: tree nodes and scores
     h->counters.rnn_nodes = rows;
+    h->counters.rnn_scores = 0;
   }
   k_best_path<<<(NS + 127) / 128, 128, 0, st>>>(bv, h->cfg, bf[jpp_b200_handle::B_PATHLEN].as<u32>(), bf[jpp_b200_handle::B_PATHNODES].as<u32>(), h->windowNodeBase);
   CU_CHECK(h, cudaGetLastError());
@@ -1735,9 +1831,17 @@ jpp_b200_status jpp_b200_score_resident(jpp_b200_handle* h) {
   // counters
   unsigned long long dc[8] = {0};
   CU_CHECK(h, cudaMemcpy(dc, bf[jpp_b200_handle::B_COUNTERS].p, 64, cudaMemcpyDeviceToHost));
-  if (dc[7]) return fail(h, JPP_B200_INVALID_PARAMETER, "batch.node_entry_row holds an index >= num_entry_rows");
+  if (h->hasRnn) {
+    u32 nScores = 0;
+    CU_CHECK(h, cudaMemcpy(&nScores, h->rw.scoreTotal, 4, cudaMemcpyDeviceToHost));
+    h->counters.rnn_scores = nScores;
+  } else {
+    h->counters.rnn_nodes = 0;
+    h->counters.rnn_scores = 0;
+  }
   jpp_b200_counters& c = h->counters;
   c.sentences = NS; c.boundaries = NB; c.nodes = NN;
+  c.failed_sentences = h->failedSentences;
   // T0 runs on every node except the two BOS nodes of each sentence
   const unsigned long long t0Nodes = (unsigned long long)NN - 2ull * NS;
   c.gathers = dc[0] + t0Nodes * h->hm.ft.nUni;
@@ -1766,7 +1870,7 @@ jpp_b200_status jpp_b200_score_resident(jpp_b200_handle* h) {
   return JPP_B200_OK;
 }
 
-jpp_b200_status jpp_b200_download_result(jpp_b200_handle* h, jpp_b200_result* r) {
+static jpp_b200_status download_result_impl(jpp_b200_handle* h, jpp_b200_result* r) {
   if (!h || !r) return JPP_B200_INVALID_PARAMETER;
   if (!h->resident) return fail(h, JPP_B200_INVALID_STATE, "no batch resident");
   CU_CHECK(h, cudaSetDevice(h->device));
@@ -1782,6 +1886,16 @@ jpp_b200_status jpp_b200_download_result(jpp_b200_handle* h, jpp_b200_result* r)
   if (r->best_path_len) CU_CHECK(h, cudaMemcpyAsync(r->best_path_len + s0, h->buf[jpp_b200_handle::B_PATHLEN].p, (size_t)bv.numSentences * 4, cudaMemcpyDeviceToHost, st));
   if (r->best_path_nodes) CU_CHECK(h, cudaMemcpyAsync(r->best_path_nodes + b0, h->buf[jpp_b200_handle::B_PATHNODES].p, (size_t)bv.totalBoundaries * 4, cudaMemcpyDeviceToHost, st));
   CU_CHECK(h, cudaStreamSynchronize(st));
+  if (r->sentence_status) {
+    memcpy(r->sentence_status + s0, h->hostStatus.data(), bv.numSentences);
+  } else if (h->failedSentences) {
+    u32 first = 0;
+    while (first < bv.numSentences && !h->hostStatus[first]) ++first;
+    return fail(h, JPP_B200_INVALID_PARAMETER,
+                std::to_string(h->failedSentences) + " sentence(s) failed validation and were not scored (first: sentence " +
+                    std::to_string(s0 + first) + ", status " + std::to_string((unsigned)h->hostStatus[first]) +
+                    "); pass jpp_b200_result.sentence_status to get them per sentence");
+  }
   return JPP_B200_OK;
 }
 
@@ -1812,9 +1926,9 @@ jpp_b200_status make_lane(jpp_b200_handle* owner, jpp_b200_handle* prev) {
 jpp_b200_status run_window(jpp_b200_handle* h, const jpp_b200_batch* batch, u32 lo, u32 hi, jpp_b200_result* result) {
   jpp_b200_status st = upload_window(h, batch, lo, hi);
   if (st != JPP_B200_OK) return st;
-  st = jpp_b200_score_resident(h);
+  st = score_resident_impl(h);
   if (st != JPP_B200_OK) return st;
-  return jpp_b200_download_result(h, result);
+  return download_result_impl(h, result);
 }
 
 constexpr int kMaxLanes = 8;
@@ -1831,8 +1945,12 @@ constexpr int kMaxLanes = 8;
 // JPP_B200_LANES=n (1..8, default 6: 108.8 / 86.7 / 84.6 / 82.3 / 82.9 ms per 100 000 sentences for
 // 1 / 3 / 4 / 6 / 8 lanes, 80 ms with the batch already resident).  The handle holds no resident
 // batch afterwards.
-jpp_b200_status jpp_b200_score_batch(jpp_b200_handle* h, const jpp_b200_batch* batch, jpp_b200_result* result) {
+static jpp_b200_status score_batch_impl(jpp_b200_handle* h, const jpp_b200_batch* batch, jpp_b200_result* result) {
   if (!h || !batch || !result) return JPP_B200_INVALID_PARAMETER;
+  if (batch->num_sentences == 0) {  // nothing to score (e.g. a rank whose shard is empty)
+    h->counters = jpp_b200_counters{};
+    return JPP_B200_OK;
+  }
   const char* lanesEnv = getenv("JPP_B200_LANES");
   const char* minEnv = getenv("JPP_B200_LANE_MIN_SENTENCES");  // tests lower it to reach the multi-lane path
   int nLanes = lanesEnv ? atoi(lanesEnv) : 6;
@@ -1877,23 +1995,39 @@ jpp_b200_status jpp_b200_score_batch(jpp_b200_handle* h, const jpp_b200_batch* b
   // per 100 000 sentences with the kernels of the windows side by side), so it is off.
   std::mutex* token = (serialEnv && atoi(serialEnv) == 1) ? h->computeToken : nullptr;
   // windows start in order: a lane begins its upload when the previous one has finished its own
-  // (PCIe is one pipe; finishing window 0 early matters more than starting all at once)
-  std::atomic<int> uploaded{0};
-  auto work = [&](int k) {
+  // (PCIe is one pipe; finishing window 0 early matters more than starting all at once).  Waiting
+  // lanes sleep on a condition variable: the host cores belong to the caller's staging threads.
+  std::mutex turnMutex;
+  std::condition_variable turnCv;
+  int uploaded = 0;
+  auto work = [&](int k) noexcept {
     jpp_b200_status st = JPP_B200_OK;
-    while (uploaded.load(std::memory_order_acquire) < k) std::this_thread::yield();
-    st = upload_window(lanes[k], batch, cut[k], cut[k + 1]);
-    uploaded.store(k + 1, std::memory_order_release);
-    if (st == JPP_B200_OK) {
-      if (token) { std::lock_guard<std::mutex> turn(*token); st = jpp_b200_score_resident(lanes[k]); }
-      else st = jpp_b200_score_resident(lanes[k]);
+    {
+      std::unique_lock<std::mutex> lk(turnMutex);
+      turnCv.wait(lk, [&] { return uploaded >= k; });
     }
-    if (st == JPP_B200_OK) st = jpp_b200_download_result(lanes[k], result);
+    st = guarded(lanes[k], [&] { return upload_window(lanes[k], batch, cut[k], cut[k + 1]); });
+    {
+      std::lock_guard<std::mutex> lk(turnMutex);
+      uploaded = k + 1;
+    }
+    turnCv.notify_all();
+    if (st == JPP_B200_OK) {
+      if (token) { std::lock_guard<std::mutex> turn(*token); st = guarded(lanes[k], [&] { return score_resident_impl(lanes[k]); }); }
+      else st = guarded(lanes[k], [&] { return score_resident_impl(lanes[k]); });
+    }
+    if (st == JPP_B200_OK) st = guarded(lanes[k], [&] { return download_result_impl(lanes[k], result); });
     sts[k] = st;
   };
-  for (int k = 1; k < nLanes; ++k) workers[k] = std::thread(work, k);
+  int started = 1;
+  try {
+    for (int k = 1; k < nLanes; ++k) { workers[k] = std::thread(work, k); started = k + 1; }
+  } catch (...) {
+    // a worker could not be started: the ones that run finish their windows, the rest is run here
+  }
   work(0);
-  for (int k = 1; k < nLanes; ++k) workers[k].join();
+  for (int k = started; k < nLanes; ++k) work(k);
+  for (int k = 1; k < started; ++k) workers[k].join();
   for (int k = 0; k < nLanes; ++k) lanes[k]->resident = false;
   for (int k = 0; k < nLanes; ++k)
     if (sts[k] != JPP_B200_OK) {
@@ -1907,10 +2041,26 @@ jpp_b200_status jpp_b200_score_batch(jpp_b200_handle* h, const jpp_b200_batch* b
     c.sentences += d.sentences; c.boundaries += d.boundaries; c.nodes += d.nodes; c.gathers += d.gathers;
     c.algorithmic_bytes += d.algorithmic_bytes; c.rnn_nodes += d.rnn_nodes; c.rnn_scores += d.rnn_scores;
     c.walk_gathers += d.walk_gathers; c.walk_bytes += d.walk_bytes; c.launches += d.launches;
-    c.walk_gathers_issued += d.walk_gathers_issued;
+    c.walk_gathers_issued += d.walk_gathers_issued; c.failed_sentences += d.failed_sentences;
     for (int i = 0; i < 8; ++i) c.kernel_ms[i] = std::max(c.kernel_ms[i], d.kernel_ms[i]);
   }
   return JPP_B200_OK;
+}
+
+jpp_b200_status jpp_b200_create(const jpp_b200_model* model, const jpp_b200_config* config, int device, jpp_b200_handle** out) {
+  return guarded(nullptr, [&] { return create_impl(model, config, device, out); });
+}
+jpp_b200_status jpp_b200_upload_batch(jpp_b200_handle* h, const jpp_b200_batch* b) {
+  return guarded(h, [&] { return upload_batch_impl(h, b); });
+}
+jpp_b200_status jpp_b200_score_resident(jpp_b200_handle* h) {
+  return guarded(h, [&] { return score_resident_impl(h); });
+}
+jpp_b200_status jpp_b200_download_result(jpp_b200_handle* h, jpp_b200_result* r) {
+  return guarded(h, [&] { return download_result_impl(h, r); });
+}
+jpp_b200_status jpp_b200_score_batch(jpp_b200_handle* h, const jpp_b200_batch* batch, jpp_b200_result* result) {
+  return guarded(h, [&] { return score_batch_impl(h, batch, result); });
 }
 
 jpp_b200_status jpp_b200_get_counters(const jpp_b200_handle* h, jpp_b200_counters* out) {

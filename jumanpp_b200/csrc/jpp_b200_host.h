@@ -35,6 +35,9 @@ inline jpp_b200_status compile_host_model(const jpp_b200_model* m, HostModel* ou
   ft.nPrim = m->num_primitives; ft.nComp = m->num_computations; ft.nPat = m->num_patterns;
   ft.nStored = m->num_stored_patterns; ft.entrySize = m->entry_size; ft.nPlaceholders = m->num_placeholders;
   ft.mask = (u32)((1ull << m->log2_weights) - 1);
+  if (m->float_order != JPP_B200_ORDER_STATIC_CODEGEN && m->float_order != JPP_B200_ORDER_DYNAMIC)
+    return bad(JPP_B200_INVALID_PARAMETER, "unknown float_order");
+  ft.dynamicOrder = m->float_order == JPP_B200_ORDER_DYNAMIC ? 1u : 0u;
   for (u32 i = 0; i < m->num_primitives; ++i) {
     const jpp_b200_primitive& p = m->primitives[i];
     switch (p.kind) {

@@ -67,7 +67,7 @@ struct FeatTables {
   u32 nUni, nBi, nTri, nPat, nStored, nPrim, nComp, entrySize, nPlaceholders;
   u32 uniVars, biVars, triVars;  // accumulator counts of the generated code
   u32 mask;
-  u32 pad_;
+  u32 dynamicOrder;  // 1: every sum through computeUnrolled4RawPerceptron (the reference's dynamic feature path)
   u64 uniState[MAX_UNI];  // Hasher{}.mix(3).mix(index).mix(UnigramSeed)
   u64 biState[MAX_BI];
   u64 triState[MAX_TRI];
@@ -120,6 +120,7 @@ struct BatchView {
   u32* bndSent;    // [boundaries] sentence of the boundary
   u32* endNode;    // [ends] global node index an end entry points at
   u32* sentOrder;  // [sentences] longest first (work queue order)
+  const u8* sentStatus;  // [sentences] 0 = ok; a failed sentence is skipped by every kernel (may be null)
   // results
   jpp_b200_beam_element* beam;  // [nodes][B]
   float* beamScores;            // [nodes][B][S]
@@ -147,6 +148,7 @@ struct BatchView {
 struct ScoreCfg {
   i32 beam, gbeam, rcheck, rbeam;
   u32 S;  // scorers
+  u32 dyn;  // FeatTables::dynamicOrder (the connection-score sum depends on it too)
 };
 
 JPP_HD u64 pack_cand(float score, u32 left, u32 beam) {
@@ -179,6 +181,14 @@ struct PatRow {
   JPP_HD u64 operator[](u32 p) const { return base[(size_t)p * pstride]; }
 };
 JPP_HD PatRow pat_row(const BatchView& bv, u32 node) { return PatRow{bv.patterns + (size_t)node * bv.patNodeStride, bv.patPStride}; }
+
+// first boundary and boundary count of a sentence; a failed sentence (jpp_b200_result::sentence_status != 0)
+// counts as having no boundaries, which is what makes every stage skip it
+JPP_HD u32 sent_span(const BatchView& bv, u32 sent, u32& b0) {
+  b0 = bv.sentBndOff[sent];
+  if (bv.sentStatus && bv.sentStatus[sent]) return 0u;
+  return bv.sentBndOff[sent + 1] - b0;
+}
 
 JPP_HD bool is_fake(const jpp_b200_beam_element& e) { return e.left == 0xFFFFu && e.prev_beam == 0xFFFFu; }
 
@@ -309,11 +319,17 @@ JPP_HD u64 pattern_value(const FeatTables& ft, u32 p, const u64* prim) {
 template <typename WL, bool LEAN = true>
 JPP_HD void t0_node(const FeatTables& ft, const BatchView& bv, const WL& wl, u32 node) {
   const u32 gb = bv.nodeBnd[node];
+  if (gb == 0xFFFFFFFFu) return;  // node of no valid boundary (failed sentence)
   const u32 sent = bv.bndSent[gb];
   const u32 localBnd = gb - bv.sentBndOff[sent];
   const u32 SP = ft.nStored;
   u64* pout = bv.patterns + (size_t)node * bv.patNodeStride;
   const size_t pstr = bv.patPStride;
+  if (bv.sentStatus && bv.sentStatus[sent]) {
+    for (u32 p = 0; p < SP; ++p) pout[p * pstr] = 0;
+    bv.t0[node] = 0.0f;
+    return;
+  }
   const jpp_b200_node_info ni = bv.nodeInfo[node];
   if (localBnd < 2) {  // BOS rows, lattice_builder.cc:171-176
     for (u32 p = 0; p < SP; ++p) pout[p * pstr] = (u64)(u32)ni.entry_ptr;
@@ -329,10 +345,7 @@ JPP_HD void t0_node(const FeatTables& ft, const BatchView& bv, const WL& wl, u32
     entry = bv.nodeEntry + (size_t)node * ft.entrySize;
   } else {
     u32 row = bv.nodeEntryRow[node];
-    if (row >= bv.numEntryRows) {  // reported as INVALID_PARAMETER after the step
-      row = 0;
-      if (bv.counters) bv.counters[7] = 1;
-    }
+    if (row >= bv.numEntryRows) row = 0;  // cannot happen: the upload's validation fails such a sentence
     entry = bv.entryRows + (size_t)row * ft.entrySize;
     if (!ph && bv.rowPlaceholders) ph = bv.rowPlaceholders + (size_t)row * ft.nPlaceholders;
   }
@@ -351,7 +364,7 @@ JPP_HD void t0_node(const FeatTables& ft, const BatchView& bv, const WL& wl, u32
   // first uniVars terms then "+=" (pattern_feature_codegen.cc:229-236), summed
   // p0 + p1 + ...; the last row goes through computeUnrolled4RawPerceptron
   // (perceptron.h:46-72): four accumulators started at 0.
-  const bool lastRow = (node + 1 == bv.bndNodeOff[gb + 1]);
+  const bool lastRow = ft.dynamicOrder || (node + 1 == bv.bndNodeOff[gb + 1]);
   const u32 nv = lastRow ? 4u : ft.uniVars;
   float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
   const u32 nU = ft.nUni, mask = ft.mask;
@@ -825,8 +838,8 @@ JPP_HD void write_beam(const BatchView& bv, const ScoreCfg& cfg, u32 node, const
 // W0: BOS beams of every sentence (analyzer_impl.cc:185-192) and the degenerate
 // "no codepoints" lattice (:255-258)
 JPP_HD void wave_init_sentence(const BatchView& bv, const ScoreCfg& cfg, u32 sent) {
-  const u32 b0 = bv.sentBndOff[sent];
-  const u32 nb = bv.sentBndOff[sent + 1] - b0;
+  u32 b0;
+  const u32 nb = sent_span(bv, sent, b0);
   const u32 B = (u32)cfg.beam;
   for (u32 bb = 0; bb < 2 && bb < nb; ++bb) {
     const u32 n0 = bv.bndNodeOff[b0 + bb];
@@ -852,8 +865,8 @@ JPP_HD void wave_init_sentence(const BatchView& bv, const ScoreCfg& cfg, u32 sen
 // One thread scans the L x B left beam elements and keeps the G largest packed
 // keys (distinct by construction: score_processor.h:81-115) in sorted order.
 JPP_HD void wave_gbeam(const BatchView& bv, const ScoreCfg& cfg, const WaveView& wv, u32 sent, u32 bnd) {
-  const u32 b0 = bv.sentBndOff[sent];
-  const u32 nb = bv.sentBndOff[sent + 1] - b0;
+  u32 b0;
+  const u32 nb = sent_span(bv, sent, b0);
   if (bnd >= nb || nb <= 3) return;
   const u32 gB = b0 + bnd;
   const u32 R = bv.bndNodeOff[gB + 1] - bv.bndNodeOff[gB];
@@ -982,7 +995,7 @@ JPP_HD void wave_prescore(const FeatTables& ft, const BatchView& bv, const Score
   const u32 theMax = (u32)cfg.rcheck < G ? (u32)cfg.rcheck : G;
   if (theMax == 0) return;
   const u32 GMAX = (u32)cfg.gbeam, mask = ft.mask;
-  const bool lastRow = (node + 1 == bv.bndNodeOff[gB + 1]);
+  const bool lastRow = ft.dynamicOrder || (node + 1 == bv.bndNodeOff[gB + 1]);
   const PatRow P = pat_row(bv, node);
   const float t0 = bv.t0[node];
   for (u32 i = 0; i < theMax; ++i) {
@@ -1002,7 +1015,7 @@ JPP_HD void wave_prescore(const FeatTables& ft, const BatchView& bv, const Score
         default: gsum_triple<1>(wl, ft.nBi, biIdx, sNV, sPair, s4); break;
       }
       sc += lastRow ? s4 : sNV;
-      bv.bi0[node] = (U == 1) ? s4 : sPair;  // applyBiTriFullKernel row of unique t1 0
+      bv.bi0[node] = (U == 1 || ft.dynamicOrder) ? s4 : sPair;  // applyBiTriFullKernel row of unique t1 0
     } else {
       sc += gsum_row(wl, ft.nBi, ft.biVars, biIdx, lastRow);
     }
@@ -1073,8 +1086,8 @@ JPP_HD void emit_items(const BatchView& bv, const ScoreCfg& cfg, const WaveView&
 // std::nth_element replay -- the work counters of the boundary, the list of selected nodes
 // and their W4 items.
 JPP_HD void wave_cutoff(const FeatTables& ft, const BatchView& bv, const ScoreCfg& cfg, const WaveView& wv, u32 sent, u32 bnd) {
-  const u32 b0 = bv.sentBndOff[sent];
-  const u32 nb = bv.sentBndOff[sent + 1] - b0;
+  u32 b0;
+  const u32 nb = sent_span(bv, sent, b0);
   if (bnd >= nb || nb <= 3) return;
   const u32 gB = b0 + bnd;
   const u32 n0 = bv.bndNodeOff[gB];
@@ -1134,7 +1147,7 @@ JPP_HD void wave_item_bigram(const FeatTables& ft, const BatchView& bv, const Wa
   auto biIdx = [&](u32 f) -> u32 { return (u32)mix(mix(ft.biState[f], P[ft.biT0[f]]), t1[ft.biT1[f]]) & mask; };
   float a[2], s4;
   gsum_dual<2, 8>(wl, ft.nBi, biIdx, a, s4);
-  wv.scb[it.slot & ~ITEM_LAST] = (it.slot & ITEM_LAST) ? s4 : a[0] + a[1];
+  wv.scb[it.slot & ~ITEM_LAST] = ((it.slot & ITEM_LAST) || ft.dynamicOrder) ? s4 : a[0] + a[1];
 }
 
 // W4, trigram item: the trigram part of the same kernel for one (selected right node, global
@@ -1152,7 +1165,7 @@ JPP_HD void wave_item_trigram(const FeatTables& ft, const BatchView& bv, const W
   float a[2], s4;
   gsum_dual<2, 4>(wl, ft.nTri, triIdx, a, s4);
   float* out = wv.tri + 2 * (size_t)(it.slot & ~ITEM_LAST);
-  if (it.slot & ITEM_LAST) { out[0] = s4; out[1] = 0.0f; }
+  if ((it.slot & ITEM_LAST) || ft.dynamicOrder) { out[0] = s4; out[1] = 0.0f; }
   else { out[0] = a[0]; out[1] = a[1]; }
 }
 
@@ -1169,7 +1182,7 @@ JPP_HD float step_local_score(const BatchView& bv, const ScoreCfg& cfg, const Wa
   const u32 ti = t1idx[gi];
   const float sc = (ti < first_bigram_item(cfg)) ? bv.bi0[node] : wv.scb[(size_t)pos * GMAX + ti];
   const float* tr = wv.tri + 2 * ((size_t)pos * GMAX + gi);
-  float v = (gi + 1 == G) ? sc + tr[0] : sc + tr[0] + tr[1];
+  float v = (gi + 1 == G || cfg.dyn) ? sc + tr[0] : sc + tr[0] + tr[1];
   v += t0;  // copyT0Scores(tail, t0Score)
   return v;
 }
@@ -1274,7 +1287,7 @@ JPP_HD u32 wave_full_node(const FeatTables& ft, const BatchView& bv, const Score
   const u32 B = (u32)cfg.beam, mask = ft.mask;
   const u32 e0 = bv.bndEndOff[gB];
   const u32 L = bv.bndEndOff[gB + 1] - e0;
-  const bool lastRow = (node + 1 == bv.bndNodeOff[gB + 1]);
+  const bool lastRow = ft.dynamicOrder || (node + 1 == bv.bndNodeOff[gB + 1]);
   const PatRow P = pat_row(bv, node);
   const float t0 = bv.t0[node];
   u64 top[MAX_BEAM];
@@ -1330,8 +1343,8 @@ JPP_HD u32 wave_full_node(const FeatTables& ft, const BatchView& bv, const Score
 // links (analysis_result.cc:25-76) and store the node indices in sentence order.
 JPP_HD void best_path_sentence(const BatchView& bv, const ScoreCfg& cfg, u32* pathLen, u32* pathNodes, u32 sent,
                                 u32 nodeBase = 0) {
-  const u32 b0 = bv.sentBndOff[sent];
-  const u32 nb = bv.sentBndOff[sent + 1] - b0;
+  u32 b0;
+  const u32 nb = sent_span(bv, sent, b0);
   const u32 B = (u32)cfg.beam;
   pathLen[sent] = 0;
   u32 len = 0;

@@ -69,8 +69,8 @@ JPP_HD u64 fast_hash1_mix(u64 state, u64 data) {
 
 // R1: literal restatement of addPath / addPrevChain, iterative instead of recursive.
 JPP_HD void rnn_build_tree(const BatchView& bv, const ScoreCfg& cfg, const RnnWork& rw, u32 sent) {
-  const u32 b0 = bv.sentBndOff[sent];
-  const u32 nb = bv.sentBndOff[sent + 1] - b0;
+  u32 b0;
+  const u32 nb = sent_span(bv, sent, b0);
   const u32 B = (u32)cfg.beam, GMAX = (u32)cfg.gbeam;
   const u32 base0 = rw.rnOff[sent];
   rw.rnCount[sent] = 0;
@@ -275,8 +275,8 @@ JPP_HD float rnn_finish_score(const RnnTables& rt, float dot, i32 prevId, i32 id
 
 // remakeEosBeam (analyzer_impl.cc:286-294): the EOS row from the re-scored global beam
 JPP_HD void rerank_eos(const BatchView& bv, const ScoreCfg& cfg, float w0, float w1, u32 sent) {
-  const u32 b0 = bv.sentBndOff[sent];
-  const u32 nb = bv.sentBndOff[sent + 1] - b0;
+  u32 b0;
+  const u32 nb = sent_span(bv, sent, b0);
   const u32 B = (u32)cfg.beam, GMAX = (u32)cfg.gbeam, S = cfg.S;
   const u32 eosB = b0 + nb - 1;
   const u32 eosNode = bv.bndNodeOff[eosB];
@@ -323,8 +323,8 @@ JPP_HD void rerank_eos(const BatchView& bv, const ScoreCfg& cfg, float w0, float
 
 // R4: adjustBeamScores + remakeEosBeam, one thread per sentence
 JPP_HD void rerank_sentence(const BatchView& bv, const ScoreCfg& cfg, float w0, float w1, u32 sent) {
-  const u32 b0 = bv.sentBndOff[sent];
-  const u32 nb = bv.sentBndOff[sent + 1] - b0;
+  u32 b0;
+  const u32 nb = sent_span(bv, sent, b0);
   if (nb <= 3) return;
   const u32 B = (u32)cfg.beam, GMAX = (u32)cfg.gbeam, S = cfg.S;
   for (u32 bnd = 3; bnd < nb; ++bnd) {

@@ -149,7 +149,8 @@ class LatticeScorer:
         return {"sentences": c.sentences, "boundaries": c.boundaries, "nodes": c.nodes, "gathers": c.gathers,
                 "algorithmic_bytes": c.algorithmic_bytes, "rnn_nodes": c.rnn_nodes,
                 "walk_gathers": c.walk_gathers, "walk_bytes": c.walk_bytes, "launches": c.launches,
-                "walk_gathers_issued": c.walk_gathers_issued,
+                "walk_gathers_issued": c.walk_gathers_issued, "rnn_scores": c.rnn_scores,
+                "failed_sentences": c.failed_sentences,
                 "kernel_ms": {n: float(c.kernel_ms[i]) for i, n in enumerate(names)}}
 
     def close(self) -> None:

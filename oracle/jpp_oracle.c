@@ -98,6 +98,8 @@ typedef struct {
   u32 triT0[64], triT1[64], triT2[64];
   u64 patState[256];
   int uniVars, biVars, triVars;
+  int dyn; /* jpp_b200_model.float_order == DYNAMIC: every sum through computeUnrolled4RawPerceptron
+              (PartialNgramDynamicFeatureApply, feature_impl_ngram_partial.h:196-371) */
 } CModel;
 
 static int compile_model(const jpp_b200_model* m, const float* w, CModel* c) {
@@ -133,6 +135,7 @@ static int compile_model(const jpp_b200_model* m, const float* w, CModel* c) {
     c->patState[p] = mix(mix(mix(SEA_SEED0, pt->index), pt->ref_len), PATTERN_SEED);
   }
   /* accumulator counts of the generated code */
+  c->dyn = m->float_order == JPP_B200_ORDER_DYNAMIC;
   c->uniVars = c->nUni >= 8 ? 4 : (c->nUni >= 4 ? 2 : 1);            /* pattern_feature_codegen.cc:202-208 */
   c->biVars = c->nBi >= 8 ? 8 : (c->nBi >= 4 ? 4 : (c->nBi >= 2 ? 2 : 1)); /* partial_ngram_feature_codegen.cc:15-22 */
   c->triVars = c->nTri >= 8 ? 8 : (c->nTri >= 4 ? 4 : (c->nTri >= 2 ? 2 : 1)); /* :86-93 */
@@ -751,7 +754,7 @@ static int score_sentence(const Ctx* c, Scratch* s, u32 sent) {
       for (u32 p = 0; p < SP; ++p) patsOut[(size_t)node * SP + p] = P[p];
       u32 idx[256];
       for (u32 u = 0; u < nU; ++u) idx[u] = (u32)mix(cm->uniState[u], P[cm->uniT0[u]]) & mask;
-      if (r + 1 < R) s->t0[r] = accum_sum(w, idx, (int)nU, cm->uniVars, 1);
+      if (!cm->dyn && r + 1 < R) s->t0[r] = accum_sum(w, idx, (int)nU, cm->uniVars, 1);
       else s->t0[r] = unrolled4(w, idx, (int)nU);
       for (u32 f = 0; f < nB; ++f) s->biSt[(size_t)r * nB + f] = mix(cm->biState[f], P[cm->biT0[f]]);
       for (u32 f = 0; f < nT; ++f) s->triSt[(size_t)r * nT + f] = mix(cm->triState[f], P[cm->triT0[f]]);
@@ -770,7 +773,7 @@ static int score_sentence(const Ctx* c, Scratch* s, u32 sent) {
         for (u32 r = 0; r < R; ++r) {
           u32 idx[256];
           for (u32 f = 0; f < nB; ++f) idx[f] = (u32)mix(s->biSt[(size_t)r * nB + f], p1[cm->biT1[f]]) & mask;
-          float add = (r + 1 < R) ? accum_sum(w, idx, (int)nB, cm->biVars, 0) : unrolled4(w, idx, (int)nB);
+          float add = (!cm->dyn && r + 1 < R) ? accum_sum(w, idx, (int)nB, cm->biVars, 0) : unrolled4(w, idx, (int)nB);
           s->T1[r] = s->t0[r] + add;
           for (u32 f = 0; f < nT; ++f) s->triSt2[(size_t)r * nT + f] = mix(s->triSt[(size_t)r * nT + f], p1[cm->triT1[f]]);
         }
@@ -783,7 +786,7 @@ static int score_sentence(const Ctx* c, Scratch* s, u32 sent) {
           for (u32 r = 0; r < R; ++r) {
             u32 idx[64];
             for (u32 f = 0; f < nT; ++f) idx[f] = (u32)mix(s->triSt2[(size_t)r * nT + f], p2[cm->triT2[f]]) & mask;
-            float add = (r + 1 < R) ? accum_sum(w, idx, (int)nT, cm->triVars, 0) : unrolled4(w, idx, (int)nT);
+            float add = (!cm->dyn && r + 1 < R) ? accum_sum(w, idx, (int)nT, cm->triVars, 0) : unrolled4(w, idx, (int)nT);
             s->fullScores[((size_t)r * c->beam + bi) * L + t1] = s->T1[r] + add;
           }
           gathers += (u64)R * nT;
@@ -876,13 +879,13 @@ static int score_sentence(const Ctx* c, Scratch* s, u32 sent) {
           u32 idx[256];
           sc[r] = s->t0[r];
           for (u32 f = 0; f < nB; ++f) idx[f] = (u32)mix(s->biSt[(size_t)r * nB + f], t1[cm->biT1[f]]) & mask;
-          sc[r] += (r + 1 < R) ? accum_sum(w, idx, (int)nB, cm->biVars, 0) : unrolled4(w, idx, (int)nB);
+          sc[r] += (!cm->dyn && r + 1 < R) ? accum_sum(w, idx, (int)nB, cm->biVars, 0) : unrolled4(w, idx, (int)nB);
         }
         for (u32 r = 0; r < R; ++r) {
           u32 idx[64];
           for (u32 f = 0; f < nT; ++f)
             idx[f] = (u32)mix(mix(s->triSt[(size_t)r * nT + f], t1[cm->triT1[f]]), t2[cm->triT2[f]]) & mask;
-          sc[r] += (r + 1 < R) ? accum_sum(w, idx, (int)nT, cm->triVars, 0) : unrolled4(w, idx, (int)nT);
+          sc[r] += (!cm->dyn && r + 1 < R) ? accum_sum(w, idx, (int)nT, cm->triVars, 0) : unrolled4(w, idx, (int)nT);
         }
         gathers += (u64)R * (nB + nT);
       }
@@ -915,7 +918,7 @@ static int score_sentence(const Ctx* c, Scratch* s, u32 sent) {
             u32 idx[256];
             const u64* t1 = s->t1pat + (size_t)u * SP;
             for (u32 f = 0; f < nB; ++f) idx[f] = (u32)mix(bs[f], t1[cm->biT1[f]]) & mask;
-            if (u + 1 < U) {
+            if (!cm->dyn && u + 1 < U) {
               float r1, r2;
               accum2(w, idx, (int)nB, &r1, &r2);
               s->scbuf[u] = r1 + r2;
@@ -930,7 +933,7 @@ static int score_sentence(const Ctx* c, Scratch* s, u32 sent) {
             const u64* t2 = s->t2pat + (size_t)gi * SP;
             for (u32 f = 0; f < nT; ++f) idx[f] = (u32)mix(mix(ts[f], t1[cm->triT1[f]]), t2[cm->triT2[f]]) & mask;
             float v;
-            if (j + 1 < remaining) {
+            if (!cm->dyn && j + 1 < remaining) {
               float r1, r2;
               accum2(w, idx, (int)nT, &r1, &r2);
               v = s->scbuf[s->t1idx[gi]] + r1 + r2;
@@ -962,7 +965,7 @@ static int score_sentence(const Ctx* c, Scratch* s, u32 sent) {
             u32 idx[256];
             const u64* t1 = s->t1pat + (size_t)u * SP;
             for (u32 f = 0; f < nB; ++f) idx[f] = (u32)mix(bs[f], t1[cm->biT1[f]]) & mask;
-            if (u + 1 < U) {
+            if (!cm->dyn && u + 1 < U) {
               float r1, r2;
               accum2(w, idx, (int)nB, &r1, &r2);
               s->scbuf[u] = r1 + r2;
@@ -976,7 +979,7 @@ static int score_sentence(const Ctx* c, Scratch* s, u32 sent) {
             const u64* t2 = s->t2pat + (size_t)gi * SP;
             for (u32 f = 0; f < nT; ++f) idx[f] = (u32)mix(mix(ts[f], t1[cm->triT1[f]]), t2[cm->triT2[f]]) & mask;
             float v;
-            if (gi + 1 < G) {
+            if (!cm->dyn && gi + 1 < G) {
               float r1, r2;
               accum2(w, idx, (int)nT, &r1, &r2);
               v = s->scbuf[s->t1idx[gi]] + r1 + r2;

@@ -488,7 +488,7 @@ int cmdStage(const Args& a) {
         JppbWriter w;
         std::vector<int32_t> cfg{env.sconf.beamSize, env.acfg.globalBeamSize, env.acfg.rightGbeamCheck,
                                  env.acfg.rightGbeamSize, env.sconf.numScorers, (int32_t)a.num("log2w", 20),
-                                 (int32_t)a.num("wseed", 1), expected ? 1 : 0};
+                                 (int32_t)a.num("wseed", 1), expected ? 1 : 0, a.num("dynamic", 0) != 0 ? 1 : 0};
         std::vector<float> fcfg{(float)a.real("wscale", 0.5), env.sdef.scoreWeights[0],
                                 env.sdef.scoreWeights.size() > 1 ? env.sdef.scoreWeights[1] : 0.0f};
         w.add("cfg", I32, cfg);

@@ -17,12 +17,13 @@ RNN_MODELS = {
     "rnn_h128": dict(layer_size=128, maxent_order=3, maxent_size=1 << 16, nce_lnz=9.0, seed=11, vocab=4000),
     "rnn_h48": dict(layer_size=48, maxent_order=2, maxent_size=1 << 14, nce_lnz=8.0, seed=13, vocab=2000),
     "rnn_h256": dict(layer_size=256, maxent_order=3, maxent_size=1 << 15, nce_lnz=9.0, seed=17, vocab=2000),
+    "dyn_rnn": dict(layer_size=32, maxent_order=3, maxent_size=1 << 16, nce_lnz=9.0, seed=2, vocab=5000),
 }
 
 LINEAR_GBEAM = ["default", "beam20", "beam20_all", "gbeam20_partition", "beam3_ties", "beam1", "rcheck0",
-                "ref_codegen_fixture_gbeam"]
-FULL_BEAM = ["ref_codegen_fixture"]
-RNN = ["rnn_default", "rnn_beam20", "rnn_h128", "rnn_h48", "rnn_h256"]
+                "ref_codegen_fixture_gbeam", "dyn_default", "dyn_beam3_ties"]
+FULL_BEAM = ["ref_codegen_fixture", "dyn_full"]
+RNN = ["rnn_default", "rnn_beam20", "rnn_h128", "rnn_h48", "rnn_h256", "dyn_rnn"]
 
 
 def pytest_configure(config):

@@ -30,7 +30,7 @@ extern "C" int jpp_b200_emul_score_batch(const jpp_b200_model* model, const jpp_
   }
   const FeatTables& ft = hm.ft;
   ScoreCfg cfg{config->beam_size, config->global_beam_size, config->right_gbeam_check, config->right_gbeam_size,
-               model->num_scorers};
+               model->num_scorers, ft.dynamicOrder};
   const u32 NS = b->num_sentences, NB = b->sent_boundary_off[NS], NN = b->boundary_node_off[NB],
             NE = b->boundary_end_off[NB];
   const u32 B = (u32)cfg.beam, G = (u32)std::max(1, cfg.gbeam), S = cfg.S, SP = ft.nStored;

@@ -48,6 +48,12 @@ CONFIGS = {
     "rnn_h128": ("beam=5 gbeam=6 rcheck=1 rbeam=5 log2w=18 wseed=5 rnn=RNN3", 12),
     "rnn_h48": ("beam=4 gbeam=5 rcheck=1 rbeam=4 log2w=16 wseed=6 rnn=RNN4", 10),
     "rnn_h256": ("beam=20 gbeam=20 rcheck=1 rbeam=5 log2w=16 wseed=8 rnn=RNN5", 8),
+    # the reference WITHOUT its generated code (CoreHolder::initialize(nullptr): PartialNgramDynamicFeatureApply,
+    # every sum through computeUnrolled4RawPerceptron) -> jpp_b200_model.float_order = JPP_B200_ORDER_DYNAMIC
+    "dyn_default": ("beam=5 gbeam=6 rcheck=1 rbeam=5 log2w=20 wseed=1 dynamic=1", 20),
+    "dyn_beam3_ties": ("beam=3 gbeam=4 rcheck=2 rbeam=3 log2w=12 wseed=9 dynamic=1", 20),
+    "dyn_full": ("beam=5 gbeam=0 rcheck=0 rbeam=0 log2w=14 wseed=4 dynamic=1", 10),
+    "dyn_rnn": ("beam=5 gbeam=6 rcheck=1 rbeam=5 log2w=18 wseed=1 rnn=RNN1 dynamic=1", 12),
 }
 
 
@@ -77,7 +83,10 @@ def main() -> None:
         words = synth.rnn_vocabulary(dic, prm["vocab"])
         synth.write_rnn_model(tmp / name, words, prm["layer_size"], prm["maxent_order"], prm["maxent_size"],
                               prm["nce_lnz"], prm["seed"])
+    only = set(sys.argv[1:])   # names to (re)generate; default: all
     for name, (args, nsent) in CONFIGS.items():
+        if only and name not in only:
+            continue
         corpus = tmp / f"{name}.txt"
         chosen = sents[:nsent]
         if name == "rcheck0":
@@ -115,6 +124,8 @@ def main() -> None:
     (tmp / "cg.txt").write_text(sentence + "\n", encoding="utf-8")
     for name, extra in (("ref_codegen_fixture", "beam=5 gbeam=0 rcheck=0 rbeam=0"),
                         ("ref_codegen_fixture_gbeam", "beam=5 gbeam=6 rcheck=1 rbeam=5")):
+        if only and name not in only:
+            continue
         out = tmp / f"{name}.jppb"
         run([str(HARNESS), "stage", f"dict={REF / 'test/jumandic/codegen.mdic'}", f"corpus={tmp / 'cg.txt'}",
              f"out={out}", "log2w=6", f"weights_file={wfile}", *extra.split()])
