@@ -270,11 +270,15 @@ def emit_result(line: dict) -> None:
 
 def walk_kernel_name(wl) -> str:
     """The dominant kernel of the step as the library will run it for this configuration
-    (jpp_b200.cu fused_walk_ok): the fused walk, or the wavefront kernels."""
-    fused = (wl["rcheck"] > 0 and 0 < wl["gbeam"] <= 8 and wl["beam"] <= 8 and "JPP_B200_WAVEFRONT" not in os.environ)
-    if fused:
-        return ("k_walk_fused: a block of 256 threads walks 32 sentences through all their boundaries "
-                "(global beam, prescore, cutoff, n-gram items, beam rows; n-gram hash + weight gather + beams)")
+    (jpp_b200.cu fused_walk_ok / jpp_b200_walk.cuh)."""
+    if wl["rcheck"] > 0 and wl["gbeam"] > 0 and "JPP_B200_WAVEFRONT" not in os.environ:
+        narrow = wl["beam"] <= 8 and wl["gbeam"] <= 8
+        if narrow and "JPP_B200_BLOCK_WALK" in os.environ:
+            return "k_walk_fused (round 1): a block of 256 threads walks 32 sentences through all their boundaries"
+        static = "JPP_B200_NO_STATIC" not in os.environ
+        return (f"k_walk_warp<{8 if narrow else 32}>: a warp walks {'4 sentences' if narrow else '1 sentence'} through all "
+                "boundaries (global beam, prescore, cutoff, n-gram items, beam rows: n-gram hash + weight gather + beams), "
+                + ("compiled-in Jumandic n-gram program, pattern rows in registers" if static else "table-driven n-gram program"))
     return ("wave loop: k_w_gbeam_warp + k_w_prescore + k_w_cutoff_group + k_w_items + k_w_final per boundary number "
             "(n-gram hash + weight gather + beams)")
 

@@ -528,7 +528,7 @@ __device__ __forceinline__ u32 block_max_u32(u32 v, u32* scratch) {
 
 inline bool fused_walk_ok(const ScoreCfg& cfg) {
   static const bool off = getenv("JPP_B200_WAVEFRONT") != nullptr;  // A/B and per-kernel profiling
-  return !off && cfg.rcheck > 0 && cfg.gbeam > 0 && cfg.gbeam <= 8 && cfg.beam <= 8;
+  return !off && cfg.rcheck > 0 && cfg.gbeam > 0;  // any beam / global beam the library accepts (<= 32)
 }
 
 template <bool SMALL>
@@ -613,6 +613,10 @@ __global__ void __launch_bounds__(kFusedThreads, 3) k_walk_fused(const __grid_co
     __syncthreads();
   }
 }
+
+}  // namespace
+#include "jpp_b200_walk.cuh"
+namespace {
 
 // full-beam mode: the whole boundary step of a right node in one thread
 __global__ void __launch_bounds__(128) k_w_full(const __grid_constant__ FeatTables ft, BatchView bv, ScoreCfg cfg, WaveView wv,
@@ -1145,6 +1149,7 @@ struct jpp_b200_handle {
   float* dWeights = nullptr;
   RnnTables rt{};
   bool hasRnn = false;
+  bool staticProgram = false;  // the uploaded n-gram program is the compiled-in one (jpp_b200_static_jumandic.h)
   float* dRnnBlocks[4] = {nullptr, nullptr, nullptr, nullptr};
   float* dRnnWt = nullptr;  // transposed recurrent matrix
   // window of the caller's batch that is resident (upload_window): offsets of its first sentence /
@@ -1320,6 +1325,7 @@ static jpp_b200_status create_impl(const jpp_b200_model* model, const jpp_b200_c
                     model->num_scorers, hm.ft.dynamicOrder};
   h->scoreW[0] = model->score_weights[0];
   h->scoreW[1] = model->score_weights[1];
+  h->staticProgram = matches_static_program(h->hm.ft);
 #define CREATE_CHECK(expr)                                                                      \
   do {                                                                                          \
     cudaError_t e_ = (expr);                                                                    \
@@ -1686,10 +1692,30 @@ static jpp_b200_status score_resident_impl(jpp_b200_handle* h) {
     u32 launches = 1;
     const bool fused = fused_walk_ok(cfg) && !profileOn;
     if (fused) {
-      const u32 itemCap = kFusedSent * (u32)cfg.rbeam * (u32)cfg.gbeam;
-      const u32 blocks = (NS + kFusedSent - 1) / kFusedSent;
-      if (small_gbeam_ok(cfg)) k_walk_fused<true><<<blocks, kFusedThreads, 0, st>>>(ft, bv, cfg, wv, h->dWeights, itemCap);
-      else k_walk_fused<false><<<blocks, kFusedThreads, 0, st>>>(ft, bv, cfg, wv, h->dWeights, itemCap);
+      static const bool blockWalk = getenv("JPP_B200_BLOCK_WALK") != nullptr;  // A/B: round 1's block-scope walk
+      static const bool noStatic = getenv("JPP_B200_NO_STATIC") != nullptr;    // A/B: table-driven n-gram program
+      const bool narrow = cfg.beam <= 8 && cfg.gbeam <= 8;
+      if (blockWalk && narrow) {
+        const u32 itemCap = kFusedSent * (u32)cfg.rbeam * (u32)cfg.gbeam;
+        const u32 blocks = (NS + kFusedSent - 1) / kFusedSent;
+        if (small_gbeam_ok(cfg)) k_walk_fused<true><<<blocks, kFusedThreads, 0, st>>>(ft, bv, cfg, wv, h->dWeights, itemCap);
+        else k_walk_fused<false><<<blocks, kFusedThreads, 0, st>>>(ft, bv, cfg, wv, h->dWeights, itemCap);
+      } else {
+        // a warp owns 4 sentences (beams <= 8: 8 lanes per sentence in W1 / W3) or one
+        const u32 spw = narrow ? 4u : 1u;
+        const u32 warps = (NS + spw - 1) / spw;
+        const u32 blocks = (warps + kWarpWalkThreads / 32 - 1) / (kWarpWalkThreads / 32);
+        const u32 itemCap = spw * (u32)cfg.rbeam * (u32)cfg.gbeam;
+        const bool stat = h->staticProgram && !noStatic;
+#define JPP_WALK(GW, KB, SM, ST) k_walk_warp<GW, KB, SM, ST><<<blocks, kWarpWalkThreads, 0, st>>>(ft, bv, cfg, wv, h->dWeights, itemCap)
+        if (narrow) {
+          if (small_gbeam_ok(cfg)) { if (stat) JPP_WALK(8, 8, true, true); else JPP_WALK(8, 8, true, false); }
+          else { if (stat) JPP_WALK(8, 8, false, true); else JPP_WALK(8, 8, false, false); }
+        } else {
+          if (stat) JPP_WALK(32, MAX_BEAM, false, true); else JPP_WALK(32, MAX_BEAM, false, false);
+        }
+#undef JPP_WALK
+      }
       ++launches;
     }
     for (u32 bnd = 2; bnd < h->maxNb && !fused; ++bnd) {
@@ -1911,6 +1937,7 @@ jpp_b200_status make_lane(jpp_b200_handle* owner, jpp_b200_handle* prev) {
   l->device = h->device; l->hm = h->hm; l->cfg = h->cfg; l->pubCfg = h->pubCfg;
   l->dFt = h->dFt; l->dWeights = h->dWeights; l->rt = h->rt; l->hasRnn = h->hasRnn;
   for (int i = 0; i < 4; ++i) l->dRnnBlocks[i] = h->dRnnBlocks[i];
+  l->staticProgram = h->staticProgram;
   l->dRnnWt = h->dRnnWt; l->scoreW[0] = h->scoreW[0]; l->scoreW[1] = h->scoreW[1]; l->smCount = h->smCount;
   l->ownsModel = false;
   cudaError_t e = cudaStreamCreateWithFlags(&l->stream, cudaStreamNonBlocking);

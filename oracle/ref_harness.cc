@@ -48,6 +48,8 @@
 #include "core/dic/dictionary.h"
 #include "core/impl/feature_impl_types.h"
 #include "core/impl/model_io.h"
+#include "core/impl/perceptron_io.h"
+#include "util/serialization.h"
 #include <unistd.h>
 #include "jpp_jumandic_cg.h"
 #include "jumandic/shared/jumandic_spec.h"
@@ -161,6 +163,7 @@ struct RefEnv {
   dic::DictionaryBuilder builder;
   model::FilesystemModel fsModel;
   model::ModelInfo modelInfo;
+  model::ModelInfo dicOnlyInfo;
   dic::BuiltDictionary restored;
   dic::DictionaryHolder dic;
   std::unique_ptr<CoreHolder> core;
@@ -194,7 +197,7 @@ struct RefEnv {
     {
       dic::DictionaryHolder probe;
       check(probe.load(builder.result()), "dic probe load");
-      model::ModelInfo nfo{};
+      model::ModelInfo& nfo = dicOnlyInfo;  // fillModelPart may run once per builder: cmdModel reuses this part
       nfo.parts.emplace_back();
       check(builder.fillModelPart(&nfo.parts.back()), "fillModelPart");
       model::ModelSaver saver;
@@ -620,6 +623,35 @@ int cmdBench(const Args& a) {
   return 0;
 }
 
+// model : write a complete model file (dictionary + perceptron + optional RNN parts, the container
+//         of src/core/impl/model_io.cc) that the STOCK CLI loads with --model: the same synthetic
+//         Jumandic model the other commands build in memory.  Perceptron part as
+//         SoftConfidenceWeighted::exportModel writes it (scw.cc:129-151), RNN part through
+//         RnnScorerGbeamFactory::makeInfo (rnn_scorer_gbeam.cc:375-399).
+int cmdModel(const Args& a) {
+  RefEnv env;
+  env.init(a);
+  model::ModelInfo nfo = env.dicOnlyInfo;
+  util::CodedBuffer cbuf;
+  util::serialization::Saver svr{&cbuf};
+  PerceptronInfo pi;
+  pi.modelSizeExponent = (u32)a.num("log2w", 20);
+  svr.save(pi);
+  model::ModelPart perc;
+  perc.kind = model::ModelPartKind::Perceprton;
+  perc.comment = "synthetic";
+  perc.data.push_back(cbuf.contents());
+  perc.data.push_back(StringPiece{reinterpret_cast<const char*>(env.weights),
+                                  reinterpret_cast<const char*>(env.weights) + env.numWeights * sizeof(float)});
+  nfo.parts.push_back(std::move(perc));
+  if (env.hasRnn) check(env.rnnFactory.makeInfo(&nfo, "synthetic"), "rnn makeInfo");
+  model::ModelSaver saver;
+  check(saver.open(a.str("out")), "saver open");
+  check(saver.save(nfo), "saver save");
+  std::printf("{\"model\": \"%s\", \"parts\": %zu}\n", a.str("out").c_str(), nfo.parts.size());
+  return 0;
+}
+
 int cmdSpec(const Args& a) {
   RefEnv env;
   env.init(a);
@@ -637,7 +669,8 @@ void usage() {
                "          [rnn=PREFIX rnn_weight=0.0176 perc_weight=1 nce_bias= unk_const= unk_len=] [dynamic=1]\n"
                "  stage : corpus=TXT out=FILE [expected=1] [chunk=N] [threads=T] [max_sent=N]\n"
                "  bench : corpus=TXT [threads=T] [repeat=R] [max_sent=N]\n"
-               "  spec  : out=FILE\n";
+               "  spec  : out=FILE\n"
+               "  model : out=FILE   (a model file the stock jumanpp_v2 --model loads)\n";
 }
 
 }  // namespace
@@ -658,6 +691,7 @@ int main(int argc, char** argv) {
   if (cmd == "stage") return cmdStage(a);
   if (cmd == "bench") return cmdBench(a);
   if (cmd == "spec") return cmdSpec(a);
+  if (cmd == "model") return cmdModel(a);
   usage();
   return 2;
 }
