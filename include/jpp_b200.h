@@ -241,7 +241,27 @@ typedef struct jpp_b200_batch {
    * compact form, when the per-node arrays above are NULL. */
   const int32_t* row_placeholders;      /* [num_entry_rows][num_placeholders] or NULL */
   const int32_t* row_rnn_id;            /* [num_entry_rows] or NULL                   */
+  /* Resident form (ABI 3): node_entry AND node_entry_row are NULL.  The entry
+   * buffer of a dictionary node (node_info.entry_ptr >= 0) comes from the table the handle
+   * holds on the device (jpp_b200_add_entry_rows): the host stages NOTHING per dictionary
+   * node beyond its 8-byte NodeInfo -- no fillEntryBuffer, no RNN id lookup.  Only the nodes
+   * the analyzer made up for this sentence (unknown words etc.: entry_ptr < 0, EntryPtr::extPtr()
+   * = ~entry_ptr is their index in the sentence's ExtraNodesContext, core_types.h:38-41) bring
+   * rows: extra node i of sentence s is entry_rows[sent_extra_row_off[s] + i] (with
+   * row_placeholders / row_rnn_id beside it).  BOS / EOS entries need no row: every field of
+   * theirs is the entry_ptr itself (feature_impl_types.h:130-133). */
+  const uint32_t* sent_extra_row_off;   /* [num_sentences + 1] or NULL                */
 } jpp_b200_batch;
+
+/* Pre-decoded dictionary entries: what PrimitiveFeatureContext::fillEntryBuffer
+ * (feature_impl_types.h:128-148) and RnnIdContainer::resolveId (rnn_id_resolver.cc:278-309)
+ * return for a dictionary EntryPtr depends on the dictionary alone, so it is computed once. */
+typedef struct jpp_b200_entry_table {
+  uint32_t num_rows;
+  const int32_t* entry_ptr; /* [num_rows] EntryPtr::rawValue() (>= 0) of each row's entry      */
+  const int32_t* rows;      /* [num_rows][entry_size]                                          */
+  const int32_t* rnn_id;    /* [num_rows], NULL for a model without RNN                        */
+} jpp_b200_entry_table;
 
 /* ConnectionBeamElement (lattice_config.h:70-73) without the raw pointer: the
  * `previous` link is (boundary/position of ends[left], beam index `prev_beam`);
@@ -301,7 +321,8 @@ typedef enum jpp_b200_sentence_status {
   JPP_B200_SENT_BAD_ENDS = 4,     /* ends[] entry that names a later boundary or a node the
                                      boundary does not have                                   */
   JPP_B200_SENT_BAD_SPAN = 8,     /* node_info.start/end outside the sentence's codepoints     */
-  JPP_B200_SENT_BAD_ENTRY = 16,   /* node_entry_row >= num_entry_rows                          */
+  JPP_B200_SENT_BAD_ENTRY = 16,   /* node_entry_row >= num_entry_rows; resident form: entry_ptr
+                                     without a resident row / extra index past the sentence's rows */
   JPP_B200_SENT_BAD_RNN_ID = 32   /* RNN id outside [-1, vocab_size)                           */
 } jpp_b200_sentence_status;
 
@@ -361,6 +382,13 @@ jpp_b200_status jpp_b200_upload_batch(jpp_b200_handle* h,
 jpp_b200_status jpp_b200_score_resident(jpp_b200_handle* h);
 jpp_b200_status jpp_b200_download_result(jpp_b200_handle* h,
                                          jpp_b200_result* result);
+
+/* Adds rows to the handle's resident entry table (device copy; the whole dictionary at
+ * start-up, or the entries of each batch that were not seen before).  A row whose entry_ptr
+ * is already resident replaces the old one.  Not to be called while another thread scores
+ * on the same handle. */
+jpp_b200_status jpp_b200_add_entry_rows(jpp_b200_handle* h,
+                                        const jpp_b200_entry_table* rows);
 
 jpp_b200_status jpp_b200_get_counters(const jpp_b200_handle* h,
                                       jpp_b200_counters* out);

@@ -82,7 +82,11 @@ class Batch(C.Structure):
                 ("node_info", C.c_void_p), ("node_entry", C.c_void_p), ("node_placeholders", C.c_void_p),
                 ("node_rnn_id", C.c_void_p), ("ends", C.c_void_p), ("codepoints", C.c_void_p),
                 ("node_entry_row", C.c_void_p), ("entry_rows", C.c_void_p), ("num_entry_rows", C.c_uint32),
-                ("row_placeholders", C.c_void_p), ("row_rnn_id", C.c_void_p)]
+                ("row_placeholders", C.c_void_p), ("row_rnn_id", C.c_void_p), ("sent_extra_row_off", C.c_void_p)]
+
+
+class EntryTableStruct(C.Structure):
+    _fields_ = [("num_rows", C.c_uint32), ("entry_ptr", C.c_void_p), ("rows", C.c_void_p), ("rnn_id", C.c_void_p)]
 
 
 class Result(C.Structure):
@@ -265,6 +269,7 @@ class StagedBatch:
     entry_rows: np.ndarray | None = None       # [rows][entry_size] i32
     row_placeholders: np.ndarray | None = None # [rows][placeholders] i32 (then node_placeholders is None)
     row_rnn_id: np.ndarray | None = None       # [rows] i32 (then node_rnn_id is None)
+    sent_extra_row_off: np.ndarray | None = None   # resident form: [sentences + 1] u32, rows = the sentences' extra nodes
 
     @property
     def num_sentences(self) -> int:
@@ -309,8 +314,11 @@ class StagedBatch:
         b.node_entry_row = _ptr(self.node_entry_row)
         b.entry_rows = _ptr(self.entry_rows)
         b.num_entry_rows = 0 if self.entry_rows is None else len(self.entry_rows)
+        if self.sent_extra_row_off is not None:
+            b.num_entry_rows = int(self.sent_extra_row_off[-1])
         b.row_placeholders = _ptr(self.row_placeholders)
         b.row_rnn_id = _ptr(self.row_rnn_id)
+        b.sent_extra_row_off = _ptr(self.sent_extra_row_off)
         b.node_placeholders = _ptr(self.node_placeholders)
         b.node_rnn_id = _ptr(self.node_rnn_id)
         b.ends = _ptr(self.ends)
@@ -419,8 +427,69 @@ class StagedBatch:
         """Bytes jpp_b200_upload_batch copies to the device for this batch."""
         arrs = (self.sent_boundary_off, self.sent_codepoint_off, self.boundary_node_off, self.boundary_end_off,
                 self.node_info, self.node_entry, self.node_placeholders, self.node_rnn_id, self.ends, self.codepoints,
-                self.node_entry_row, self.entry_rows, self.row_placeholders, self.row_rnn_id)
+                self.node_entry_row, self.entry_rows, self.row_placeholders, self.row_rnn_id, self.sent_extra_row_off)
         return int(sum(a.nbytes for a in arrs if a is not None))
+
+    def resident_form(self, pin=None) -> tuple["StagedBatch", "EntryTable"]:
+        """The same batch in the resident form of jpp_b200_batch (dictionary rows on the device, only the
+        sentences' extra nodes bring rows) + the table of the dictionary entries it uses.  Built from an
+        inline batch: a C++ stager makes the table from the dictionary once and never touches
+        fillEntryBuffer for a dictionary node (binding/)."""
+        assert self.node_entry is not None, "start from the inline form"
+        pin = pin or (lambda a: a)
+        ep = self.node_info["entry_ptr"]
+        BOS, EOS = -(1 << 31), -(1 << 31) + 2
+        dic = ep >= 0
+        # dictionary table: one row per distinct entry_ptr
+        uniq, first = np.unique(ep[dic], return_index=True)
+        dic_idx = np.nonzero(dic)[0][first]
+        table = EntryTable(np.ascontiguousarray(uniq.astype(np.int32)), np.ascontiguousarray(self.node_entry[dic_idx]),
+                           None if self.node_rnn_id is None else np.ascontiguousarray(self.node_rnn_id[dic_idx]))
+        # a function of the entry: check it
+        inv = np.searchsorted(uniq, ep[dic])
+        assert np.array_equal(table.rows[inv], self.node_entry[dic]), "entry buffer is not a function of entry_ptr"
+        if self.node_rnn_id is not None:
+            assert np.array_equal(table.rnn_id[inv], self.node_rnn_id[dic]), "rnn id is not a function of entry_ptr"
+        if self.node_placeholders is not None:
+            assert not self.node_placeholders[dic].any(), "dictionary nodes carry placeholders"
+        # extra nodes: row index ~entry_ptr inside the sentence
+        extra = (~dic) & (ep != BOS) & (ep != EOS)
+        node_sent = np.searchsorted(self.sent_boundary_off, np.searchsorted(self.boundary_node_off, np.arange(len(ep)), side="right") - 1,
+                                    side="right") - 1
+        xi = (~ep[extra]).astype(np.int64)
+        xs = node_sent[extra]
+        cnt = np.zeros(self.num_sentences, np.int64)
+        np.maximum.at(cnt, xs, xi + 1)
+        off = np.zeros(self.num_sentences + 1, np.uint32)
+        off[1:] = np.cumsum(cnt)
+        nrows = int(off[-1])
+        es = self.node_entry.shape[1]
+        rows = np.zeros((max(1, nrows), es), np.int32)
+        rows[off[xs] + xi] = self.node_entry[extra]
+        ph = rid = None
+        if self.node_placeholders is not None:
+            ph = np.zeros((max(1, nrows), self.node_placeholders.shape[1]), np.int32)
+            ph[off[xs] + xi] = self.node_placeholders[extra]
+        if self.node_rnn_id is not None:
+            rid = np.zeros(max(1, nrows), np.int32)
+            rid[off[xs] + xi] = self.node_rnn_id[extra]
+            # BOS / EOS nodes resolve to id 0 on the device
+            assert not self.node_rnn_id[(ep == BOS) | (ep == EOS)].any()
+        out = dataclasses.replace(self, node_entry=None, node_placeholders=None, node_rnn_id=None, node_entry_row=None,
+                                  entry_rows=pin(rows[:max(1, nrows)]), row_placeholders=None if ph is None else pin(ph),
+                                  row_rnn_id=None if rid is None else pin(rid), sent_extra_row_off=pin(off))
+        return out, table
+
+
+@dataclass
+class EntryTable:
+    """Pre-decoded dictionary entries for jpp_b200_add_entry_rows."""
+    entry_ptr: np.ndarray        # [rows] i32, EntryPtr::rawValue() >= 0
+    rows: np.ndarray             # [rows][entry_size] i32
+    rnn_id: np.ndarray | None    # [rows] i32
+
+    def as_struct(self) -> EntryTableStruct:
+        return EntryTableStruct(len(self.entry_ptr), _ptr(self.entry_ptr), _ptr(self.rows), _ptr(self.rnn_id))
 
 
 @dataclass

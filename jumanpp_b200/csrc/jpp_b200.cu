@@ -85,10 +85,22 @@ __global__ void k_validate(BatchView bv, ValidateArgs va) {
       const jpp_b200_node_info ni = bv.nodeInfo[n];
       if (lb >= 2 && lb + 1 != nb && (ni.start > ni.end || ni.end > ncp)) bad |= JPP_B200_SENT_BAD_SPAN;
       i32 id = 0;
-      if (!bv.nodeEntry) {
+      if (bv.nodeEntry) {
+      } else if (bv.nodeEntryRow) {
         const u32 row = bv.nodeEntryRow[n];
         if (row >= bv.numEntryRows) bad |= JPP_B200_SENT_BAD_ENTRY;
         else if (bv.rowRnnId) id = bv.rowRnnId[row];
+      } else if (lb >= 2) {  // resident form
+        const i32 ep = ni.entry_ptr;
+        if (ep >= 0) {
+          const i32 row = (u32)ep < bv.dicPtrLimit ? bv.dicRowOfPtr[ep] : -1;
+          if (row < 0) bad |= JPP_B200_SENT_BAD_ENTRY;
+          else if (bv.dicRnnId) id = bv.dicRnnId[row];
+        } else if (ep != kEntryBos && ep != kEntryEos) {
+          const u32 x0 = bv.sentExtraOff[s], x1 = bv.sentExtraOff[s + 1];
+          if (x1 < x0 || x1 > bv.numEntryRows || (u32)~ep >= x1 - x0) bad |= JPP_B200_SENT_BAD_ENTRY;
+          else if (bv.rowRnnId) id = bv.rowRnnId[x0 + (u32)~ep];
+        }
       }
       if (bv.nodeRnnId) id = bv.nodeRnnId[n];
       if (va.hasRnn && (id < -1 || (id >= 0 && (u32)id >= va.vocab))) bad |= JPP_B200_SENT_BAD_RNN_ID;
@@ -1149,6 +1161,12 @@ struct jpp_b200_handle {
   float* dWeights = nullptr;
   RnnTables rt{};
   bool hasRnn = false;
+  // resident entry table (jpp_b200_add_entry_rows); lanes share the owner's device arrays
+  struct EntryTable {
+    i32* dRowOfPtr = nullptr; u32 ptrLimit = 0, ptrCap = 0;
+    i32* dRows = nullptr; i32* dRnnId = nullptr; u32 numRows = 0, rowCap = 0 /* i32 elements */, idCap = 0;
+  } dic;
+  std::vector<i32> hostRowOfPtr;  // owner only: host copy of the direct map
   bool staticProgram = false;  // the uploaded n-gram program is the compiled-in one (jpp_b200_static_jumandic.h)
   float* dRnnBlocks[4] = {nullptr, nullptr, nullptr, nullptr};
   float* dRnnWt = nullptr;  // transposed recurrent matrix
@@ -1166,7 +1184,7 @@ struct jpp_b200_handle {
   enum { B_SBO, B_SCO, B_BNO, B_BEO, B_INFO, B_ENTRY, B_ENTRYROW, B_PH, B_RNNID, B_ENDS, B_CPS, B_NODEBND, B_BNDSENT, B_ENDNODE,
          B_ORDER, B_BEAM, B_BSCORES, B_PATS, B_T0, B_PRE, B_CUT, B_CUTIDX, B_SELPOS, B_BI0, B_GBNODE, B_GBSLOT, B_GBLBND, B_GBCNT,
          B_EOSG, B_EOSLOC, B_EOSRNN, B_COUNTERS, B_WORK,
-         B_PATHLEN, B_PATHNODES, B_STATUS,
+         B_PATHLEN, B_PATHNODES, B_STATUS, B_EXTRAOFF,
          W_GBKEY, W_GBLNODE, W_GBT2, W_GBT1IDX, W_T1NODE, W_GCNT, W_UCNT, W_SELCNT, W_BIITEMS, W_TRIITEMS, W_SCB, W_TRI, W_NODES, W_OFF, W_CURSOR,
          R_OFF, R_ID, R_PREV, R_NEXT, R_BND, R_LEN, R_DEPTH, R_HASH, R_RNCNT, R_RSNODE, R_RSSLOT, R_RSEOSG, R_RSRNODE,
          R_RSCNT, R_CONN, R_BNDHEAD, R_CTX, R_CHNODE, R_CHSLOT, R_CHBND, R_CHID, R_CHLEN, R_SCLIST, R_SCTOTAL, R_LVLCNT, R_LVLOFF, R_LVLLIST, R_CTXOFF, R_RNSENT, R_CURSOR, R_CUBTMP,
@@ -1206,6 +1224,22 @@ jpp_b200_status guarded(jpp_b200_handle* h, F&& f) noexcept {
   } catch (...) {
     return JPP_B200_INVALID_STATE;
   }
+}
+
+// grows a device array, keeping its first `keep` elements
+template <typename T>
+cudaError_t grow_device(T** p, u32* cap, u32 want, u32 keep, cudaStream_t st) {
+  if (want <= *cap) return cudaSuccess;
+  u32 ncap = std::max<u32>(want, *cap + *cap / 2 + 1024);
+  T* np = nullptr;
+  cudaError_t e = cudaMalloc(&np, (size_t)ncap * sizeof(T));
+  if (e != cudaSuccess) return e;
+  if (*p && keep) e = cudaMemcpyAsync(np, *p, (size_t)keep * sizeof(T), cudaMemcpyDeviceToDevice, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (*p) cudaFree(*p);
+  *p = np;
+  *cap = ncap;
+  return e;
 }
 
 #define CU_CHECK(h, expr)                                                                         \
@@ -1426,6 +1460,9 @@ void jpp_b200_destroy(jpp_b200_handle* h) {
     if (h->dWeights) cudaFree(h->dWeights);
     for (auto& p : h->dRnnBlocks) if (p) cudaFree(p);
     if (h->dRnnWt) cudaFree(h->dRnnWt);
+    if (h->dic.dRowOfPtr) cudaFree(h->dic.dRowOfPtr);
+    if (h->dic.dRows) cudaFree(h->dic.dRows);
+    if (h->dic.dRnnId) cudaFree(h->dic.dRnnId);
   }
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -1440,13 +1477,23 @@ static jpp_b200_status upload_window(jpp_b200_handle* h, const jpp_b200_batch* b
   CU_CHECK(h, cudaSetDevice(h->device));
   if (b->num_sentences == 0 || lo >= hi || hi > b->num_sentences) return fail(h, JPP_B200_INVALID_PARAMETER, "empty batch");
   if (!b->sent_boundary_off || !b->sent_codepoint_off || !b->boundary_node_off || !b->boundary_end_off || !b->node_info ||
-      (!b->node_entry && (!b->node_entry_row || !b->entry_rows || b->num_entry_rows == 0)) || !b->ends || (!b->codepoints && b->sent_codepoint_off[b->num_sentences] > 0))
+      !b->ends || (!b->codepoints && b->sent_codepoint_off[b->num_sentences] > 0))
     return fail(h, JPP_B200_INVALID_PARAMETER, "batch has null arrays");
+  const bool residentForm = !b->node_entry && !b->node_entry_row;
+  if (residentForm) {
+    if (!b->sent_extra_row_off || (b->num_entry_rows > 0 && !b->entry_rows))
+      return fail(h, JPP_B200_INVALID_PARAMETER, "resident form needs sent_extra_row_off (and entry_rows for the extra nodes)");
+    if (h->dic.numRows == 0) return fail(h, JPP_B200_INVALID_STATE, "resident form without a resident entry table: call jpp_b200_add_entry_rows first");
+    if (b->sent_extra_row_off[hi] < b->sent_extra_row_off[lo] || b->sent_extra_row_off[hi] > b->num_entry_rows)
+      return fail(h, JPP_B200_INVALID_PARAMETER, "sent_extra_row_off runs past entry_rows");
+  } else if (!b->node_entry && (!b->entry_rows || b->num_entry_rows == 0)) {
+    return fail(h, JPP_B200_INVALID_PARAMETER, "batch has null arrays");
+  }
   const bool rowPh = !b->node_placeholders && !b->node_entry && b->row_placeholders;
   const bool rowRnn = !b->node_rnn_id && !b->node_entry && b->row_rnn_id;
-  if (h->hm.ft.nPlaceholders > 0 && !b->node_placeholders && !rowPh)
+  if (h->hm.ft.nPlaceholders > 0 && !b->node_placeholders && !rowPh && !(residentForm && b->num_entry_rows == 0))
     return fail(h, JPP_B200_INVALID_PARAMETER, "model has placeholders but batch.node_placeholders (or row_placeholders) is null");
-  if (h->hasRnn && !b->node_rnn_id && !rowRnn)
+  if (h->hasRnn && !b->node_rnn_id && !rowRnn && !(residentForm && b->num_entry_rows == 0))
     return fail(h, JPP_B200_INVALID_PARAMETER, "model has an RNN but batch.node_rnn_id (or row_rnn_id) is null");
   const u32 NS = hi - lo;
   const u32* sbo = b->sent_boundary_off + lo;
@@ -1494,10 +1541,14 @@ static jpp_b200_status upload_window(jpp_b200_handle* h, const jpp_b200_batch* b
   ENSURE(B_BNO, (size_t)(NB + 1) * 4); ENSURE(B_BEO, (size_t)(NB + 1) * 4);
   ENSURE(B_INFO, (size_t)NN * sizeof(jpp_b200_node_info));
   const bool compactEntries = b->node_entry == nullptr;
-  ENSURE(B_ENTRY, (size_t)(compactEntries ? b->num_entry_rows : NN) * h->hm.ft.entrySize * 4);
-  if (compactEntries) ENSURE(B_ENTRYROW, (size_t)NN * 4);
-  ENSURE(B_PH, (size_t)(rowPh ? b->num_entry_rows : NN) * std::max(1u, h->hm.ft.nPlaceholders) * 4);
-  ENSURE(B_RNNID, (size_t)(rowRnn ? b->num_entry_rows : NN) * 4);
+  // rows that travel with the batch: all of them (compact form) or the window's extra nodes (resident form)
+  const u32 xBase = residentForm ? b->sent_extra_row_off[lo] : 0u;
+  const u32 batchRows = residentForm ? b->sent_extra_row_off[hi] - xBase : b->num_entry_rows;
+  ENSURE(B_ENTRY, (size_t)std::max(1u, compactEntries ? batchRows : NN) * h->hm.ft.entrySize * 4);
+  if (compactEntries && !residentForm) ENSURE(B_ENTRYROW, (size_t)NN * 4);
+  if (residentForm) ENSURE(B_EXTRAOFF, (size_t)(NS + 1) * 4);
+  ENSURE(B_PH, (size_t)std::max(1u, rowPh ? batchRows : NN) * std::max(1u, h->hm.ft.nPlaceholders) * 4);
+  ENSURE(B_RNNID, (size_t)std::max(1u, rowRnn ? batchRows : NN) * 4);
   ENSURE(B_ENDS, (size_t)NE * sizeof(jpp_b200_node_ptr));
   ENSURE(B_CPS, (size_t)std::max(1u, NC) * sizeof(jpp_b200_codepoint));
   ENSURE(B_NODEBND, (size_t)NN * 4); ENSURE(B_BNDSENT, (size_t)NB * 4); ENSURE(B_ENDNODE, (size_t)NE * 4);
@@ -1528,18 +1579,22 @@ static jpp_b200_status upload_window(jpp_b200_handle* h, const jpp_b200_batch* b
     k_rebase<<<(NB + 256) / 256, 256, 0, st>>>(bf[jpp_b200_handle::B_BEO].as<u32>(), NB + 1, eBase);
   }
   H2D(B_INFO, b->node_info + nBase, (size_t)NN * sizeof(jpp_b200_node_info));
-  if (compactEntries) {
+  if (residentForm) {
+    if (batchRows) H2D(B_ENTRY, b->entry_rows + (size_t)xBase * h->hm.ft.entrySize, (size_t)batchRows * h->hm.ft.entrySize * 4);
+    H2D(B_EXTRAOFF, b->sent_extra_row_off + lo, (size_t)(NS + 1) * 4);
+    if (xBase) k_rebase<<<(NS + 256) / 256, 256, 0, st>>>(bf[jpp_b200_handle::B_EXTRAOFF].as<u32>(), NS + 1, xBase);
+  } else if (compactEntries) {
     H2D(B_ENTRY, b->entry_rows, (size_t)b->num_entry_rows * h->hm.ft.entrySize * 4);
     H2D(B_ENTRYROW, b->node_entry_row + nBase, (size_t)NN * 4);
   } else {
     H2D(B_ENTRY, b->node_entry + (size_t)nBase * h->hm.ft.entrySize, (size_t)NN * h->hm.ft.entrySize * 4);
   }
   if (h->hm.ft.nPlaceholders) {
-    if (rowPh) H2D(B_PH, b->row_placeholders, (size_t)b->num_entry_rows * h->hm.ft.nPlaceholders * 4);
+    if (rowPh) { if (batchRows) H2D(B_PH, b->row_placeholders + (size_t)xBase * h->hm.ft.nPlaceholders, (size_t)batchRows * h->hm.ft.nPlaceholders * 4); }
     else H2D(B_PH, b->node_placeholders + (size_t)nBase * h->hm.ft.nPlaceholders, (size_t)NN * h->hm.ft.nPlaceholders * 4);
   }
   if (h->hasRnn) {
-    if (rowRnn) H2D(B_RNNID, b->row_rnn_id, (size_t)b->num_entry_rows * 4);
+    if (rowRnn) { if (batchRows) H2D(B_RNNID, b->row_rnn_id + xBase, (size_t)batchRows * 4); }
     else H2D(B_RNNID, b->node_rnn_id + nBase, (size_t)NN * 4);
   }
   H2D(B_ENDS, b->ends + eBase, (size_t)NE * sizeof(jpp_b200_node_ptr));
@@ -1552,8 +1607,12 @@ static jpp_b200_status upload_window(jpp_b200_handle* h, const jpp_b200_batch* b
 #define P(idx, T) bf[jpp_b200_handle::idx].as<T>()
   bv.sentBndOff = P(B_SBO, u32); bv.sentCpOff = P(B_SCO, u32); bv.bndNodeOff = P(B_BNO, u32); bv.bndEndOff = P(B_BEO, u32);
   bv.nodeInfo = P(B_INFO, jpp_b200_node_info); bv.nodeEntry = compactEntries ? nullptr : P(B_ENTRY, i32);
-  bv.nodeEntryRow = compactEntries ? P(B_ENTRYROW, u32) : nullptr; bv.entryRows = compactEntries ? P(B_ENTRY, i32) : nullptr;
-  bv.numEntryRows = compactEntries ? b->num_entry_rows : 0;
+  bv.nodeEntryRow = (compactEntries && !residentForm) ? P(B_ENTRYROW, u32) : nullptr; bv.entryRows = compactEntries ? P(B_ENTRY, i32) : nullptr;
+  bv.numEntryRows = compactEntries ? batchRows : 0;
+  if (residentForm) {
+    bv.sentExtraOff = P(B_EXTRAOFF, u32);
+    bv.dicRowOfPtr = h->dic.dRowOfPtr; bv.dicPtrLimit = h->dic.ptrLimit; bv.dicRows = h->dic.dRows; bv.dicRnnId = h->hasRnn ? h->dic.dRnnId : nullptr;
+  }
   bv.nodePlaceholders = (h->hm.ft.nPlaceholders && !rowPh) ? P(B_PH, i32) : nullptr;
   bv.rowPlaceholders = (h->hm.ft.nPlaceholders && rowPh) ? P(B_PH, i32) : nullptr;
   bv.nodeRnnId = (h->hasRnn && !rowRnn) ? P(B_RNNID, i32) : nullptr;
@@ -2012,6 +2071,7 @@ static jpp_b200_status score_batch_impl(jpp_b200_handle* h, const jpp_b200_batch
     lanes[k] = lanes[k - 1]->lane;
     lanes[k]->cfg = h->cfg;
     lanes[k]->pubCfg = h->pubCfg;
+    lanes[k]->dic = h->dic;
   }
   jpp_b200_status sts[kMaxLanes];
   for (auto& x : sts) x = JPP_B200_OK;
@@ -2088,6 +2148,60 @@ jpp_b200_status jpp_b200_download_result(jpp_b200_handle* h, jpp_b200_result* r)
 }
 jpp_b200_status jpp_b200_score_batch(jpp_b200_handle* h, const jpp_b200_batch* batch, jpp_b200_result* result) {
   return guarded(h, [&] { return score_batch_impl(h, batch, result); });
+}
+
+static jpp_b200_status add_entry_rows_impl(jpp_b200_handle* h, const jpp_b200_entry_table* t) {
+  if (!h || !t) return JPP_B200_INVALID_PARAMETER;
+  if (!h->ownsModel) return fail(h, JPP_B200_INVALID_STATE, "not the owning handle");
+  if (t->num_rows == 0) return JPP_B200_OK;
+  if (!t->entry_ptr || !t->rows || (h->hasRnn && !t->rnn_id)) return fail(h, JPP_B200_INVALID_PARAMETER, "entry table has null arrays");
+  CU_CHECK(h, cudaSetDevice(h->device));
+  const u32 es = h->hm.ft.entrySize;
+  i32 maxPtr = -1;
+  for (u32 i = 0; i < t->num_rows; ++i) {
+    if (t->entry_ptr[i] < 0) return fail(h, JPP_B200_INVALID_PARAMETER, "entry table row with a negative entry_ptr (not a dictionary entry)");
+    maxPtr = std::max(maxPtr, t->entry_ptr[i]);
+  }
+  auto& d = h->dic;
+  cudaStream_t st = h->stream;
+  // rows: new ones are appended, known entry_ptrs overwritten in place
+  if (h->hostRowOfPtr.size() < (size_t)maxPtr + 1) h->hostRowOfPtr.resize((size_t)maxPtr + 1, -1);
+  std::vector<u32> dst(t->num_rows);
+  u32 next = d.numRows;
+  for (u32 i = 0; i < t->num_rows; ++i) {
+    i32& slot = h->hostRowOfPtr[t->entry_ptr[i]];
+    if (slot < 0) slot = (i32)next++;
+    dst[i] = (u32)slot;
+  }
+  CU_CHECK(h, grow_device(&d.dRows, &d.rowCap, next * es, d.numRows * es, st));
+  if (h->hasRnn) CU_CHECK(h, grow_device(&d.dRnnId, &d.idCap, next, d.numRows, st));
+  // contiguous runs of appended rows go up in one copy each (the common case: everything new)
+  u32 i = 0;
+  while (i < t->num_rows) {
+    u32 j = i + 1;
+    while (j < t->num_rows && dst[j] == dst[j - 1] + 1) ++j;
+    CU_CHECK(h, cudaMemcpyAsync(d.dRows + (size_t)dst[i] * es, t->rows + (size_t)i * es, (size_t)(j - i) * es * 4, cudaMemcpyHostToDevice, st));
+    if (h->hasRnn) CU_CHECK(h, cudaMemcpyAsync(d.dRnnId + dst[i], t->rnn_id + i, (size_t)(j - i) * 4, cudaMemcpyHostToDevice, st));
+    i = j;
+  }
+  d.numRows = next;
+  // direct map entry_ptr -> row
+  const u32 limit = (u32)h->hostRowOfPtr.size();
+  if (limit > d.ptrCap) {
+    if (d.dRowOfPtr) cudaFree(d.dRowOfPtr);
+    d.dRowOfPtr = nullptr;
+    d.ptrCap = limit + limit / 4 + 1024;
+    CU_CHECK(h, cudaMalloc(&d.dRowOfPtr, (size_t)d.ptrCap * 4));
+  }
+  CU_CHECK(h, cudaMemcpyAsync(d.dRowOfPtr, h->hostRowOfPtr.data(), (size_t)limit * 4, cudaMemcpyHostToDevice, st));
+  d.ptrLimit = limit;
+  CU_CHECK(h, cudaStreamSynchronize(st));
+  h->resident = false;
+  return JPP_B200_OK;
+}
+
+jpp_b200_status jpp_b200_add_entry_rows(jpp_b200_handle* h, const jpp_b200_entry_table* rows) {
+  return guarded(h, [&] { return add_entry_rows_impl(h, rows); });
 }
 
 jpp_b200_status jpp_b200_get_counters(const jpp_b200_handle* h, jpp_b200_counters* out) {

@@ -113,6 +113,13 @@ struct BatchView {
   const i32* rowRnnId;          // compact form, when nodeRnnId is null
   const i32* nodePlaceholders;  // may be null
   const i32* nodeRnnId;         // may be null
+  // resident form (nodeEntry and nodeEntryRow null): dictionary rows live in the handle's table,
+  // rows of a sentence's extra nodes in entryRows at sentExtraOff[sent] + ~entry_ptr
+  const u32* sentExtraOff;
+  const i32* dicRowOfPtr;       // [dicPtrLimit] row of EntryPtr::rawValue(), -1 = not resident
+  u32 dicPtrLimit;
+  const i32* dicRows;           // [rows][entrySize]
+  const i32* dicRnnId;          // [rows] or null
   const jpp_b200_node_ptr* ends;
   const jpp_b200_codepoint* cps;
   // derived on upload
@@ -254,6 +261,57 @@ struct WLoadCached {
 };
 #endif
 
+// ------------------------------------------------------- entry of a node -----
+// EntryPtr::BOS() / EOS() (core_types.h:43-51)
+constexpr i32 kEntryBos = (i32)0x80000000u, kEntryEos = (i32)0x80000002u;
+
+struct NodeEntry {
+  const i32* entry;  // null: every field = entry_ptr (BOS / EOS)
+  const i32* ph;     // null: placeholders are 0
+};
+
+// the three batch forms of include/jpp_b200.h: inline rows, compact rows, resident table
+JPP_HD NodeEntry node_entry(const FeatTables& ft, const BatchView& bv, u32 node, u32 sent, i32 entryPtr) {
+  NodeEntry e;
+  e.ph = bv.nodePlaceholders ? bv.nodePlaceholders + (size_t)node * ft.nPlaceholders : nullptr;
+  if (bv.nodeEntry) {
+    e.entry = bv.nodeEntry + (size_t)node * ft.entrySize;
+  } else if (bv.nodeEntryRow) {
+    u32 row = bv.nodeEntryRow[node];
+    if (row >= bv.numEntryRows) row = 0;  // cannot happen: the upload's validation fails such a sentence
+    e.entry = bv.entryRows + (size_t)row * ft.entrySize;
+    if (!e.ph && bv.rowPlaceholders) e.ph = bv.rowPlaceholders + (size_t)row * ft.nPlaceholders;
+  } else if (entryPtr >= 0) {
+    const i32 row = (u32)entryPtr < bv.dicPtrLimit ? bv.dicRowOfPtr[entryPtr] : -1;
+    e.entry = bv.dicRows + (size_t)(row < 0 ? 0 : row) * ft.entrySize;  // row < 0: validation has failed the sentence
+    e.ph = nullptr;                                                       // providedFeature() is 0 for dictionary entries
+  } else if (entryPtr == kEntryBos || entryPtr == kEntryEos) {
+    e.entry = nullptr;
+    e.ph = nullptr;
+  } else {
+    const u32 row = bv.sentExtraOff[sent] + (u32)~entryPtr;
+    e.entry = bv.entryRows + (size_t)row * ft.entrySize;
+    e.ph = bv.rowPlaceholders ? bv.rowPlaceholders + (size_t)row * ft.nPlaceholders : nullptr;
+  }
+  return e;
+}
+
+// RnnIdContainer::resolveId of a node, wherever the batch form keeps it
+JPP_HD i32 node_rnn_id(const BatchView& bv, u32 node, u32 sent, i32 entryPtr) {
+  if (bv.nodeRnnId) return bv.nodeRnnId[node];
+  if (bv.nodeEntry) return 0;
+  if (bv.nodeEntryRow) {
+    const u32 row = bv.nodeEntryRow[node];
+    return bv.rowRnnId ? bv.rowRnnId[row < bv.numEntryRows ? row : 0u] : 0;
+  }
+  if (entryPtr >= 0) {
+    const i32 row = (u32)entryPtr < bv.dicPtrLimit ? bv.dicRowOfPtr[entryPtr] : -1;
+    return (bv.dicRnnId && row >= 0) ? bv.dicRnnId[row] : 0;
+  }
+  if (entryPtr == kEntryBos || entryPtr == kEntryEos) return 0;
+  return bv.rowRnnId ? bv.rowRnnId[bv.sentExtraOff[sent] + (u32)~entryPtr] : 0;
+}
+
 // ------------------------------------------------------------ T0 kernel -----
 // One thread per node: primitive features -> 38 pattern hashes -> 32 unigram
 // hashes -> weight gather + ordered sum.  Replaces the generated
@@ -262,8 +320,9 @@ JPP_HD u64 prim_value(const FeatTables& ft, u32 p, const i32* entry, const i32* 
                       const jpp_b200_codepoint* cps, u32 ncp) {
   const i32 a = ft.primA[p];
   switch (ft.primKind[p]) {
-    case JPP_B200_PRIM_COPY: return (u64)(u32)entry[a];
-    case JPP_B200_PRIM_SHIFT_MASK: return (u64)(((u32)entry[a] >> ft.primB[p]) & (u32)ft.primC[p]);
+    // entry == nullptr: a BOS / EOS row, every field is the entry pointer itself (feature_impl_types.h:130-133)
+    case JPP_B200_PRIM_COPY: return (u64)(u32)(entry ? entry[a] : ni.entry_ptr);
+    case JPP_B200_PRIM_SHIFT_MASK: return (u64)(((u32)(entry ? entry[a] : ni.entry_ptr) >> ft.primB[p]) & (u32)ft.primC[p]);
     case JPP_B200_PRIM_PROVIDED: return ph ? (u64)(u32)ph[a] : 0;
     case JPP_B200_PRIM_SURFACE_CODEPOINT_SIZE: return (u64)(i32)((i32)ni.end - (i32)ni.start);
     case JPP_B200_PRIM_CODEPOINT: {
@@ -339,16 +398,9 @@ JPP_HD void t0_node(const FeatTables& ft, const BatchView& bv, const WL& wl, u32
   const u32 cp0 = bv.sentCpOff[sent];
   const u32 ncp = bv.sentCpOff[sent + 1] - cp0;
   const jpp_b200_codepoint* cps = bv.cps + cp0;
-  const i32* entry;
-  const i32* ph = bv.nodePlaceholders ? bv.nodePlaceholders + (size_t)node * ft.nPlaceholders : nullptr;
-  if (bv.nodeEntry) {
-    entry = bv.nodeEntry + (size_t)node * ft.entrySize;
-  } else {
-    u32 row = bv.nodeEntryRow[node];
-    if (row >= bv.numEntryRows) row = 0;  // cannot happen: the upload's validation fails such a sentence
-    entry = bv.entryRows + (size_t)row * ft.entrySize;
-    if (!ph && bv.rowPlaceholders) ph = bv.rowPlaceholders + (size_t)row * ft.nPlaceholders;
-  }
+  const NodeEntry ne = node_entry(ft, bv, node, sent, ni.entry_ptr);
+  const i32* entry = ne.entry;
+  const i32* ph = ne.ph;
   u64 prim[MAX_PRIM];
   for (u32 i = 0; i < ft.nPrim; ++i) prim[i] = prim_value(ft, i, entry, ph, ni, cps, ncp);
   u64 pat[LEAN ? 1 : MAX_PAT];

@@ -111,14 +111,8 @@ JPP_HD void rnn_build_tree(const BatchView& bv, const ScoreCfg& cfg, const RnnWo
         rw.chainSlot[base0 + len] = (u16)curSlot;
         rw.chainBnd[base0 + len] = (u16)curBnd;
         {  // id / length of this node: off the critical path here, ready when the chain is unwound
-          i32 nid;
-          if (bv.nodeRnnId) {
-            nid = bv.nodeRnnId[curNode];
-          } else {
-            const u32 row = bv.nodeEntryRow[curNode];
-            nid = bv.rowRnnId[row < bv.numEntryRows ? row : 0u];  // a bad row fails the call (t0_node flags it)
-          }
           const jpp_b200_node_info ni = bv.nodeInfo[curNode];
+          const i32 nid = node_rnn_id(bv, curNode, sent, ni.entry_ptr);
           rw.chainId[base0 + len] = nid;
           rw.chainLen[base0 + len] = (i32)ni.end - (i32)ni.start;
         }

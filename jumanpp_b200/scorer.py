@@ -61,6 +61,8 @@ def load_library() -> C.CDLL:
     lib.jpp_b200_score_resident.argtypes = [H]
     lib.jpp_b200_download_result.restype = C.c_int
     lib.jpp_b200_download_result.argtypes = [H, C.POINTER(abi.Result)]
+    lib.jpp_b200_add_entry_rows.restype = C.c_int
+    lib.jpp_b200_add_entry_rows.argtypes = [H, C.POINTER(abi.EntryTableStruct)]
     lib.jpp_b200_get_counters.restype = C.c_int
     lib.jpp_b200_get_counters.argtypes = [H, C.POINTER(abi.Counters)]
     lib.jpp_b200_last_error.restype = C.c_char_p
@@ -74,7 +76,7 @@ def load_library() -> C.CDLL:
 
 
 EXPORTED_SYMBOLS = ["jpp_b200_create", "jpp_b200_set_config", "jpp_b200_score_batch", "jpp_b200_upload_batch",
-                    "jpp_b200_score_resident", "jpp_b200_download_result", "jpp_b200_get_counters",
+                    "jpp_b200_score_resident", "jpp_b200_download_result", "jpp_b200_get_counters", "jpp_b200_add_entry_rows",
                     "jpp_b200_last_error", "jpp_b200_destroy", "jpp_b200_abi_version", "jpp_b200_build_info"]
 
 
@@ -120,6 +122,11 @@ class LatticeScorer:
             rs.node_t0_score = None
         self._check(self._lib.jpp_b200_score_batch(self._h, C.byref(bs), C.byref(rs)))
         return res
+
+    # -- pre-decoded dictionary entries resident on the device
+    def add_entry_rows(self, table: abi.EntryTable) -> None:
+        ts = table.as_struct()
+        self._check(self._lib.jpp_b200_add_entry_rows(self._h, C.byref(ts)))
 
     def upload(self, batch: abi.StagedBatch) -> None:
         bs = batch.as_struct()
