@@ -393,6 +393,12 @@ jpp_b200_status jpp_b200_add_entry_rows(jpp_b200_handle* h,
 jpp_b200_status jpp_b200_get_counters(const jpp_b200_handle* h,
                                       jpp_b200_counters* out);
 
+/* Page-locked host memory for the staged batch / result arrays (the H2D / D2H copies of a
+ * batch in pinned memory run at full PCIe rate and asynchronously).  The host side needs no
+ * CUDA header: this library is the only thing it links. */
+jpp_b200_status jpp_b200_alloc_pinned(size_t bytes, void** out);
+void jpp_b200_free_pinned(void* p);
+
 /* Replaces: Status::message(); valid until the next call on the handle.
  * With h == NULL returns the message of the last failed jpp_b200_create on
  * this thread. */

@@ -2204,6 +2204,21 @@ jpp_b200_status jpp_b200_add_entry_rows(jpp_b200_handle* h, const jpp_b200_entry
   return guarded(h, [&] { return add_entry_rows_impl(h, rows); });
 }
 
+jpp_b200_status jpp_b200_alloc_pinned(size_t bytes, void** out) {
+  if (!out) return JPP_B200_INVALID_PARAMETER;
+  *out = nullptr;
+  const cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault);
+  if (e != cudaSuccess) {
+    try { g_create_error = std::string("cudaHostAlloc: ") + cudaGetErrorString(e); } catch (...) {}
+    return JPP_B200_CUDA_ERROR;
+  }
+  return JPP_B200_OK;
+}
+
+void jpp_b200_free_pinned(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
 jpp_b200_status jpp_b200_get_counters(const jpp_b200_handle* h, jpp_b200_counters* out) {
   if (!h || !out) return JPP_B200_INVALID_PARAMETER;
   *out = h->counters;

