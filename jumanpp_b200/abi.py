@@ -504,12 +504,12 @@ class ScoreResult:
     sentence_status: np.ndarray | None = None   # [sentences] u8, 0 = scored (jpp_b200_sentence_status bits)
 
     @staticmethod
-    def allocate(num_nodes: int, beam: int, num_scorers: int, stored: int, num_sentences: int = 0,
+    def allocate(num_nodes: int, beam: int, num_scorers: int, stored: int, num_sentences: int | None = None,
                  num_boundaries: int = 0) -> "ScoreResult":
         r = ScoreResult(np.zeros((num_nodes, beam), BEAM_EL_DT),
                         np.zeros((num_nodes, beam, num_scorers), np.float32),
                         np.zeros((num_nodes, stored), np.uint64), np.zeros(num_nodes, np.float32))
-        if num_sentences:
+        if num_sentences is not None:
             r.best_path_len = np.zeros(num_sentences, np.uint32)
             r.best_path_nodes = np.zeros(num_boundaries, np.uint32)
             r.sentence_status = np.zeros(num_sentences, np.uint8)

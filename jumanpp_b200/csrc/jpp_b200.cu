@@ -514,17 +514,7 @@ __global__ void __launch_bounds__(128) k_w_final(BatchView bv, ScoreCfg cfg, Wav
 }
 
 // ------------------------------------------------------------ fused walk -----
-// The five phases of a wave need each other's results only within a sentence.  A block of 256
-// threads therefore owns 32 sentences (neighbours in the longest-first order, so of similar
-// length) and walks them through ALL their boundaries on its own: the same device functions as
-// the wavefront kernels, __syncthreads() where those have a kernel boundary, the lists of
-// selected nodes / items private to the block (counters in shared memory, no global atomics).
-// Blocks drift apart in phase, so while one block chases the dependent loads of its global
-// beams another one keeps the gather pipe busy -- across kernels that overlap does not exist.
-// Used when the right check is on (a selected-node bound per sentence exists) and beam / global
-// beam fit the 8-lane groups; other configurations take the wavefront kernels.
-constexpr u32 kFusedSent = 32;     // sentences per block
-constexpr u32 kFusedThreads = 256;
+// (the kernel itself: jpp_b200_walk.cuh)
 
 // block-wide maximum through a 4-word shared scratch (all threads call it)
 __device__ __forceinline__ u32 block_max_u32(u32 v, u32* scratch) {
@@ -541,89 +531,6 @@ __device__ __forceinline__ u32 block_max_u32(u32 v, u32* scratch) {
 inline bool fused_walk_ok(const ScoreCfg& cfg) {
   static const bool off = getenv("JPP_B200_WAVEFRONT") != nullptr;  // A/B and per-kernel profiling
   return !off && cfg.rcheck > 0 && cfg.gbeam > 0;  // any beam / global beam the library accepts (<= 32)
-}
-
-template <bool SMALL>
-__global__ void __launch_bounds__(kFusedThreads, 3) k_walk_fused(const __grid_constant__ FeatTables ft, BatchView bv, ScoreCfg cfg,
-                                                               WaveView wv, const float* __restrict__ w, u32 itemCap) {
-  __shared__ u32 sCount[4];                 // selected nodes, bigram items, trigram items of the current wave
-  __shared__ u32 sNodeOff[kFusedSent + 1];  // right nodes of the block's sentences at the current boundary (prefix)
-  __shared__ u32 sNode0[kFusedSent];
-  const u32 NS = bv.numSentences;
-  const u32 firstSent = blockIdx.x * kFusedSent;
-  if (firstSent >= NS) return;
-  const u32 nHere = NS - firstSent < kFusedSent ? NS - firstSent : kFusedSent;
-  const u32 grp = threadIdx.x / 8u, sub = threadIdx.x % 8u;
-  // the block's private lists
-  WaveView lw = wv;
-  lw.selCount = sCount;
-  lw.biItems = wv.biItems + (size_t)blockIdx.x * itemCap;
-  lw.triItems = wv.triItems + (size_t)blockIdx.x * itemCap;
-  lw.scb = wv.scb + (size_t)blockIdx.x * itemCap;
-  lw.tri = wv.tri + 2 * (size_t)blockIdx.x * itemCap;
-  const WLoadDirect wl{w};
-  const u32 mySent = grp < nHere ? bv.sentOrder[firstSent + grp] : 0xFFFFFFFFu;
-  u32 myB0 = 0, myNb = 0;
-  if (mySent != 0xFFFFFFFFu) myNb = sent_span(bv, mySent, myB0);
-  // longest sentence of the block (the first one in the longest-first order, unless that one failed
-  // validation on the device after the order was made)
-  const u32 maxNb = block_max_u32(myNb, sCount);
-  for (u32 bnd = 2; bnd < maxNb; ++bnd) {
-    // W1 + the block's node list of this wave
-    if (threadIdx.x < 3) sCount[threadIdx.x] = 0;
-    u32 R = 0, n0 = 0;
-    if (mySent != 0xFFFFFFFFu && bnd < myNb && myNb > 3) {
-      n0 = bv.bndNodeOff[myB0 + bnd];
-      R = bv.bndNodeOff[myB0 + bnd + 1] - n0;
-      gbeam_group<8, 8>(bv, cfg, lw, mySent, bnd);
-    }
-    if (sub == 0) { sNodeOff[grp + 1] = R; sNode0[grp] = n0; }
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      u32 v = sNodeOff[threadIdx.x + 1];
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const u32 t = __shfl_up_sync(0xffffffffu, v, d);
-        if ((int)threadIdx.x >= d) v += t;
-      }
-      sNodeOff[threadIdx.x + 1] = v;
-      if (threadIdx.x == 0) sNodeOff[0] = 0;
-    }
-    __syncthreads();
-    const u32 T = sNodeOff[kFusedSent];
-    // W2
-    for (u32 i = threadIdx.x; i < T; i += kFusedThreads) {
-      u32 lo = 0, hi = kFusedSent;  // sentence j with sNodeOff[j] <= i < sNodeOff[j + 1]
-      while (hi - lo > 1) {
-        const u32 m = (lo + hi) >> 1;
-        if (sNodeOff[m] <= i) lo = m; else hi = m;
-      }
-      wave_prescore(ft, bv, cfg, lw, wl, sNode0[lo] + (i - sNodeOff[lo]));
-    }
-    __syncthreads();
-    // W3 (positions and items are private to the block: counters in shared memory)
-    cutoff_group_block(ft, bv, cfg, lw, firstSent + nHere, bnd, firstSent);
-    __syncthreads();
-    // W4
-    {
-      const u32 n1 = sCount[1], n2 = sCount[2];
-      for (u32 i = threadIdx.x; i < n1 + n2; i += kFusedThreads) {
-        if (i < n1) wave_item_bigram(ft, bv, lw, wl, lw.biItems[i]);
-        else wave_item_trigram(ft, bv, lw, wl, lw.triItems[i - n1]);
-      }
-    }
-    __syncthreads();
-    // W5
-    for (u32 i = threadIdx.x; i < T; i += kFusedThreads) {
-      u32 lo = 0, hi = kFusedSent;
-      while (hi - lo > 1) {
-        const u32 m = (lo + hi) >> 1;
-        if (sNodeOff[m] <= i) lo = m; else hi = m;
-      }
-      wave_final_node<SMALL>(bv, cfg, lw, sNode0[lo] + (i - sNodeOff[lo]));
-    }
-    __syncthreads();
-  }
 }
 
 }  // namespace
@@ -1751,30 +1658,19 @@ static jpp_b200_status score_resident_impl(jpp_b200_handle* h) {
     u32 launches = 1;
     const bool fused = fused_walk_ok(cfg) && !profileOn;
     if (fused) {
-      static const bool blockWalk = getenv("JPP_B200_BLOCK_WALK") != nullptr;  // A/B: round 1's block-scope walk
-      static const bool noStatic = getenv("JPP_B200_NO_STATIC") != nullptr;    // A/B: table-driven n-gram program
+      static const bool noStatic = getenv("JPP_B200_NO_STATIC") != nullptr;  // A/B: table-driven n-gram program
       const bool narrow = cfg.beam <= 8 && cfg.gbeam <= 8;
-      if (blockWalk && narrow) {
-        const u32 itemCap = kFusedSent * (u32)cfg.rbeam * (u32)cfg.gbeam;
-        const u32 blocks = (NS + kFusedSent - 1) / kFusedSent;
-        if (small_gbeam_ok(cfg)) k_walk_fused<true><<<blocks, kFusedThreads, 0, st>>>(ft, bv, cfg, wv, h->dWeights, itemCap);
-        else k_walk_fused<false><<<blocks, kFusedThreads, 0, st>>>(ft, bv, cfg, wv, h->dWeights, itemCap);
+      const u32 itemCap = kFusedSent * (u32)cfg.rbeam * (u32)cfg.gbeam;
+      const u32 blocks = (NS + kFusedSent - 1) / kFusedSent;
+      const bool stat = h->staticProgram && !noStatic;
+#define JPP_WALK(GW, KB, SM, ST) k_walk_fused<GW, KB, SM, ST><<<blocks, kFusedThreads, 0, st>>>(ft, bv, cfg, wv, h->dWeights, itemCap)
+      if (narrow) {
+        if (small_gbeam_ok(cfg)) { if (stat) JPP_WALK(8, 8, true, true); else JPP_WALK(8, 8, true, false); }
+        else { if (stat) JPP_WALK(8, 8, false, true); else JPP_WALK(8, 8, false, false); }
       } else {
-        // a warp owns 4 sentences (beams <= 8: 8 lanes per sentence in W1 / W3) or one
-        const u32 spw = narrow ? 4u : 1u;
-        const u32 warps = (NS + spw - 1) / spw;
-        const u32 blocks = (warps + kWarpWalkThreads / 32 - 1) / (kWarpWalkThreads / 32);
-        const u32 itemCap = spw * (u32)cfg.rbeam * (u32)cfg.gbeam;
-        const bool stat = h->staticProgram && !noStatic;
-#define JPP_WALK(GW, KB, SM, ST) k_walk_warp<GW, KB, SM, ST><<<blocks, kWarpWalkThreads, 0, st>>>(ft, bv, cfg, wv, h->dWeights, itemCap)
-        if (narrow) {
-          if (small_gbeam_ok(cfg)) { if (stat) JPP_WALK(8, 8, true, true); else JPP_WALK(8, 8, true, false); }
-          else { if (stat) JPP_WALK(8, 8, false, true); else JPP_WALK(8, 8, false, false); }
-        } else {
-          if (stat) JPP_WALK(32, MAX_BEAM, false, true); else JPP_WALK(32, MAX_BEAM, false, false);
-        }
-#undef JPP_WALK
+        if (stat) JPP_WALK(32, MAX_BEAM, false, true); else JPP_WALK(32, MAX_BEAM, false, false);
       }
+#undef JPP_WALK
       ++launches;
     }
     for (u32 bnd = 2; bnd < h->maxNb && !fused; ++bnd) {
