@@ -62,15 +62,22 @@ def log(*a):
 
 
 # ------------------------------------------------------------------ workload --
-def prepare_workload(args, rank: int) -> dict:
+def prepare_workload(args, rank: int, world: int = 1) -> dict:
     wl = WORKLOADS[args.workload]
     cache = Path(args.cache)
-    tag = f"{args.workload}_d{args.dict_rows}_n{args.sentences}_l{args.min_len}-{args.max_len}_s{args.seed + rank}_w{args.log2w}"
+    sharded = args.shard_corpus and world > 1
+    # weak scaling: every rank its own corpus (seed + rank); --shard-corpus: ONE corpus, rank r stages its shard
+    seed = args.seed if sharded else args.seed + rank
+    tag = f"{args.workload}_d{args.dict_rows}_n{args.sentences}_l{args.min_len}-{args.max_len}_s{seed}_w{args.log2w}"
+    if sharded:
+        tag += f"_shard{rank}of{world}"
     d = cache / tag
     d.mkdir(parents=True, exist_ok=True)
     dic, corpus, rnn = d / "dict.csv", d / "corpus.txt", d / "rnn"
     done = d / "staged.done"
-    info = dict(dir=d, dict=dic, corpus=corpus, rnn=rnn if wl["rnn"] else None, wl=wl)
+    info = dict(dir=d, dict=dic, corpus=corpus, rnn=rnn if wl["rnn"] else None, wl=wl, shard=None)
+    if sharded and (d / "shard.json").exists():
+        info["shard"] = json.loads((d / "shard.json").read_text())
     if done.exists():
         return info
     if not HARNESS.exists():
@@ -78,7 +85,19 @@ def prepare_workload(args, rank: int) -> dict:
                          "/root/reference is mounted (the host lattice builder is the reference's)")
     t0 = time.time()
     surfaces = synth.write_dictionary(dic, args.dict_rows, 20260923)
-    synth.write_corpus(corpus, args.sentences, args.min_len, args.max_len, args.seed + rank, surfaces)
+    if sharded:
+        # the whole corpus is generated (deterministic), the rank keeps its contiguous shard, balanced by codepoints
+        full = d / "corpus_full.txt"
+        synth.write_corpus(full, args.sentences, args.min_len, args.max_len, seed, surfaces)
+        lines = full.read_text(encoding="utf-8").splitlines()
+        bounds = shard.shard_bounds(np.array([len(x) for x in lines], np.int64), world)
+        lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+        corpus.write_text("\n".join(lines[lo:hi]) + "\n", encoding="utf-8")
+        full.unlink()
+        info["shard"] = {"lo": lo, "hi": hi, "total": len(lines), "bounds": [int(x) for x in bounds]}
+        (d / "shard.json").write_text(json.dumps(info["shard"]))
+    else:
+        synth.write_corpus(corpus, args.sentences, args.min_len, args.max_len, seed, surfaces)
     if wl["rnn"]:
         words = synth.rnn_vocabulary(dic, 50000)
         synth.write_rnn_model(rnn, words, wl["H"], 3, 1 << 22, 9.0, 2)
@@ -103,25 +122,41 @@ def harness_model_args(args, wl, rnn, log2w=None) -> list[str]:
     return a
 
 
-def load_staged(info, args, pin) -> tuple[abi.ModelSpec, abi.ScoringConfig, abi.StagedBatch]:
+def load_staged(info, args, pin) -> tuple[abi.ModelSpec, abi.ScoringConfig, list[abi.StagedBatch], abi.EntryTable | None]:
+    """The staged lattices as a list of windows (one for the default 100 000 sentences; --window cuts larger
+    workloads so that one window's lattices + results fit the device comfortably), in the batch form asked
+    for: compact (one row per distinct entry of the window), resident (dictionary rows in a device table,
+    SURVEY 8f1) or inline."""
     files = sorted(info["dir"].glob("staged.jppb*"))
     files = [f for f in files if not f.name.endswith(".done")]
-    parts, first = [], None
-    for f in files:
-        dd = jppb.load(f)
-        first = first or dd
-        part = abi.StagedBatch.from_jppb(dd)
-        parts.append(part if args.inline_entries else part.compact_entries())
+    first = jppb.load(files[0])
     model = abi.ModelSpec.from_jppb(first, str(info["rnn"]) if info["rnn"] else None)
     model.log2_weights, model.weight_seed, model.weight_scale = args.log2w, args.wseed, 0.5
     cfg = abi.ScoringConfig.from_jppb(first)
-    if args.inline_entries:
-        batch = abi.StagedBatch.concat(parts, pin=pin)
-    else:   # one entry row per distinct entry of the whole batch (jpp_b200_batch.node_entry_row / entry_rows)
-        batch = abi.StagedBatch.concat(parts).compact_entries()
+    per_file = max(1, args.stage_chunk)
+    files_per_window = max(1, (args.window + per_file - 1) // per_file)
+    windows, tables = [], []
+    for w0 in range(0, len(files), files_per_window):
+        parts = [abi.StagedBatch.from_jppb(jppb.load(f)) for f in files[w0:w0 + files_per_window]]
+        form = args.batch_form
+        if form == "inline":
+            batch = abi.StagedBatch.concat(parts)
+        elif form == "resident":
+            batch, table = abi.StagedBatch.concat(parts).resident_form()
+            tables.append(table)
+        else:  # one entry row per distinct entry of the window (jpp_b200_batch.node_entry_row / entry_rows)
+            batch = abi.StagedBatch.concat([p.compact_entries() for p in parts]).compact_entries()
         batch = dataclasses.replace(batch, **{f.name: pin(getattr(batch, f.name)) for f in dataclasses.fields(batch)
                                               if getattr(batch, f.name) is not None})
-    return model, cfg, batch
+        windows.append(batch)
+    table = None
+    if tables:   # the union over the windows: uploaded once, before any timed region
+        ep = np.concatenate([t.entry_ptr for t in tables])
+        uniq, firsti = np.unique(ep, return_index=True)
+        rows = np.concatenate([t.rows for t in tables])[firsti]
+        rid = None if tables[0].rnn_id is None else np.concatenate([t.rnn_id for t in tables])[firsti]
+        table = abi.EntryTable(np.ascontiguousarray(uniq), np.ascontiguousarray(rows), None if rid is None else np.ascontiguousarray(rid))
+    return model, cfg, windows, table
 
 
 # -------------------------------------------------------------------- clocks --
@@ -241,7 +276,7 @@ def run_harness_bench(info, args, sample: int, threads: int, steps: int = 1, war
 def reference_arm(args, rank: int, world: int) -> None:
     if rank != 0:
         return
-    info = prepare_workload(args, 0)
+    info = prepare_workload(args, 0, 1)
     # one process per thread count: model loaded once, W untimed + K timed passes over the sample
     rr = reference_runs(info, args, steps=args.steps, warmup=max(1, args.warmup))
     best = rr["best"]
@@ -251,7 +286,7 @@ def reference_arm(args, rank: int, world: int) -> None:
         "unit": "sentences/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1000.0 * best["score_path_s_max_thread"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64 hash / f32 sums", "data": "synthetic",
-        "config": workload_config(args, info["wl"]),
+        "config": workload_config(args, info["wl"], 1),
         "cpu_baseline": cpu_baseline_record(rr),
         "e2e": {"value": value, "unit": "sentences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -273,21 +308,25 @@ def walk_kernel_name(wl) -> str:
     (jpp_b200.cu fused_walk_ok / jpp_b200_walk.cuh)."""
     if wl["rcheck"] > 0 and wl["gbeam"] > 0 and "JPP_B200_WAVEFRONT" not in os.environ:
         narrow = wl["beam"] <= 8 and wl["gbeam"] <= 8
-        if narrow and "JPP_B200_BLOCK_WALK" in os.environ:
-            return "k_walk_fused (round 1): a block of 256 threads walks 32 sentences through all their boundaries"
         static = "JPP_B200_NO_STATIC" not in os.environ
-        return (f"k_walk_warp<{8 if narrow else 32}>: a warp walks {'4 sentences' if narrow else '1 sentence'} through all "
+        return (f"k_walk_fused<GW={8 if narrow else 32}>: a block of 256 threads walks 32 sentences through all their "
                 "boundaries (global beam, prescore, cutoff, n-gram items, beam rows: n-gram hash + weight gather + beams), "
                 + ("compiled-in Jumandic n-gram program, pattern rows in registers" if static else "table-driven n-gram program"))
     return ("wave loop: k_w_gbeam_warp + k_w_prescore + k_w_cutoff_group + k_w_items + k_w_final per boundary number "
             "(n-gram hash + weight gather + beams)")
 
 
-def workload_config(args, wl) -> dict:
-    return {"workload": wl["desc"], "sentences_per_gpu": args.sentences, "length_codepoints": [args.min_len, args.max_len],
-            "dictionary_rows": args.dict_rows, "weights": f"float[2^{args.log2w}] counter-based synthetic",
-            "beam": wl["beam"], "global_beam": wl["gbeam"], "right_check": wl["rcheck"], "right_beam": wl["rbeam"],
-            "rnn_layer": wl["H"], "l2_policy": "inputs of one step (several GB of staged lattices + 256 MiB table) exceed the 126 MB L2"}
+def workload_config(args, wl, world: int = 1) -> dict:
+    c = {"workload": wl["desc"], "sentences_per_gpu": args.sentences, "length_codepoints": [args.min_len, args.max_len],
+         "dictionary_rows": args.dict_rows, "weights": f"float[2^{args.log2w}] counter-based synthetic",
+         "beam": wl["beam"], "global_beam": wl["gbeam"], "right_check": wl["rcheck"], "right_beam": wl["rbeam"],
+         "rnn_layer": wl["H"], "batch_form": args.batch_form, "window_sentences": min(args.window, args.sentences),
+         "l2_policy": "inputs of one step (several GB of staged lattices + 256 MiB table) exceed the 126 MB L2"}
+    if args.shard_corpus and world > 1:
+        c["sentences_per_gpu"] = None
+        c["sentences_total"] = args.sentences
+        c["sharding"] = f"ONE corpus of {args.sentences} sentences cut into {world} contiguous shards balanced by codepoints (jumanpp_b200/shard.py)"
+    return c
 
 
 # --------------------------------------------------------------- product arm --
@@ -303,14 +342,24 @@ def product_arm(args, rank: int, world: int, local_rank: int) -> None:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from jumanpp_b200.scorer import LatticeScorer, pinned_copy
 
-    info = prepare_workload(args, rank)
+    info = prepare_workload(args, rank, world)
     t0 = time.time()
-    model, cfg, batch = load_staged(info, args, pin=pinned_copy)
-    log(f"rank {rank}: staged batch in pinned memory: {batch.num_sentences} sentences, {batch.num_nodes} nodes, "
-        f"{batch.num_boundaries} boundaries ({time.time() - t0:.1f}s)")
+    model, cfg, windows, table = load_staged(info, args, pin=pinned_copy)
+    n_sent = sum(w.num_sentences for w in windows)
+    n_nodes = sum(w.num_nodes for w in windows)
+    log(f"rank {rank}: staged lattices in pinned memory: {n_sent} sentences, {n_nodes} nodes, {len(windows)} window(s), "
+        f"form {args.batch_form} ({time.time() - t0:.1f}s)")
     scorer = LatticeScorer(model, cfg, device=local_rank)
-    res = scorer.allocate_result(batch)
-    h2d = batch.h2d_bytes()
+    if table is not None:
+        scorer.add_entry_rows(table)   # the pre-decoded dictionary: once, like the weights
+    results = []
+    for w in windows:
+        r = scorer.allocate_result(w)
+        r.best_path_len, r.best_path_nodes = pinned_copy(r.best_path_len), pinned_copy(r.best_path_nodes)
+        r.sentence_status = pinned_copy(r.sentence_status)
+        results.append(r)
+    h2d = sum(w.h2d_bytes() for w in windows)
+    d2h = sum(r.best_path_len.nbytes + r.best_path_nodes.nbytes + r.sentence_status.nbytes for r in results)
 
     def barrier():
         torch.cuda.synchronize()
@@ -318,90 +367,64 @@ def product_arm(args, rank: int, world: int, local_rank: int) -> None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident throughput (`value`)
-    scorer.upload(batch)
+    # ---- device-resident throughput (`value`): lattices of a window already in HBM when its timed region
+    # starts; the step's time = CUDA events around all kernels, summed over the windows
+    scorer.upload(windows[0])
     for _ in range(args.warmup):
         scorer.score_resident()
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
     t0 = time.perf_counter()
-    kms = []
-    for _ in range(args.steps):
-        scorer.score_resident()          # synchronises its own stream (CUDA events inside)
-        kms.append(scorer.counters()["kernel_ms"])
+    kms, counters = [], None
+    one_lane_paths = None
+    for step in range(args.steps):
+        km, cn = None, None
+        for wi, w in enumerate(windows):
+            if len(windows) > 1 or step == 0:
+                if not (wi == 0 and step == 0):
+                    scorer.upload(w)             # untimed (outside the events of score_resident)
+            scorer.score_resident()              # synchronises its own stream (CUDA events inside)
+            c = scorer.counters()
+            km = c["kernel_ms"] if km is None else {k: km[k] + v for k, v in c["kernel_ms"].items()}
+            cn = c if cn is None else {k: (cn[k] + v if isinstance(v, int) else v) for k, v in c.items()}
+            if step == 0 and wi == 0:
+                scorer.download(results[0], paths_only=True)   # 1-best paths of the resident (one-lane) run
+                one_lane_paths = (results[0].best_path_len.copy(), results[0].best_path_nodes.copy())
+        kms.append(km)
+        counters = cn
     torch.cuda.synchronize()
     dt_res = time.perf_counter() - t0
     clocks = sampler.stop()
-    cnt = scorer.counters()
-    # device-side time of the step = events around all kernels of score_resident
+    cnt = counters
     dev_ms = [k["score_total"] for k in kms]
     t_res = torch.tensor([sum(dev_ms) / 1000.0, dt_res], dtype=torch.float64, device="cuda")
-    # ---- end to end through the C ABI with host buffers (`e2e`): staged lattices in
-    # pinned host memory -> H2D -> all kernels -> D2H of the device-resolved 1-best paths
-    # (what the CLI's default output consumes; jpp_b200_result.best_path_*).
-    # (a) one call for the whole batch
-    res.best_path_len = pinned_copy(res.best_path_len)
-    res.best_path_nodes = pinned_copy(res.best_path_nodes)
-    d2h = res.best_path_len.nbytes + res.best_path_nodes.nbytes
-    scorer.download(res, paths_only=True)                      # 1-best paths of the resident (one-lane) run
-    one_lane_paths = (res.best_path_len.copy(), res.best_path_nodes.copy())
+    # ---- end to end through the C ABI with host buffers (`e2e`): staged lattices in pinned host memory
+    # -> H2D -> all kernels -> D2H of the device-resolved 1-best paths + per-sentence status (what the
+    # CLI's default output consumes), one jpp_b200_score_batch call per window
     for _ in range(min(2, args.warmup)):
-        scorer.compute_scores(batch, res, paths_only=True)
+        scorer.compute_scores(windows[0], results[0], paths_only=True)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        scorer.compute_scores(batch, res, paths_only=True)     # jpp_b200_score_batch: H2D + kernels + D2H
+        for w, r in zip(windows, results):
+            scorer.compute_scores(w, r, paths_only=True)       # H2D + kernels + D2H
     torch.cuda.synchronize()
-    dt_single = time.perf_counter() - t0
-    lanes_agree = bool(np.array_equal(one_lane_paths[0], res.best_path_len) and
-                       np.array_equal(one_lane_paths[1], res.best_path_nodes))
-    dt_e2e = dt_single
-    pipelined = None
-    workers = [scorer]
-    if args.e2e_chunks >= 2:
-        # (b) optional: the batch in pieces over two handles / host threads (copies of one piece
-        # overlap the kernels of the other).  Measured slower than the single call at this size
-        # (profiles/README.md), so it is off by default.
-        nchunk = args.e2e_chunks
-        bounds = shard.shard_bounds(np.diff(batch.sent_codepoint_off.astype(np.int64)), nchunk)
-        chunks = []
-        for c in range(nchunk):
-            sub = abi.StagedBatch.concat([batch.select(int(bounds[c]), int(bounds[c + 1]))], pin=pinned_copy)
-            r = abi.ScoreResult.allocate(0, cfg.beam_size, model.num_scorers, model.num_stored_patterns,
-                                         sub.num_sentences, sub.num_boundaries)
-            r.best_path_len, r.best_path_nodes = pinned_copy(r.best_path_len), pinned_copy(r.best_path_nodes)
-            chunks.append((sub, r))
-        workers = [scorer, LatticeScorer(model, cfg, device=local_rank)]
-
-        def run_worker(wi):
-            for ci in range(wi, nchunk, 2):
-                sub, r = chunks[ci]
-                workers[wi].upload(sub); workers[wi].score_resident(); workers[wi].download(r, paths_only=True)
-
-        def pipelined_step():
-            ts = [threading.Thread(target=run_worker, args=(wi,)) for wi in range(2)]
-            for t in ts: t.start()
-            for t in ts: t.join()
-
-        for _ in range(2):
-            pipelined_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            pipelined_step()
-        torch.cuda.synchronize()
-        pipelined = {"chunks": nchunk, "ms_per_step": 1000.0 * (time.perf_counter() - t0) / args.steps}
-        assert np.array_equal(np.concatenate([r.best_path_len for _, r in chunks]), res.best_path_len)
-    t_e2e = torch.tensor([dt_e2e, dt_single], dtype=torch.float64, device="cuda")
-    counts = torch.tensor([batch.num_sentences, cnt["gathers"], cnt["nodes"]], dtype=torch.float64, device="cuda")
+    dt_e2e = time.perf_counter() - t0
+    lanes_agree = bool(np.array_equal(one_lane_paths[0], results[0].best_path_len) and
+                       np.array_equal(one_lane_paths[1], results[0].best_path_nodes))
+    failed = int(sum(int(r.sentence_status.astype(bool).sum()) for r in results))
+    t_e2e = torch.tensor([dt_e2e], dtype=torch.float64, device="cuda")
+    counts = torch.tensor([n_sent, cnt["gathers"], n_nodes, failed], dtype=torch.float64, device="cuda")
+    gathered = None
     if dist:
         dist.all_reduce(t_res, op=dist.ReduceOp.MAX)
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
         dist.all_reduce(counts, op=dist.ReduceOp.SUM)   # NCCL: gather the per-rank counters
+        if args.shard_corpus:
+            gathered = gather_paths_in_corpus_order(torch, dist, rank, world, windows, results, info)
     total_sent = float(counts[0].item())
     dev_s, wall_s, e2e_s = float(t_res[0].item()), float(t_res[1].item()), float(t_e2e[0].item())
-    single_s = float(t_e2e[1].item())
     value = total_sent * args.steps / dev_s
     e2e_value = total_sent * args.steps / e2e_s
 
@@ -415,27 +438,28 @@ def product_arm(args, rank: int, world: int, local_rank: int) -> None:
         peak = float(peaks.get("hbm_gbs", 6650.0))
         achieved = cnt["walk_bytes"] / (walk_ms / 1000.0) / 1e9
         traffic = None
-        tf = ROOT / "profiles" / "r1_walk_traffic.json"
+        tf = ROOT / "profiles" / "walk_traffic.json"
         if tf.exists():
             try:
-                t = json.loads(tf.read_text())
-                if t.get("workload") == args.workload and t.get("sentences") == args.sentences:
+                t = json.loads(tf.read_text()).get(args.workload)
+                if t and t.get("sentences") == args.sentences and t.get("kernel", "") in walk_kernel_name(info["wl"]):
                     traffic = t["dram_bytes_per_launch"]
             except Exception:
                 pass
         line = {
             "metric": "sentences/sec Jumandic beam=5 (lattice-scoring path)", "value": value, "unit": "sentences/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dev_s / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 hash / f32 sums",
-            "data": "synthetic", "config": workload_config(args, info["wl"]),
+            "higher_is_better": True, "scaling": "strong" if (args.shard_corpus and world > 1) else "weak",
+            "vs_baseline": None, "dtype": "u64 hash / f32 sums",
+            "data": "synthetic", "config": workload_config(args, info["wl"], world),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "sentences/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": 1000.0 * e2e_s / args.steps,
-                    "entry_rows": (None if batch.entry_rows is None else int(len(batch.entry_rows))),
-                    "how": "one jpp_b200_score_batch call per step from pinned host buffers, six internal lanes (JPP_B200_LANES) "
-                           "(entry buffers sent " + ("inline, one per node" if batch.entry_rows is None else "as one row per distinct entry + a row index per node") + "); "
-                           "D2H = device-resolved 1-best paths (jpp_b200_result.best_path_*)",
-                    "paths_equal_to_one_lane_run": lanes_agree, "pipelined_two_handles": pipelined},
+                    "how": f"one jpp_b200_score_batch call per window ({len(windows)} per step) from pinned host buffers, six internal "
+                           f"lanes (JPP_B200_LANES); batch form '{args.batch_form}'"
+                           + (f" with {len(table.entry_ptr)} dictionary rows resident on the device" if table is not None else "")
+                           + "; D2H = device-resolved 1-best paths + per-sentence status",
+                    "paths_equal_to_one_lane_run": lanes_agree},
             "gpu_launches": int(cnt["launches"]) * args.steps,
             "wall_ms_per_step_resident": 1000.0 * wall_s / args.steps,
             "stage_ms": {k: statistics.mean(x[k] for x in kms) for k in kms[0]},
@@ -444,22 +468,32 @@ def product_arm(args, rank: int, world: int, local_rank: int) -> None:
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                          "algorithmic_bytes_per_launch": int(cnt["walk_bytes"]), "kernel_ms": walk_ms,
                          "gathers_per_launch": int(cnt["walk_gathers"]),
-                         "gathers_issued_per_launch": int(cnt["walk_gathers_issued"]), "traffic": traffic},
+                         "gathers_issued_per_launch": int(cnt["walk_gathers_issued"]), "traffic": traffic,
+                         "per": "step (all windows)"},
             "work": {"sentences": int(total_sent), "nodes": int(counts[2].item()), "gathers": int(counts[1].item()),
-                     "rnn_nodes": int(cnt["rnn_nodes"])},
+                     "rnn_nodes": int(cnt["rnn_nodes"]), "rnn_scores": int(cnt["rnn_scores"]),
+                     "failed_sentences": int(counts[3].item())},
         }
+        if gathered is not None:
+            line["sharded"] = gathered
         if not args.no_cpu_baseline:
-            line.update(cpu_baseline_leg(args, info, model, cfg, batch, workers[0], res))
+            line.update(cpu_baseline_leg(args, info, model, cfg, windows[0], scorer, results[0]))
+        if args.e2e_full and world == 1:
+            line["e2e_full"] = e2e_full_leg(args, info, local_rank, line.get("cpu_baseline"))
         # a run whose own correctness checks fail is not a result: say so and exit non-zero
         problems = []
         if not lanes_agree:
             problems.append("1-best paths of the multi-lane call differ from the one-lane resident run")
+        if counts[3].item():
+            problems.append(f"{int(counts[3].item())} sentences failed validation on the device")
         par = line.get("parity")
         if par is not None:
             if "error" in par:
                 problems.append("parity check failed to run: " + par["error"])
             else:
                 problems += [f"parity: {k} = {v}" for k, v in par.items() if k.endswith("_mismatches") and v]
+        if gathered is not None and not gathered["in_corpus_order"]:
+            problems.append("gathered shards do not cover the corpus in order")
         line["valid"] = not problems
         if problems:
             line["invalid_because"] = problems
@@ -467,11 +501,106 @@ def product_arm(args, rank: int, world: int, local_rank: int) -> None:
         if problems:
             log("INVALID RESULT:", "; ".join(problems))
             FAILED.append(1)
-    for wk in workers:
-        wk.close()
+    scorer.close()
     if dist:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def gather_paths_in_corpus_order(torch, dist, rank, world, windows, results, info) -> dict | None:
+    """BASELINE configs[4]: the 1-best paths of every shard back on rank 0 in corpus order (NCCL gather of
+    the per-sentence path lengths and of the path nodes, made sentence-relative so that they are comparable
+    across ranks).  Rank 0 checks that the pieces cover sentences [0, total) without gap or overlap."""
+    lens = np.concatenate([r.best_path_len for r in results]).astype(np.int64)
+    rel = []
+    for w, r in zip(windows, results):
+        sbo, bno = w.sent_boundary_off.astype(np.int64), w.boundary_node_off.astype(np.int64)
+        first_node = bno[sbo[:-1]]
+        for s in range(w.num_sentences):
+            k = int(r.best_path_len[s])
+            rel.append(r.best_path_nodes[int(sbo[s]):int(sbo[s]) + k].astype(np.int64) - first_node[s])
+    nodes = np.concatenate(rel) if rel else np.zeros(0, np.int64)
+    meta = torch.tensor([len(lens), len(nodes), info["shard"]["lo"], info["shard"]["hi"]], dtype=torch.int64, device="cuda")
+    metas = [torch.zeros_like(meta) for _ in range(world)]
+    dist.all_gather(metas, meta)
+    metas = [m.cpu().numpy() for m in metas]
+    max_l, max_n = max(int(m[0]) for m in metas), max(int(m[1]) for m in metas)
+    tl = torch.zeros(max_l, dtype=torch.int64, device="cuda"); tl[:len(lens)] = torch.from_numpy(lens).cuda()
+    tn = torch.zeros(max_n, dtype=torch.int64, device="cuda"); tn[:len(nodes)] = torch.from_numpy(nodes).cuda()
+    gl = [torch.zeros_like(tl) for _ in range(world)] if rank == 0 else None
+    gn = [torch.zeros_like(tn) for _ in range(world)] if rank == 0 else None
+    dist.gather(tl, gl, dst=0)
+    dist.gather(tn, gn, dst=0)
+    if rank != 0:
+        return None
+    import hashlib
+    total = info["shard"]["total"]
+    cursor, ok = 0, True
+    all_l, all_n = [], []
+    for r in range(world):
+        nl, nn, lo, hi = (int(x) for x in metas[r])
+        ok = ok and lo == cursor and hi - lo == nl
+        cursor = hi
+        all_l.append(gl[r][:nl].cpu().numpy()); all_n.append(gn[r][:nn].cpu().numpy())
+    ok = ok and cursor == total
+    all_l, all_n = np.concatenate(all_l), np.concatenate(all_n)
+    ok = ok and int(all_l.sum()) == len(all_n)
+    return {"in_corpus_order": bool(ok), "sentences": int(len(all_l)), "path_nodes": int(len(all_n)),
+            "shard_sentences": [int(m[0]) for m in metas],
+            "paths_sha256_16": hashlib.sha256(all_l.tobytes() + all_n.tobytes()).hexdigest()[:16]}
+
+
+GPU_CLI = ROOT / "binding" / "_build" / "jumanpp_v2_gpu"
+
+
+def e2e_full_leg(args, info, device: int, cpu_baseline: dict | None) -> dict:
+    """SURVEY 8(d)'s metric through the reference-side binding: text in -> lattices built on host threads ->
+    staged -> jpp_b200_score_batch -> un-staged into the reference's Lattice -> formatted by the reference's
+    JumanFormat -> text out (binding/jumanpp_v2_gpu), beside the reference doing the same work per sentence
+    (Analyzer::analyze + JumanFormat) on the same host cores."""
+    out = {}
+    try:
+        wl = info["wl"]
+        modelf = info["dir"] / "cli.model"
+        if not modelf.exists():
+            cmd = [str(HARNESS), "model", f"dict={info['dict']}", f"out={modelf}", *harness_model_args(args, wl, info["rnn"])]
+            subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        n = min(args.sentences, args.e2e_full_sentences)
+        sub = info["dir"] / f"corpus_{n}.txt"
+        if not sub.exists():
+            with open(info["corpus"], encoding="utf-8") as f, open(sub, "w", encoding="utf-8") as g:
+                for i, l in enumerate(f):
+                    if i >= n:
+                        break
+                    g.write(l)
+        bud = cpu_budget()
+        flags = [f"--beam={wl['beam']}", f"--global-beam={wl['gbeam']}", f"--right-check={wl['rcheck']}", f"--right-beam={wl['rbeam']}"]
+        cmd = [str(GPU_CLI), "--gpu-stats", f"--gpu-device={device}", f"--gpu-batch={args.e2e_full_batch}",
+               f"--gpu-threads={bud['cores_effective']}", f"--model={modelf}", *flags, "--output=/dev/null", str(sub)]
+        r = subprocess.run(cmd, capture_output=True, text=True, check=True)
+        import re
+        st = json.loads(re.findall(r'\{"gpu_stats".*\}\}', r.stderr)[-1])["gpu_stats"]
+        out = {"value": st["sentences"] / st["total_s"], "unit": "sentences/s", "sentences": st["sentences"],
+               "host_threads": st["threads"], "batch_sentences": st["batch"], "stages_s": {k: st[k] for k in st if k.endswith("_s")},
+               "h2d_bytes": st["h2d_bytes"], "d2h_bytes": st["d2h_bytes"], "entry_rows_added": st["entry_rows_added"],
+               "compute_scores_calls": st["compute_scores_calls"], "failed": st["failed"],
+               "how": "binding/_build/jumanpp_v2_gpu: text -> buildLattice on host threads -> resident-form staging in pinned "
+                      "buffers -> jpp_b200_score_batch -> un-stage into the reference Lattice -> JumanFormat -> /dev/null; "
+                      "total_s excludes model load and analyzer construction (init_s)"}
+        # the reference doing the same per sentence: Analyzer::analyze + JumanFormat, all effective cores
+        best = None
+        for threads in (bud["cores_effective"], 2 * bud["cores_effective"]):
+            cmdr = [str(HARNESS), "bench", f"dict={info['dict']}", f"corpus={sub}", f"threads={threads}", "steps=1", "warmup=1",
+                    "format=1", f"max_sent={min(n, args.cpu_sample_per_core * threads)}", *harness_model_args(args, wl, info["rnn"])]
+            o = json.loads(subprocess.run(cmdr, check=True, capture_output=True, text=True).stdout.strip().splitlines()[-1])
+            if best is None or o["analyze_sentences_per_s"] > best["value"]:
+                best = {"value": o["analyze_sentences_per_s"], "threads": threads, "sentences": o["sentences"]}
+        out["reference"] = {**best, "unit": "sentences/s", "cores_effective": bud["cores_effective"],
+                            "how": "oracle/_ref/jpp_ref_harness bench format=1: Analyzer::analyze + JumanFormat per sentence"}
+        out["ratio"] = out["value"] / best["value"]
+    except Exception as e:  # pragma: no cover
+        out = {"error": repr(e)[:2000]}
+    return out
 
 
 def cpu_baseline_leg(args, info, model, cfg, batch, scorer, res) -> dict:
@@ -527,10 +656,16 @@ def main() -> None:
     ap.add_argument("--cache", default=os.environ.get("JPP_B200_CACHE", "/tmp/jpp_b200_cache"))
     ap.add_argument("--cpu-sample-per-core", type=int, default=1500)
     ap.add_argument("--parity-sample", type=int, default=2000)
-    ap.add_argument("--e2e-chunks", type=int, default=0)
+    ap.add_argument("--window", type=int, default=131072,
+                    help="sentences per jpp_b200_score_batch call (larger workloads are streamed window by window)")
+    ap.add_argument("--shard-corpus", action="store_true",
+                    help="N>1: ONE corpus of --sentences cut into contiguous shards (strong scaling, BASELINE configs[4]) "
+                         "instead of one corpus per rank")
+    ap.add_argument("--batch-form", default="compact", choices=["compact", "resident", "inline"])
+    ap.add_argument("--e2e-full", action="store_true", help="also run the reference-side binding end to end (text in, text out)")
+    ap.add_argument("--e2e-full-sentences", type=int, default=100_000)
+    ap.add_argument("--e2e-full-batch", type=int, default=8192)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--inline-entries", action="store_true",
-                    help="send one entry buffer per node (jpp_b200_batch.node_entry) instead of the compact row table")
     args = ap.parse_args()
     # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version
     # banner to stdout at init): keep the real stdout aside for the result and point fd 1 at stderr.

@@ -315,10 +315,11 @@ __global__ void __launch_bounds__(kCacheThreads) k_w_prescore(const __grid_const
 // body for a block of 256 threads = 32 sentences: `firstSent` is the block's first index into the
 // longest-first sentence order; the three list counters wv.selCount may live in global memory
 // (wavefront kernels: one atomic per block and list) or in the block's shared memory (fused walk)
+template <u32 SPB>  // sentences per block = blockDim.x / 8
 __device__ __forceinline__ void cutoff_group_block(const FeatTables& ft, const BatchView& bv, const ScoreCfg& cfg,
                                                    const WaveView& wv, u32 nActive, u32 bnd, u32 firstSent) {
-  constexpr u32 GW = 8, SPB = 256 / GW;
-  static_assert(SPB == 32, "the block prefix below is one warp wide");
+  constexpr u32 GW = 8;
+  static_assert(SPB <= 32, "the block prefix below is one warp wide");
   __shared__ u32 sSel[SPB], sBi[SPB], sTri[SPB], sBase[3];
   __shared__ unsigned long long sCnt[3];
   const u32 lane = threadIdx.x & 31u, sub = lane % GW, grp = threadIdx.x / GW;
@@ -442,7 +443,8 @@ __device__ __forceinline__ void cutoff_group_block(const FeatTables& ft, const B
   }
   __syncthreads();
   if (threadIdx.x < 32) {
-    u32 v[3] = {sSel[lane], sBi[lane], sTri[lane]};
+    u32 v[3] = {0, 0, 0};
+    if (lane < SPB) { v[0] = sSel[lane]; v[1] = sBi[lane]; v[2] = sTri[lane]; }
     u32 inc[3] = {v[0], v[1], v[2]};
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -457,9 +459,11 @@ __device__ __forceinline__ void cutoff_group_block(const FeatTables& ft, const B
       sBase[1] = inc[1] ? atomicAdd(wv.selCount + 1, inc[1]) : 0u;
       sBase[2] = inc[2] ? atomicAdd(wv.selCount + 2, inc[2]) : 0u;
     }
-    sSel[lane] = inc[0] - v[0];
-    sBi[lane] = inc[1] - v[1];
-    sTri[lane] = inc[2] - v[2];
+    if (lane < SPB) {
+      sSel[lane] = inc[0] - v[0];
+      sBi[lane] = inc[1] - v[1];
+      sTri[lane] = inc[2] - v[2];
+    }
   }
   __syncthreads();
   if (threadIdx.x == 0 && bv.counters && (sCnt[0] | sCnt[1])) {
@@ -491,7 +495,7 @@ __device__ __forceinline__ void cutoff_group_block(const FeatTables& ft, const B
 
 __global__ void __launch_bounds__(256) k_w_cutoff_group(const __grid_constant__ FeatTables ft, BatchView bv, ScoreCfg cfg,
                                                        WaveView wv, u32 nActive, u32 bnd) {
-  cutoff_group_block(ft, bv, cfg, wv, nActive, bnd, blockIdx.x * 32u);
+  cutoff_group_block<32>(ft, bv, cfg, wv, nActive, bnd, blockIdx.x * 32u);
 }
 
 // W4: bigram items first, trigram items after them; one 16-byte item per thread
@@ -1553,7 +1557,7 @@ static jpp_b200_status upload_window(jpp_b200_handle* h, const jpp_b200_batch* b
       size_t selCap = NN;
       if (h->cfg.rcheck > 0) selCap = std::min<size_t>(NN, (size_t)NS * (u32)h->cfg.rbeam);
       // the fused walk gives every block of 32 sentences a fixed slice
-      if (fused_walk_ok(h->cfg)) selCap = (size_t)((NS + kFusedSent - 1) / kFusedSent) * kFusedSent * (u32)h->cfg.rbeam;
+      if (fused_walk_ok(h->cfg)) selCap = (size_t)((NS + 31) / 32) * 32 * (u32)h->cfg.rbeam;  // covers 16 or 32 sentences per block
       if (selCap * G >= 0x7FFFFFFFull) return fail(h, JPP_B200_INVALID_PARAMETER, "batch too large for the item lists; split it");
       ENSURE(W_BIITEMS, (selCap * G + 4) * sizeof(WaveItem)); ENSURE(W_TRIITEMS, (selCap * G + 4) * sizeof(WaveItem));
       ENSURE(W_SCB, (selCap * G + 4) * 4); ENSURE(W_TRI, (selCap * G + 4) * 8);
@@ -1659,11 +1663,14 @@ static jpp_b200_status score_resident_impl(jpp_b200_handle* h) {
     const bool fused = fused_walk_ok(cfg) && !profileOn;
     if (fused) {
       static const bool noStatic = getenv("JPP_B200_NO_STATIC") != nullptr;  // A/B: table-driven n-gram program
+      static const int sentEnv = getenv("JPP_B200_FUSED_SENT") ? atoi(getenv("JPP_B200_FUSED_SENT")) : 0;  // A/B: sentences per block
       const bool narrow = cfg.beam <= 8 && cfg.gbeam <= 8;
-      const u32 itemCap = kFusedSent * (u32)cfg.rbeam * (u32)cfg.gbeam;
-      const u32 blocks = (NS + kFusedSent - 1) / kFusedSent;
+      const u32 SENT = sentEnv == 16 || sentEnv == 32 ? (u32)sentEnv : kFusedSentDefault;
+      const u32 itemCap = SENT * (u32)cfg.rbeam * (u32)cfg.gbeam;
+      const u32 blocks = (NS + SENT - 1) / SENT;
       const bool stat = h->staticProgram && !noStatic;
-#define JPP_WALK(GW, KB, SM, ST) k_walk_fused<GW, KB, SM, ST><<<blocks, kFusedThreads, 0, st>>>(ft, bv, cfg, wv, h->dWeights, itemCap)
+#define JPP_WALK2(GW, KB, SM, ST, SE) k_walk_fused<GW, KB, SM, ST, SE><<<blocks, SE * 8, 0, st>>>(ft, bv, cfg, wv, h->dWeights, itemCap)
+#define JPP_WALK(GW, KB, SM, ST) do { if (SENT == 16) JPP_WALK2(GW, KB, SM, ST, 16); else JPP_WALK2(GW, KB, SM, ST, 32); } while (0)
       if (narrow) {
         if (small_gbeam_ok(cfg)) { if (stat) JPP_WALK(8, 8, true, true); else JPP_WALK(8, 8, true, false); }
         else { if (stat) JPP_WALK(8, 8, false, true); else JPP_WALK(8, 8, false, false); }
@@ -1671,6 +1678,7 @@ static jpp_b200_status score_resident_impl(jpp_b200_handle* h) {
         if (stat) JPP_WALK(32, MAX_BEAM, false, true); else JPP_WALK(32, MAX_BEAM, false, false);
       }
 #undef JPP_WALK
+#undef JPP_WALK2
       ++launches;
     }
     for (u32 bnd = 2; bnd < h->maxNb && !fused; ++bnd) {

@@ -384,11 +384,7 @@ JPP_HD void t0_node(const FeatTables& ft, const BatchView& bv, const WL& wl, u32
   const u32 SP = ft.nStored;
   u64* pout = bv.patterns + (size_t)node * bv.patNodeStride;
   const size_t pstr = bv.patPStride;
-  if (bv.sentStatus && bv.sentStatus[sent]) {
-    for (u32 p = 0; p < SP; ++p) pout[p * pstr] = 0;
-    bv.t0[node] = 0.0f;
-    return;
-  }
+  // (nodes of a sentence that failed validation never get here: their nodeBnd stays 0xFFFFFFFF)
   const jpp_b200_node_info ni = bv.nodeInfo[node];
   if (localBnd < 2) {  // BOS rows, lattice_builder.cc:171-176
     for (u32 p = 0; p < SP; ++p) pout[p * pstr] = (u64)(u32)ni.entry_ptr;

@@ -18,7 +18,7 @@ namespace {
 using namespace jppb200;
 
 #ifndef JPP_FUSED_MINBLOCKS_STATIC
-#define JPP_FUSED_MINBLOCKS_STATIC 2   // rows in registers: ~120 registers per thread
+#define JPP_FUSED_MINBLOCKS_STATIC 3   // measured: 39.2 ms at 3 blocks (85 registers, some spills) against 42.5 ms at 2 (128 registers)
 #endif
 
 // ------------------------------------------------------------ rows in registers ----
@@ -180,16 +180,19 @@ __device__ __forceinline__ void wave_item_trigram_static(const FeatTables& ft, c
 // GW = lanes per sentence in W1 (8 when beam and global beam are <= 8: the block's 32 sentences in
 // one pass; 32 for wider beams: four passes of eight sentences), KB = beam slots a lane holds in
 // W1, SMALL = register beam build of W5 (global beam <= 8), STATIC = compiled-in n-gram program.
-constexpr u32 kFusedSent = 32;     // sentences per block
-constexpr u32 kFusedThreads = 256;
+#ifndef JPP_FUSED_SENT_DEFAULT
+#define JPP_FUSED_SENT_DEFAULT 32
+#endif
+constexpr u32 kFusedSentDefault = JPP_FUSED_SENT_DEFAULT;  // sentences per block (8 threads each): 32 or 16
 #ifndef JPP_FUSED_MINBLOCKS
-#define JPP_FUSED_MINBLOCKS 3
+#define JPP_FUSED_MINBLOCKS 3      // blocks of 256 threads per SM (twice that for 128): ~85 registers per thread
 #endif
 
-template <int GW, int KB, bool SMALL, bool STATIC>
-__global__ void __launch_bounds__(kFusedThreads, STATIC ? JPP_FUSED_MINBLOCKS_STATIC : JPP_FUSED_MINBLOCKS)
+template <int GW, int KB, bool SMALL, bool STATIC, int SENT>
+__global__ void __launch_bounds__(SENT * 8, (STATIC ? JPP_FUSED_MINBLOCKS_STATIC : JPP_FUSED_MINBLOCKS) * (32 / SENT))
     k_walk_fused(const __grid_constant__ FeatTables ft, BatchView bv, ScoreCfg cfg, WaveView wv, const float* __restrict__ w,
                  u32 itemCap) {
+  constexpr u32 kFusedSent = SENT, kFusedThreads = SENT * 8;
   __shared__ u32 sCount[4];                 // selected nodes, bigram items, trigram items of the current wave
   __shared__ u32 sNodeOff[kFusedSent + 1];  // right nodes of the block's sentences at the current boundary (prefix)
   __shared__ u32 sNode0[kFusedSent];
@@ -238,13 +241,13 @@ __global__ void __launch_bounds__(kFusedThreads, STATIC ? JPP_FUSED_MINBLOCKS_ST
     }
     __syncthreads();
     if (threadIdx.x < 32) {
-      u32 v = sNodeOff[threadIdx.x + 1];
+      u32 v = threadIdx.x < kFusedSent ? sNodeOff[threadIdx.x + 1] : 0u;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
         const u32 t = __shfl_up_sync(0xffffffffu, v, d);
         if ((int)threadIdx.x >= d) v += t;
       }
-      sNodeOff[threadIdx.x + 1] = v;
+      if (threadIdx.x < kFusedSent) sNodeOff[threadIdx.x + 1] = v;
       if (threadIdx.x == 0) sNodeOff[0] = 0;
     }
     __syncthreads();
@@ -262,7 +265,7 @@ __global__ void __launch_bounds__(kFusedThreads, STATIC ? JPP_FUSED_MINBLOCKS_ST
     }
     __syncthreads();
     // W3 (positions and items are private to the block: counters in shared memory)
-    cutoff_group_block(ft, bv, cfg, lw, firstSent + nHere, bnd, firstSent);
+    cutoff_group_block<kFusedSent>(ft, bv, cfg, lw, firstSent + nHere, bnd, firstSent);
     __syncthreads();
     // W4
     {

@@ -52,7 +52,9 @@
 #include "util/serialization.h"
 #include <unistd.h>
 #include "jpp_jumandic_cg.h"
+#include "jumandic/shared/juman_format.h"
 #include "jumandic/shared/jumandic_spec.h"
+#include "core/analysis/analyzer.h"
 #include "rnn/mikolov_rnn.h"
 #include "util/mmap.h"
 
@@ -564,6 +566,20 @@ int cmdBench(const Args& a) {
   using clk = std::chrono::steady_clock;
   std::vector<std::unique_ptr<AnalyzerImpl>> anas;
   for (unsigned t = 0; t < nt; ++t) anas.push_back(env.makeAnalyzer());
+  // format=1: the default Juman output of every sentence is produced too (JumanFormat over an Analyzer
+  // wrapped around the same AnalyzerImpl), inside analyze_s: the whole per-sentence work of the CLI
+  const bool withFormat = a.num("format", 0) != 0;
+  std::vector<std::unique_ptr<Analyzer>> wrappers;
+  std::vector<std::unique_ptr<jumandic::output::JumanFormat>> formats;
+  if (withFormat) {
+    for (unsigned t = 0; t < nt; ++t) {
+      wrappers.emplace_back(new Analyzer{});
+      check(wrappers.back()->initialize(anas[t].get(), &env.sdef), "analyzer wrapper");
+      formats.emplace_back(new jumandic::output::JumanFormat{});
+      check(formats.back()->initialize(wrappers.back()->output()), "juman format");
+    }
+  }
+  std::vector<size_t> outBytes(nt, 0);
   std::vector<double> stepScore, stepTotal, stepWall;
   long n = 0;
   double cs = 0;
@@ -584,6 +600,10 @@ int cmdBench(const Args& a) {
           if (s) s = ana->bootstrapAnalysis();
           auto t1 = clk::now();
           if (s) s = ana->computeScores(&env.sdef);
+          if (s && withFormat) {
+            s = formats[t]->format(*wrappers[t], StringPiece{});
+            outBytes[t] += formats[t]->result().size();
+          }
           auto t2 = clk::now();
           if (!s) continue;
           scoreSec[t] += std::chrono::duration<double>(t2 - t1).count();

@@ -101,8 +101,14 @@ def test_compact_entry_rows():
     bad.node_entry_row[3] = len(compact.entry_rows) + 5
     sc = LatticeScorer(model, cfg)
     try:
+        # a row index past the table fails ITS sentence (ABI 3: jpp_b200_result.sentence_status) ...
+        res = sc.compute_scores(bad)
+        assert res.sentence_status[0] & abi_mod().SENT_BAD_ENTRY and not res.sentence_status[1:].any()
+        # ... and the call, when the caller did not ask for per-sentence status
+        blind = sc.allocate_result(bad)
+        blind.sentence_status = None
         with pytest.raises(ScorerError) as e:
-            sc.compute_scores(bad)
+            sc.compute_scores(bad, blind)
         assert e.value.code == abi_mod().INVALID_PARAMETER
         again = sc.compute_scores(compact)        # the handle stays usable
         assert again.node_beam.tobytes() == inline.node_beam.tobytes()
