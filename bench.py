@@ -422,7 +422,9 @@ def product_arm(args, rank: int, world: int, local_rank: int) -> None:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
         dist.all_reduce(counts, op=dist.ReduceOp.SUM)   # NCCL: gather the per-rank counters
         if args.shard_corpus:
-            gathered = gather_paths_in_corpus_order(torch, dist, rank, world, windows, results, info)
+            lens, nodes = shard.relative_paths(windows, results)
+            gathered = shard.gather_in_corpus_order(lens, nodes, info["shard"]["lo"], info["shard"]["hi"], info["shard"]["total"],
+                                                    dist, torch.device("cuda", local_rank))
     total_sent = float(counts[0].item())
     dev_s, wall_s, e2e_s = float(t_res[0].item()), float(t_res[1].item()), float(t_e2e[0].item())
     value = total_sent * args.steps / dev_s
@@ -475,7 +477,7 @@ def product_arm(args, rank: int, world: int, local_rank: int) -> None:
                      "failed_sentences": int(counts[3].item())},
         }
         if gathered is not None:
-            line["sharded"] = gathered
+            line["sharded"] = {k: v for k, v in gathered.items() if k not in ("lens", "nodes")}
         if not args.no_cpu_baseline:
             line.update(cpu_baseline_leg(args, info, model, cfg, windows[0], scorer, results[0]))
         if args.e2e_full and world == 1:
@@ -505,49 +507,6 @@ def product_arm(args, rank: int, world: int, local_rank: int) -> None:
     if dist:
         dist.barrier()
         dist.destroy_process_group()
-
-
-def gather_paths_in_corpus_order(torch, dist, rank, world, windows, results, info) -> dict | None:
-    """BASELINE configs[4]: the 1-best paths of every shard back on rank 0 in corpus order (NCCL gather of
-    the per-sentence path lengths and of the path nodes, made sentence-relative so that they are comparable
-    across ranks).  Rank 0 checks that the pieces cover sentences [0, total) without gap or overlap."""
-    lens = np.concatenate([r.best_path_len for r in results]).astype(np.int64)
-    rel = []
-    for w, r in zip(windows, results):
-        sbo, bno = w.sent_boundary_off.astype(np.int64), w.boundary_node_off.astype(np.int64)
-        first_node = bno[sbo[:-1]]
-        for s in range(w.num_sentences):
-            k = int(r.best_path_len[s])
-            rel.append(r.best_path_nodes[int(sbo[s]):int(sbo[s]) + k].astype(np.int64) - first_node[s])
-    nodes = np.concatenate(rel) if rel else np.zeros(0, np.int64)
-    meta = torch.tensor([len(lens), len(nodes), info["shard"]["lo"], info["shard"]["hi"]], dtype=torch.int64, device="cuda")
-    metas = [torch.zeros_like(meta) for _ in range(world)]
-    dist.all_gather(metas, meta)
-    metas = [m.cpu().numpy() for m in metas]
-    max_l, max_n = max(int(m[0]) for m in metas), max(int(m[1]) for m in metas)
-    tl = torch.zeros(max_l, dtype=torch.int64, device="cuda"); tl[:len(lens)] = torch.from_numpy(lens).cuda()
-    tn = torch.zeros(max_n, dtype=torch.int64, device="cuda"); tn[:len(nodes)] = torch.from_numpy(nodes).cuda()
-    gl = [torch.zeros_like(tl) for _ in range(world)] if rank == 0 else None
-    gn = [torch.zeros_like(tn) for _ in range(world)] if rank == 0 else None
-    dist.gather(tl, gl, dst=0)
-    dist.gather(tn, gn, dst=0)
-    if rank != 0:
-        return None
-    import hashlib
-    total = info["shard"]["total"]
-    cursor, ok = 0, True
-    all_l, all_n = [], []
-    for r in range(world):
-        nl, nn, lo, hi = (int(x) for x in metas[r])
-        ok = ok and lo == cursor and hi - lo == nl
-        cursor = hi
-        all_l.append(gl[r][:nl].cpu().numpy()); all_n.append(gn[r][:nn].cpu().numpy())
-    ok = ok and cursor == total
-    all_l, all_n = np.concatenate(all_l), np.concatenate(all_n)
-    ok = ok and int(all_l.sum()) == len(all_n)
-    return {"in_corpus_order": bool(ok), "sentences": int(len(all_l)), "path_nodes": int(len(all_n)),
-            "shard_sentences": [int(m[0]) for m in metas],
-            "paths_sha256_16": hashlib.sha256(all_l.tobytes() + all_n.tobytes()).hexdigest()[:16]}
 
 
 GPU_CLI = ROOT / "binding" / "_build" / "jumanpp_v2_gpu"

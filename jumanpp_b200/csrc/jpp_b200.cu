@@ -1034,6 +1034,10 @@ __global__ void __launch_bounds__(256) k_rerank(BatchView bv, ScoreCfg cfg, floa
   if (sub == 0) rerank_eos(bv, cfg, w0, w1, sent);
 }
 
+}  // namespace
+#include "jpp_b200_rnn_tc.cuh"
+namespace {
+
 // ------------------------------------------------------------- helpers ------
 struct DevBuf {
   void* p = nullptr;
@@ -1081,6 +1085,7 @@ struct jpp_b200_handle {
   bool staticProgram = false;  // the uploaded n-gram program is the compiled-in one (jpp_b200_static_jumandic.h)
   float* dRnnBlocks[4] = {nullptr, nullptr, nullptr, nullptr};
   float* dRnnWt = nullptr;  // transposed recurrent matrix
+  float* dRnnWImage = nullptr;  // layer size 128: the two TF32 planes of W in the tensor-core operand layout (jpp_b200_rnn_tc.cuh)
   // window of the caller's batch that is resident (upload_window): offsets of its first sentence /
   // boundary / node; results go to the matching slices of the caller's arrays
   u32 windowSentBase = 0, windowBndBase = 0, windowNodeBase = 0;
@@ -1315,6 +1320,26 @@ static jpp_b200_status create_impl(const jpp_b200_model* model, const jpp_b200_c
         for (u32 k = 0; k < H; ++k) wt[(size_t)k * H + i] = r->matrix[(size_t)i * H + k];
       CREATE_CHECK(cudaMalloc(&h->dRnnWt, wt.size() * sizeof(float)));
       CREATE_CHECK(cudaMemcpy(h->dRnnWt, wt.data(), wt.size() * sizeof(float), cudaMemcpyHostToDevice));
+      if (H == kTcH) {
+        // W = Wh + Wl (top 19 bits + exact remainder), each plane in the shared-memory image of the UMMA A operand
+        std::vector<float> img(2 * (size_t)H * H, 0.0f);
+        for (u32 i = 0; i < H; ++i)
+          for (u32 k = 0; k < H; ++k) {
+            const float v = r->matrix[(size_t)i * H + k];
+            u32 bits;
+            memcpy(&bits, &v, 4);
+            bits &= 0xFFFFE000u;
+            float hi;
+            memcpy(&hi, &bits, 4);
+            const float lo = v - hi;
+            const u32 o = tc_operand_offset(H, i, k) / 4;
+            img[o] = hi;
+            img[(size_t)H * H + o] = lo;
+          }
+        CREATE_CHECK(cudaMalloc(&h->dRnnWImage, img.size() * sizeof(float)));
+        CREATE_CHECK(cudaMemcpy(h->dRnnWImage, img.data(), img.size() * sizeof(float), cudaMemcpyHostToDevice));
+        CREATE_CHECK(cudaFuncSetAttribute(k_rnn_level_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
+      }
       if (32 * H * sizeof(float) > 200 * 1024) {
         g_create_error = "rnn layer too large for the level kernel's shared-memory tile";
         jpp_b200_destroy(h);
@@ -1371,6 +1396,7 @@ void jpp_b200_destroy(jpp_b200_handle* h) {
     if (h->dWeights) cudaFree(h->dWeights);
     for (auto& p : h->dRnnBlocks) if (p) cudaFree(p);
     if (h->dRnnWt) cudaFree(h->dRnnWt);
+    if (h->dRnnWImage) cudaFree(h->dRnnWImage);
     if (h->dic.dRowOfPtr) cudaFree(h->dic.dRowOfPtr);
     if (h->dic.dRows) cudaFree(h->dic.dRows);
     if (h->dic.dRnnId) cudaFree(h->dic.dRnnId);
@@ -1768,7 +1794,14 @@ static jpp_b200_status score_resident_impl(jpp_b200_handle* h) {
       const u32 split = rnn_level_split(H);
       const dim3 grid((u32)h->smCount * 2 / split, split);
       const size_t wsBytes = (size_t)H * H * sizeof(float) / split;
+      // JPP_B200_RNN_TC=1: the level step as tcgen05 tensor-core MMAs (3xTF32), layer size 128
+      static const bool tcOn = getenv("JPP_B200_RNN_TC") && atoi(getenv("JPP_B200_RNN_TC")) != 0;
+      const bool useTc = tcOn && H == kTcH && h->dRnnWImage != nullptr;
       for (u32 level = 1; level <= h->maxNb; ++level) {
+        if (useTc) {
+          k_rnn_level_tc<<<h->smCount, kTcThreads, kTcSmem, st>>>(rw, h->rt, h->dRnnWImage, ctxOff, rnSent, level);
+          continue;
+        }
         if (!crossLane) {
           k_rnn_level<8><<<h->smCount * 4, 128, 4 * 8 * H * sizeof(float), st>>>(rw, h->rt, h->dRnnWt, ctxOff, rnSent, level);
           continue;
@@ -1901,7 +1934,7 @@ jpp_b200_status make_lane(jpp_b200_handle* owner, jpp_b200_handle* prev) {
   l->dFt = h->dFt; l->dWeights = h->dWeights; l->rt = h->rt; l->hasRnn = h->hasRnn;
   for (int i = 0; i < 4; ++i) l->dRnnBlocks[i] = h->dRnnBlocks[i];
   l->staticProgram = h->staticProgram;
-  l->dRnnWt = h->dRnnWt; l->scoreW[0] = h->scoreW[0]; l->scoreW[1] = h->scoreW[1]; l->smCount = h->smCount;
+  l->dRnnWt = h->dRnnWt; l->dRnnWImage = h->dRnnWImage; l->scoreW[0] = h->scoreW[0]; l->scoreW[1] = h->scoreW[1]; l->smCount = h->smCount;
   l->ownsModel = false;
   cudaError_t e = cudaStreamCreateWithFlags(&l->stream, cudaStreamNonBlocking);
   for (auto& ev : l->ev) if (e == cudaSuccess) e = cudaEventCreate(&ev);

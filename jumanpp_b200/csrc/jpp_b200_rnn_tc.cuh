@@ -1,0 +1,203 @@
+// jpp_b200_rnn_tc.cuh -- the RNN level step on the 5th-generation tensor cores.
+//
+// One level of the prefix tree is a dense contraction: ctx'[n][i] = sigmoid(sum_k W[i][k] ctx[prev(n)][k] +
+// emb[id_n][i]) for the ~50 000 tree nodes n of the level (reference mikolov_rnn_impl.h:202-214, batched
+// over sentences here) -- D[128 x N] = W[128 x 128] . C^T[128 x N].  k_rnn_level_x runs it on the FP32
+// pipes in the float order of oracle/eigen_shim (32 residue partials, bit-pinned to the oracle);
+// this kernel runs it as tcgen05.mma (kind::tf32, FP32 accumulator in TMEM) with the 3xTF32 split
+//     W = Wh + Wl,  c = ch + cl  (h = top 19 bits, l = the exact remainder)
+//     W.c ~= Wh.ch + Wl.ch + Wh.cl            (the dropped Wl.cl is 2^-22 of the product)
+// so the result carries about as many good bits as the FP32 path, in a different association: it is
+// held to the contract of BASELINE.json (RNN scores within 1e-4 relative, 1-best identical), not to
+// bit equality, and can be switched off (JPP_B200_RNN_TC=0).  Layer size 128 only (the bench model);
+// other sizes take k_rnn_level_x.
+//
+// Block = 5 warps.  Warps 0-3: stage the previous contexts of a tile of 64 tree nodes into shared
+// memory (split into the two TF32 planes, K-major, 128-byte swizzle: the canonical UMMA operand
+// layout), and, after the MMAs, read the accumulator back (tcgen05.ld, thread = output i = TMEM lane)
+// for the epilogue: + embedding, sigmoid, coalesced store of the new context rows.  Warp 4, one
+// elected lane: issues the 48 tcgen05.mma of a tile and commits them to an mbarrier.  W (both planes,
+// 128 KB, prepared in the shared-memory image once per model) stays in shared memory for the launch.
+#pragma once
+
+namespace {
+
+using namespace jppb200;
+
+constexpr u32 kTcH = 128;          // layer size this kernel is built for
+constexpr u32 kTcTile = 64;        // tree nodes per tile (UMMA N)
+constexpr u32 kTcThreads = 160;    // 4 producer / epilogue warps + 1 MMA warp
+constexpr u32 kTcChunkK = 32;      // tf32 elements per 128-byte swizzle row
+constexpr u32 kTcABytes = kTcH * kTcH * 4;        // one plane of W
+constexpr u32 kTcBBytes = kTcTile * kTcH * 4;     // one plane of a context tile
+constexpr u32 kTcSmem = 2 * kTcABytes + 2 * kTcBBytes + 1024 /* alignment */ + 64;
+
+// byte offset of element (row r, k) of a K-major operand with `rows` rows in the UMMA SWIZZLE_128B layout:
+// per 32-element K chunk a region of rows x 128 B; inside, 8-row groups of 1024 B, the 16-byte column of a
+// row XORed with (row % 8)
+__host__ __device__ inline u32 tc_operand_offset(u32 rows, u32 r, u32 k) {
+  const u32 kc = k / kTcChunkK, kk = k % kTcChunkK;
+  const u32 c16 = (kk * 4) / 16, within = (kk * 4) % 16;
+  return kc * rows * 128 + (r / 8) * 1024 + (r % 8) * 128 + ((c16 ^ (r % 8)) * 16) + within;
+}
+
+__device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+
+// UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor): start >> 4 | LBO >> 4 << 16 | SBO >> 4 << 32 |
+// version 1 << 46 | layout SWIZZLE_128B (2) << 61.  K-major + swizzle: LBO is not used (1), SBO = 1024 B
+// between 8-row groups.
+__device__ __forceinline__ u64 tc_smem_desc(u32 saddr) {
+  return (u64)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | ((u64)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, N >> 3, M >> 4
+constexpr u32 kTcIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((kTcTile >> 3) << 17) | ((kTcH >> 4) << 24);
+
+__device__ __forceinline__ void tc_mma(u32 tmemD, u64 descA, u64 descB, u32 accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmemD), "l"(descA), "l"(descB), "r"(kTcIdesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}\n" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+    k_rnn_level_tc(RnnWork rw, RnnTables rt, const float* __restrict__ wImage /* [2][H*H] planes in the smem image */,
+                   const u32* ctxOff, const u32* rnSent, u32 level) {
+  extern __shared__ unsigned char tcSmemRaw[];
+  __shared__ __align__(8) unsigned long long sBar;
+  __shared__ u32 sTmem;
+  __shared__ u32 sInRow[kTcTile], sOutRow[kTcTile], sEmbRow[kTcTile];
+  const u32 cnt = rw.levelCount[level];
+  const u32 tiles = (cnt + kTcTile - 1) / kTcTile;
+  if (blockIdx.x >= tiles) return;
+  // operands need 1024-byte alignment (the swizzle is a function of the address bits)
+  unsigned char* base = tcSmemRaw + ((1024 - (smem_u32(tcSmemRaw) & 1023)) & 1023);
+  unsigned char* sA = base;                    // [2 planes][H x H]
+  unsigned char* sB = base + 2 * kTcABytes;    // [2 planes][tile x H]
+  const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  const u32 off = rw.levelOff[level];
+
+  // one-time: W planes into shared memory, the mbarrier, the TMEM accumulator (64 columns)
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(wImage);
+    uint4* dst = reinterpret_cast<uint4*>(sA);
+    for (u32 i = threadIdx.x; i < 2 * kTcABytes / 16; i += kTcThreads) dst[i] = __ldg(src + i);
+  }
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sBar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sTmem)), "r"(kTcTile));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the generic-proxy writes of W become visible to the MMA
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const u32 tmemD = sTmem;
+  u32 phase = 0;
+
+  for (u32 tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const u32 first = tile * kTcTile;
+    const u32 nvalid = (cnt - first) < kTcTile ? (cnt - first) : kTcTile;
+    if (threadIdx.x < kTcTile) {
+      const u32 j = threadIdx.x;
+      const u32 q = rw.levelList[off + first + (j < nvalid ? j : 0u)];
+      sInRow[j] = (u32)ctx_row(rw, ctxOff, rnSent, (u32)rw.prev[q]);
+      sOutRow[j] = (u32)ctx_row(rw, ctxOff, rnSent, q);
+      i32 id = rw.id[q];
+      if (id == -1) id = 0;  // rnn_scorer_gbeam.cc:126-129
+      sEmbRow[j] = (u32)id;
+    }
+    __syncthreads();
+    if (warp < 4) {
+      // previous contexts -> the two TF32 planes of the B operand (row = tree node, K-major)
+      for (u32 r = warp; r < kTcTile; r += 4) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(rw.ctx + (size_t)sInRow[r] * kTcH) + lane);
+        float4 hi, lo;
+        hi.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); lo.x = __fsub_rn(v.x, hi.x);
+        hi.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); lo.y = __fsub_rn(v.y, hi.y);
+        hi.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); lo.z = __fsub_rn(v.z, hi.z);
+        hi.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); lo.w = __fsub_rn(v.w, hi.w);
+        const u32 o = tc_operand_offset(kTcTile, r, 4 * lane);
+        *reinterpret_cast<float4*>(sB + o) = hi;
+        *reinterpret_cast<float4*>(sB + kTcBBytes + o) = lo;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 4) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (lane == 0) {
+        const u32 aBase = smem_u32(sA), bBase = smem_u32(sB);
+        u32 acc = 0;
+        // small terms first: Wl.ch, Wh.cl, then Wh.ch
+#pragma unroll 1
+        for (u32 term = 0; term < 3; ++term) {
+          const u32 aPlane = term == 0 ? 1u : 0u, bPlane = term == 1 ? 1u : 0u;
+          for (u32 kc = 0; kc < kTcH / kTcChunkK; ++kc) {
+            for (u32 ks = 0; ks < kTcChunkK / 8; ++ks) {
+              const u64 da = tc_smem_desc(aBase + aPlane * kTcABytes + kc * kTcH * 128 + ks * 32);
+              const u64 db = tc_smem_desc(bBase + bPlane * kTcBBytes + kc * kTcTile * 128 + ks * 32);
+              tc_mma(tmemD, da, db, acc);
+              acc = 1;
+            }
+          }
+        }
+        // arrives on the barrier when every MMA above has completed (implies fence::before_thread_sync)
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&sBar)) : "memory");
+      }
+      __syncwarp();
+    } else {
+      mbar_wait(smem_u32(&sBar), phase);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      // thread = output i = TMEM lane; 64 columns = the tile's tree nodes
+      const u32 i = threadIdx.x;
+      const u32 taddr = tmemD + ((warp * 32u) << 16);
+#pragma unroll
+      for (u32 c0 = 0; c0 < kTcTile; c0 += 16) {
+        u32 v[16];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+            : "r"(taddr + c0));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (u32 j = 0; j < 16; ++j) {
+          const u32 n = c0 + j;
+          if (n < nvalid) {
+            const float x = __fadd_rn(__uint_as_float(v[j]), __ldg(rt.emb + (size_t)sEmbRow[n] * kTcH + i));
+            rw.ctx[(size_t)sOutRow[n] * kTcH + i] = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x)));
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    phase ^= 1u;
+    __syncthreads();  // B planes, the row lists and the accumulator are free for the next tile
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmemD), "r"(kTcTile));
+  }
+}
+
+}  // namespace

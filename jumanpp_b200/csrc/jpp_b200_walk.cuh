@@ -18,7 +18,7 @@ namespace {
 using namespace jppb200;
 
 #ifndef JPP_FUSED_MINBLOCKS_STATIC
-#define JPP_FUSED_MINBLOCKS_STATIC 3   // measured: 39.2 ms at 3 blocks (85 registers, some spills) against 42.5 ms at 2 (128 registers)
+#define JPP_FUSED_MINBLOCKS_STATIC 4   // blocks of 256 threads per SM (measured, walk of the bench batch: 2 -> 42.5 ms, 3 -> 39.2 ms, 4 -> 37.5 ms)
 #endif
 
 // ------------------------------------------------------------ rows in registers ----
@@ -185,7 +185,7 @@ __device__ __forceinline__ void wave_item_trigram_static(const FeatTables& ft, c
 #endif
 constexpr u32 kFusedSentDefault = JPP_FUSED_SENT_DEFAULT;  // sentences per block (8 threads each): 32 or 16
 #ifndef JPP_FUSED_MINBLOCKS
-#define JPP_FUSED_MINBLOCKS 3      // blocks of 256 threads per SM (twice that for 128): ~85 registers per thread
+#define JPP_FUSED_MINBLOCKS 4      // table-driven program: the same
 #endif
 
 template <int GW, int KB, bool SMALL, bool STATIC, int SENT>

@@ -30,9 +30,11 @@ def workload(tmp_path_factory):
         pytest.skip("oracle/_ref/jpp_ref_harness is not built (it ships with the repo snapshot to the GPU box)")
     cache = tmp_path_factory.mktemp("wl")
     args = argparse.Namespace(workload="jumandic_beam5", cache=str(cache), dict_rows=30000, sentences=N_SENT, min_len=4,
-                              max_len=96, seed=11, log2w=22, wseed=3, stage_chunk=2048, gpus=1, inline_entries=True)
+                              max_len=96, seed=11, log2w=22, wseed=3, stage_chunk=2048, gpus=1, batch_form="inline",
+                              shard_corpus=False, window=1 << 30)
     info = bench.prepare_workload(args, 0)
-    model, cfg, batch = bench.load_staged(info, args, pin=lambda a: a)
+    model, cfg, windows, _ = bench.load_staged(info, args, pin=lambda a: a)
+    batch = windows[0]
     return dict(args=args, info=info, model=model, cfg=cfg, batch=batch, bench=bench, abi=abi, jppb=jppb)
 
 

@@ -31,6 +31,23 @@ def _worker(rank, world, port, out_dir):
     res, st = oracle_lib.oracle_score(model, cfg, sub)      # stand-in scorer: no GPU on this box
     tot = shard.reduce_counters({"sentences": sub.num_sentences, "nodes": sub.num_nodes, "gathers": st.gathers}, dist)
     np.save(Path(out_dir) / f"beam_{rank}.npy", res.node_beam.view(np.uint8))
+    # BASELINE configs[4]: the shards' 1-best paths back on rank 0 in corpus order (bench.py --shard-corpus)
+    from jumanpp_b200 import abi
+    paths = abi.best_paths(sub, res)
+    res.best_path_len = np.array([len(p) for p in paths], np.uint32)
+    res.best_path_nodes = np.full(sub.num_boundaries, 0xFFFFFFFF, np.uint32)
+    for s_, p_ in enumerate(paths):
+        b0 = int(sub.sent_boundary_off[s_])
+        for k_, (bnd, pos) in enumerate(p_):
+            res.best_path_nodes[b0 + k_] = int(sub.boundary_node_off[b0 + bnd]) + pos
+    lens, nodes = shard.relative_paths([sub], [res])
+    g = shard.gather_in_corpus_order(lens, nodes, lo, hi, batch.num_sentences, dist, "cpu")
+    if rank == 0:
+        assert g["in_corpus_order"] and g["sentences"] == batch.num_sentences
+        np.save(Path(out_dir) / "gathered_lens.npy", g["lens"])
+        np.save(Path(out_dir) / "gathered_nodes.npy", g["nodes"])
+    else:
+        assert g is None
     np.save(Path(out_dir) / f"meta_{rank}.npy", np.array([lo, hi, tot["sentences"], tot["nodes"], tot["gathers"]]))
     dist.barrier()
     dist.destroy_process_group()
@@ -51,6 +68,15 @@ def test_two_ranks_shard_and_reduce(tmp_path):
     assert m0[4] == m1[4] == st.gathers
     stitched = np.concatenate([np.load(tmp_path / "beam_0.npy"), np.load(tmp_path / "beam_1.npy")])
     assert stitched.tobytes() == whole.node_beam.view(np.uint8).tobytes()
+    # the gathered paths are the whole batch's paths, in corpus order
+    from jumanpp_b200 import abi
+    paths = abi.best_paths(batch, whole)
+    want_len = np.array([len(p) for p in paths], np.int64)
+    want_nodes = np.array([int(batch.boundary_node_off[int(batch.sent_boundary_off[s]) + bnd]) + pos
+                           - int(batch.boundary_node_off[int(batch.sent_boundary_off[s])])
+                           for s, p in enumerate(paths) for bnd, pos in p], np.int64)
+    assert np.array_equal(np.load(tmp_path / "gathered_lens.npy"), want_len)
+    assert np.array_equal(np.load(tmp_path / "gathered_nodes.npy"), want_nodes)
 
 
 def test_shard_bounds_balance_codepoints():
