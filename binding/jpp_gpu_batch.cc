@@ -149,21 +149,23 @@ Status BatchAnalyzer::initialize(const JumanppEnv& env, const AnalyzerConfig& ac
 }
 
 Status BatchAnalyzer::makeAnalyzers() {
-  impls_.resize(opts_.maxBatch);
-  analyzers_.resize(opts_.maxBatch);
-  statuses_.clear();
-  std::vector<Status> errs;
-  for (u32 i = 0; i < opts_.maxBatch; ++i) {
-    statuses_.emplace_back(Status::Ok());
-    errs.emplace_back(Status::Ok());
+  for (auto& sl : slots_) {
+    sl.impls.resize(opts_.maxBatch);
+    sl.analyzers.resize(opts_.maxBatch);
+    sl.statuses.clear();
+    std::vector<Status> errs;
+    for (u32 i = 0; i < opts_.maxBatch; ++i) {
+      sl.statuses.emplace_back(Status::Ok());
+      errs.emplace_back(Status::Ok());
+    }
+    sl.shapes.resize(opts_.maxBatch);
+    runner_->run(opts_.maxBatch, [&](size_t i, u32) {
+      sl.impls[i].reset(new AnalyzerImpl{env_->coreHolder(), sconf_, acfg_});
+      sl.analyzers[i].reset(new Analyzer{});
+      errs[i] = sl.analyzers[i]->initialize(sl.impls[i].get(), &scorerDef_);
+    });
+    for (auto& s : errs) JPP_RETURN_IF_ERROR(std::move(s));
   }
-  shapes_.resize(opts_.maxBatch);
-  runner_->run(opts_.maxBatch, [&](size_t i, u32) {
-    impls_[i].reset(new AnalyzerImpl{env_->coreHolder(), sconf_, acfg_});
-    analyzers_[i].reset(new Analyzer{});
-    errs[i] = analyzers_[i]->initialize(impls_[i].get(), &scorerDef_);
-  });
-  for (auto& s : errs) JPP_RETURN_IF_ERROR(std::move(s));
   return Status::Ok();
 }
 
@@ -316,6 +318,10 @@ Status BatchAnalyzer::buildModel(const JumanppEnv& env, StringPiece rnnFile) {
   size_t limit = 0;
   if (dicPart && dicPart->data.size() > 3) limit = dicPart->data[3].size() * 2 + 2;
   resident_.assign(std::max<size_t>(limit, 1024), 0);
+  // size the device table once (an entry takes at least one byte per field): rows can then be added
+  // while another batch is being scored
+  st = jpp_b200_reserve_entry_rows(handle_, (u32)(resident_.size() / (2 * std::max(1u, entrySize_)) + 1024), (u32)resident_.size());
+  if (st != JPP_B200_OK) return gpuError(handle_, st, "jpp_b200_reserve_entry_rows");
   return Status::Ok();
 }
 
@@ -329,18 +335,18 @@ i32 BatchAnalyzer::resolveRnnId(core::analysis::rnn::RnnReprBuilder* bldr, Entry
 }
 
 // host pipeline of one sentence, unmodified (Analyzer::analyze, analyzer.cc:45-53, up to the scoring call)
-void BatchAnalyzer::buildOne(size_t i, StringPiece input) {
-  auto* impl = impls_[i].get();
-  SentenceShape& sh = shapes_[i];
+void BatchAnalyzer::buildOne(Slot& sl, size_t i, StringPiece input) {
+  auto* impl = sl.impls[i].get();
+  SentenceShape& sh = sl.shapes[i];
   sh = SentenceShape{};
   Status s = impl->resetForInput(input);
   if (s) s = impl->prepareNodeSeeds();
   if (s) s = impl->buildLattice();
   if (!s) {
-    statuses_[i] = std::move(s);
+    sl.statuses[i] = std::move(s);
     return;
   }
-  statuses_[i] = Status::Ok();
+  sl.statuses[i] = Status::Ok();
   auto lat = impl->lattice();
   // BOS beams: the part of bootstrapAnalysis (analyzer_impl.cc:185-192) that the output side reads
   // (the ScoreProcessor it also allocates is the CPU scorer's scratch: not needed)
@@ -368,24 +374,24 @@ void BatchAnalyzer::buildOne(size_t i, StringPiece input) {
 }
 
 // the sentence's slices of the staged arrays (resident form of jpp_b200_batch)
-void BatchAnalyzer::stageOne(size_t i, u32 worker) {
-  if (!statuses_[i]) return;
-  auto* impl = impls_[i].get();
+void BatchAnalyzer::stageOne(Slot& sl, size_t i, u32 worker) {
+  if (!sl.statuses[i]) return;
+  auto* impl = sl.impls[i].get();
   auto lat = impl->lattice();
   auto xtra = impl->extraNodesContext();
-  const u32 nb = shapes_[i].boundaries;
-  const u32 bBase = sentBndOff_[i], xBase = sentExtraOff_[i], cBase = sentCpOff_[i];
-  u32 n = sentNodeOff_[i], e = sentEndOff_[i];
+  const u32 nb = sl.shapes[i].boundaries;
+  const u32 bBase = sl.sentBndOff[i], xBase = sl.sentExtraOff[i], cBase = sl.sentCpOff[i];
+  u32 n = sl.sentNodeOff[i], e = sl.sentEndOff[i];
   features::impl::PrimitiveFeatureContext pfc{xtra, impl->dic().fields(), impl->dic().entries(), impl->input().codepoints()};
   core::analysis::rnn::RnnReprBuilder reprBldr;
   auto& missing = missingPerWorker_[worker];
   for (u32 b = 0; b < nb; ++b) {
     auto bnd = lat->boundary(b);
-    hBndNodeOff_[bBase + b] = n;
-    hBndEndOff_[bBase + b] = e;
+    sl.hBndNodeOff[bBase + b] = n;
+    sl.hBndEndOff[bBase + b] = e;
     for (auto& ni : bnd->starts()->nodeInfo()) {
       const EntryPtr ep = ni.entryPtr();
-      hNodeInfo_[n++] = jpp_b200_node_info{ep.rawValue(), ni.start(), ni.end()};
+      sl.hNodeInfo[n++] = jpp_b200_node_info{ep.rawValue(), ni.start(), ni.end()};
       if (ep.isDic()) {
         // the row of a dictionary entry lives on the device: note the ones it has not seen yet
         const size_t raw = (size_t)ep.rawValue();
@@ -393,16 +399,16 @@ void BatchAnalyzer::stageOne(size_t i, u32 worker) {
       } else if (ep != kBos && ep != kEos) {
         // a node the analyzer made up for this sentence (unknown word, alias): its row travels
         const size_t row = (size_t)xBase + (size_t)ep.extPtr();
-        util::MutableArraySlice<i32> buf{hExtraRows_.data() + row * entrySize_, entrySize_};
+        util::MutableArraySlice<i32> buf{sl.hExtraRows.data() + row * entrySize_, entrySize_};
         pfc.fillEntryBuffer(ep, buf);
-        for (u32 p = 0; p < numPlaceholders_; ++p) hExtraPh_[row * numPlaceholders_ + p] = pfc.providedFeature(ep, p);
-        if (hasRnn_) hExtraRnn_[row] = (b >= 2 && b + 1 != nb) ? resolveRnnId(&reprBldr, ep, buf, xtra) : 0;
+        for (u32 p = 0; p < numPlaceholders_; ++p) sl.hExtraPh[row * numPlaceholders_ + p] = pfc.providedFeature(ep, p);
+        if (hasRnn_) sl.hExtraRnn[row] = (b >= 2 && b + 1 != nb) ? resolveRnnId(&reprBldr, ep, buf, xtra) : 0;
       }
     }
-    for (auto& p : bnd->ends()->nodePtrs()) hEnds_[e++] = jpp_b200_node_ptr{p.boundary, p.position};
+    for (auto& p : bnd->ends()->nodePtrs()) sl.hEnds[e++] = jpp_b200_node_ptr{p.boundary, p.position};
   }
   u32 c = cBase;
-  for (auto& cp : impl->input().codepoints()) hCps_[c++] = jpp_b200_codepoint{(u32)cp.codepoint, (u32)cp.charClass};
+  for (auto& cp : impl->input().codepoints()) sl.hCps[c++] = jpp_b200_codepoint{(u32)cp.codepoint, (u32)cp.charClass};
 }
 
 // decode the dictionary entries this batch met for the first time and make them resident
@@ -440,17 +446,17 @@ Status BatchAnalyzer::addMissingRows() {
 
 // GPU result -> the sentence's Lattice, in the form the output side reads (analysis_result.cc:25-76,
 // lattice_format.cc): beam rows with their `previous` links, per-connection scores
-void BatchAnalyzer::unstageOne(size_t i) {
-  if (!statuses_[i]) return;
-  if (hStatus_[i] != 0) {
-    statuses_[i] = JPPS_INVALID_STATE << "the lattice failed validation on the device (status " << (int)hStatus_[i] << ")";
+void BatchAnalyzer::unstageOne(Slot& sl, size_t i) {
+  if (!sl.statuses[i]) return;
+  if (sl.hStatus[i] != 0) {
+    sl.statuses[i] = JPPS_INVALID_STATE << "the lattice failed validation on the device (status " << (int)sl.hStatus[i] << ")";
     return;
   }
-  auto lat = impls_[i]->lattice();
-  const u32 nb = shapes_[i].boundaries;
-  const u32 bBase = sentBndOff_[i];
+  auto lat = sl.impls[i]->lattice();
+  const u32 nb = sl.shapes[i].boundaries;
+  const u32 bBase = sl.sentBndOff[i];
   const u32 B = beam_, S = numScorers_;
-  auto nodeOf = [&](u32 bnd, u32 pos) { return hBndNodeOff_[bBase + bnd] + pos; };
+  auto nodeOf = [&](u32 bnd, u32 pos) { return sl.hBndNodeOff[bBase + bnd] + pos; };
   if (opts_.fullBeams) {
     for (u32 b = 2; b < nb; ++b) {
       auto bnd = lat->boundary(b);
@@ -461,7 +467,7 @@ void BatchAnalyzer::unstageOne(size_t i) {
         const u32 node = nodeOf(b, r);
         auto row = starts->beamData().row(r);
         for (u32 k = 0; k < B; ++k) {
-          const jpp_b200_beam_element& el = hBeam_[(size_t)node * B + k];
+          const jpp_b200_beam_element& el = sl.hBeam[(size_t)node * B + k];
           if (el.left == 0xFFFFu && el.prev_beam == 0xFFFFu) {
             row.at(k) = EntryBeam::fake();
             continue;
@@ -472,7 +478,7 @@ void BatchAnalyzer::unstageOne(size_t i) {
           out.ptr = ConnectionPtr{(u16)b, el.left, (u16)r, el.prev_beam, &prev.ptr};
           out.totalScore = el.total_score;
           auto sc = bnd->scores()->nodeScores(r).beamLeft(el.prev_beam, el.left);
-          for (u32 s = 0; s < S; ++s) sc.at(s) = hBeamScores_[((size_t)node * B + k) * S + s];
+          for (u32 s = 0; s < S; ++s) sc.at(s) = sl.hBeamScores[((size_t)node * B + k) * S + s];
         }
       }
     }
@@ -480,7 +486,7 @@ void BatchAnalyzer::unstageOne(size_t i) {
   }
   // 1-best chain only: the element of every node on the path goes to slot 0 of its row, so that the
   // walk of AnalysisPath::fillIn (beam index of the previous node = `beam`) sees exactly this chain
-  const u32 len = hPathLen_[i];
+  const u32 len = sl.hPathLen[i];
   const ConnectionPtr* prevPtr = &lat->boundary(1)->starts()->beamData().row(0).at(0).ptr;
   u32 prevBnd = 1, prevPos = 0;
   auto link = [&](u32 b, u32 r) {
@@ -498,96 +504,115 @@ void BatchAnalyzer::unstageOne(size_t i) {
   };
   u32 bCursor = 2;
   for (u32 k = 0; k < len; ++k) {
-    const u32 node = hPathNodes_[bBase + k];
-    while (bCursor + 1 < nb && hBndNodeOff_[bBase + bCursor + 1] <= node) ++bCursor;  // path nodes come in boundary order
-    link(bCursor, node - hBndNodeOff_[bBase + bCursor]);
+    const u32 node = sl.hPathNodes[bBase + k];
+    while (bCursor + 1 < nb && sl.hBndNodeOff[bBase + bCursor + 1] <= node) ++bCursor;  // path nodes come in boundary order
+    link(bCursor, node - sl.hBndNodeOff[bBase + bCursor]);
   }
   if (len > 0 || nb == 3) {
     if (nb > 3) link(nb - 1, 0);
   } else {
-    statuses_[i] = JPPS_INVALID_STATE << "no path reaches the end of the sentence";
+    sl.statuses[i] = JPPS_INVALID_STATE << "no path reaches the end of the sentence";
   }
 }
 
-Status BatchAnalyzer::analyzeBatch(const std::vector<StringPiece>& inputs) {
+Status BatchAnalyzer::prepare(int slot, const std::vector<StringPiece>& inputs) {
+  Slot& sl = slots_[slot];
   const size_t N = inputs.size();
   if (N > opts_.maxBatch) return JPPS_INVALID_PARAMETER << "batch of " << N << " sentences, at most " << opts_.maxBatch;
-  batchSize_ = N;
+  sl.batchSize = N;
   if (N == 0) return Status::Ok();
   double t0 = now();
-  runner_->run(N, [&](size_t i, u32) { buildOne(i, inputs[i]); }, 16);
+  runner_->run(N, [&](size_t i, u32) { buildOne(sl, i, inputs[i]); }, 16);
   double t1 = now();
   // CSR offsets: a failed sentence takes no room (the device sees it as a sentence without boundaries
   // and reports it, which un-staging maps back to the status the host already has)
-  sentBndOff_.assign(N + 1, 0); sentCpOff_.assign(N + 1, 0); sentExtraOff_.assign(N + 1, 0);
-  sentNodeOff_.assign(N + 1, 0); sentEndOff_.assign(N + 1, 0);
+  sl.sentBndOff.assign(N + 1, 0); sl.sentCpOff.assign(N + 1, 0); sl.sentExtraOff.assign(N + 1, 0);
+  sl.sentNodeOff.assign(N + 1, 0); sl.sentEndOff.assign(N + 1, 0);
   for (size_t i = 0; i < N; ++i) {
-    const SentenceShape z = statuses_[i] ? shapes_[i] : SentenceShape{};
-    sentBndOff_[i + 1] = sentBndOff_[i] + z.boundaries;
-    sentCpOff_[i + 1] = sentCpOff_[i] + z.codepoints;
-    sentExtraOff_[i + 1] = sentExtraOff_[i] + z.extras;
-    sentNodeOff_[i + 1] = sentNodeOff_[i] + z.nodes;
-    sentEndOff_[i + 1] = sentEndOff_[i] + z.ends;
+    const SentenceShape z = sl.statuses[i] ? sl.shapes[i] : SentenceShape{};
+    sl.sentBndOff[i + 1] = sl.sentBndOff[i] + z.boundaries;
+    sl.sentCpOff[i + 1] = sl.sentCpOff[i] + z.codepoints;
+    sl.sentExtraOff[i + 1] = sl.sentExtraOff[i] + z.extras;
+    sl.sentNodeOff[i + 1] = sl.sentNodeOff[i] + z.nodes;
+    sl.sentEndOff[i + 1] = sl.sentEndOff[i] + z.ends;
   }
-  const size_t NB = sentBndOff_[N], NN = sentNodeOff_[N], NE = sentEndOff_[N], NC = sentCpOff_[N], NX = sentExtraOff_[N];
-  JPP_RETURN_IF_ERROR(hSentBndOff_.ensure(N + 1)); JPP_RETURN_IF_ERROR(hSentCpOff_.ensure(N + 1));
-  JPP_RETURN_IF_ERROR(hSentExtraOff_.ensure(N + 1));
-  JPP_RETURN_IF_ERROR(hBndNodeOff_.ensure(NB + 1)); JPP_RETURN_IF_ERROR(hBndEndOff_.ensure(NB + 1));
-  JPP_RETURN_IF_ERROR(hNodeInfo_.ensure(NN)); JPP_RETURN_IF_ERROR(hEnds_.ensure(NE)); JPP_RETURN_IF_ERROR(hCps_.ensure(NC));
-  JPP_RETURN_IF_ERROR(hExtraRows_.ensure(std::max<size_t>(1, NX) * entrySize_));
-  JPP_RETURN_IF_ERROR(hExtraPh_.ensure(std::max<size_t>(1, NX) * std::max(1u, numPlaceholders_)));
-  JPP_RETURN_IF_ERROR(hExtraRnn_.ensure(std::max<size_t>(1, NX)));
-  JPP_RETURN_IF_ERROR(hPathLen_.ensure(N)); JPP_RETURN_IF_ERROR(hPathNodes_.ensure(NB)); JPP_RETURN_IF_ERROR(hStatus_.ensure(N));
+  const size_t NB = sl.sentBndOff[N], NN = sl.sentNodeOff[N], NE = sl.sentEndOff[N], NC = sl.sentCpOff[N], NX = sl.sentExtraOff[N];
+  sl.NB = NB; sl.NN = NN; sl.NE = NE; sl.NC = NC; sl.NX = NX;
+  JPP_RETURN_IF_ERROR(sl.hSentBndOff.ensure(N + 1)); JPP_RETURN_IF_ERROR(sl.hSentCpOff.ensure(N + 1));
+  JPP_RETURN_IF_ERROR(sl.hSentExtraOff.ensure(N + 1));
+  JPP_RETURN_IF_ERROR(sl.hBndNodeOff.ensure(NB + 1)); JPP_RETURN_IF_ERROR(sl.hBndEndOff.ensure(NB + 1));
+  JPP_RETURN_IF_ERROR(sl.hNodeInfo.ensure(NN)); JPP_RETURN_IF_ERROR(sl.hEnds.ensure(NE)); JPP_RETURN_IF_ERROR(sl.hCps.ensure(NC));
+  JPP_RETURN_IF_ERROR(sl.hExtraRows.ensure(std::max<size_t>(1, NX) * entrySize_));
+  JPP_RETURN_IF_ERROR(sl.hExtraPh.ensure(std::max<size_t>(1, NX) * std::max(1u, numPlaceholders_)));
+  JPP_RETURN_IF_ERROR(sl.hExtraRnn.ensure(std::max<size_t>(1, NX)));
+  JPP_RETURN_IF_ERROR(sl.hPathLen.ensure(N)); JPP_RETURN_IF_ERROR(sl.hPathNodes.ensure(NB)); JPP_RETURN_IF_ERROR(sl.hStatus.ensure(N));
   if (opts_.fullBeams) {
-    JPP_RETURN_IF_ERROR(hBeam_.ensure(NN * beam_));
-    JPP_RETURN_IF_ERROR(hBeamScores_.ensure(NN * beam_ * numScorers_));
+    JPP_RETURN_IF_ERROR(sl.hBeam.ensure(NN * beam_));
+    JPP_RETURN_IF_ERROR(sl.hBeamScores.ensure(NN * beam_ * numScorers_));
   }
-  std::memcpy(hSentBndOff_.data(), sentBndOff_.data(), (N + 1) * 4);
-  std::memcpy(hSentCpOff_.data(), sentCpOff_.data(), (N + 1) * 4);
-  std::memcpy(hSentExtraOff_.data(), sentExtraOff_.data(), (N + 1) * 4);
-  hBndNodeOff_[NB] = (u32)NN;
-  hBndEndOff_[NB] = (u32)NE;
+  std::memcpy(sl.hSentBndOff.data(), sl.sentBndOff.data(), (N + 1) * 4);
+  std::memcpy(sl.hSentCpOff.data(), sl.sentCpOff.data(), (N + 1) * 4);
+  std::memcpy(sl.hSentExtraOff.data(), sl.sentExtraOff.data(), (N + 1) * 4);
+  sl.hBndNodeOff[NB] = (u32)NN;
+  sl.hBndEndOff[NB] = (u32)NE;
   // rows of extra indices that no lattice node uses stay defined
-  std::memset(hExtraRows_.data(), 0, std::max<size_t>(1, NX) * entrySize_ * 4);
-  std::memset(hExtraPh_.data(), 0, std::max<size_t>(1, NX) * std::max(1u, numPlaceholders_) * 4);
-  std::memset(hExtraRnn_.data(), 0, std::max<size_t>(1, NX) * 4);
-  runner_->run(N, [&](size_t i, u32 w) { stageOne(i, w); }, 16);
+  std::memset(sl.hExtraRows.data(), 0, std::max<size_t>(1, NX) * entrySize_ * 4);
+  std::memset(sl.hExtraPh.data(), 0, std::max<size_t>(1, NX) * std::max(1u, numPlaceholders_) * 4);
+  std::memset(sl.hExtraRnn.data(), 0, std::max<size_t>(1, NX) * 4);
+  runner_->run(N, [&](size_t i, u32 w) { stageOne(sl, i, w); }, 16);
   double t2 = now();
   JPP_RETURN_IF_ERROR(addMissingRows());
   double t3 = now();
-
-  jpp_b200_batch b{};
-  b.num_sentences = (u32)N;
-  b.sent_boundary_off = hSentBndOff_.data(); b.sent_codepoint_off = hSentCpOff_.data();
-  b.boundary_node_off = hBndNodeOff_.data(); b.boundary_end_off = hBndEndOff_.data();
-  b.node_info = hNodeInfo_.data(); b.ends = hEnds_.data(); b.codepoints = hCps_.data();
-  b.entry_rows = hExtraRows_.data(); b.num_entry_rows = (u32)NX;
-  b.row_placeholders = numPlaceholders_ ? hExtraPh_.data() : nullptr;
-  b.row_rnn_id = hasRnn_ ? hExtraRnn_.data() : nullptr;
-  b.sent_extra_row_off = hSentExtraOff_.data();
-  jpp_b200_result r{};
-  r.best_path_len = hPathLen_.data();
-  r.best_path_nodes = hPathNodes_.data();
-  r.sentence_status = hStatus_.data();
-  if (opts_.fullBeams) {
-    r.node_beam = hBeam_.data();
-    r.node_beam_scores = hBeamScores_.data();
-  }
-  if (NB > 0) {
-    jpp_b200_status st = jpp_b200_score_batch(handle_, &b, &r);  // <- the scoring
-    if (st != JPP_B200_OK) return gpuError(handle_, st, "jpp_b200_score_batch");
-  } else {
-    std::memset(hStatus_.data(), 0, N);
-  }
-  double t4 = now();
-  runner_->run(N, [&](size_t i, u32) { unstageOne(i); }, 16);
-  double t5 = now();
+  std::lock_guard<std::mutex> lk(timingsMutex_);
   timings_.buildSec += t1 - t0; timings_.stageSec += t2 - t1; timings_.tableSec += t3 - t2;
-  timings_.scoreSec += t4 - t3; timings_.unstageSec += t5 - t4;
   timings_.sentences += N; timings_.nodes += NN;
   timings_.h2dBytes += (N + 1) * 12 + (NB + 1) * 8 + NN * 8 + NE * 4 + NC * 8 + NX * (entrySize_ + numPlaceholders_ + 1) * 4;
   timings_.d2hBytes += N * 5 + NB * 4 + (opts_.fullBeams ? NN * beam_ * (8 + 4 * numScorers_) : 0);
-  for (size_t i = 0; i < N; ++i) timings_.failed += !statuses_[i];
+  return Status::Ok();
+}
+
+Status BatchAnalyzer::score(int slot) {
+  Slot& sl = slots_[slot];
+  const size_t N = sl.batchSize;
+  if (N == 0) return Status::Ok();
+  double t0 = now();
+  jpp_b200_batch b{};
+  b.num_sentences = (u32)N;
+  b.sent_boundary_off = sl.hSentBndOff.data(); b.sent_codepoint_off = sl.hSentCpOff.data();
+  b.boundary_node_off = sl.hBndNodeOff.data(); b.boundary_end_off = sl.hBndEndOff.data();
+  b.node_info = sl.hNodeInfo.data(); b.ends = sl.hEnds.data(); b.codepoints = sl.hCps.data();
+  b.entry_rows = sl.hExtraRows.data(); b.num_entry_rows = (u32)sl.NX;
+  b.row_placeholders = numPlaceholders_ ? sl.hExtraPh.data() : nullptr;
+  b.row_rnn_id = hasRnn_ ? sl.hExtraRnn.data() : nullptr;
+  b.sent_extra_row_off = sl.hSentExtraOff.data();
+  jpp_b200_result r{};
+  r.best_path_len = sl.hPathLen.data();
+  r.best_path_nodes = sl.hPathNodes.data();
+  r.sentence_status = sl.hStatus.data();
+  if (opts_.fullBeams) {
+    r.node_beam = sl.hBeam.data();
+    r.node_beam_scores = sl.hBeamScores.data();
+  }
+  if (sl.NB > 0) {
+    jpp_b200_status st = jpp_b200_score_batch(handle_, &b, &r);  // <- the scoring
+    if (st != JPP_B200_OK) return gpuError(handle_, st, "jpp_b200_score_batch");
+  } else {
+    std::memset(sl.hStatus.data(), 0, N);
+  }
+  std::lock_guard<std::mutex> lk(timingsMutex_);
+  timings_.scoreSec += now() - t0;
+  return Status::Ok();
+}
+
+Status BatchAnalyzer::finish(int slot) {
+  Slot& sl = slots_[slot];
+  const size_t N = sl.batchSize;
+  if (N == 0) return Status::Ok();
+  double t0 = now();
+  runner_->run(N, [&](size_t i, u32) { unstageOne(sl, i); }, 16);
+  std::lock_guard<std::mutex> lk(timingsMutex_);
+  timings_.unstageSec += now() - t0;
+  for (size_t i = 0; i < N; ++i) timings_.failed += !sl.statuses[i];
   return Status::Ok();
 }
 

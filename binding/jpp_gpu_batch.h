@@ -114,26 +114,60 @@ class BatchAnalyzer {
 
   // inputs.size() <= maxBatch().  On return analyzer(i) holds sentence i (status(i) says whether
   // it could be analysed; a failed sentence is the caller's `# ERROR`).
-  Status analyzeBatch(const std::vector<StringPiece>& inputs);
+  Status analyzeBatch(const std::vector<StringPiece>& inputs) {
+    JPP_RETURN_IF_ERROR(prepare(0, inputs));
+    JPP_RETURN_IF_ERROR(score(0));
+    return finish(0);
+  }
+
+  // The same in three steps over two sets of resident analyzers ("slots"), so that a caller can build
+  // and stage batch k+1 and format batch k-1 on the host threads while the GPU scores batch k:
+  //   prepare(slot)  lattices built and staged, new dictionary rows made resident   (host threads)
+  //   score(slot)    jpp_b200_score_batch; may run on another thread, concurrently with prepare /
+  //                  finish of the OTHER slot
+  //   finish(slot)   beams / paths written back into the lattices                   (host threads)
+  Status prepare(int slot, const std::vector<StringPiece>& inputs);
+  Status score(int slot);
+  Status finish(int slot);
 
   u32 maxBatch() const { return opts_.maxBatch; }
-  core::analysis::Analyzer* analyzer(size_t i) { return analyzers_[i].get(); }
-  const Status& status(size_t i) const { return statuses_[i]; }
+  core::analysis::Analyzer* analyzer(size_t i, int slot = 0) { return slots_[slot].analyzers[i].get(); }
+  const Status& status(size_t i, int slot = 0) const { return slots_[slot].statuses[i]; }
   ParallelRunner& runner() { return *runner_; }
   const BatchTimings& timings() const { return timings_; }
   const core::analysis::ScorerDef* scorerDef() const { return &scorerDef_; }
+  static constexpr int kSlots = 2;
 
  private:
   struct SentenceShape {
     u32 boundaries = 0, nodes = 0, ends = 0, codepoints = 0, extras = 0;
   };
 
+  // one set of resident analyzers with its staged batch (pinned) and its result (pinned)
+  struct Slot {
+    std::vector<std::unique_ptr<core::analysis::AnalyzerImpl>> impls;
+    std::vector<std::unique_ptr<core::analysis::Analyzer>> analyzers;
+    std::vector<Status> statuses;
+    std::vector<SentenceShape> shapes;
+    std::vector<u32> sentBndOff, sentCpOff, sentExtraOff, sentNodeOff, sentEndOff;
+    PinnedArray<u32> hSentBndOff, hSentCpOff, hSentExtraOff, hBndNodeOff, hBndEndOff;
+    PinnedArray<jpp_b200_node_info> hNodeInfo;
+    PinnedArray<jpp_b200_node_ptr> hEnds;
+    PinnedArray<jpp_b200_codepoint> hCps;
+    PinnedArray<i32> hExtraRows, hExtraPh, hExtraRnn;
+    PinnedArray<jpp_b200_beam_element> hBeam;
+    PinnedArray<float> hBeamScores;
+    PinnedArray<u32> hPathLen, hPathNodes;
+    PinnedArray<u8> hStatus;
+    size_t batchSize = 0, NB = 0, NN = 0, NE = 0, NC = 0, NX = 0;
+  };
+
   Status buildModel(const core::JumanppEnv& env, StringPiece rnnFile);
   Status makeAnalyzers();
-  void buildOne(size_t i, StringPiece input);
-  void stageOne(size_t i, u32 worker);
+  void buildOne(Slot& s, size_t i, StringPiece input);
+  void stageOne(Slot& s, size_t i, u32 worker);
   Status addMissingRows();
-  void unstageOne(size_t i);
+  void unstageOne(Slot& s, size_t i);
   i32 resolveRnnId(core::analysis::rnn::RnnReprBuilder* bldr, core::EntryPtr eptr, util::ArraySlice<i32> entry,
                    const core::analysis::ExtraNodesContext* xtra) const;
 
@@ -143,11 +177,9 @@ class BatchAnalyzer {
   core::ScoringConfig sconf_;
   core::analysis::ScorerDef scorerDef_;  // weights as the environment's, no ScoreComputer instances
   std::unique_ptr<ParallelRunner> runner_;
-  std::vector<std::unique_ptr<core::analysis::AnalyzerImpl>> impls_;
-  std::vector<std::unique_ptr<core::analysis::Analyzer>> analyzers_;
-  std::vector<Status> statuses_;
-  std::vector<SentenceShape> shapes_;
+  Slot slots_[kSlots];
   BatchTimings timings_;
+  std::mutex timingsMutex_;
 
   // device
   jpp_b200_handle* handle_ = nullptr;
@@ -156,24 +188,10 @@ class BatchAnalyzer {
   // RNN id resolution (RnnIdContainer::resolveId, rnn_id_resolver.cc:278-309)
   core::analysis::rnn::RnnIdResolver resolver_;
   core::dic::DoubleArray knownIdx_, unkIdx_;
-  std::vector<float> rnnBlocksOwned_[4];
 
   // resident entry table bookkeeping: which dictionary entries are already on the device
   std::vector<u8> resident_;                       // [entry_ptr] 1 = row is on the device
   std::vector<std::vector<i32>> missingPerWorker_;  // entry_ptrs met for the first time in this batch
-
-  // staged batch (pinned) and result (pinned)
-  std::vector<u32> sentBndOff_, sentCpOff_, sentExtraOff_, sentNodeOff_, sentEndOff_;
-  PinnedArray<u32> hSentBndOff_, hSentCpOff_, hSentExtraOff_, hBndNodeOff_, hBndEndOff_;
-  PinnedArray<jpp_b200_node_info> hNodeInfo_;
-  PinnedArray<jpp_b200_node_ptr> hEnds_;
-  PinnedArray<jpp_b200_codepoint> hCps_;
-  PinnedArray<i32> hExtraRows_, hExtraPh_, hExtraRnn_;
-  PinnedArray<jpp_b200_beam_element> hBeam_;
-  PinnedArray<float> hBeamScores_;
-  PinnedArray<u32> hPathLen_, hPathNodes_;
-  PinnedArray<u8> hStatus_;
-  size_t batchSize_ = 0;
 };
 
 }  // namespace b200

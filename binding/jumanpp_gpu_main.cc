@@ -19,6 +19,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <future>
 #include <iostream>
 #include <string>
 #include <vector>
@@ -247,11 +248,13 @@ int main(int argc, const char** argv) {
     std::cerr << "failed to initialise the GPU scorer: " << s << "\n";
     return 1;
   }
-  std::vector<std::unique_ptr<core::OutputFormat>> formats(batch.maxBatch());
-  {
+  // every resident analyzer (two sets: one being scored, one being built / printed) gets its formatter
+  std::vector<std::unique_ptr<core::OutputFormat>> formats[b200::BatchAnalyzer::kSlots];
+  for (int sl = 0; sl < b200::BatchAnalyzer::kSlots; ++sl) {
+    formats[sl].resize(batch.maxBatch());
     std::vector<Status> errs;
     for (u32 i = 0; i < batch.maxBatch(); ++i) errs.emplace_back(Status::Ok());
-    batch.runner().run(batch.maxBatch(), [&](size_t i, u32) { errs[i] = makeFormat(cf, env, *batch.analyzer(i), &formats[i]); });
+    batch.runner().run(batch.maxBatch(), [&](size_t i, u32) { errs[i] = makeFormat(cf, env, *batch.analyzer(i, sl), &formats[sl][i]); });
     for (auto& e : errs)
       if (!e) {
         std::cerr << "failed to initialise the output format: " << e << "\n";
@@ -262,65 +265,105 @@ int main(int argc, const char** argv) {
 
   LineSource src{&cf.inputFiles.value()};
   if (!src.open()) return 1;
-  std::vector<Example> examples(batch.maxBatch());
-  std::vector<StringPiece> inputs;
-  std::vector<size_t> slot;  // example -> index in the batch (examples that could not be read take none)
+  struct InFlight {
+    size_t n = 0;
+    std::vector<Example> examples;
+    std::vector<StringPiece> inputs;
+    std::vector<size_t> slot;  // example -> index in the batch (examples that could not be read take none)
+    std::future<Status> scoring;
+  } fl[b200::BatchAnalyzer::kSlots];
+  for (auto& f : fl) f.examples.resize(batch.maxBatch());
   std::vector<Status> fmtStatus;
   for (u32 i = 0; i < batch.maxBatch(); ++i) fmtStatus.emplace_back(Status::Ok());
   double formatSec = 0, writeSec = 0, readSec = 0, total0 = now();
   int result = 0;
   const std::string empty = exec.emptyResult().str();
-  while (src.hasNext()) {
-    double r0 = now();
-    size_t n = 0;
-    inputs.clear();
-    slot.assign(batch.maxBatch(), (size_t)-1);
-    while (n < batch.maxBatch() && src.hasNext()) {
-      src.read(&examples[n]);
-      if (examples[n].readStatus) {
-        slot[n] = inputs.size();
-        inputs.emplace_back(examples[n].input);
-      }
-      ++n;
-    }
-    double r1 = now();
-    s = batch.analyzeBatch(inputs);
-    if (!s) {
-      std::cerr << s << "\n";
-      return 1;
+
+  // un-stage, format (in parallel: every analyzer has its own formatter) and write (in input order) one batch
+  auto emit = [&](int sl) -> bool {
+    InFlight& f = fl[sl];
+    Status s2 = batch.finish(sl);
+    if (!s2) {
+      std::cerr << s2 << "\n";
+      return false;
     }
     double f0 = now();
-    // format in parallel (every analyzer has its own formatter), write in input order
-    std::vector<size_t> exampleOfSlot(inputs.size());
-    for (size_t e = 0; e < n; ++e)
-      if (slot[e] != (size_t)-1) exampleOfSlot[slot[e]] = e;
-    batch.runner().run(inputs.size(), [&](size_t k, u32) {
-      if (!batch.status(k)) return;
-      const std::string& c = examples[exampleOfSlot[k]].comment;
+    std::vector<size_t> exampleOfSlot(f.inputs.size());
+    for (size_t e = 0; e < f.n; ++e)
+      if (f.slot[e] != (size_t)-1) exampleOfSlot[f.slot[e]] = e;
+    batch.runner().run(f.inputs.size(), [&](size_t k, u32) {
+      if (!batch.status(k, sl)) return;
+      const std::string& c = f.examples[exampleOfSlot[k]].comment;
       StringPiece comment = c.size() < 2 ? EMPTY_SP : StringPiece{c}.from(2);
-      fmtStatus[k] = formats[k]->format(*batch.analyzer(k), comment);
+      fmtStatus[k] = formats[sl][k]->format(*batch.analyzer(k, sl), comment);
     }, 8);
     double f1 = now();
-    for (size_t e = 0; e < n; ++e) {
-      if (!examples[e].readStatus) {
-        std::cerr << "failed to read an example: " << examples[e].readStatus;
+    for (size_t e = 0; e < f.n; ++e) {
+      if (!f.examples[e].readStatus) {
+        std::cerr << "failed to read an example: " << f.examples[e].readStatus;
         result = 1;
         continue;
       }
       result = 0;
-      const size_t k = slot[e];
-      if (!batch.status(k)) {
-        std::cerr << batch.status(k);
+      const size_t k = f.slot[e];
+      if (!batch.status(k, sl)) {
+        std::cerr << batch.status(k, sl);
         *out << empty;
         continue;
       }
       if (!fmtStatus[k]) std::cerr << fmtStatus[k];
-      else *out << formats[k]->result();
+      else *out << formats[sl][k]->result();
     }
-    double w1 = now();
-    readSec += r1 - r0;
     formatSec += f1 - f0;
-    writeSec += w1 - f1;
+    writeSec += now() - f1;
+    return true;
+  };
+
+  // pipeline: while the GPU scores batch k (a thread of its own inside jpp_b200_score_batch), the host
+  // threads print batch k-1 and build + stage batch k+1
+  int cur = 0;
+  bool havePrev = false;
+  while (src.hasNext()) {
+    InFlight& f = fl[cur];
+    double r0 = now();
+    f.n = 0;
+    f.inputs.clear();
+    f.slot.assign(batch.maxBatch(), (size_t)-1);
+    while (f.n < batch.maxBatch() && src.hasNext()) {
+      src.read(&f.examples[f.n]);
+      if (f.examples[f.n].readStatus) {
+        f.slot[f.n] = f.inputs.size();
+        f.inputs.emplace_back(f.examples[f.n].input);
+      }
+      ++f.n;
+    }
+    readSec += now() - r0;
+    s = batch.prepare(cur, f.inputs);
+    if (!s) {
+      std::cerr << s << "\n";
+      return 1;
+    }
+    const int prev = cur ^ 1;
+    if (havePrev) {
+      s = fl[prev].scoring.get();
+      if (!s) {
+        std::cerr << s << "\n";
+        return 1;
+      }
+    }
+    f.scoring = std::async(std::launch::async, [&batch, cur] { return batch.score(cur); });
+    if (havePrev && !emit(prev)) return 1;
+    havePrev = true;
+    cur ^= 1;
+  }
+  if (havePrev) {
+    const int last = cur ^ 1;
+    s = fl[last].scoring.get();
+    if (!s) {
+      std::cerr << s << "\n";
+      return 1;
+    }
+    if (!emit(last)) return 1;
   }
   out->flush();
   double total1 = now();

@@ -386,9 +386,16 @@ jpp_b200_status jpp_b200_download_result(jpp_b200_handle* h,
 /* Adds rows to the handle's resident entry table (device copy; the whole dictionary at
  * start-up, or the entries of each batch that were not seen before).  A row whose entry_ptr
  * is already resident replaces the old one.  Not to be called while another thread scores
- * on the same handle. */
+ * on the same handle, unless the table was sized with jpp_b200_reserve_entry_rows. */
 jpp_b200_status jpp_b200_add_entry_rows(jpp_b200_handle* h,
                                         const jpp_b200_entry_table* rows);
+/* Sizes the resident table for `max_rows` rows and entry_ptr values below `entry_ptr_limit` once.
+ * Within that reservation jpp_b200_add_entry_rows never moves the device arrays and runs on a
+ * stream of its own, so a stager MAY add the rows of the next batch while jpp_b200_score_batch of
+ * the previous one is still running on another thread (that batch only names rows added before
+ * it started). */
+jpp_b200_status jpp_b200_reserve_entry_rows(jpp_b200_handle* h, uint32_t max_rows,
+                                            uint32_t entry_ptr_limit);
 
 jpp_b200_status jpp_b200_get_counters(const jpp_b200_handle* h,
                                       jpp_b200_counters* out);

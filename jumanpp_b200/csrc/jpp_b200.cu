@@ -1082,6 +1082,7 @@ struct jpp_b200_handle {
     i32* dRows = nullptr; i32* dRnnId = nullptr; u32 numRows = 0, rowCap = 0 /* i32 elements */, idCap = 0;
   } dic;
   std::vector<i32> hostRowOfPtr;  // owner only: host copy of the direct map
+  cudaStream_t tableStream = nullptr;  // owner only: uploads of table rows (never waits for a batch in flight)
   bool staticProgram = false;  // the uploaded n-gram program is the compiled-in one (jpp_b200_static_jumandic.h)
   float* dRnnBlocks[4] = {nullptr, nullptr, nullptr, nullptr};
   float* dRnnWt = nullptr;  // transposed recurrent matrix
@@ -1400,6 +1401,7 @@ void jpp_b200_destroy(jpp_b200_handle* h) {
     if (h->dic.dRowOfPtr) cudaFree(h->dic.dRowOfPtr);
     if (h->dic.dRows) cudaFree(h->dic.dRows);
     if (h->dic.dRnnId) cudaFree(h->dic.dRnnId);
+    if (h->tableStream) cudaStreamDestroy(h->tableStream);
   }
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -2100,7 +2102,8 @@ static jpp_b200_status add_entry_rows_impl(jpp_b200_handle* h, const jpp_b200_en
     maxPtr = std::max(maxPtr, t->entry_ptr[i]);
   }
   auto& d = h->dic;
-  cudaStream_t st = h->stream;
+  if (!h->tableStream) CU_CHECK(h, cudaStreamCreateWithFlags(&h->tableStream, cudaStreamNonBlocking));
+  cudaStream_t st = h->tableStream;
   // rows: new ones are appended, known entry_ptrs overwritten in place
   if (h->hostRowOfPtr.size() < (size_t)maxPtr + 1) h->hostRowOfPtr.resize((size_t)maxPtr + 1, -1);
   std::vector<u32> dst(t->num_rows);
@@ -2129,12 +2132,44 @@ static jpp_b200_status add_entry_rows_impl(jpp_b200_handle* h, const jpp_b200_en
     d.dRowOfPtr = nullptr;
     d.ptrCap = limit + limit / 4 + 1024;
     CU_CHECK(h, cudaMalloc(&d.dRowOfPtr, (size_t)d.ptrCap * 4));
+    CU_CHECK(h, cudaMemcpyAsync(d.dRowOfPtr, h->hostRowOfPtr.data(), (size_t)limit * 4, cudaMemcpyHostToDevice, st));
+  } else {
+    // the span of the map that holds the new entries (the others in it are rewritten with the values a
+    // batch in flight may be reading: harmless)
+    i32 minPtr = maxPtr;
+    for (u32 i = 0; i < t->num_rows; ++i) minPtr = std::min(minPtr, t->entry_ptr[i]);
+    CU_CHECK(h, cudaMemcpyAsync(d.dRowOfPtr + minPtr, h->hostRowOfPtr.data() + minPtr, (size_t)(maxPtr - minPtr + 1) * 4,
+                                cudaMemcpyHostToDevice, st));
   }
-  CU_CHECK(h, cudaMemcpyAsync(d.dRowOfPtr, h->hostRowOfPtr.data(), (size_t)limit * 4, cudaMemcpyHostToDevice, st));
-  d.ptrLimit = limit;
+  if (limit > d.ptrLimit) d.ptrLimit = limit;
   CU_CHECK(h, cudaStreamSynchronize(st));
-  h->resident = false;
   return JPP_B200_OK;
+}
+
+static jpp_b200_status reserve_entry_rows_impl(jpp_b200_handle* h, uint32_t maxRows, uint32_t ptrLimit) {
+  if (!h) return JPP_B200_INVALID_PARAMETER;
+  if (!h->ownsModel) return fail(h, JPP_B200_INVALID_STATE, "not the owning handle");
+  CU_CHECK(h, cudaSetDevice(h->device));
+  if (!h->tableStream) CU_CHECK(h, cudaStreamCreateWithFlags(&h->tableStream, cudaStreamNonBlocking));
+  auto& d = h->dic;
+  const u32 es = h->hm.ft.entrySize;
+  CU_CHECK(h, grow_device(&d.dRows, &d.rowCap, maxRows * es, d.numRows * es, h->tableStream));
+  if (h->hasRnn) CU_CHECK(h, grow_device(&d.dRnnId, &d.idCap, maxRows, d.numRows, h->tableStream));
+  if (ptrLimit > d.ptrCap) {
+    if (h->hostRowOfPtr.size() < ptrLimit) h->hostRowOfPtr.resize(ptrLimit, -1);
+    i32* np = nullptr;
+    CU_CHECK(h, cudaMalloc(&np, (size_t)ptrLimit * 4));
+    CU_CHECK(h, cudaMemcpy(np, h->hostRowOfPtr.data(), (size_t)ptrLimit * 4, cudaMemcpyHostToDevice));
+    if (d.dRowOfPtr) cudaFree(d.dRowOfPtr);
+    d.dRowOfPtr = np;
+    d.ptrCap = ptrLimit;
+    d.ptrLimit = ptrLimit;
+  }
+  return JPP_B200_OK;
+}
+
+jpp_b200_status jpp_b200_reserve_entry_rows(jpp_b200_handle* h, uint32_t max_rows, uint32_t entry_ptr_limit) {
+  return guarded(h, [&] { return reserve_entry_rows_impl(h, max_rows, entry_ptr_limit); });
 }
 
 jpp_b200_status jpp_b200_add_entry_rows(jpp_b200_handle* h, const jpp_b200_entry_table* rows) {

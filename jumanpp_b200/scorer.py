@@ -77,7 +77,7 @@ def load_library() -> C.CDLL:
 
 EXPORTED_SYMBOLS = ["jpp_b200_create", "jpp_b200_set_config", "jpp_b200_score_batch", "jpp_b200_upload_batch",
                     "jpp_b200_score_resident", "jpp_b200_download_result", "jpp_b200_get_counters", "jpp_b200_add_entry_rows",
-                    "jpp_b200_alloc_pinned", "jpp_b200_free_pinned",
+                    "jpp_b200_alloc_pinned", "jpp_b200_free_pinned", "jpp_b200_reserve_entry_rows",
                     "jpp_b200_last_error", "jpp_b200_destroy", "jpp_b200_abi_version", "jpp_b200_build_info"]
 
 
