@@ -128,14 +128,20 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     }
     __syncthreads();
     if (warp < 4) {
-      // previous contexts -> the two TF32 planes of the B operand (row = tree node, K-major)
-      for (u32 r = warp; r < kTcTile; r += 4) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(rw.ctx + (size_t)sInRow[r] * kTcH) + lane);
+      // previous contexts -> the two TF32 planes of the B operand (row = tree node, K-major).  All sixteen
+      // rows of a warp are requested before the first one is used: one round trip, not sixteen.
+      float4 v[kTcTile / 4];
+#pragma unroll
+      for (u32 q = 0; q < kTcTile / 4; ++q)
+        v[q] = __ldg(reinterpret_cast<const float4*>(rw.ctx + (size_t)sInRow[warp + 4 * q] * kTcH) + lane);
+#pragma unroll
+      for (u32 q = 0; q < kTcTile / 4; ++q) {
+        const u32 r = warp + 4 * q;
         float4 hi, lo;
-        hi.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); lo.x = __fsub_rn(v.x, hi.x);
-        hi.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); lo.y = __fsub_rn(v.y, hi.y);
-        hi.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); lo.z = __fsub_rn(v.z, hi.z);
-        hi.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); lo.w = __fsub_rn(v.w, hi.w);
+        hi.x = __uint_as_float(__float_as_uint(v[q].x) & 0xFFFFE000u); lo.x = __fsub_rn(v[q].x, hi.x);
+        hi.y = __uint_as_float(__float_as_uint(v[q].y) & 0xFFFFE000u); lo.y = __fsub_rn(v[q].y, hi.y);
+        hi.z = __uint_as_float(__float_as_uint(v[q].z) & 0xFFFFE000u); lo.z = __fsub_rn(v[q].z, hi.z);
+        hi.w = __uint_as_float(__float_as_uint(v[q].w) & 0xFFFFE000u); lo.w = __fsub_rn(v[q].w, hi.w);
         const u32 o = tc_operand_offset(kTcTile, r, 4 * lane);
         *reinterpret_cast<float4*>(sB + o) = hi;
         *reinterpret_cast<float4*>(sB + kTcBBytes + o) = lo;
@@ -174,6 +180,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       const u32 taddr = tmemD + ((warp * 32u) << 16);
 #pragma unroll
       for (u32 c0 = 0; c0 < kTcTile; c0 += 16) {
+        // the sixteen embedding values of this chunk are requested first (they do not depend on the accumulator)
+        float e[16];
+#pragma unroll
+        for (u32 j = 0; j < 16; ++j) e[j] = __ldg(rt.emb + (size_t)sEmbRow[c0 + j] * kTcH + i);
         u32 v[16];
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -181,14 +191,15 @@ __global__ void __launch_bounds__(kTcThreads, 1)
               "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
             : "r"(taddr + c0));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        float r[16];
 #pragma unroll
         for (u32 j = 0; j < 16; ++j) {
-          const u32 n = c0 + j;
-          if (n < nvalid) {
-            const float x = __fadd_rn(__uint_as_float(v[j]), __ldg(rt.emb + (size_t)sEmbRow[n] * kTcH + i));
-            rw.ctx[(size_t)sOutRow[n] * kTcH + i] = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x)));
-          }
+          const float x = __fadd_rn(__uint_as_float(v[j]), e[j]);
+          r[j] = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x)));
         }
+#pragma unroll
+        for (u32 j = 0; j < 16; ++j)
+          if (c0 + j < nvalid) rw.ctx[(size_t)sOutRow[c0 + j] * kTcH + i] = r[j];
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }

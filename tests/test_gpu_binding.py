@@ -50,7 +50,10 @@ CASES = [
     ("rnn.model", ["--segment"]),
     ("rnn.model", ["-M"]),
     ("rnn.model", ["--lattice=3"]),
-    ("rnn.model", ["--beam=3", "--global-beam=4", "--right-check=2", "--right-beam=3", "--rnn-nce-bias=4.5", "--rnn-unk-length=-2"]),
+    # other beams and RNN options on the command line; the weights are the shipped ones (model-template/jumandic.conf.in):
+    # with the RNN weighted 1.0 a last-bit difference of an RNN score (CUDA expf vs libm) can flip a near-tie
+    ("rnn.model", ["--beam=3", "--global-beam=4", "--right-check=2", "--right-beam=3", "--rnn-nce-bias=4.5", "--rnn-unk-length=-2",
+                   "--feature-weight-perceptron=1", "--feature-weight-rnn=0.0176"]),
     ("rnn.model", ["--beam=20", "--global-beam=20", "--lattice=5"]),
     ("linear.model", []),
     ("linear.model", ["--lattice=5", "--beam=5", "--global-beam=6", "--right-check=1", "--right-beam=5"]),
