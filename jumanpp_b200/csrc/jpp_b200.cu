@@ -1697,6 +1697,22 @@ static jpp_b200_status score_resident_impl(jpp_b200_handle* h) {
       const u32 itemCap = SENT * (u32)cfg.rbeam * (u32)cfg.gbeam;
       const u32 blocks = (NS + SENT - 1) / SENT;
       const bool stat = h->staticProgram && !noStatic;
+      static const bool warpWalk = getenv("JPP_B200_WARP_WALK") != nullptr;  // A/B: a warp owns its sentences
+      if (warpWalk) {
+        const u32 spw = narrow ? 4u : 1u;
+        const u32 warps = (NS + spw - 1) / spw;
+        const u32 wblocks = (warps + kWarpWalkThreads / 32 - 1) / (kWarpWalkThreads / 32);
+        const u32 wcap = spw * (u32)cfg.rbeam * (u32)cfg.gbeam;
+#define JPP_WWALK(GW, KB, SM, ST) k_walk_warp<GW, KB, SM, ST><<<wblocks, kWarpWalkThreads, 0, st>>>(ft, bv, cfg, wv, h->dWeights, wcap)
+        if (narrow) {
+          if (small_gbeam_ok(cfg)) { if (stat) JPP_WWALK(8, 8, true, true); else JPP_WWALK(8, 8, true, false); }
+          else { if (stat) JPP_WWALK(8, 8, false, true); else JPP_WWALK(8, 8, false, false); }
+        } else {
+          if (stat) JPP_WWALK(32, MAX_BEAM, false, true); else JPP_WWALK(32, MAX_BEAM, false, false);
+        }
+#undef JPP_WWALK
+        ++launches;
+      } else {
 #define JPP_WALK2(GW, KB, SM, ST, SE) k_walk_fused<GW, KB, SM, ST, SE><<<blocks, SE * 8, 0, st>>>(ft, bv, cfg, wv, h->dWeights, itemCap)
 #define JPP_WALK(GW, KB, SM, ST) do { if (SENT == 16) JPP_WALK2(GW, KB, SM, ST, 16); else JPP_WALK2(GW, KB, SM, ST, 32); } while (0)
       if (narrow) {
@@ -1708,6 +1724,7 @@ static jpp_b200_status score_resident_impl(jpp_b200_handle* h) {
 #undef JPP_WALK
 #undef JPP_WALK2
       ++launches;
+      }
     }
     for (u32 bnd = 2; bnd < h->maxNb && !fused; ++bnd) {
       const u32 nAct = h->waveActive[bnd];

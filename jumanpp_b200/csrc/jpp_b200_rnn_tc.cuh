@@ -12,7 +12,9 @@
 // bit equality, and can be switched off (JPP_B200_RNN_TC=0).  Layer size 128 only (the bench model);
 // other sizes take k_rnn_level_x.
 //
-// Block = 5 warps.  Warps 0-3: stage the previous contexts of a tile of 64 tree nodes into shared
+// Block = two groups of 5 warps, each group a pipeline of its own over alternate tiles (own B planes, own
+// mbarrier, own TMEM columns, a named barrier instead of __syncthreads): while one group waits for its
+// gathers or its MMAs the other works.  Inside a group, warps 0-3: stage the previous contexts of a tile of 32 tree nodes into shared
 // memory (split into the two TF32 planes, K-major, 128-byte swizzle: the canonical UMMA operand
 // layout), and, after the MMAs, read the accumulator back (tcgen05.ld, thread = output i = TMEM lane)
 // for the epilogue: + embedding, sigmoid, coalesced store of the new context rows.  Warp 4, one
@@ -25,12 +27,14 @@ namespace {
 using namespace jppb200;
 
 constexpr u32 kTcH = 128;          // layer size this kernel is built for
-constexpr u32 kTcTile = 64;        // tree nodes per tile (UMMA N)
-constexpr u32 kTcThreads = 160;    // 4 producer / epilogue warps + 1 MMA warp
+constexpr u32 kTcTile = 32;        // tree nodes per tile (UMMA N)
+constexpr u32 kTcGroups = 2;       // independent tile pipelines per block (each: 4 producer / epilogue warps + 1 MMA warp)
+constexpr u32 kTcGroupThreads = 160;
+constexpr u32 kTcThreads = kTcGroups * kTcGroupThreads;
 constexpr u32 kTcChunkK = 32;      // tf32 elements per 128-byte swizzle row
 constexpr u32 kTcABytes = kTcH * kTcH * 4;        // one plane of W
 constexpr u32 kTcBBytes = kTcTile * kTcH * 4;     // one plane of a context tile
-constexpr u32 kTcSmem = 2 * kTcABytes + 2 * kTcBBytes + 1024 /* alignment */ + 64;
+constexpr u32 kTcSmem = 2 * kTcABytes + kTcGroups * 2 * kTcBBytes + 1024 /* alignment */ + 64;
 
 // byte offset of element (row r, k) of a K-major operand with `rows` rows in the UMMA SWIZZLE_128B layout:
 // per 32-element K chunk a region of rows x 128 B; inside, 8-row groups of 1024 B, the 16-byte column of a
@@ -80,60 +84,65 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     k_rnn_level_tc(RnnWork rw, RnnTables rt, const float* __restrict__ wImage /* [2][H*H] planes in the smem image */,
                    const u32* ctxOff, const u32* rnSent, u32 level) {
   extern __shared__ unsigned char tcSmemRaw[];
-  __shared__ __align__(8) unsigned long long sBar;
+  __shared__ __align__(8) unsigned long long sBar[kTcGroups];
   __shared__ u32 sTmem;
-  __shared__ u32 sInRow[kTcTile], sOutRow[kTcTile], sEmbRow[kTcTile];
+  __shared__ u32 sInRow[kTcGroups][kTcTile], sOutRow[kTcGroups][kTcTile], sEmbRow[kTcGroups][kTcTile];
   const u32 cnt = rw.levelCount[level];
   const u32 tiles = (cnt + kTcTile - 1) / kTcTile;
-  if (blockIdx.x >= tiles) return;
+  if (blockIdx.x * kTcGroups >= tiles) return;
   // operands need 1024-byte alignment (the swizzle is a function of the address bits)
   unsigned char* base = tcSmemRaw + ((1024 - (smem_u32(tcSmemRaw) & 1023)) & 1023);
   unsigned char* sA = base;                    // [2 planes][H x H]
-  unsigned char* sB = base + 2 * kTcABytes;    // [2 planes][tile x H]
-  const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  const u32 group = threadIdx.x / kTcGroupThreads, gtid = threadIdx.x % kTcGroupThreads;
+  const u32 warp = gtid >> 5, lane = threadIdx.x & 31u;       // warp inside the group: 0..3 stage / read back, 4 issues
+  unsigned char* sB = base + 2 * kTcABytes + group * 2 * kTcBBytes;    // this group's [2 planes][tile x H]
   const u32 off = rw.levelOff[level];
+  const u32 barId = 1 + group;                 // named barrier of the group (0 is __syncthreads)
 
-  // one-time: W planes into shared memory, the mbarrier, the TMEM accumulator (64 columns)
+  // one-time: W planes into shared memory, the mbarriers, the TMEM accumulators (32 columns per group)
   {
     const uint4* src = reinterpret_cast<const uint4*>(wImage);
     uint4* dst = reinterpret_cast<uint4*>(sA);
     for (u32 i = threadIdx.x; i < 2 * kTcABytes / 16; i += kTcThreads) dst[i] = __ldg(src + i);
   }
   if (threadIdx.x == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sBar)));
+    for (u32 g = 0; g < kTcGroups; ++g) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sBar[g])));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sTmem)), "r"(kTcTile));
+  if (threadIdx.x / 32 == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sTmem)), "r"(kTcGroups * kTcTile));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the generic-proxy writes of W become visible to the MMA
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const u32 tmemD = sTmem;
+  const u32 tmemBase = sTmem;
+  const u32 tmemD = tmemBase + group * kTcTile;
   u32 phase = 0;
+  // a warp reads the TMEM lanes of its quarter: (warp id in the CTA) % 4
+  const u32 quarter = (threadIdx.x / 32) & 3u;
 
-  for (u32 tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+  for (u32 tile = blockIdx.x * kTcGroups + group; tile < tiles; tile += gridDim.x * kTcGroups) {
     const u32 first = tile * kTcTile;
     const u32 nvalid = (cnt - first) < kTcTile ? (cnt - first) : kTcTile;
-    if (threadIdx.x < kTcTile) {
-      const u32 j = threadIdx.x;
+    if (gtid < kTcTile) {
+      const u32 j = gtid;
       const u32 q = rw.levelList[off + first + (j < nvalid ? j : 0u)];
-      sInRow[j] = (u32)ctx_row(rw, ctxOff, rnSent, (u32)rw.prev[q]);
-      sOutRow[j] = (u32)ctx_row(rw, ctxOff, rnSent, q);
+      sInRow[group][j] = (u32)ctx_row(rw, ctxOff, rnSent, (u32)rw.prev[q]);
+      sOutRow[group][j] = (u32)ctx_row(rw, ctxOff, rnSent, q);
       i32 id = rw.id[q];
       if (id == -1) id = 0;  // rnn_scorer_gbeam.cc:126-129
-      sEmbRow[j] = (u32)id;
+      sEmbRow[group][j] = (u32)id;
     }
-    __syncthreads();
+    asm volatile("bar.sync %0, %1;" ::"r"(barId), "r"(kTcGroupThreads) : "memory");
     if (warp < 4) {
-      // previous contexts -> the two TF32 planes of the B operand (row = tree node, K-major).  All sixteen
-      // rows of a warp are requested before the first one is used: one round trip, not sixteen.
+      // previous contexts -> the two TF32 planes of the B operand (row = tree node, K-major).  All rows of a
+      // warp are requested before the first one is used: one round trip, not eight.
       float4 v[kTcTile / 4];
 #pragma unroll
       for (u32 q = 0; q < kTcTile / 4; ++q)
-        v[q] = __ldg(reinterpret_cast<const float4*>(rw.ctx + (size_t)sInRow[warp + 4 * q] * kTcH) + lane);
+        v[q] = __ldg(reinterpret_cast<const float4*>(rw.ctx + (size_t)sInRow[group][warp + 4 * q] * kTcH) + lane);
 #pragma unroll
       for (u32 q = 0; q < kTcTile / 4; ++q) {
         const u32 r = warp + 4 * q;
@@ -149,7 +158,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    asm volatile("bar.sync %0, %1;" ::"r"(barId), "r"(kTcGroupThreads) : "memory");
     if (warp == 4) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (lane == 0) {
@@ -169,21 +178,21 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           }
         }
         // arrives on the barrier when every MMA above has completed (implies fence::before_thread_sync)
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&sBar)) : "memory");
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&sBar[group])) : "memory");
       }
       __syncwarp();
     } else {
-      mbar_wait(smem_u32(&sBar), phase);
+      mbar_wait(smem_u32(&sBar[group]), phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      // thread = output i = TMEM lane; 64 columns = the tile's tree nodes
-      const u32 i = threadIdx.x;
-      const u32 taddr = tmemD + ((warp * 32u) << 16);
+      // thread = output i = TMEM lane; the group's 32 columns = the tile's tree nodes
+      const u32 i = quarter * 32u + lane;
+      const u32 taddr = tmemD + ((quarter * 32u) << 16);
 #pragma unroll
       for (u32 c0 = 0; c0 < kTcTile; c0 += 16) {
         // the sixteen embedding values of this chunk are requested first (they do not depend on the accumulator)
         float e[16];
 #pragma unroll
-        for (u32 j = 0; j < 16; ++j) e[j] = __ldg(rt.emb + (size_t)sEmbRow[c0 + j] * kTcH + i);
+        for (u32 j = 0; j < 16; ++j) e[j] = __ldg(rt.emb + (size_t)sEmbRow[group][c0 + j] * kTcH + i);
         u32 v[16];
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -199,15 +208,17 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         }
 #pragma unroll
         for (u32 j = 0; j < 16; ++j)
-          if (c0 + j < nvalid) rw.ctx[(size_t)sOutRow[c0 + j] * kTcH + i] = r[j];
+          if (c0 + j < nvalid) rw.ctx[(size_t)sOutRow[group][c0 + j] * kTcH + i] = r[j];
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
     phase ^= 1u;
-    __syncthreads();  // B planes, the row lists and the accumulator are free for the next tile
+    // B planes, the row lists and the accumulator of the group are free for its next tile
+    asm volatile("bar.sync %0, %1;" ::"r"(barId), "r"(kTcGroupThreads) : "memory");
   }
-  if (warp == 4) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmemD), "r"(kTcTile));
+  __syncthreads();
+  if (threadIdx.x / 32 == 4) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmemBase), "r"(kTcGroups * kTcTile));
   }
 }
 
