@@ -62,10 +62,10 @@ def log(*a):
 
 
 # ------------------------------------------------------------------ workload --
-def prepare_workload(args, rank: int, world: int = 1) -> dict:
+def prepare_workload(args, rank: int, world: int = 1, dist=None) -> dict:
     wl = WORKLOADS[args.workload]
     cache = Path(args.cache)
-    sharded = args.shard_corpus and world > 1
+    sharded = getattr(args, "shard_corpus", False) and world > 1
     # weak scaling: every rank its own corpus (seed + rank); --shard-corpus: ONE corpus, rank r stages its shard
     seed = args.seed if sharded else args.seed + rank
     tag = f"{args.workload}_d{args.dict_rows}_n{args.sentences}_l{args.min_len}-{args.max_len}_s{seed}_w{args.log2w}"
@@ -86,14 +86,23 @@ def prepare_workload(args, rank: int, world: int = 1) -> dict:
     t0 = time.time()
     surfaces = synth.write_dictionary(dic, args.dict_rows, 20260923)
     if sharded:
-        # the whole corpus is generated (deterministic), the rank keeps its contiguous shard, balanced by codepoints
-        full = d / "corpus_full.txt"
-        synth.write_corpus(full, args.sentences, args.min_len, args.max_len, seed, surfaces)
-        lines = full.read_text(encoding="utf-8").splitlines()
+        # ONE corpus = `world` chunks generated side by side (rank c writes chunk c, seed 1000 * seed + c), concatenated
+        # in chunk order; every rank then reads the chunks and keeps its contiguous shard, balanced by codepoints
+        common = cache / (tag.rsplit("_shard", 1)[0] + "_chunks")
+        common.mkdir(parents=True, exist_ok=True)
+        per = [args.sentences // world + (1 if c < args.sentences % world else 0) for c in range(world)]
+        synth.write_corpus(common / f"chunk_{rank}.txt", per[rank], args.min_len, args.max_len, 1000 * seed + rank, surfaces)
+        (common / f"chunk_{rank}.done").write_text("ok")
+        if dist is not None:
+            dist.barrier()
+        while not all((common / f"chunk_{c}.done").exists() for c in range(world)):
+            time.sleep(0.2)
+        lines = []
+        for c in range(world):
+            lines += (common / f"chunk_{c}.txt").read_text(encoding="utf-8").splitlines()
         bounds = shard.shard_bounds(np.array([len(x) for x in lines], np.int64), world)
         lo, hi = int(bounds[rank]), int(bounds[rank + 1])
         corpus.write_text("\n".join(lines[lo:hi]) + "\n", encoding="utf-8")
-        full.unlink()
         info["shard"] = {"lo": lo, "hi": hi, "total": len(lines), "bounds": [int(x) for x in bounds]}
         (d / "shard.json").write_text(json.dumps(info["shard"]))
     else:
@@ -329,6 +338,32 @@ def workload_config(args, wl, world: int = 1) -> dict:
     return c
 
 
+def bind_to_gpu_numa(device: int) -> dict:
+    """Keeps this rank's threads (and so its first-touched and pinned host pages) on the NUMA node the GPU
+    hangs off: eight ranks uploading ~1 GB each per step across the socket link is what made e2e creep at
+    N = 8.  Returns what was done; never fails the run."""
+    import torch
+    info = {"bound": False}
+    try:
+        p = torch.cuda.get_device_properties(device)
+        addr = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        node = int(Path(f"/sys/bus/pci/devices/{addr}/numa_node").read_text())
+        info.update(pci=addr, node=node)
+        if node < 0:
+            return info
+        cpus = set()
+        for part in Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        mine = os.sched_getaffinity(0) & cpus
+        if mine:
+            os.sched_setaffinity(0, mine)
+            info.update(bound=True, cpus=len(mine))
+    except Exception as e:
+        info["error"] = repr(e)
+    return info
+
+
 # --------------------------------------------------------------- product arm --
 def product_arm(args, rank: int, world: int, local_rank: int) -> None:
     import torch
@@ -342,7 +377,10 @@ def product_arm(args, rank: int, world: int, local_rank: int) -> None:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from jumanpp_b200.scorer import LatticeScorer, pinned_copy
 
-    info = prepare_workload(args, rank, world)
+    info = prepare_workload(args, rank, world, dist)
+    all_cpus = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa(local_rank) if not args.no_numa_bind else {"bound": False}
+    log(f"rank {rank}: NUMA {numa}")
     t0 = time.time()
     model, cfg, windows, table = load_staged(info, args, pin=pinned_copy)
     n_sent = sum(w.num_sentences for w in windows)
@@ -448,6 +486,21 @@ def product_arm(args, rank: int, world: int, local_rank: int) -> None:
                     traffic = t["dram_bytes_per_launch"]
             except Exception:
                 pass
+        # the ceiling of the access pattern itself on this device: independent random 4-byte reads of the same
+        # table (jpp_b200_gather_probe, after the timed region), best of three in-flight depths
+        probe = None
+        if not args.no_gather_probe:
+            try:
+                rates = {ilp: scorer.gather_probe(1 << 31, ilp, 8) for ilp in (4, 8, 16)}
+                best = max(rates.values())
+                issued = float(cnt["walk_gathers_issued"])
+                probe = {"peak_gathers_per_s": best, "by_ilp": rates,
+                         "achieved_gathers_per_s": issued / (walk_ms / 1000.0),
+                         "frac": issued / (walk_ms / 1000.0) / best,
+                         "what": "table reads the walk issues per second / random 4-byte reads per second the device serves "
+                                 "from the same table with nothing else to do (8 blocks of 256 threads per SM)"}
+            except Exception as e:   # a diagnostic never fails the bench line
+                probe = {"error": str(e)}
         line = {
             "metric": "sentences/sec Jumandic beam=5 (lattice-scoring path)", "value": value, "unit": "sentences/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dev_s / args.steps,
@@ -472,12 +525,15 @@ def product_arm(args, rank: int, world: int, local_rank: int) -> None:
                          "gathers_per_launch": int(cnt["walk_gathers"]),
                          "gathers_issued_per_launch": int(cnt["walk_gathers_issued"]), "traffic": traffic,
                          "per": "step (all windows)"},
+            "gather_roofline": probe,
             "work": {"sentences": int(total_sent), "nodes": int(counts[2].item()), "gathers": int(counts[1].item()),
                      "rnn_nodes": int(cnt["rnn_nodes"]), "rnn_scores": int(cnt["rnn_scores"]),
                      "failed_sentences": int(counts[3].item())},
         }
+        line["numa"] = numa
         if gathered is not None:
             line["sharded"] = {k: v for k, v in gathered.items() if k not in ("lens", "nodes")}
+        os.sched_setaffinity(0, all_cpus)   # the CPU legs below use every core this process was given
         if not args.no_cpu_baseline:
             line.update(cpu_baseline_leg(args, info, model, cfg, windows[0], scorer, results[0]))
         if args.e2e_full and world == 1:
@@ -615,6 +671,8 @@ def main() -> None:
     ap.add_argument("--cache", default=os.environ.get("JPP_B200_CACHE", "/tmp/jpp_b200_cache"))
     ap.add_argument("--cpu-sample-per-core", type=int, default=1500)
     ap.add_argument("--parity-sample", type=int, default=2000)
+    ap.add_argument("--no-gather-probe", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true")
     ap.add_argument("--window", type=int, default=131072,
                     help="sentences per jpp_b200_score_batch call (larger workloads are streamed window by window)")
     ap.add_argument("--shard-corpus", action="store_true",

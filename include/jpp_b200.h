@@ -400,6 +400,13 @@ jpp_b200_status jpp_b200_reserve_entry_rows(jpp_b200_handle* h, uint32_t max_row
 jpp_b200_status jpp_b200_get_counters(const jpp_b200_handle* h,
                                       jpp_b200_counters* out);
 
+/* Diagnostic, not part of the scored path: the rate at which THIS device serves independent 4-byte reads
+ * at random indices of the handle's perceptron table (about `gathers` of them, `ilp` = 4 / 8 / 16 in flight
+ * per thread, `blocks_per_sm` blocks of 256 threads; 0 = defaults).  bench.py reports the scoring kernels'
+ * table reads per second against it ("HBM-gather roofline"). */
+jpp_b200_status jpp_b200_gather_probe(jpp_b200_handle* h, uint64_t gathers, uint32_t ilp,
+                                      uint32_t blocks_per_sm, double* gathers_per_second);
+
 /* Page-locked host memory for the staged batch / result arrays (the H2D / D2H copies of a
  * batch in pinned memory run at full PCIe rate and asynchronously).  The host side needs no
  * CUDA header: this library is the only thing it links. */

@@ -25,28 +25,23 @@ def build(force: bool = False, verbose: bool = False, defines: list[str] | None 
     """`defines`/`out` build tuning variants (e.g. JPP_FUSED_MINBLOCKS) beside the product; the default build is the product."""
     newest = max(p.stat().st_mtime for p in SOURCES + HEADERS)
     if out is not None:
-        global LIB
-        lib_default, LIB = LIB, Path(out)
-        try:
-            return _compile(verbose, defines or [])
-        finally:
-            LIB = lib_default
+        return _compile(verbose, defines or [], Path(out))
     if not force and LIB.exists() and LIB.stat().st_mtime >= newest:
         return LIB
-    return _compile(verbose, defines or [])
+    return _compile(verbose, defines or [], LIB)
 
 
-def _compile(verbose: bool, defines: list[str]) -> Path:
+def _compile(verbose: bool, defines: list[str], lib: Path) -> Path:
     cmd = [nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
            "-fmad=false", "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v" if verbose else "-O3",
            *[f"-D{d}" for d in defines],
-           f"-I{ROOT / 'include'}", f"-I{PKG / 'csrc'}", *map(str, SOURCES), "-o", str(LIB), "-lcudart", "-lpthread"]
+           f"-I{ROOT / 'include'}", f"-I{PKG / 'csrc'}", *map(str, SOURCES), "-o", str(lib), "-lcudart", "-lpthread"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + r.stdout[-3000:] + r.stderr[-6000:])
     if verbose:
         print(r.stderr)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":

@@ -145,6 +145,7 @@ template <bool LEAN>
 __global__ void __launch_bounds__(128) k_t0(const FeatTables* __restrict__ ftg, BatchView bv, const float* __restrict__ w) {
   // per-thread (divergent) table indices here: shared memory, not the constant bank
   __shared__ FeatTables ft;
+  extern __shared__ __align__(16) unsigned long long sPrim[];  // [nPrim][128]: the threads' primitive values
   {
     const u32* src = reinterpret_cast<const u32*>(ftg);
     u32* dst = reinterpret_cast<u32*>(&ft);
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(128) k_t0(const FeatTables* __restrict__ ftg, 
   __syncthreads();
   const WLoadDirect wl{w};
   const u32 node = blockIdx.x * blockDim.x + threadIdx.x;
-  if (node < bv.totalNodes) t0_node<WLoadDirect, LEAN>(ft, bv, wl, node);
+  if (node < bv.totalNodes) t0_node<WLoadDirect, LEAN>(ft, bv, wl, node, reinterpret_cast<u64*>(sPrim) + threadIdx.x, blockDim.x);
 }
 
 // ---- wavefront walk kernels (see jpp_b200_kernels.h "wavefront walk") ----
@@ -1065,6 +1066,29 @@ struct DevBuf {
 
 namespace { struct WaveProfile; }
 
+// ---------------------------------------------------------------- gather probe (diagnostic) ----
+// What this GPU can do for the access pattern of the scored path and nothing else: every thread issues
+// `perThread` independent 4-byte reads at hash-random indices of the handle's own perceptron table, ILP at a
+// time, the values summed.  No lattice, no ordering, no barriers: the rate it reaches is the ceiling any
+// kernel that gathers from this table can have ("HBM-gather roofline"), bench.py quotes the walk against it.
+template <int ILP>
+__global__ void __launch_bounds__(256) k_gather_probe(const float* __restrict__ w, u32 mask, u64 seed, u32 perThread, float* sink) {
+  u64 x = (seed ^ ((u64)(blockIdx.x * blockDim.x + threadIdx.x) * 0x9E3779B97F4A7C15ull)) | 1ull;
+  float acc = 0.f;
+  for (u32 i = 0; i < perThread; i += ILP) {
+    float v[ILP];
+#pragma unroll
+    for (int j = 0; j < ILP; ++j) {
+      x ^= x >> 12; x ^= x << 25; x ^= x >> 27;   // xorshift64*
+      const u32 idx = (u32)((x * 0x2545F4914F6CDD1Dull) >> 32) & mask;
+      v[j] = __ldg(w + idx);
+    }
+#pragma unroll
+    for (int j = 0; j < ILP; ++j) acc += v[j];
+  }
+  if (acc == 1234567.0f) *sink = acc;  // keeps the loads alive
+}
+
 struct jpp_b200_handle {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -1292,6 +1316,8 @@ static jpp_b200_status create_impl(const jpp_b200_model* model, const jpp_b200_c
   h->smCount = prop.multiProcessorCount;
   CREATE_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CREATE_CHECK(cudaFuncSetAttribute(k_w_prescore, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kCacheSlots * 8)));
+  CREATE_CHECK(cudaFuncSetAttribute(k_t0<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MAX_PRIM * 128 * 8)));
+  CREATE_CHECK(cudaFuncSetAttribute(k_t0<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MAX_PRIM * 128 * 8)));
   CREATE_CHECK(cudaFuncSetAttribute(k_w_items, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kCacheSlots * 8)));
   for (auto& e : h->ev) CREATE_CHECK(cudaEventCreate(&e));
   CREATE_CHECK(cudaMalloc(&h->dFt, sizeof(FeatTables)));
@@ -1670,8 +1696,9 @@ static jpp_b200_status score_resident_impl(jpp_b200_handle* h) {
   CU_CHECK(h, cudaEventRecord(h->ev[2], st));
   {
     static const bool t0Array = getenv("JPP_B200_T0_ARRAY") != nullptr;  // A/B: all patterns in a local array
-    if (t0Array) k_t0<false><<<(NN + 127) / 128, 128, 0, st>>>(h->dFt, bv, h->dWeights);
-    else k_t0<true><<<(NN + 127) / 128, 128, 0, st>>>(h->dFt, bv, h->dWeights);
+    const size_t primBytes = (size_t)std::max(1u, h->hm.ft.nPrim) * 128 * 8;
+    if (t0Array) k_t0<false><<<(NN + 127) / 128, 128, primBytes, st>>>(h->dFt, bv, h->dWeights);
+    else k_t0<true><<<(NN + 127) / 128, 128, primBytes, st>>>(h->dFt, bv, h->dWeights);
   }
   CU_CHECK(h, cudaGetLastError());
   CU_CHECK(h, cudaEventRecord(h->ev[3], st));
@@ -1697,22 +1724,6 @@ static jpp_b200_status score_resident_impl(jpp_b200_handle* h) {
       const u32 itemCap = SENT * (u32)cfg.rbeam * (u32)cfg.gbeam;
       const u32 blocks = (NS + SENT - 1) / SENT;
       const bool stat = h->staticProgram && !noStatic;
-      static const bool warpWalk = getenv("JPP_B200_WARP_WALK") != nullptr;  // A/B: a warp owns its sentences
-      if (warpWalk) {
-        const u32 spw = narrow ? 4u : 1u;
-        const u32 warps = (NS + spw - 1) / spw;
-        const u32 wblocks = (warps + kWarpWalkThreads / 32 - 1) / (kWarpWalkThreads / 32);
-        const u32 wcap = spw * (u32)cfg.rbeam * (u32)cfg.gbeam;
-#define JPP_WWALK(GW, KB, SM, ST) k_walk_warp<GW, KB, SM, ST><<<wblocks, kWarpWalkThreads, 0, st>>>(ft, bv, cfg, wv, h->dWeights, wcap)
-        if (narrow) {
-          if (small_gbeam_ok(cfg)) { if (stat) JPP_WWALK(8, 8, true, true); else JPP_WWALK(8, 8, true, false); }
-          else { if (stat) JPP_WWALK(8, 8, false, true); else JPP_WWALK(8, 8, false, false); }
-        } else {
-          if (stat) JPP_WWALK(32, MAX_BEAM, false, true); else JPP_WWALK(32, MAX_BEAM, false, false);
-        }
-#undef JPP_WWALK
-        ++launches;
-      } else {
 #define JPP_WALK2(GW, KB, SM, ST, SE) k_walk_fused<GW, KB, SM, ST, SE><<<blocks, SE * 8, 0, st>>>(ft, bv, cfg, wv, h->dWeights, itemCap)
 #define JPP_WALK(GW, KB, SM, ST) do { if (SENT == 16) JPP_WALK2(GW, KB, SM, ST, 16); else JPP_WALK2(GW, KB, SM, ST, 32); } while (0)
       if (narrow) {
@@ -1724,7 +1735,6 @@ static jpp_b200_status score_resident_impl(jpp_b200_handle* h) {
 #undef JPP_WALK
 #undef JPP_WALK2
       ++launches;
-      }
     }
     for (u32 bnd = 2; bnd < h->maxNb && !fused; ++bnd) {
       const u32 nAct = h->waveActive[bnd];
@@ -1813,8 +1823,9 @@ static jpp_b200_status score_resident_impl(jpp_b200_handle* h) {
       const u32 split = rnn_level_split(H);
       const dim3 grid((u32)h->smCount * 2 / split, split);
       const size_t wsBytes = (size_t)H * H * sizeof(float) / split;
-      // JPP_B200_RNN_TC=1: the level step as tcgen05 tensor-core MMAs (3xTF32), layer size 128
-      static const bool tcOn = getenv("JPP_B200_RNN_TC") && atoi(getenv("JPP_B200_RNN_TC")) != 0;
+      // layer size 128: the level step as tcgen05 tensor-core MMAs (3xTF32); JPP_B200_RNN_TC=0 selects the
+      // FFMA kernel (an A/B switch for measurements and for bisecting a numeric difference)
+      static const bool tcOn = !(getenv("JPP_B200_RNN_TC") && atoi(getenv("JPP_B200_RNN_TC")) == 0);
       const bool useTc = tcOn && H == kTcH && h->dRnnWImage != nullptr;
       for (u32 level = 1; level <= h->maxNb; ++level) {
         if (useTc) {
@@ -2206,6 +2217,42 @@ jpp_b200_status jpp_b200_alloc_pinned(size_t bytes, void** out) {
 
 void jpp_b200_free_pinned(void* p) {
   if (p) cudaFreeHost(p);
+}
+
+jpp_b200_status jpp_b200_gather_probe(jpp_b200_handle* h, uint64_t gathers, uint32_t ilp, uint32_t blocks_per_sm,
+                                      double* gathers_per_second) {
+  if (!h || !gathers_per_second || gathers == 0) return JPP_B200_INVALID_PARAMETER;
+  return guarded(h, [&]() -> jpp_b200_status {
+    *gathers_per_second = 0;
+    CU_CHECK(h, cudaSetDevice(h->device));
+    const u32 bps = blocks_per_sm ? std::min<u32>(blocks_per_sm, 8u) : 8u;
+    const u32 blocks = (u32)h->smCount * bps;
+    const u64 threads = (u64)blocks * 256u;
+    const u32 unit = ilp == 4 ? 4u : (ilp == 16 ? 16u : 8u);
+    const u32 perThread = (u32)std::max<u64>(unit, (gathers / threads + unit - 1) / unit * unit);
+    float* sink = nullptr;
+    CU_CHECK(h, cudaMalloc(&sink, sizeof(float)));
+    cudaEvent_t a = nullptr, b = nullptr;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    float best = 0.f;
+    for (int rep = 0; rep < 4; ++rep) {  // the first repetition is the warm-up
+      cudaEventRecord(a, h->stream);
+      const u64 seed = 0xA5A5A5A5u + (u64)rep * 977u;
+      if (unit == 4) k_gather_probe<4><<<blocks, 256, 0, h->stream>>>(h->dWeights, h->hm.ft.mask, seed, perThread, sink);
+      else if (unit == 16) k_gather_probe<16><<<blocks, 256, 0, h->stream>>>(h->dWeights, h->hm.ft.mask, seed, perThread, sink);
+      else k_gather_probe<8><<<blocks, 256, 0, h->stream>>>(h->dWeights, h->hm.ft.mask, seed, perThread, sink);
+      cudaEventRecord(b, h->stream);
+      cudaEventSynchronize(b);
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, a, b);
+      if (rep > 0 && (best == 0.f || ms < best)) best = ms;
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    cudaFree(sink);
+    CU_CHECK(h, cudaGetLastError());
+    if (best > 0.f) *gathers_per_second = (double)threads * perThread / (best * 1e-3);
+    return JPP_B200_OK;
+  });
 }
 
 jpp_b200_status jpp_b200_get_counters(const jpp_b200_handle* h, jpp_b200_counters* out) {

@@ -354,18 +354,19 @@ JPP_HD u64 prim_value(const FeatTables& ft, u32 p, const i32* entry, const i32* 
 }
 
 // hash of pattern p over the primitive values (pattern_feature_codegen.cc:199-313)
-JPP_HD u64 pattern_value(const FeatTables& ft, u32 p, const u64* prim) {
+// primitive i lives at prim[i * ps] (ps = 1: a private array; ps = block size: the block's shared-memory slab)
+JPP_HD u64 pattern_value(const FeatTables& ft, u32 p, const u64* prim, u32 ps = 1) {
   u64 h = ft.patState[p];
   const u32 off = ft.patRefOff[p];
   for (u32 k = 0; k < ft.patRefLen[p]; ++k) {
     const u32 c = ft.patRefPool[off + k];
     const u32 tl = ft.compTrueLen[c], fl = ft.compFalseLen[c];
     if (tl == 0 && fl == 0) {
-      h = mix(h, prim[ft.compPrim[c]]);
-    } else if (prim[ft.compPrim[c]] != 0) {
-      for (u32 t = 0; t < tl; ++t) h = mix(h, prim[ft.branchPool[ft.compTrueOff[c] + t]]);
+      h = mix(h, prim[ft.compPrim[c] * ps]);
+    } else if (prim[ft.compPrim[c] * ps] != 0) {
+      for (u32 t = 0; t < tl; ++t) h = mix(h, prim[ft.branchPool[ft.compTrueOff[c] + t] * ps]);
     } else {
-      for (u32 t = 0; t < fl; ++t) h = mix(h, prim[ft.branchPool[ft.compFalseOff[c] + t]]);
+      for (u32 t = 0; t < fl; ++t) h = mix(h, prim[ft.branchPool[ft.compFalseOff[c] + t] * ps]);
     }
   }
   return h;
@@ -376,7 +377,7 @@ JPP_HD u64 pattern_value(const FeatTables& ft, u32 p, const u64* prim) {
 // 0.6 MB of local memory per SM, evicted through L2 to HBM: ncu showed 28 GB written by a kernel
 // whose output is 5 GB (profiles/r2_ncu_summary.md).  The primitive values (8 B x nPrim) stay.
 template <typename WL, bool LEAN = true>
-JPP_HD void t0_node(const FeatTables& ft, const BatchView& bv, const WL& wl, u32 node) {
+JPP_HD void t0_node(const FeatTables& ft, const BatchView& bv, const WL& wl, u32 node, u64* primStore = nullptr, u32 ps = 1) {
   const u32 gb = bv.nodeBnd[node];
   if (gb == 0xFFFFFFFFu) return;  // node of no valid boundary (failed sentence)
   const u32 sent = bv.bndSent[gb];
@@ -397,16 +398,35 @@ JPP_HD void t0_node(const FeatTables& ft, const BatchView& bv, const WL& wl, u32
   const NodeEntry ne = node_entry(ft, bv, node, sent, ni.entry_ptr);
   const i32* entry = ne.entry;
   const i32* ph = ne.ph;
-  u64 prim[MAX_PRIM];
-  for (u32 i = 0; i < ft.nPrim; ++i) prim[i] = prim_value(ft, i, entry, ph, ni, cps, ncp);
+  // The primitive values are indexed by the feature program (dynamically): as a private array they are
+  // local memory -- ncu r2e: 1.49 G local-load sectors, more than the kernel's 1.31 G sectors of weight
+  // gathers.  The kernel passes a slab of shared memory instead ([primitive][thread]: conflict-free).
+#if defined(__CUDA_ARCH__)
+  u64* prim = primStore;
+#else
+  u64 primLocal[MAX_PRIM];
+  u64* prim = primStore ? primStore : primLocal;
+#endif
+  for (u32 i = 0; i < ft.nPrim; ++i) prim[i * ps] = prim_value(ft, i, entry, ph, ni, cps, ncp);
   u64 pat[LEAN ? 1 : MAX_PAT];
   auto slot_value = [&](u32 slot) -> u64 {
     if (!LEAN) return pat[slot];
     const u32 p = ft.patOfSlot[slot];
-    return p == 0xFFu ? 0ull : pattern_value(ft, p, prim);
+    return p == 0xFFu ? 0ull : pattern_value(ft, p, prim, ps);
   };
   if (!LEAN)
-    for (u32 p = 0; p < ft.nPat; ++p) pat[ft.patIndex[p]] = pattern_value(ft, p, prim);
+    for (u32 p = 0; p < ft.nPat; ++p) pat[ft.patIndex[p]] = pattern_value(ft, p, prim, ps);
+#if defined(__CUDA_ARCH__)
+  if (pstr == 1 && (SP & 1u) == 0) {
+    // the row is 16-byte aligned (SP even, 8-byte slots): half as many stores, whole 16-byte pieces of a sector
+    for (u32 p = 0; p < SP; p += 2) {
+      ulonglong2 v;
+      v.x = slot_value(p);
+      v.y = slot_value(p + 1);
+      *reinterpret_cast<ulonglong2*>(pout + p) = v;
+    }
+  } else
+#endif
   for (u32 p = 0; p < SP; ++p) pout[p * pstr] = slot_value(p);
   // unigram score.  Rows 0..R-2 of a boundary: "float score_part_j = w" for the
   // first uniVars terms then "+=" (pattern_feature_codegen.cc:229-236), summed

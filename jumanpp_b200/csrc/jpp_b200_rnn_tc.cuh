@@ -27,13 +27,20 @@ namespace {
 using namespace jppb200;
 
 constexpr u32 kTcH = 128;          // layer size this kernel is built for
-constexpr u32 kTcTile = 32;        // tree nodes per tile (UMMA N)
-constexpr u32 kTcGroups = 2;       // independent tile pipelines per block (each: 4 producer / epilogue warps + 1 MMA warp)
+#ifndef JPP_TC_TILE
+#define JPP_TC_TILE 32
+#endif
+#ifndef JPP_TC_GROUPS
+#define JPP_TC_GROUPS 2
+#endif
+constexpr u32 kTcTile = JPP_TC_TILE;      // tree nodes per tile (UMMA N): 16 or 32
+constexpr u32 kTcGroups = JPP_TC_GROUPS;  // independent tile pipelines per block (each: 4 producer / epilogue warps + 1 MMA warp)
 constexpr u32 kTcGroupThreads = 160;
 constexpr u32 kTcThreads = kTcGroups * kTcGroupThreads;
 constexpr u32 kTcChunkK = 32;      // tf32 elements per 128-byte swizzle row
 constexpr u32 kTcABytes = kTcH * kTcH * 4;        // one plane of W
 constexpr u32 kTcBBytes = kTcTile * kTcH * 4;     // one plane of a context tile
+constexpr u32 kTcTmemCols = kTcGroups * kTcTile <= 32 ? 32 : (kTcGroups * kTcTile <= 64 ? 64 : 128);  // power of two >= 32
 constexpr u32 kTcSmem = 2 * kTcABytes + kTcGroups * 2 * kTcBBytes + 1024 /* alignment */ + 64;
 
 // byte offset of element (row r, k) of a K-major operand with `rows` rows in the UMMA SWIZZLE_128B layout:
@@ -109,8 +116,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     for (u32 g = 0; g < kTcGroups; ++g) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sBar[g])));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (threadIdx.x / 32 == 4) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sTmem)), "r"(kTcGroups * kTcTile));
+  if (threadIdx.x / 32 == 4) {  // (the MMA warp of group 0)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sTmem)), "r"(kTcTmemCols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the generic-proxy writes of W become visible to the MMA
@@ -218,7 +225,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   }
   __syncthreads();
   if (threadIdx.x / 32 == 4) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmemBase), "r"(kTcGroups * kTcTile));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmemBase), "r"(kTcTmemCols));
   }
 }
 

@@ -172,10 +172,11 @@ __device__ __forceinline__ void wave_item_trigram_static(const FeatTables& ft, c
 // apart in phase, so while one block chases the dependent loads of its global beams another one
 // keeps the gather pipe busy -- across kernels that overlap does not exist.  All warps of a block
 // are in the same phase at the same time, which also keeps the instruction working set of an SM to
-// a few phases: a variant in which every WARP walked its own four sentences (no block barriers at
-// all) was measured and lost -- 94 ms against 41 ms for the table-driven program, 70 ms with the
-// compiled-in one (profiles/README.md r2b): sixteen warps per SM in sixteen different phases of a
-// kernel this size do not fit the instruction caches.
+// a few phases.  A variant in which every WARP walked its own four sentences (`__syncwarp` only, no
+// block barriers at all; git history: "Warp-scope beam walk") was measured at 128 / 85 / 64 registers
+// per thread and lost every time -- 69.6 / 60.4 / 57.6 ms against 37.4 ms (profiles/README.md r2b,
+// r2g): without other warps of the same block to run, every lane-0 serial section (the exact
+// nth_element replay, the beam sorts) idles 31 lanes for its whole length.
 //
 // GW = lanes per sentence in W1 (8 when beam and global beam are <= 8: the block's 32 sentences in
 // one pass; 32 for wider beams: four passes of eight sentences), KB = beam slots a lane holds in
@@ -291,264 +292,6 @@ __global__ void __launch_bounds__(SENT * 8, (STATIC ? JPP_FUSED_MINBLOCKS_STATIC
       wave_final_node<SMALL>(bv, cfg, lw, sNode0[lo] + (i - sNodeOff[lo]));
     }
     __syncthreads();
-  }
-}
-
-// ------------------------------------------------------------- warp-scope variant ----
-// The same walk with a WARP owning its sentences (4 of global beam <= 8, or one with wider beams) and
-// __syncwarp() where the block walk has __syncthreads(): no barrier stalls at all, but every serial
-// section idles its whole warp.  Selected with JPP_B200_WARP_WALK=1 (A/B; profiles/README.md).
-constexpr u32 kWarpWalkThreads = 128;  // 4 warps: no block-level cooperation, the size only sets the launch granularity
-#ifndef JPP_WARP_WALK_MINBLOCKS
-#define JPP_WARP_WALK_MINBLOCKS 8      // 64 registers per thread: 32 warps per SM
-#endif
-
-// ------------------------------------------------------------------ W3 per warp ----
-// makeT0cutoffBeam for the (at most four) sentences of a warp, 8 lanes per sentence: the logic of
-// cutoff_group_block with the block-wide prefix replaced by a prefix over the warp's groups.
-// `sent` is the sentence of this lane's 8-lane group or 0xFFFFFFFF.  sCut / sIdx: this warp's
-// scratch, [4][64].  Returns the warp's item counts (identical on every lane).
-struct WarpCounts {
-  u32 nBi, nTri;
-};
-
-__device__ __forceinline__ WarpCounts cutoff_group_warp(const FeatTables& ft, const BatchView& bv, const ScoreCfg& cfg,
-                                                        const WaveView& wv, u32 sent, u32 bnd, float (*sCut)[64], u32 (*sIdx)[64],
-                                                        unsigned long long (&cnt)[3]) {
-  constexpr u32 GW = 8, SM_R = 64;
-  const unsigned full = 0xffffffffu;
-  const u32 lane = threadIdx.x & 31u, sub = lane % GW, grp = lane / GW;
-  const unsigned gshift = lane - sub;
-  const unsigned gmask = ((1u << GW) - 1u) << gshift;
-  bool active = sent != 0xFFFFFFFFu;
-  u32 gB = 0, n0 = 0, R = 0, G = 0, U = 0, L = 0;
-  if (active) {
-    u32 b0;
-    const u32 nb = sent_span(bv, sent, b0);
-    if (bnd >= nb || nb <= 3) {
-      active = false;
-    } else {
-      gB = b0 + bnd;
-      n0 = bv.bndNodeOff[gB];
-      R = bv.bndNodeOff[gB + 1] - n0;
-      if (R == 0) active = false;
-    }
-  }
-  StepSizes z = step_sizes(cfg, R, 0);
-  if (active) {
-    G = wv.gCount[sent];
-    U = wv.uCount[sent];
-    L = bv.bndEndOff[gB + 1] - bv.bndEndOff[gB];
-    z = step_sizes(cfg, R, G);
-  }
-  const bool bits = active && R <= SM_R;
-  unsigned long long selBits = 0;
-  u32 nsel = 0;
-  if (active) {
-    if (!(cfg.rcheck > 0 && R > z.toKeep)) {
-      if (bits) selBits = ~0ull;
-      else for (u32 r = sub; r < R; r += GW) bv.selPos[n0 + r] = 0;
-      nsel = R;
-    } else {
-      nsel = z.toKeep;
-      bool exact = true;  // std::nth_element has to be replayed
-      if (R <= GW) {
-        // rank count: when no run of equal scores straddles the cut it IS the selection
-        const bool valid = sub < R;
-        float v = 0;
-        if (valid) for (u32 j = 0; j < z.full; ++j) v += bv.pre[(size_t)j * bv.totalNodes + n0 + sub];
-        u32 greater = 0, eq = 0;
-        for (u32 j = 0; j < R; ++j) {
-          const float vj = __shfl_sync(gmask, v, j, GW);
-          if (vj > v) ++greater;
-          else if (!(v > vj)) ++eq;  // counts the lane itself
-        }
-        const bool sure = valid && greater + eq <= z.toKeep;
-        const bool out = valid && greater >= z.toKeep;
-        const unsigned amb = __ballot_sync(gmask, valid && !sure && !out) & gmask;
-        if (amb == 0) {
-          exact = false;
-          selBits = (unsigned long long)((__ballot_sync(gmask, sure) & gmask) >> gshift);
-        } else {
-          if (valid) { sCut[grp][sub] = v; sIdx[grp][sub] = sub; }
-        }
-      } else if (bits) {
-        for (u32 r = sub; r < R; r += GW) {
-          float c = 0;
-          for (u32 j = 0; j < z.full; ++j) c += bv.pre[(size_t)j * bv.totalNodes + n0 + r];
-          sCut[grp][r] = c;
-          sIdx[grp][r] = r;
-        }
-      }
-      if (exact && bits) {
-        __syncwarp(gmask);
-        u32 lo = 0, hi = 0;
-        if (sub == 0) {
-          em_std_nth_element(sIdx[grp], (long)z.toKeep, (long)R, ScoreCmp{sCut[grp]});
-          for (u32 k = 0; k < z.toKeep; ++k) {
-            const u32 r = sIdx[grp][k];
-            if (r < 32) lo |= 1u << r; else hi |= 1u << (r - 32);
-          }
-        }
-        lo = __shfl_sync(gmask, lo, 0, GW);
-        hi = __shfl_sync(gmask, hi, 0, GW);
-        selBits = ((unsigned long long)hi << 32) | lo;
-      } else if (exact) {
-        if (sub == 0) {
-          u32* idx = bv.cutIdx + n0;
-          float* cut = bv.cut + n0;
-          for (u32 r = 0; r < R; ++r) {
-            float c = 0;
-            for (u32 j = 0; j < z.full; ++j) c += bv.pre[(size_t)j * bv.totalNodes + n0 + r];
-            cut[r] = c;
-            idx[r] = r;
-            bv.selPos[n0 + r] = NOT_SELECTED;
-          }
-          em_std_nth_element(idx, (long)z.toKeep, (long)R, ScoreCmp{cut});
-          for (u32 k = 0; k < z.toKeep; ++k) bv.selPos[n0 + idx[k]] = 0;
-        }
-        __syncwarp(gmask);
-      }
-    }
-  }
-  const bool scoreTail = active && z.remaining > 0 && G > 0;
-  const u32 u0 = first_bigram_item(cfg);
-  const u32 biPer = scoreTail && U > u0 ? U - u0 : 0u;
-  const u32 triPer = scoreTail ? z.remaining : 0u;
-  if (sub == 0 && active) {
-    unsigned long long g = 0, sb = 0, gi = 0;
-    step_counters(ft, cfg, z, R, L, G, U, nsel, g, sb, gi);
-    cnt[0] += g;
-    cnt[1] += sb;
-    cnt[2] += gi;
-  }
-  // exclusive prefix of (selected nodes, bigram items, trigram items) over the warp's four groups
-  u32 base = 0, biBase = 0, triBase = 0, totBi = 0, totTri = 0;
-  {
-    const u32 mySel = active ? nsel : 0u, myBi = mySel * biPer, myTri = mySel * triPer;
-#pragma unroll
-    for (u32 g = 0; g < 32 / GW; ++g) {
-      const u32 s = __shfl_sync(full, mySel, g * GW), b = __shfl_sync(full, myBi, g * GW), t = __shfl_sync(full, myTri, g * GW);
-      if (g < grp) { base += s; biBase += b; triBase += t; }
-      totBi += b;
-      totTri += t;
-    }
-  }
-  if (active) {
-    u32 run = 0;
-    for (u32 r0 = 0; r0 < R; r0 += GW) {
-      const u32 r = r0 + sub;
-      const bool valid = r < R;
-      const bool sel = valid && (bits ? ((selBits >> r) & 1ull) != 0 : bv.selPos[n0 + r] != NOT_SELECTED);
-      const unsigned m = (__ballot_sync(gmask, sel) & gmask) >> gshift;
-      if (sel) {
-        const u32 k = run + __popc(m & ((1u << sub) - 1u));
-        const u32 pos = base + k;
-        bv.selPos[n0 + r] = pos;
-        if (scoreTail)
-          emit_items(bv, cfg, wv, sent, z, G, U, n0 + r, pos, wv.biItems + biBase + (size_t)k * biPer,
-                     wv.triItems + triBase + (size_t)k * triPer);
-      } else if (valid) {
-        bv.selPos[n0 + r] = NOT_SELECTED;
-      }
-      run += __popc(m);
-    }
-  }
-  return WarpCounts{totBi, totTri};
-}
-
-// ------------------------------------------------------------------- the kernel ----
-// GW = lanes per sentence in W1 (8: four sentences per warp; 32: one), KB = beam slots a lane
-// holds in W1, SMALL = register beam build of W5 (global beam <= 8), STATIC = compiled-in program.
-template <int GW, int KB, bool SMALL, bool STATIC>
-__global__ void __launch_bounds__(kWarpWalkThreads, JPP_WARP_WALK_MINBLOCKS)
-    k_walk_warp(const __grid_constant__ FeatTables ft, BatchView bv, ScoreCfg cfg, WaveView wv, const float* __restrict__ w,
-                u32 itemCap) {
-  constexpr u32 SPW = 32 / GW;                     // sentences per warp
-  constexpr u32 WPB = kWarpWalkThreads / 32;       // warps per block
-  __shared__ float sCutAll[WPB][4][64];
-  __shared__ u32 sIdxAll[WPB][4][64];
-  const unsigned full = 0xffffffffu;
-  const u32 lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
-  const u32 warpId = blockIdx.x * WPB + wib;
-  const u32 NS = bv.numSentences;
-  const u32 firstSent = warpId * SPW;
-  if (firstSent >= NS) return;  // the whole warp: nothing below synchronises across warps
-  const u32 grp = lane / GW;
-  // the warp's private lists
-  WaveView lw = wv;
-  lw.selCount = nullptr;
-  lw.biItems = wv.biItems + (size_t)warpId * itemCap;
-  lw.triItems = wv.triItems + (size_t)warpId * itemCap;
-  lw.scb = wv.scb + (size_t)warpId * itemCap;
-  lw.tri = wv.tri + 2 * (size_t)warpId * itemCap;
-  const WLoadDirect wl{w};
-  const u32 mySent = firstSent + grp < NS ? bv.sentOrder[firstSent + grp] : 0xFFFFFFFFu;
-  u32 myB0 = 0, myNb = 0;
-  if (mySent != 0xFFFFFFFFu) myNb = sent_span(bv, mySent, myB0);
-  const u32 maxNb = __reduce_max_sync(full, myNb);
-  // sentence of this lane's 8-lane group in W3 (with GW = 32 only lanes 0..7 work there)
-  const u32 cutSentAny = __shfl_sync(full, mySent, ((lane / 8u) % SPW) * GW);
-  const u32 cutSent = (lane / 8u) < SPW ? cutSentAny : 0xFFFFFFFFu;
-  unsigned long long cnt[3] = {0, 0, 0};
-  for (u32 bnd = 2; bnd < maxNb; ++bnd) {
-    // W1 + the warp's node list of this boundary
-    u32 R = 0, n0 = 0;
-    if (mySent != 0xFFFFFFFFu && bnd < myNb && myNb > 3) {
-      n0 = bv.bndNodeOff[myB0 + bnd];
-      R = bv.bndNodeOff[myB0 + bnd + 1] - n0;
-      gbeam_group<KB, GW>(bv, cfg, lw, mySent, bnd);
-    }
-    u32 Rg[SPW], N0g[SPW], T = 0;
-#pragma unroll
-    for (u32 g = 0; g < SPW; ++g) {
-      Rg[g] = __shfl_sync(full, R, g * GW);
-      N0g[g] = __shfl_sync(full, n0, g * GW);
-      T += Rg[g];
-    }
-    __syncwarp();
-    // W2
-    for (u32 i = lane; i < T; i += 32) {
-      u32 node = 0, acc = 0;
-#pragma unroll
-      for (u32 g = 0; g < SPW; ++g) {
-        if (i >= acc && i < acc + Rg[g]) node = N0g[g] + (i - acc);
-        acc += Rg[g];
-      }
-      if (STATIC) wave_prescore_static(ft, bv, cfg, lw, w, node);
-      else wave_prescore(ft, bv, cfg, lw, wl, node);
-    }
-    __syncwarp();
-    // W3
-    const WarpCounts wc = cutoff_group_warp(ft, bv, cfg, lw, cutSent, bnd, sCutAll[wib], sIdxAll[wib], cnt);
-    __syncwarp();
-    // W4
-    for (u32 i = lane; i < wc.nBi + wc.nTri; i += 32) {
-      if (i < wc.nBi) {
-        if (STATIC) wave_item_bigram_static(ft, bv, lw, w, lw.biItems[i]);
-        else wave_item_bigram(ft, bv, lw, wl, lw.biItems[i]);
-      } else {
-        if (STATIC) wave_item_trigram_static(ft, bv, lw, w, lw.triItems[i - wc.nBi]);
-        else wave_item_trigram(ft, bv, lw, wl, lw.triItems[i - wc.nBi]);
-      }
-    }
-    __syncwarp();
-    // W5
-    for (u32 i = lane; i < T; i += 32) {
-      u32 node = 0, acc = 0;
-#pragma unroll
-      for (u32 g = 0; g < SPW; ++g) {
-        if (i >= acc && i < acc + Rg[g]) node = N0g[g] + (i - acc);
-        acc += Rg[g];
-      }
-      wave_final_node<SMALL>(bv, cfg, lw, node);
-    }
-    __syncwarp();
-  }
-  if (bv.counters && (cnt[0] | cnt[1])) {
-    atomicAdd(bv.counters + 0, cnt[0]);
-    atomicAdd(bv.counters + 1, cnt[1]);
-    atomicAdd(bv.counters + 2, cnt[2]);
   }
 }
 

@@ -63,6 +63,8 @@ def load_library() -> C.CDLL:
     lib.jpp_b200_download_result.argtypes = [H, C.POINTER(abi.Result)]
     lib.jpp_b200_add_entry_rows.restype = C.c_int
     lib.jpp_b200_add_entry_rows.argtypes = [H, C.POINTER(abi.EntryTableStruct)]
+    lib.jpp_b200_gather_probe.restype = C.c_int
+    lib.jpp_b200_gather_probe.argtypes = [H, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(C.c_double)]
     lib.jpp_b200_get_counters.restype = C.c_int
     lib.jpp_b200_get_counters.argtypes = [H, C.POINTER(abi.Counters)]
     lib.jpp_b200_last_error.restype = C.c_char_p
@@ -77,7 +79,7 @@ def load_library() -> C.CDLL:
 
 EXPORTED_SYMBOLS = ["jpp_b200_create", "jpp_b200_set_config", "jpp_b200_score_batch", "jpp_b200_upload_batch",
                     "jpp_b200_score_resident", "jpp_b200_download_result", "jpp_b200_get_counters", "jpp_b200_add_entry_rows",
-                    "jpp_b200_alloc_pinned", "jpp_b200_free_pinned", "jpp_b200_reserve_entry_rows",
+                    "jpp_b200_alloc_pinned", "jpp_b200_free_pinned", "jpp_b200_reserve_entry_rows", "jpp_b200_gather_probe",
                     "jpp_b200_last_error", "jpp_b200_destroy", "jpp_b200_abi_version", "jpp_b200_build_info"]
 
 
@@ -160,6 +162,12 @@ class LatticeScorer:
                 "walk_gathers_issued": c.walk_gathers_issued, "rnn_scores": c.rnn_scores,
                 "failed_sentences": c.failed_sentences,
                 "kernel_ms": {n: float(c.kernel_ms[i]) for i, n in enumerate(names)}}
+
+    def gather_probe(self, gathers: int = 1 << 31, ilp: int = 8, blocks_per_sm: int = 8) -> float:
+        """Diagnostic: random 4-byte reads per second this device serves from the handle's perceptron table."""
+        out = C.c_double(0.0)
+        self._check(self._lib.jpp_b200_gather_probe(self._h, gathers, ilp, blocks_per_sm, C.byref(out)))
+        return float(out.value)
 
     def close(self) -> None:
         if self._h:

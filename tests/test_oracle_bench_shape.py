@@ -24,9 +24,11 @@ def test_oracle_equals_reference_on_a_fresh_bench_like_sample(tmp_path, workload
     if not bench.HARNESS.exists():
         pytest.skip("oracle/_ref/jpp_ref_harness is not built")
     args = argparse.Namespace(workload=workload, cache=str(tmp_path), dict_rows=20000, sentences=n, min_len=4,
-                              max_len=96, seed=seed, log2w=20, wseed=5, stage_chunk=2048, gpus=1, inline_entries=True)
+                              max_len=96, seed=seed, log2w=20, wseed=5, stage_chunk=2048, gpus=1, batch_form="inline", window=131072,
+                              shard_corpus=False)
     info = bench.prepare_workload(args, 0)
-    model, cfg, batch = bench.load_staged(info, args, pin=lambda a: a)
+    model, cfg, windows, _ = bench.load_staged(info, args, pin=lambda a: a)
+    batch = windows[0]
     out = info["dir"] / "expected.jppb"
     cmd = [str(bench.HARNESS), "stage", f"dict={info['dict']}", f"corpus={info['corpus']}", f"out={out}", "expected=1",
            f"max_sent={n}", *bench.harness_model_args(args, info["wl"], info["rnn"])]
