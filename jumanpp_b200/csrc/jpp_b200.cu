@@ -1696,7 +1696,11 @@ static jpp_b200_status score_resident_impl(jpp_b200_handle* h) {
   CU_CHECK(h, cudaEventRecord(h->ev[2], st));
   {
     static const bool t0Array = getenv("JPP_B200_T0_ARRAY") != nullptr;  // A/B: all patterns in a local array
+#ifdef JPP_T0_PRIM_SMEM
     const size_t primBytes = (size_t)std::max(1u, h->hm.ft.nPrim) * 128 * 8;
+#else
+    const size_t primBytes = 0;
+#endif
     if (t0Array) k_t0<false><<<(NN + 127) / 128, 128, primBytes, st>>>(h->dFt, bv, h->dWeights);
     else k_t0<true><<<(NN + 127) / 128, 128, primBytes, st>>>(h->dFt, bv, h->dWeights);
   }

@@ -224,14 +224,38 @@ JPP_HD jpp_b200_beam_element fake_elem() {
 // the same slot by different threads cannot produce a torn pair; the value is a
 // pure function of the index, so whoever wins, a hit returns exactly what the
 // table holds -- results are bit-identical to WLoadDirect.
+// One read of the perceptron table.  The table (256 MB on the bench model) is read at hash-random indices: a
+// line brought into L1 is practically never hit again, while everything else the kernels touch (pattern rows,
+// beams, item lists) is.  A/B builds: JPP_GATHER_NA = the read does not allocate in L1; JPP_GATHER_L2_LAST = its
+// L2 line is marked evict-last (the streamed lattice data, not the table, should leave L2 first).
+JPP_HD float gather_weight(const float* __restrict__ w, u32 id) {
+#if defined(__CUDA_ARCH__) && (defined(JPP_GATHER_NA) || defined(JPP_GATHER_L2_LAST))
+  float v;
+#if defined(JPP_GATHER_L2_LAST)
+  unsigned long long pol;
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+#if defined(JPP_GATHER_NA)
+  asm("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(w + id), "l"(pol));
+#else
+  asm("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(w + id), "l"(pol));
+#endif
+#else
+  asm("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(w + id));
+#endif
+  return v;
+#else
+  return JPP_LDG(w + id);
+#endif
+}
+
 struct WLoadDirect {
   const float* __restrict__ w;
   template <int N>
   JPP_HD void get(const u32 (&id)[N], float (&x)[N]) const {
 #pragma unroll
-    for (int j = 0; j < N; ++j) x[j] = JPP_LDG(w + id[j]);
+    for (int j = 0; j < N; ++j) x[j] = gather_weight(w, id[j]);
   }
-  JPP_HD float one(u32 id) const { return JPP_LDG(w + id); }
+  JPP_HD float one(u32 id) const { return gather_weight(w, id); }
 };
 
 #if defined(__CUDACC__)
@@ -399,13 +423,17 @@ JPP_HD void t0_node(const FeatTables& ft, const BatchView& bv, const WL& wl, u32
   const i32* entry = ne.entry;
   const i32* ph = ne.ph;
   // The primitive values are indexed by the feature program (dynamically): as a private array they are
-  // local memory -- ncu r2e: 1.49 G local-load sectors, more than the kernel's 1.31 G sectors of weight
-  // gathers.  The kernel passes a slab of shared memory instead ([primitive][thread]: conflict-free).
-#if defined(__CUDA_ARCH__)
+  // local memory -- ncu r2e: 1.49 G local-load sectors (L1 hits), more than the kernel's 1.31 G sectors of
+  // weight gathers.  JPP_T0_PRIM_SMEM (A/B build) keeps them in a slab of shared memory the kernel passes
+  // ([primitive][thread]: conflict-free): measured SLOWER, 13.7 -> 18.2 ms (profiles/README.md r2h) -- 8 B x
+  // nPrim x 128 threads of shared memory per block cost more occupancy than the local loads cost L1 time.
+#if defined(__CUDA_ARCH__) && defined(JPP_T0_PRIM_SMEM)
   u64* prim = primStore;
 #else
   u64 primLocal[MAX_PRIM];
-  u64* prim = primStore ? primStore : primLocal;
+  u64* prim = primLocal;
+  ps = 1;
+  (void)primStore;
 #endif
   for (u32 i = 0; i < ft.nPrim; ++i) prim[i * ps] = prim_value(ft, i, entry, ph, ni, cps, ncp);
   u64 pat[LEAN ? 1 : MAX_PAT];
@@ -416,7 +444,7 @@ JPP_HD void t0_node(const FeatTables& ft, const BatchView& bv, const WL& wl, u32
   };
   if (!LEAN)
     for (u32 p = 0; p < ft.nPat; ++p) pat[ft.patIndex[p]] = pattern_value(ft, p, prim, ps);
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && defined(JPP_T0_STORE16)
   if (pstr == 1 && (SP & 1u) == 0) {
     // the row is 16-byte aligned (SP even, 8-byte slots): half as many stores, whole 16-byte pieces of a sector
     for (u32 p = 0; p < SP; p += 2) {

@@ -28,10 +28,10 @@ using namespace jppb200;
 
 constexpr u32 kTcH = 128;          // layer size this kernel is built for
 #ifndef JPP_TC_TILE
-#define JPP_TC_TILE 32
+#define JPP_TC_TILE 16
 #endif
 #ifndef JPP_TC_GROUPS
-#define JPP_TC_GROUPS 2
+#define JPP_TC_GROUPS 6
 #endif
 constexpr u32 kTcTile = JPP_TC_TILE;      // tree nodes per tile (UMMA N): 16 or 32
 constexpr u32 kTcGroups = JPP_TC_GROUPS;  // independent tile pipelines per block (each: 4 producer / epilogue warps + 1 MMA warp)

@@ -36,29 +36,41 @@ __device__ __forceinline__ void load_row(const u64* __restrict__ base, u64 (&r)[
 
 typedef JumandicNgramProgram SP;
 
+#ifndef JPP_STATIC_BATCH
+#define JPP_STATIC_BATCH 8
+#endif
+constexpr int kGatherBatch = JPP_STATIC_BATCH;  // table reads a thread has in flight in the bigram sums (a multiple of 8)
+static_assert(kGatherBatch % 8 == 0, "accumulator j % NV / j % 2 / j % 4 of feature f = batch * k + j needs 8 | batch");
+
+struct LeftRow {
+  u64 r[SP::kStored];
+  __device__ __forceinline__ void load(const u64* __restrict__ base) { load_row(base, r); }
+  __device__ __forceinline__ u64 operator[](int s) const { return r[s]; }
+};
+
 // One pass over the bigram features of (right node row P, left node row T1): the NV interleaved
 // accumulators of the generated applyBiStep2 rows, the r1/r2 pair of applyBiTriFullKernel and the
 // four of computeUnrolled4RawPerceptron, fed from the same gathered values (gsum_triple's orders).
 __device__ __forceinline__ void static_bigram_sums(const float* __restrict__ w, u32 mask, const u64 (&P)[SP::kStored],
-                                                   const u64 (&T1)[SP::kStored], float& sumNV, float& sumPair, float& sum4) {
+                                                   const LeftRow& T1, float& sumNV, float& sumPair, float& sum4) {
   constexpr int NV = SP::kBiVars;
   float a[NV], c[2] = {0.0f, 0.0f}, b[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
   for (int j = 0; j < NV; ++j) a[j] = 0.0f;
 #pragma unroll
-  for (int B = 0; B < (SP::kBi + 7) / 8; ++B) {
-    u32 id[8];
-    float x[8];
+  for (int B = 0; B < (SP::kBi + kGatherBatch - 1) / kGatherBatch; ++B) {
+    u32 id[kGatherBatch];
+    float x[kGatherBatch];
 #define X(f, st, s0, s1) \
-  if ((f) / 8 == B) id[(f) % 8] = (u32)mix(mix(st, P[s0]), T1[s1]) & mask;
+  if ((f) / kGatherBatch == B) id[(f) % kGatherBatch] = (u32)mix(mix(st, P[s0]), T1[s1]) & mask;
     JPP_STATIC_BIGRAMS(X)
 #undef X
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (B * 8 + j < SP::kBi) x[j] = __ldg(w + id[j]);
+    for (int j = 0; j < kGatherBatch; ++j)
+      if (B * kGatherBatch + j < SP::kBi) x[j] = gather_weight(w, id[j]);
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (B * 8 + j < SP::kBi) {  // feature B*8+j: accumulator j % NV / j % 2 / j % 4 (8 is a multiple of each)
+    for (int j = 0; j < kGatherBatch; ++j)
+      if (B * kGatherBatch + j < SP::kBi) {  // feature B*batch+j: accumulator j % NV / j % 2 / j % 4 (the batch is a multiple of each)
         a[j % NV] += x[j];
         c[j % 2] += x[j];
         b[j % 4] += x[j];
@@ -89,7 +101,7 @@ __device__ __forceinline__ void static_trigram_sums(const float* __restrict__ w,
 #undef X
 #pragma unroll
     for (int j = 0; j < 8; ++j)
-      if (B * 8 + j < SP::kTri) x[j] = __ldg(w + id[j]);
+      if (B * 8 + j < SP::kTri) x[j] = gather_weight(w, id[j]);
 #pragma unroll
     for (int j = 0; j < 8; ++j)
       if (B * 8 + j < SP::kTri) {
@@ -123,8 +135,9 @@ __device__ __forceinline__ void wave_prescore_static(const FeatTables& ft, const
   for (int i = 0; i < SP::kTriSlots; ++i) P3[i] = P[i];
   const float t0 = bv.t0[node];
   for (u32 i = 0; i < theMax; ++i) {
-    u64 T1[SP::kStored], T1t[SP::kTriSlots], T2[SP::kTriSlots];
-    load_row(bv.patterns + (size_t)wv.gbLnode[(size_t)sent * GMAX + i] * SP::kStored, T1);
+    LeftRow T1;
+    u64 T1t[SP::kTriSlots], T2[SP::kTriSlots];
+    T1.load(bv.patterns + (size_t)wv.gbLnode[(size_t)sent * GMAX + i] * SP::kStored);
     load_row(bv.patterns + (size_t)wv.gbT2node[(size_t)sent * GMAX + i] * SP::kStored, T2);
 #pragma unroll
     for (int q = 0; q < SP::kTriSlots; ++q) T1t[q] = T1[q];
@@ -143,9 +156,10 @@ __device__ __forceinline__ void wave_prescore_static(const FeatTables& ft, const
 // W4 items with the rows in registers: the same results as wave_item_bigram / wave_item_trigram
 __device__ __forceinline__ void wave_item_bigram_static(const FeatTables& ft, const BatchView& bv, const WaveView& wv,
                                                         const float* __restrict__ w, const WaveItem& it) {
-  u64 P[SP::kStored], T1[SP::kStored];
+  u64 P[SP::kStored];
+  LeftRow T1;
   load_row(bv.patterns + (size_t)it.a * SP::kStored, P);
-  load_row(bv.patterns + (size_t)it.b * SP::kStored, T1);
+  T1.load(bv.patterns + (size_t)it.b * SP::kStored);
   float sNV, sPair, s4;
   static_bigram_sums(w, ft.mask, P, T1, sNV, sPair, s4);
   wv.scb[it.slot & ~ITEM_LAST] = ((it.slot & ITEM_LAST) || ft.dynamicOrder) ? s4 : sPair;
