@@ -22,6 +22,7 @@
 #include "jpp_b200_host.h"
 #include "jpp_b200_kernels.h"
 #include "jpp_b200_rnn.h"
+#include "jpp_b200_t0_static.h"
 
 using namespace jppb200;
 
@@ -155,6 +156,17 @@ __global__ void __launch_bounds__(128) k_t0(const FeatTables* __restrict__ ftg, 
   const WLoadDirect wl{w};
   const u32 node = blockIdx.x * blockDim.x + threadIdx.x;
   if (node < bv.totalNodes) t0_node<WLoadDirect, LEAN>(ft, bv, wl, node, reinterpret_cast<u64*>(sPrim) + threadIdx.x, blockDim.x);
+}
+
+// T0 with the compiled-in program (jpp_b200_t0_static.h): no program tables, so none to copy into shared memory;
+// the handful of scalars it still reads from FeatTables are uniform (constant bank)
+#ifndef JPP_T0_STATIC_MINBLOCKS
+#define JPP_T0_STATIC_MINBLOCKS 6   // 80 registers: primitives, the patterns in flight and 32 table reads
+#endif
+__global__ void __launch_bounds__(128, JPP_T0_STATIC_MINBLOCKS) k_t0_static(const __grid_constant__ FeatTables ft, BatchView bv, const float* __restrict__ w) {
+  const WLoadDirect wl{w};
+  const u32 node = blockIdx.x * blockDim.x + threadIdx.x;
+  if (node < bv.totalNodes) t0_node_static(ft, bv, wl, node);
 }
 
 // ---- wavefront walk kernels (see jpp_b200_kernels.h "wavefront walk") ----
@@ -570,7 +582,10 @@ __global__ void k_rnn_tree(BatchView bv, ScoreCfg cfg, RnnWork rw) {
 }
 
 // level lists (the histogram is accumulated by k_rnn_tree); 8 lanes share a sentence's nodes
-__global__ void k_rnn_level_fill(BatchView bv, RnnWork rw, u32* cursor) {
+struct __align__(16) LevelRec {  // = TcRec of jpp_b200_rnn_tc.cuh
+  u32 inRow, outRow, embRow, rnode;
+};
+__global__ void k_rnn_level_fill(BatchView bv, RnnWork rw, u32* cursor, const u32* __restrict__ ctxOff, LevelRec* levelRec) {
   const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
   const u32 s = t >> 3, sub = t & 7u;
   if (s >= bv.numSentences) return;
@@ -584,6 +599,17 @@ __global__ void k_rnn_level_fill(BatchView bv, RnnWork rw, u32* cursor) {
       const u32 d = (u32)rw.depth[q];
       const u32 pos = atomicAdd(cursor + d, 1u);
       rw.levelList[rw.levelOff[d] + pos] = q;
+      if (levelRec) {  // the tensor-core level kernel reads its rows from here (prev is a node of the same sentence)
+        const u32 c0 = ctxOff[s];
+        i32 id = rw.id[q];
+        if (id == -1) id = 0;  // rnn_scorer_gbeam.cc:126-129
+        LevelRec r;
+        r.inRow = c0 + ((u32)rw.prev[q] - base0);
+        r.outRow = c0 + i;
+        r.embRow = (u32)id;
+        r.rnode = q;
+        levelRec[rw.levelOff[d] + pos] = r;
+      }
     }
   }
 }
@@ -1108,6 +1134,7 @@ struct jpp_b200_handle {
   std::vector<i32> hostRowOfPtr;  // owner only: host copy of the direct map
   cudaStream_t tableStream = nullptr;  // owner only: uploads of table rows (never waits for a batch in flight)
   bool staticProgram = false;  // the uploaded n-gram program is the compiled-in one (jpp_b200_static_jumandic.h)
+  bool staticT0 = false;       // ... and so is its per-node part (jpp_b200_static_jumandic_t0.h)
   float* dRnnBlocks[4] = {nullptr, nullptr, nullptr, nullptr};
   float* dRnnWt = nullptr;  // transposed recurrent matrix
   float* dRnnWImage = nullptr;  // layer size 128: the two TF32 planes of W in the tensor-core operand layout (jpp_b200_rnn_tc.cuh)
@@ -1128,7 +1155,7 @@ struct jpp_b200_handle {
          B_PATHLEN, B_PATHNODES, B_STATUS, B_EXTRAOFF,
          W_GBKEY, W_GBLNODE, W_GBT2, W_GBT1IDX, W_T1NODE, W_GCNT, W_UCNT, W_SELCNT, W_BIITEMS, W_TRIITEMS, W_SCB, W_TRI, W_NODES, W_OFF, W_CURSOR,
          R_OFF, R_ID, R_PREV, R_NEXT, R_BND, R_LEN, R_DEPTH, R_HASH, R_RNCNT, R_RSNODE, R_RSSLOT, R_RSEOSG, R_RSRNODE,
-         R_RSCNT, R_CONN, R_BNDHEAD, R_CTX, R_CHNODE, R_CHSLOT, R_CHBND, R_CHID, R_CHLEN, R_SCLIST, R_SCTOTAL, R_LVLCNT, R_LVLOFF, R_LVLLIST, R_CTXOFF, R_RNSENT, R_CURSOR, R_CUBTMP,
+         R_RSCNT, R_CONN, R_BNDHEAD, R_CTX, R_CHNODE, R_CHSLOT, R_CHBND, R_CHID, R_CHLEN, R_SCLIST, R_SCTOTAL, R_LVLCNT, R_LVLOFF, R_LVLLIST, R_LVLREC, R_CTXOFF, R_RNSENT, R_CURSOR, R_CUBTMP,
          NUM_BUFS };
   DevBuf buf[NUM_BUFS];
   BatchView bv{};
@@ -1301,6 +1328,7 @@ static jpp_b200_status create_impl(const jpp_b200_model* model, const jpp_b200_c
   h->scoreW[0] = model->score_weights[0];
   h->scoreW[1] = model->score_weights[1];
   h->staticProgram = matches_static_program(h->hm.ft);
+  h->staticT0 = matches_static_t0(h->hm.ft);
 #define CREATE_CHECK(expr)                                                                      \
   do {                                                                                          \
     cudaError_t e_ = (expr);                                                                    \
@@ -1652,7 +1680,8 @@ static jpp_b200_status upload_window(jpp_b200_handle* h, const jpp_b200_batch* b
     ENSURE(R_RSNODE, rnTotal * 4); ENSURE(R_RSSLOT, rnTotal * 2); ENSURE(R_RSEOSG, rnTotal * 2); ENSURE(R_RSRNODE, rnTotal * 4);
     ENSURE(R_RSCNT, (size_t)NS * 4); ENSURE(R_CONN, (size_t)NN * B * 4); ENSURE(R_BNDHEAD, (size_t)NB * 4);
     ENSURE(R_LVLCNT, (size_t)(maxNb + 4) * 4); ENSURE(R_LVLOFF, (size_t)(maxNb + 4) * 4); ENSURE(R_CURSOR, (size_t)(maxNb + 4) * 4);
-    ENSURE(R_LVLLIST, rnTotal * 4); ENSURE(R_CTXOFF, (size_t)(NS + 1) * 4); ENSURE(R_RNSENT, rnTotal * 4);
+    ENSURE(R_LVLLIST, rnTotal * 4); if (h->dRnnWImage) ENSURE(R_LVLREC, rnTotal * 16);
+    ENSURE(R_CTXOFF, (size_t)(NS + 1) * 4); ENSURE(R_RNSENT, rnTotal * 4);
     ENSURE(R_CHNODE, rnTotal * 4); ENSURE(R_CHSLOT, rnTotal * 2); ENSURE(R_CHBND, rnTotal * 2); ENSURE(R_CHID, rnTotal * 4); ENSURE(R_CHLEN, rnTotal * 4); ENSURE(R_SCLIST, rnTotal * 4);
     ENSURE(R_SCTOTAL, 16);
     RnnWork& rw = h->rw;
@@ -1701,7 +1730,9 @@ static jpp_b200_status score_resident_impl(jpp_b200_handle* h) {
 #else
     const size_t primBytes = 0;
 #endif
-    if (t0Array) k_t0<false><<<(NN + 127) / 128, 128, primBytes, st>>>(h->dFt, bv, h->dWeights);
+    static const bool noStaticT0 = getenv("JPP_B200_NO_STATIC") != nullptr || getenv("JPP_B200_NO_STATIC_T0") != nullptr;  // A/B: table-driven program
+    if (h->staticT0 && !noStaticT0 && !t0Array) k_t0_static<<<(NN + 127) / 128, 128, 0, st>>>(h->hm.ft, bv, h->dWeights);
+    else if (t0Array) k_t0<false><<<(NN + 127) / 128, 128, primBytes, st>>>(h->dFt, bv, h->dWeights);
     else k_t0<true><<<(NN + 127) / 128, 128, primBytes, st>>>(h->dFt, bv, h->dWeights);
   }
   CU_CHECK(h, cudaGetLastError());
@@ -1817,7 +1848,12 @@ static jpp_b200_status score_resident_impl(jpp_b200_handle* h) {
     cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, rw.levelCount, rw.levelOff, (int)(h->maxNb + 2), st);
     CU_CHECK(h, bf[jpp_b200_handle::R_CUBTMP].ensure(tmpBytes + 16));
     cub::DeviceScan::ExclusiveSum(bf[jpp_b200_handle::R_CUBTMP].p, tmpBytes, rw.levelCount, rw.levelOff, (int)(h->maxNb + 2), st);
-    k_rnn_level_fill<<<(NS * 8 + 255) / 256, 256, 0, st>>>(bv, rw, bf[jpp_b200_handle::R_CURSOR].as<u32>());
+    // layer size 128: the level step as tcgen05 tensor-core MMAs (3xTF32); JPP_B200_RNN_TC=0 selects the
+    // FFMA kernel (an A/B switch for measurements and for bisecting a numeric difference)
+    static const bool tcOn = !(getenv("JPP_B200_RNN_TC") && atoi(getenv("JPP_B200_RNN_TC")) == 0);
+    const bool useTc = tcOn && h->rt.H == kTcH && h->dRnnWImage != nullptr;
+    LevelRec* levelRec = useTc ? bf[jpp_b200_handle::R_LVLREC].as<LevelRec>() : nullptr;
+    k_rnn_level_fill<<<(NS * 8 + 255) / 256, 256, 0, st>>>(bv, rw, bf[jpp_b200_handle::R_CURSOR].as<u32>(), ctxOff, levelRec);
     k_rnn_bos<<<NS, 64, 0, st>>>(bv, rw, h->rt, ctxOff);
     CU_CHECK(h, cudaGetLastError());
     CU_CHECK(h, cudaEventRecord(h->ev[5], st));
@@ -1827,13 +1863,9 @@ static jpp_b200_status score_resident_impl(jpp_b200_handle* h) {
       const u32 split = rnn_level_split(H);
       const dim3 grid((u32)h->smCount * 2 / split, split);
       const size_t wsBytes = (size_t)H * H * sizeof(float) / split;
-      // layer size 128: the level step as tcgen05 tensor-core MMAs (3xTF32); JPP_B200_RNN_TC=0 selects the
-      // FFMA kernel (an A/B switch for measurements and for bisecting a numeric difference)
-      static const bool tcOn = !(getenv("JPP_B200_RNN_TC") && atoi(getenv("JPP_B200_RNN_TC")) == 0);
-      const bool useTc = tcOn && H == kTcH && h->dRnnWImage != nullptr;
       for (u32 level = 1; level <= h->maxNb; ++level) {
         if (useTc) {
-          k_rnn_level_tc<<<h->smCount, kTcThreads, kTcSmem, st>>>(rw, h->rt, h->dRnnWImage, ctxOff, rnSent, level);
+          k_rnn_level_tc<<<h->smCount, kTcThreads, kTcSmem, st>>>(rw, h->rt, h->dRnnWImage, reinterpret_cast<const TcRec*>(levelRec), level);
           continue;
         }
         if (!crossLane) {
@@ -1967,7 +1999,7 @@ jpp_b200_status make_lane(jpp_b200_handle* owner, jpp_b200_handle* prev) {
   l->device = h->device; l->hm = h->hm; l->cfg = h->cfg; l->pubCfg = h->pubCfg;
   l->dFt = h->dFt; l->dWeights = h->dWeights; l->rt = h->rt; l->hasRnn = h->hasRnn;
   for (int i = 0; i < 4; ++i) l->dRnnBlocks[i] = h->dRnnBlocks[i];
-  l->staticProgram = h->staticProgram;
+  l->staticProgram = h->staticProgram; l->staticT0 = h->staticT0;
   l->dRnnWt = h->dRnnWt; l->dRnnWImage = h->dRnnWImage; l->scoreW[0] = h->scoreW[0]; l->scoreW[1] = h->scoreW[1]; l->smCount = h->smCount;
   l->ownsModel = false;
   cudaError_t e = cudaStreamCreateWithFlags(&l->stream, cudaStreamNonBlocking);

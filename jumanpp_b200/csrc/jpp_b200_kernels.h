@@ -340,13 +340,14 @@ JPP_HD i32 node_rnn_id(const BatchView& bv, u32 node, u32 sent, i32 entryPtr) {
 // One thread per node: primitive features -> 38 pattern hashes -> 32 unigram
 // hashes -> weight gather + ordered sum.  Replaces the generated
 // patternsAndUnigramsApply (codegen/pattern_feature_codegen.cc:199-313).
-JPP_HD u64 prim_value(const FeatTables& ft, u32 p, const i32* entry, const i32* ph, jpp_b200_node_info ni,
-                      const jpp_b200_codepoint* cps, u32 ncp) {
-  const i32 a = ft.primA[p];
-  switch (ft.primKind[p]) {
+// (kind, a, b, c) = one row of the primitive table; with literal arguments (the compiled-in program of
+// jpp_b200_static_jumandic_t0.h) the switch folds away
+JPP_HD u64 prim_value_c(i32 kind, i32 a, i32 pb, i32 pc, const i32* entry, const i32* ph, jpp_b200_node_info ni,
+                        const jpp_b200_codepoint* cps, u32 ncp) {
+  switch (kind) {
     // entry == nullptr: a BOS / EOS row, every field is the entry pointer itself (feature_impl_types.h:130-133)
     case JPP_B200_PRIM_COPY: return (u64)(u32)(entry ? entry[a] : ni.entry_ptr);
-    case JPP_B200_PRIM_SHIFT_MASK: return (u64)(((u32)(entry ? entry[a] : ni.entry_ptr) >> ft.primB[p]) & (u32)ft.primC[p]);
+    case JPP_B200_PRIM_SHIFT_MASK: return (u64)(((u32)(entry ? entry[a] : ni.entry_ptr) >> pb) & (u32)pc);
     case JPP_B200_PRIM_PROVIDED: return ph ? (u64)(u32)ph[a] : 0;
     case JPP_B200_PRIM_SURFACE_CODEPOINT_SIZE: return (u64)(i32)((i32)ni.end - (i32)ni.start);
     case JPP_B200_PRIM_CODEPOINT: {
@@ -375,6 +376,11 @@ JPP_HD u64 prim_value(const FeatTables& ft, u32 p, const i32* entry, const i32* 
     }
     default: return 0;
   }
+}
+
+JPP_HD u64 prim_value(const FeatTables& ft, u32 p, const i32* entry, const i32* ph, jpp_b200_node_info ni,
+                      const jpp_b200_codepoint* cps, u32 ncp) {
+  return prim_value_c(ft.primKind[p], ft.primA[p], ft.primB[p], ft.primC[p], entry, ph, ni, cps, ncp);
 }
 
 // hash of pattern p over the primitive values (pattern_feature_codegen.cc:199-313)

@@ -12,14 +12,19 @@
 // bit equality, and can be switched off (JPP_B200_RNN_TC=0).  Layer size 128 only (the bench model);
 // other sizes take k_rnn_level_x.
 //
-// Block = two groups of 5 warps, each group a pipeline of its own over alternate tiles (own B planes, own
-// mbarrier, own TMEM columns, a named barrier instead of __syncthreads): while one group waits for its
-// gathers or its MMAs the other works.  Inside a group, warps 0-3: stage the previous contexts of a tile of 32 tree nodes into shared
-// memory (split into the two TF32 planes, K-major, 128-byte swizzle: the canonical UMMA operand
-// layout), and, after the MMAs, read the accumulator back (tcgen05.ld, thread = output i = TMEM lane)
-// for the epilogue: + embedding, sigmoid, coalesced store of the new context rows.  Warp 4, one
-// elected lane: issues the 48 tcgen05.mma of a tile and commits them to an mbarrier.  W (both planes,
-// 128 KB, prepared in the shared-memory image once per model) stays in shared memory for the launch.
+// Block = kTcGroups groups of 5 warps, each group a pipeline of its own over alternate tiles (own B planes,
+// own mbarrier, own TMEM columns, named barriers instead of __syncthreads): while one group waits for its
+// MMAs another stages or reads back.  Inside a group, warps 0-3: stage the previous contexts of a tile of
+// kTcTile tree nodes into shared memory (split into the two TF32 planes, K-major, 128-byte swizzle: the
+// canonical UMMA operand layout), and, after the MMAs, read the accumulator back (tcgen05.ld, thread =
+// output i = TMEM lane) for the epilogue: + embedding, sigmoid, coalesced store of the new context rows.
+// Warp 4, one elected lane: issues the 48 tcgen05.mma of a tile and commits them to an mbarrier.  The
+// group is software-pipelined: the row records and the context rows of tile t+1 are requested (into
+// registers) before the group waits for the MMAs of tile t, so the global-memory latencies of a tile hide
+// behind the tensor-core work and the epilogue of the one before.  Which rows a tile reads and writes comes
+// from one 16-byte record per tree node that k_rnn_level_fill leaves in level order (TcRec) -- not from
+// the four dependent index loads the FFMA kernel does.  W (both planes, 128 KB, prepared in the
+// shared-memory image once per model) stays in shared memory for the launch.
 #pragma once
 
 namespace {
@@ -87,13 +92,19 @@ __device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) {
       : "memory");
 }
 
+// one tree node of a level: context rows read / written and the embedding row (k_rnn_level_fill)
+struct __align__(16) TcRec {
+  u32 inRow, outRow, embRow, rnode;
+};
+
 __global__ void __launch_bounds__(kTcThreads, 1)
     k_rnn_level_tc(RnnWork rw, RnnTables rt, const float* __restrict__ wImage /* [2][H*H] planes in the smem image */,
-                   const u32* ctxOff, const u32* rnSent, u32 level) {
+                   const TcRec* __restrict__ levelRec, u32 level) {
   extern __shared__ unsigned char tcSmemRaw[];
   __shared__ __align__(8) unsigned long long sBar[kTcGroups];
   __shared__ u32 sTmem;
-  __shared__ u32 sInRow[kTcGroups][kTcTile], sOutRow[kTcGroups][kTcTile], sEmbRow[kTcGroups][kTcTile];
+  __shared__ u32 sInRow[kTcGroups][2][kTcTile];  // rows a tile reads (this tile / the group's next one)
+  __shared__ u32 sOutRow[kTcGroups][kTcTile], sEmbRow[kTcGroups][kTcTile];
   const u32 cnt = rw.levelCount[level];
   const u32 tiles = (cnt + kTcTile - 1) / kTcTile;
   if (blockIdx.x * kTcGroups >= tiles) return;
@@ -103,10 +114,11 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   const u32 group = threadIdx.x / kTcGroupThreads, gtid = threadIdx.x % kTcGroupThreads;
   const u32 warp = gtid >> 5, lane = threadIdx.x & 31u;       // warp inside the group: 0..3 stage / read back, 4 issues
   unsigned char* sB = base + 2 * kTcABytes + group * 2 * kTcBBytes;    // this group's [2 planes][tile x H]
-  const u32 off = rw.levelOff[level];
+  const TcRec* recs = levelRec + rw.levelOff[level];
   const u32 barId = 1 + group;                 // named barrier of the group (0 is __syncthreads)
+  const u32 prodBar = 1 + kTcGroups + group;   // ... of its four staging warps
 
-  // one-time: W planes into shared memory, the mbarriers, the TMEM accumulators (32 columns per group)
+  // one-time: W planes into shared memory, the mbarriers, the TMEM accumulators (kTcTile columns per group)
   {
     const uint4* src = reinterpret_cast<const uint4*>(wImage);
     uint4* dst = reinterpret_cast<uint4*>(sA);
@@ -126,30 +138,37 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const u32 tmemBase = sTmem;
   const u32 tmemD = tmemBase + group * kTcTile;
-  u32 phase = 0;
+  u32 phase = 0, buf = 0;
   // a warp reads the TMEM lanes of its quarter: (warp id in the CTA) % 4
   const u32 quarter = (threadIdx.x / 32) & 3u;
+  const u32 stride = gridDim.x * kTcGroups;
+  u32 tile = blockIdx.x * kTcGroups + group;
 
-  for (u32 tile = blockIdx.x * kTcGroups + group; tile < tiles; tile += gridDim.x * kTcGroups) {
+  // the record of tree node j of a tile is held by thread j of the group: the row it reads goes to the row
+  // list at once (the rows are requested a tile ahead), the rows of the epilogue when that tile is current
+  auto fetch_record = [&](u32 t) -> uint4 {
+    const u32 first = t * kTcTile;
+    const u32 j = first + gtid < cnt ? gtid : 0u;   // the tail of the last tile repeats its first node (never stored)
+    return __ldg(reinterpret_cast<const uint4*>(recs + first + j));
+  };
+  uint4 rec = make_uint4(0u, 0u, 0u, 0u);
+  float4 v[kTcTile / 4];  // the context rows of the tile about to be staged: row warp + 4 q, columns 4 lane .. 4 lane + 3
+  if (tile < tiles && warp < 4) {
+    if (gtid < kTcTile) {
+      rec = fetch_record(tile);
+      sInRow[group][0][gtid] = rec.x;
+    }
+    asm volatile("bar.sync %0, 128;" ::"r"(prodBar) : "memory");
+#pragma unroll
+    for (u32 q = 0; q < kTcTile / 4; ++q)
+      v[q] = __ldg(reinterpret_cast<const float4*>(rw.ctx + (size_t)sInRow[group][0][warp + 4 * q] * kTcH) + lane);
+  }
+
+  for (; tile < tiles; tile += stride) {
     const u32 first = tile * kTcTile;
     const u32 nvalid = (cnt - first) < kTcTile ? (cnt - first) : kTcTile;
-    if (gtid < kTcTile) {
-      const u32 j = gtid;
-      const u32 q = rw.levelList[off + first + (j < nvalid ? j : 0u)];
-      sInRow[group][j] = (u32)ctx_row(rw, ctxOff, rnSent, (u32)rw.prev[q]);
-      sOutRow[group][j] = (u32)ctx_row(rw, ctxOff, rnSent, q);
-      i32 id = rw.id[q];
-      if (id == -1) id = 0;  // rnn_scorer_gbeam.cc:126-129
-      sEmbRow[group][j] = (u32)id;
-    }
-    asm volatile("bar.sync %0, %1;" ::"r"(barId), "r"(kTcGroupThreads) : "memory");
     if (warp < 4) {
-      // previous contexts -> the two TF32 planes of the B operand (row = tree node, K-major).  All rows of a
-      // warp are requested before the first one is used: one round trip, not eight.
-      float4 v[kTcTile / 4];
-#pragma unroll
-      for (u32 q = 0; q < kTcTile / 4; ++q)
-        v[q] = __ldg(reinterpret_cast<const float4*>(rw.ctx + (size_t)sInRow[group][warp + 4 * q] * kTcH) + lane);
+      // previous contexts -> the two TF32 planes of the B operand (row = tree node, K-major)
 #pragma unroll
       for (u32 q = 0; q < kTcTile / 4; ++q) {
         const u32 r = warp + 4 * q;
@@ -165,6 +184,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    // B is staged, and the accumulator of the previous tile has been read back by all four warps
     asm volatile("bar.sync %0, %1;" ::"r"(barId), "r"(kTcGroupThreads) : "memory");
     if (warp == 4) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -176,7 +196,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         for (u32 term = 0; term < 3; ++term) {
           const u32 aPlane = term == 0 ? 1u : 0u, bPlane = term == 1 ? 1u : 0u;
           for (u32 kc = 0; kc < kTcH / kTcChunkK; ++kc) {
-            for (u32 ks = 0; ks < kTcChunkK / 8; ++ks) {
+#pragma unroll
+            for (u32 ks = 0; ks < kTcChunkK / 8; ++ks) {  // UMMA K = 8 for tf32: 32 bytes along the swizzled row
               const u64 da = tc_smem_desc(aBase + aPlane * kTcABytes + kc * kTcH * 128 + ks * 32);
               const u64 db = tc_smem_desc(bBase + bPlane * kTcBBytes + kc * kTcTile * 128 + ks * 32);
               tc_mma(tmemD, da, db, acc);
@@ -189,39 +210,57 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       }
       __syncwarp();
     } else {
-      mbar_wait(smem_u32(&sBar[group]), phase);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      // thread = output i = TMEM lane; the group's 32 columns = the tile's tree nodes
+      // while the tensor core works: the rows of this tile's epilogue, the record and the context rows of the
+      // group's next tile
+      const u32 next = tile + stride;
+      if (gtid < kTcTile) {
+        sOutRow[group][gtid] = rec.y;
+        sEmbRow[group][gtid] = rec.z;
+        if (next < tiles) {
+          rec = fetch_record(next);
+          sInRow[group][buf ^ 1u][gtid] = rec.x;
+        }
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(prodBar) : "memory");
+      float4 vn[kTcTile / 4] = {};
+      if (next < tiles) {
+#pragma unroll
+        for (u32 q = 0; q < kTcTile / 4; ++q)
+          vn[q] = __ldg(reinterpret_cast<const float4*>(rw.ctx + (size_t)sInRow[group][buf ^ 1u][warp + 4 * q] * kTcH) + lane);
+      }
+      // thread = output i = TMEM lane; the group's columns = the tile's tree nodes
       const u32 i = quarter * 32u + lane;
       const u32 taddr = tmemD + ((quarter * 32u) << 16);
+      bool waited = false;
 #pragma unroll
-      for (u32 c0 = 0; c0 < kTcTile; c0 += 16) {
-        // the sixteen embedding values of this chunk are requested first (they do not depend on the accumulator)
-        float e[16];
+      for (u32 c0 = 0; c0 < kTcTile; c0 += 8) {
+        // the embedding values of this chunk are requested first (they do not depend on the accumulator)
+        float e[8];
 #pragma unroll
-        for (u32 j = 0; j < 16; ++j) e[j] = __ldg(rt.emb + (size_t)sEmbRow[group][c0 + j] * kTcH + i);
-        u32 v[16];
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-            : "r"(taddr + c0));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        float r[16];
-#pragma unroll
-        for (u32 j = 0; j < 16; ++j) {
-          const float x = __fadd_rn(__uint_as_float(v[j]), e[j]);
-          r[j] = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x)));
+        for (u32 j = 0; j < 8; ++j) e[j] = __ldg(rt.emb + (size_t)sEmbRow[group][c0 + j] * kTcH + i);
+        if (!waited) {
+          mbar_wait(smem_u32(&sBar[group]), phase);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          waited = true;
         }
+        u32 a[8];
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7])
+                     : "r"(taddr + c0));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (u32 j = 0; j < 16; ++j)
-          if (c0 + j < nvalid) rw.ctx[(size_t)sOutRow[group][c0 + j] * kTcH + i] = r[j];
+        for (u32 j = 0; j < 8; ++j) {
+          const float x = __fadd_rn(__uint_as_float(a[j]), e[j]);
+          const float r = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x)));
+          if (c0 + j < nvalid) rw.ctx[(size_t)sOutRow[group][c0 + j] * kTcH + i] = r;
+        }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+#pragma unroll
+      for (u32 q = 0; q < kTcTile / 4; ++q) v[q] = vn[q];
     }
     phase ^= 1u;
-    // B planes, the row lists and the accumulator of the group are free for its next tile
-    asm volatile("bar.sync %0, %1;" ::"r"(barId), "r"(kTcGroupThreads) : "memory");
+    buf ^= 1u;
   }
   __syncthreads();
   if (threadIdx.x / 32 == 4) {

@@ -15,6 +15,7 @@
 #include "jpp_b200_host.h"
 #include "jpp_b200_kernels.h"
 #include "jpp_b200_rnn.h"
+#include "jpp_b200_t0_static.h"
 
 using namespace jppb200;
 
@@ -66,7 +67,16 @@ extern "C" int jpp_b200_emul_score_batch(const jpp_b200_model* model, const jpp_
   bv.gbNode = gbNode.data(); bv.gbSlot = gbSlot.data(); bv.gbLeftBnd = gbLeftBnd.data(); bv.gbCount = gbCount.data();
   bv.eosGbeam = eosGbeam.data(); bv.eosLocal = eosLocal.data(); bv.eosRnn = eosRnn.data(); bv.counters = counters;
   const WLoadDirect wl{weights};
-  for (u32 n = 0; n < NN; ++n) t0_node(ft, bv, wl, n);
+  // JPP_B200_EMUL_STATIC_T0=1: the compiled-in per-node program (what k_t0_static runs) instead of the tables
+  const bool staticT0 = getenv("JPP_B200_EMUL_STATIC_T0") && atoi(getenv("JPP_B200_EMUL_STATIC_T0")) != 0;
+  if (staticT0 && !matches_static_t0(ft)) {
+    if (errbuf) snprintf(errbuf, (size_t)errlen, "the model's feature program is not the compiled-in one");
+    return (int)JPP_B200_INVALID_STATE;
+  }
+  for (u32 n = 0; n < NN; ++n) {
+    if (staticT0) t0_node_static(ft, bv, wl, n);
+    else t0_node(ft, bv, wl, n);
+  }
   // wavefront walk: the kernels of jpp_b200.cu, one "launch" = one loop
   u32 maxNb = 0;
   for (u32 s = 0; s < NS; ++s) maxNb = std::max(maxNb, b->sent_boundary_off[s + 1] - b->sent_boundary_off[s]);

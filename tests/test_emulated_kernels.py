@@ -6,6 +6,7 @@ import ctypes as C
 import subprocess
 from pathlib import Path
 
+import numpy as np
 import pytest
 
 import oracle_lib
@@ -103,3 +104,17 @@ def test_compact_rows_carry_placeholders_and_rnn_ids(emul, rnn_dir):
     ora, _ = oracle_lib.oracle_score(model, cfg, compact)
     ora0, _ = oracle_lib.oracle_score(model, cfg, batch)
     assert ora.node_beam.tobytes() == ora0.node_beam.tobytes()
+
+
+@pytest.mark.parametrize("name", LINEAR_GBEAM + FULL_BEAM)
+def test_compiled_in_t0_program_equals_the_table_driven_one(emul, name, monkeypatch):
+    """jpp_b200_static_jumandic_t0.h (what k_t0_static runs) against the program tables and against the
+    reference's expected state: stored pattern rows, unigram scores and everything downstream, bit for bit."""
+    d, model, cfg, batch = load_golden(name)
+    tables = run_emul(emul, model, cfg, batch)
+    monkeypatch.setenv("JPP_B200_EMUL_STATIC_T0", "1")
+    static = run_emul(emul, model, cfg, batch)
+    assert np.array_equal(tables.node_patterns, static.node_patterns)
+    assert np.array_equal(tables.node_t0_score.view(np.uint32), static.node_t0_score.view(np.uint32))
+    rep = parity.compare_with_expected(d, batch, static, rnn=False)
+    assert rep == {"patterns": 0, "beam_links": 0, "beam_totals": 0, "conn_scores": 0}, rep
