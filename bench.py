@@ -455,7 +455,13 @@ def product_arm(args, rank: int, world: int, local_rank: int) -> None:
     t_e2e = torch.tensor([dt_e2e], dtype=torch.float64, device="cuda")
     counts = torch.tensor([n_sent, cnt["gathers"], n_nodes, failed], dtype=torch.float64, device="cuda")
     gathered = None
+    per_gpu = None
     if dist:
+        mine = torch.tensor([n_sent, float(t_res[0].item()), dt_e2e], dtype=torch.float64, device="cuda")
+        every = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+        per_gpu = [{"rank": r, "sentences": int(x[0].item()), "sentences_per_s_resident": x[0].item() * args.steps / x[1].item(),
+                    "sentences_per_s_e2e": x[0].item() * args.steps / x[2].item()} for r, x in enumerate(every)]
         dist.all_reduce(t_res, op=dist.ReduceOp.MAX)
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
         dist.all_reduce(counts, op=dist.ReduceOp.SUM)   # NCCL: gather the per-rank counters
@@ -531,6 +537,8 @@ def product_arm(args, rank: int, world: int, local_rank: int) -> None:
                      "failed_sentences": int(counts[3].item())},
         }
         line["numa"] = numa
+        if per_gpu is not None:
+            line["per_gpu"] = per_gpu
         if gathered is not None:
             line["sharded"] = {k: v for k, v in gathered.items() if k not in ("lens", "nodes")}
         os.sched_setaffinity(0, all_cpus)   # the CPU legs below use every core this process was given

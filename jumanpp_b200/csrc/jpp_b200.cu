@@ -12,6 +12,7 @@
 #include <new>
 #include <string>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <exception>
 #include <mutex>
@@ -365,7 +366,11 @@ __device__ __forceinline__ void cutoff_group_block(const FeatTables& ft, const B
   }
   // Selection as a bit per right node (boundaries of up to 64 nodes; beyond that lane 0 marks
   // selPos in global memory as the serial code does).
-  constexpr u32 SM_R = 64;
+#ifndef JPP_CUTOFF_SM_R
+#define JPP_CUTOFF_SM_R 64
+#endif
+  constexpr u32 SM_R = JPP_CUTOFF_SM_R;  // (A/B builds: a smaller copy leaves shared memory for kernels of other lanes)
+  static_assert(SM_R >= 8 && SM_R <= 64, "the selection is a 64-bit mask; rank counting uses 8 slots");
   __shared__ float sCut[SPB][SM_R];
   __shared__ u32 sIdx[SPB][SM_R];
   const bool bits = active && R <= SM_R;
@@ -1118,6 +1123,7 @@ __global__ void __launch_bounds__(256) k_gather_probe(const float* __restrict__ 
 struct jpp_b200_handle {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t upStream = nullptr;  // uploads + index kernels: highest priority (see upload_window)
   std::string error;
   HostModel hm;
   ScoreCfg cfg{};
@@ -1458,6 +1464,7 @@ void jpp_b200_destroy(jpp_b200_handle* h) {
     if (h->tableStream) cudaStreamDestroy(h->tableStream);
   }
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+  if (h->upStream) cudaStreamDestroy(h->upStream);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -1558,7 +1565,17 @@ static jpp_b200_status upload_window(jpp_b200_handle* h, const jpp_b200_batch* b
   ENSURE(B_COUNTERS, 64); ENSURE(B_WORK, 16);
   ENSURE(B_PATHLEN, (size_t)NS * 4); ENSURE(B_PATHNODES, (size_t)NB * 4);
   ENSURE(B_STATUS, h->hostStatus.size());
-  cudaStream_t st = h->stream;
+  // The copies and the small index kernels of a window run on a stream of the highest priority.  With several
+  // lanes the device is busy with the walk of the window before (thousands of blocks waiting for ~600 slots):
+  // on an equal-priority stream the index kernels of this window would be dispatched only after the last of
+  // those blocks, i.e. every upload would wait for most of the previous window's walk.
+  if (!h->upStream) {
+    int lo = 0, hi = 0;
+    CU_CHECK(h, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CU_CHECK(h, cudaStreamCreateWithPriority(&h->upStream, cudaStreamNonBlocking, hi));
+  }
+  static const bool flatPriority = getenv("JPP_B200_FLAT_PRIORITY") != nullptr;  // A/B: uploads on the compute stream
+  cudaStream_t st = flatPriority ? h->stream : h->upStream;
 #define H2D(idx, src, bytes) CU_CHECK(h, cudaMemcpyAsync(bf[jpp_b200_handle::idx].p, src, bytes, cudaMemcpyHostToDevice, st))
   CU_CHECK(h, cudaEventRecord(h->ev[0], st));
   H2D(B_SBO, sbo, (size_t)(NS + 1) * 4);
@@ -2090,13 +2107,21 @@ static jpp_b200_status score_batch_impl(jpp_b200_handle* h, const jpp_b200_batch
   std::mutex turnMutex;
   std::condition_variable turnCv;
   int uploaded = 0;
+  // JPP_B200_TRACE=1: one line per call on stderr with the host-clock timeline of every lane (ms since the call
+  // began: upload started / uploaded / scored / downloaded) -- where an end-to-end call spends its time
+  static const bool trace = getenv("JPP_B200_TRACE") != nullptr;
+  const auto tCall = std::chrono::steady_clock::now();
+  float tl[kMaxLanes][4] = {};
+  auto since = [&] { return std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - tCall).count(); };
   auto work = [&](int k) noexcept {
     jpp_b200_status st = JPP_B200_OK;
     {
       std::unique_lock<std::mutex> lk(turnMutex);
       turnCv.wait(lk, [&] { return uploaded >= k; });
     }
+    tl[k][0] = since();
     st = guarded(lanes[k], [&] { return upload_window(lanes[k], batch, cut[k], cut[k + 1]); });
+    tl[k][1] = since();
     {
       std::lock_guard<std::mutex> lk(turnMutex);
       uploaded = k + 1;
@@ -2106,7 +2131,9 @@ static jpp_b200_status score_batch_impl(jpp_b200_handle* h, const jpp_b200_batch
       if (token) { std::lock_guard<std::mutex> turn(*token); st = guarded(lanes[k], [&] { return score_resident_impl(lanes[k]); }); }
       else st = guarded(lanes[k], [&] { return score_resident_impl(lanes[k]); });
     }
+    tl[k][2] = since();
     if (st == JPP_B200_OK) st = guarded(lanes[k], [&] { return download_result_impl(lanes[k], result); });
+    tl[k][3] = since();
     sts[k] = st;
   };
   int started = 1;
@@ -2118,6 +2145,15 @@ static jpp_b200_status score_batch_impl(jpp_b200_handle* h, const jpp_b200_batch
   work(0);
   for (int k = started; k < nLanes; ++k) work(k);
   for (int k = 1; k < started; ++k) workers[k].join();
+  if (trace) {
+    std::string line = "[jpp_b200 trace] lanes (upload from, to, scored, downloaded; kernels ms):";
+    char buf[160];
+    for (int k = 0; k < nLanes; ++k) {
+      snprintf(buf, sizeof buf, " | %d: %.1f %.1f %.1f %.1f; %.1f", k, tl[k][0], tl[k][1], tl[k][2], tl[k][3], lanes[k]->counters.kernel_ms[7]);
+      line += buf;
+    }
+    fprintf(stderr, "%s\n", line.c_str());
+  }
   for (int k = 0; k < nLanes; ++k) lanes[k]->resident = false;
   for (int k = 0; k < nLanes; ++k)
     if (sts[k] != JPP_B200_OK) {
