@@ -1348,6 +1348,19 @@ static jpp_b200_status create_impl(const jpp_b200_model* model, const jpp_b200_c
   cudaDeviceProp prop;
   CREATE_CHECK(cudaGetDeviceProperties(&prop, device));
   h->smCount = prop.multiProcessorCount;
+  // L2 <- DRAM fetch granularity.  A miss of a 4-byte table read moves far more than its 32-byte sector: the
+  // gather probe reads 86 B from DRAM per gather at an 11 % L2 hit rate (ncu, profiles/r2i_probe.md) and is at
+  // 97 % of the HBM rate at 74 G gathers/s.  JPP_B200_L2_FETCH=32|64|128 sets cudaLimitMaxL2FetchGranularity
+  // (a hint, device-wide for this context) before anything is allocated.
+  if (const char* e = getenv("JPP_B200_L2_FETCH")) {
+    const int g = atoi(e);
+    if (g == 32 || g == 64 || g == 128) {
+      if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)g) != cudaSuccess) cudaGetLastError();
+      size_t got = 0;
+      cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity);
+      fprintf(stderr, "[jpp_b200] L2 fetch granularity: asked %d, device reports %zu\n", g, got);
+    }
+  }
   CREATE_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CREATE_CHECK(cudaFuncSetAttribute(k_w_prescore, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kCacheSlots * 8)));
   CREATE_CHECK(cudaFuncSetAttribute(k_t0<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MAX_PRIM * 128 * 8)));
