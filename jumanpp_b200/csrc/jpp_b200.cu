@@ -15,6 +15,7 @@
 #include <chrono>
 #include <condition_variable>
 #include <exception>
+#include <functional>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -1484,7 +1485,11 @@ void jpp_b200_destroy(jpp_b200_handle* h) {
 
 // Uploads sentences [lo, hi) of `b`.  The CSR offset arrays are copied as they are and rebased on
 // the device, so a window of a larger batch costs the host nothing.
-static jpp_b200_status upload_window(jpp_b200_handle* h, const jpp_b200_batch* b, u32 lo, u32 hi) {
+// `copiesQueued` (optional) is called once every host-to-device copy of the window has been handed to the
+// copy engine: a caller that runs several windows lets the next one queue its copies then, not when this
+// window's index kernels have finished.
+static jpp_b200_status upload_window(jpp_b200_handle* h, const jpp_b200_batch* b, u32 lo, u32 hi,
+                                     const std::function<void()>* copiesQueued = nullptr) {
   if (!h || !b) return JPP_B200_INVALID_PARAMETER;
   h->resident = false;
   CU_CHECK(h, cudaSetDevice(h->device));
@@ -1624,6 +1629,7 @@ static jpp_b200_status upload_window(jpp_b200_handle* h, const jpp_b200_batch* b
   if (NC) H2D(B_CPS, b->codepoints + cBase, (size_t)NC * sizeof(jpp_b200_codepoint));
   H2D(B_ORDER, order.data(), (size_t)NS * 4);
   H2D(B_STATUS, h->hostStatus.data(), h->hostStatus.size());
+  if (copiesQueued) (*copiesQueued)();
   BatchView& bv = h->bv;
   bv = BatchView{};
   bv.numSentences = NS; bv.totalBoundaries = NB; bv.totalNodes = NN; bv.totalEnds = NE;
@@ -2114,9 +2120,10 @@ static jpp_b200_status score_batch_impl(jpp_b200_handle* h, const jpp_b200_batch
   // JPP_B200_LANE_TURNS=1: one window computes at a time.  Measured slower (100 ms against 85 ms
   // per 100 000 sentences with the kernels of the windows side by side), so it is off.
   std::mutex* token = (serialEnv && atoi(serialEnv) == 1) ? h->computeToken : nullptr;
-  // windows start in order: a lane begins its upload when the previous one has finished its own
-  // (PCIe is one pipe; finishing window 0 early matters more than starting all at once).  Waiting
-  // lanes sleep on a condition variable: the host cores belong to the caller's staging threads.
+  // windows start in order: a lane queues its copies when the previous one has queued its own (PCIe is one
+  // pipe; finishing window 0 early matters more than starting all at once, and the copy engine never waits
+  // for a window's index kernels).  Waiting lanes sleep on a condition variable: the host cores belong to the
+  // caller's staging threads.
   std::mutex turnMutex;
   std::condition_variable turnCv;
   int uploaded = 0;
@@ -2133,13 +2140,17 @@ static jpp_b200_status score_batch_impl(jpp_b200_handle* h, const jpp_b200_batch
       turnCv.wait(lk, [&] { return uploaded >= k; });
     }
     tl[k][0] = since();
-    st = guarded(lanes[k], [&] { return upload_window(lanes[k], batch, cut[k], cut[k + 1]); });
+    bool passed = false;
+    const std::function<void()> pass = [&] {
+      if (passed) return;
+      passed = true;
+      { std::lock_guard<std::mutex> lk(turnMutex); uploaded = k + 1; }
+      turnCv.notify_all();
+    };
+    static const bool wholeTurns = getenv("JPP_B200_UPLOAD_TURNS") != nullptr;  // A/B: the next window waits for the whole upload
+    st = guarded(lanes[k], [&] { return upload_window(lanes[k], batch, cut[k], cut[k + 1], wholeTurns ? nullptr : &pass); });
     tl[k][1] = since();
-    {
-      std::lock_guard<std::mutex> lk(turnMutex);
-      uploaded = k + 1;
-    }
-    turnCv.notify_all();
+    pass();  // (an upload that failed before its copies still lets the others go on)
     if (st == JPP_B200_OK) {
       if (token) { std::lock_guard<std::mutex> turn(*token); st = guarded(lanes[k], [&] { return score_resident_impl(lanes[k]); }); }
       else st = guarded(lanes[k], [&] { return score_resident_impl(lanes[k]); });
