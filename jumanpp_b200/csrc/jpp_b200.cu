@@ -368,9 +368,12 @@ __device__ __forceinline__ void cutoff_group_block(const FeatTables& ft, const B
   // Selection as a bit per right node (boundaries of up to 64 nodes; beyond that lane 0 marks
   // selPos in global memory as the serial code does).
 #ifndef JPP_CUTOFF_SM_R
-#define JPP_CUTOFF_SM_R 64
+#define JPP_CUTOFF_SM_R 16
 #endif
-  constexpr u32 SM_R = JPP_CUTOFF_SM_R;  // (A/B builds: a smaller copy leaves shared memory for kernels of other lanes)
+  // boundaries of up to SM_R right nodes select in shared memory (a boundary has ~7).  16, not 64: 5 KB instead of
+  // 17 KB per block leaves room on an SM for the tensor-core level kernel of ANOTHER window next to four walk
+  // blocks (end-to-end 72.6 -> 69.3 ms per 100 000 sentences with six windows side by side, r2l)
+  constexpr u32 SM_R = JPP_CUTOFF_SM_R;
   static_assert(SM_R >= 8 && SM_R <= 64, "the selection is a 64-bit mask; rank counting uses 8 slots");
   __shared__ float sCut[SPB][SM_R];
   __shared__ u32 sIdx[SPB][SM_R];
@@ -582,9 +585,12 @@ __global__ void k_fill_i32(i32* p, size_t n, i32 v) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
 }
 
+// Thread i takes sentence sentOrder[i] (longest first): the 32 sentences of a warp have about the same number of
+// boundaries, so the loops of the walk back and of the unwind run about the same number of times in every lane.
+// In input order a warp ran as long as the sum of its lanes' different paths (10.5 of 32 lanes active, ncu r2e).
 __global__ void k_rnn_tree(BatchView bv, ScoreCfg cfg, RnnWork rw) {
-  const u32 s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s < bv.numSentences) rnn_build_tree(bv, cfg, rw, s);
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < bv.numSentences) rnn_build_tree(bv, cfg, rw, bv.sentOrder ? bv.sentOrder[i] : i);
 }
 
 // level lists (the histogram is accumulated by k_rnn_tree); 8 lanes share a sentence's nodes
@@ -1029,8 +1035,8 @@ __global__ void __launch_bounds__(128) k_rnn_scores_x(BatchView bv, ScoreCfg cfg
 }
 
 __global__ void k_best_path(BatchView bv, ScoreCfg cfg, u32* pathLen, u32* pathNodes, u32 nodeBase) {
-  const u32 s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s < bv.numSentences) best_path_sentence(bv, cfg, pathLen, pathNodes, s, nodeBase);
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < bv.numSentences) best_path_sentence(bv, cfg, pathLen, pathNodes, bv.sentOrder ? bv.sentOrder[i] : i, nodeBase);
 }
 
 // adjustBeamScores + remakeEosBeam (analyzer_impl.cc:286-294; serial statement: rerank_sentence).
@@ -1039,8 +1045,9 @@ __global__ void k_best_path(BatchView bv, ScoreCfg cfg, u32* pathLen, u32* pathN
 // the boundaries in order; lane 0 then rebuilds the EOS beam.
 __global__ void __launch_bounds__(256) k_rerank(BatchView bv, ScoreCfg cfg, float w0, float w1) {
   const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
-  const u32 sent = t >> 3, sub = threadIdx.x & 7u;
-  if (sent >= bv.numSentences) return;
+  const u32 sub = threadIdx.x & 7u;
+  if ((t >> 3) >= bv.numSentences) return;
+  const u32 sent = bv.sentOrder ? bv.sentOrder[t >> 3] : (t >> 3);  // the four sentences of a warp: of similar length
   const unsigned gmask = 0xFFu << ((threadIdx.x & 31u) - sub);
   u32 b0;
   const u32 nb = sent_span(bv, sent, b0);
@@ -2120,10 +2127,9 @@ static jpp_b200_status score_batch_impl(jpp_b200_handle* h, const jpp_b200_batch
   // JPP_B200_LANE_TURNS=1: one window computes at a time.  Measured slower (100 ms against 85 ms
   // per 100 000 sentences with the kernels of the windows side by side), so it is off.
   std::mutex* token = (serialEnv && atoi(serialEnv) == 1) ? h->computeToken : nullptr;
-  // windows start in order: a lane queues its copies when the previous one has queued its own (PCIe is one
-  // pipe; finishing window 0 early matters more than starting all at once, and the copy engine never waits
-  // for a window's index kernels).  Waiting lanes sleep on a condition variable: the host cores belong to the
-  // caller's staging threads.
+  // windows start in order: a lane begins its upload when the previous one has finished its own
+  // (PCIe is one pipe; finishing window 0 early matters more than starting all at once).  Waiting
+  // lanes sleep on a condition variable: the host cores belong to the caller's staging threads.
   std::mutex turnMutex;
   std::condition_variable turnCv;
   int uploaded = 0;
@@ -2147,7 +2153,10 @@ static jpp_b200_status score_batch_impl(jpp_b200_handle* h, const jpp_b200_batch
       { std::lock_guard<std::mutex> lk(turnMutex); uploaded = k + 1; }
       turnCv.notify_all();
     };
-    static const bool wholeTurns = getenv("JPP_B200_UPLOAD_TURNS") != nullptr;  // A/B: the next window waits for the whole upload
+    // JPP_B200_UPLOAD_EARLY=1: the next window queues its copies as soon as this one has queued its own.  Measured
+    // (r2m): every upload is over by 28 ms instead of 44, but window 0 starts computing at 13 ms instead of 5 and
+    // the call ends no earlier (74-79 ms against 72-75), so the turn is passed when the whole upload is done.
+    static const bool wholeTurns = getenv("JPP_B200_UPLOAD_EARLY") == nullptr;
     st = guarded(lanes[k], [&] { return upload_window(lanes[k], batch, cut[k], cut[k + 1], wholeTurns ? nullptr : &pass); });
     tl[k][1] = since();
     pass();  // (an upload that failed before its copies still lets the others go on)

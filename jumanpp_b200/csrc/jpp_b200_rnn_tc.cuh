@@ -36,10 +36,12 @@ constexpr u32 kTcH = 128;          // layer size this kernel is built for
 #define JPP_TC_TILE 16
 #endif
 #ifndef JPP_TC_GROUPS
-#define JPP_TC_GROUPS 6
+#define JPP_TC_GROUPS 4
 #endif
 constexpr u32 kTcTile = JPP_TC_TILE;      // tree nodes per tile (UMMA N): 16 or 32
-constexpr u32 kTcGroups = JPP_TC_GROUPS;  // independent tile pipelines per block (each: 4 producer / epilogue warps + 1 MMA warp)
+constexpr u32 kTcGroups = JPP_TC_GROUPS;  // independent tile pipelines per block (each: 4 producer / epilogue warps + 1 MMA warp).
+// Four, not six (contexts 6.7 against 6.0 ms alone): 193 KB of shared memory instead of 226 let the block share an SM with
+// the walk blocks of another window, which is worth more end to end (jpp_b200.cu, JPP_CUTOFF_SM_R)
 constexpr u32 kTcGroupThreads = 160;
 constexpr u32 kTcThreads = kTcGroups * kTcGroupThreads;
 constexpr u32 kTcChunkK = 32;      // tf32 elements per 128-byte swizzle row
