@@ -585,12 +585,12 @@ __global__ void k_fill_i32(i32* p, size_t n, i32 v) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
 }
 
-// Thread i takes sentence sentOrder[i] (longest first): the 32 sentences of a warp have about the same number of
-// boundaries, so the loops of the walk back and of the unwind run about the same number of times in every lane.
-// In input order a warp ran as long as the sum of its lanes' different paths (10.5 of 32 lanes active, ncu r2e).
+// Thread = sentence, in input order.  Taking the sentences in the length-sorted order instead (a warp's 32 sentences
+// then loop about equally often) was measured and is slower, 7.3 -> 7.8 ms (r2n): neighbours in input order are
+// neighbours in memory, and this kernel is all dependent loads.
 __global__ void k_rnn_tree(BatchView bv, ScoreCfg cfg, RnnWork rw) {
-  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < bv.numSentences) rnn_build_tree(bv, cfg, rw, bv.sentOrder ? bv.sentOrder[i] : i);
+  const u32 s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < bv.numSentences) rnn_build_tree(bv, cfg, rw, s);
 }
 
 // level lists (the histogram is accumulated by k_rnn_tree); 8 lanes share a sentence's nodes
@@ -1035,8 +1035,8 @@ __global__ void __launch_bounds__(128) k_rnn_scores_x(BatchView bv, ScoreCfg cfg
 }
 
 __global__ void k_best_path(BatchView bv, ScoreCfg cfg, u32* pathLen, u32* pathNodes, u32 nodeBase) {
-  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < bv.numSentences) best_path_sentence(bv, cfg, pathLen, pathNodes, bv.sentOrder ? bv.sentOrder[i] : i, nodeBase);
+  const u32 s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < bv.numSentences) best_path_sentence(bv, cfg, pathLen, pathNodes, s, nodeBase);
 }
 
 // adjustBeamScores + remakeEosBeam (analyzer_impl.cc:286-294; serial statement: rerank_sentence).
@@ -1045,9 +1045,8 @@ __global__ void k_best_path(BatchView bv, ScoreCfg cfg, u32* pathLen, u32* pathN
 // the boundaries in order; lane 0 then rebuilds the EOS beam.
 __global__ void __launch_bounds__(256) k_rerank(BatchView bv, ScoreCfg cfg, float w0, float w1) {
   const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
-  const u32 sub = threadIdx.x & 7u;
-  if ((t >> 3) >= bv.numSentences) return;
-  const u32 sent = bv.sentOrder ? bv.sentOrder[t >> 3] : (t >> 3);  // the four sentences of a warp: of similar length
+  const u32 sent = t >> 3, sub = threadIdx.x & 7u;
+  if (sent >= bv.numSentences) return;
   const unsigned gmask = 0xFFu << ((threadIdx.x & 31u) - sub);
   u32 b0;
   const u32 nb = sent_span(bv, sent, b0);
