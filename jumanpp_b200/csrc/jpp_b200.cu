@@ -1148,6 +1148,7 @@ struct jpp_b200_handle {
   cudaStream_t tableStream = nullptr;  // owner only: uploads of table rows (never waits for a batch in flight)
   bool staticProgram = false;  // the uploaded n-gram program is the compiled-in one (jpp_b200_static_jumandic.h)
   bool staticT0 = false;       // ... and so is its per-node part (jpp_b200_static_jumandic_t0.h)
+  bool rnnTc = true;           // layer size 128: tcgen05 level kernel (JPP_B200_RNN_TC=0 at create: the FFMA kernel)
   float* dRnnBlocks[4] = {nullptr, nullptr, nullptr, nullptr};
   float* dRnnWt = nullptr;  // transposed recurrent matrix
   float* dRnnWImage = nullptr;  // layer size 128: the two TF32 planes of W in the tensor-core operand layout (jpp_b200_rnn_tc.cuh)
@@ -1340,8 +1341,12 @@ static jpp_b200_status create_impl(const jpp_b200_model* model, const jpp_b200_c
                     model->num_scorers, hm.ft.dynamicOrder};
   h->scoreW[0] = model->score_weights[0];
   h->scoreW[1] = model->score_weights[1];
-  h->staticProgram = matches_static_program(h->hm.ft);
-  h->staticT0 = matches_static_t0(h->hm.ft);
+  // the compiled-in program is used when the uploaded one equals it; the switches are read when the handle is made
+  // (A/B measurements, and the tests that hold the table-driven / FFMA kernels to the same golden vectors)
+  const bool noStatic = getenv("JPP_B200_NO_STATIC") != nullptr;
+  h->staticProgram = matches_static_program(h->hm.ft) && !noStatic;
+  h->staticT0 = matches_static_t0(h->hm.ft) && !noStatic && getenv("JPP_B200_NO_STATIC_T0") == nullptr;
+  h->rnnTc = !(getenv("JPP_B200_RNN_TC") && atoi(getenv("JPP_B200_RNN_TC")) == 0);
 #define CREATE_CHECK(expr)                                                                      \
   do {                                                                                          \
     cudaError_t e_ = (expr);                                                                    \
@@ -1772,8 +1777,7 @@ static jpp_b200_status score_resident_impl(jpp_b200_handle* h) {
 #else
     const size_t primBytes = 0;
 #endif
-    static const bool noStaticT0 = getenv("JPP_B200_NO_STATIC") != nullptr || getenv("JPP_B200_NO_STATIC_T0") != nullptr;  // A/B: table-driven program
-    if (h->staticT0 && !noStaticT0 && !t0Array) k_t0_static<<<(NN + 127) / 128, 128, 0, st>>>(h->hm.ft, bv, h->dWeights);
+    if (h->staticT0 && !t0Array) k_t0_static<<<(NN + 127) / 128, 128, 0, st>>>(h->hm.ft, bv, h->dWeights);
     else if (t0Array) k_t0<false><<<(NN + 127) / 128, 128, primBytes, st>>>(h->dFt, bv, h->dWeights);
     else k_t0<true><<<(NN + 127) / 128, 128, primBytes, st>>>(h->dFt, bv, h->dWeights);
   }
@@ -1794,13 +1798,12 @@ static jpp_b200_status score_resident_impl(jpp_b200_handle* h) {
     u32 launches = 1;
     const bool fused = fused_walk_ok(cfg) && !profileOn;
     if (fused) {
-      static const bool noStatic = getenv("JPP_B200_NO_STATIC") != nullptr;  // A/B: table-driven n-gram program
       static const int sentEnv = getenv("JPP_B200_FUSED_SENT") ? atoi(getenv("JPP_B200_FUSED_SENT")) : 0;  // A/B: sentences per block
       const bool narrow = cfg.beam <= 8 && cfg.gbeam <= 8;
       const u32 SENT = sentEnv == 16 || sentEnv == 32 ? (u32)sentEnv : kFusedSentDefault;
       const u32 itemCap = SENT * (u32)cfg.rbeam * (u32)cfg.gbeam;
       const u32 blocks = (NS + SENT - 1) / SENT;
-      const bool stat = h->staticProgram && !noStatic;
+      const bool stat = h->staticProgram;
 #define JPP_WALK2(GW, KB, SM, ST, SE) k_walk_fused<GW, KB, SM, ST, SE><<<blocks, SE * 8, 0, st>>>(ft, bv, cfg, wv, h->dWeights, itemCap)
 #define JPP_WALK(GW, KB, SM, ST) do { if (SENT == 16) JPP_WALK2(GW, KB, SM, ST, 16); else JPP_WALK2(GW, KB, SM, ST, 32); } while (0)
       if (narrow) {
@@ -1892,8 +1895,7 @@ static jpp_b200_status score_resident_impl(jpp_b200_handle* h) {
     cub::DeviceScan::ExclusiveSum(bf[jpp_b200_handle::R_CUBTMP].p, tmpBytes, rw.levelCount, rw.levelOff, (int)(h->maxNb + 2), st);
     // layer size 128: the level step as tcgen05 tensor-core MMAs (3xTF32); JPP_B200_RNN_TC=0 selects the
     // FFMA kernel (an A/B switch for measurements and for bisecting a numeric difference)
-    static const bool tcOn = !(getenv("JPP_B200_RNN_TC") && atoi(getenv("JPP_B200_RNN_TC")) == 0);
-    const bool useTc = tcOn && h->rt.H == kTcH && h->dRnnWImage != nullptr;
+    const bool useTc = h->rnnTc && h->rt.H == kTcH && h->dRnnWImage != nullptr;
     LevelRec* levelRec = useTc ? bf[jpp_b200_handle::R_LVLREC].as<LevelRec>() : nullptr;
     k_rnn_level_fill<<<(NS * 8 + 255) / 256, 256, 0, st>>>(bv, rw, bf[jpp_b200_handle::R_CURSOR].as<u32>(), ctxOff, levelRec);
     k_rnn_bos<<<NS, 64, 0, st>>>(bv, rw, h->rt, ctxOff);
@@ -2041,7 +2043,7 @@ jpp_b200_status make_lane(jpp_b200_handle* owner, jpp_b200_handle* prev) {
   l->device = h->device; l->hm = h->hm; l->cfg = h->cfg; l->pubCfg = h->pubCfg;
   l->dFt = h->dFt; l->dWeights = h->dWeights; l->rt = h->rt; l->hasRnn = h->hasRnn;
   for (int i = 0; i < 4; ++i) l->dRnnBlocks[i] = h->dRnnBlocks[i];
-  l->staticProgram = h->staticProgram; l->staticT0 = h->staticT0;
+  l->staticProgram = h->staticProgram; l->staticT0 = h->staticT0; l->rnnTc = h->rnnTc;
   l->dRnnWt = h->dRnnWt; l->dRnnWImage = h->dRnnWImage; l->scoreW[0] = h->scoreW[0]; l->scoreW[1] = h->scoreW[1]; l->smCount = h->smCount;
   l->ownsModel = false;
   cudaError_t e = cudaStreamCreateWithFlags(&l->stream, cudaStreamNonBlocking);

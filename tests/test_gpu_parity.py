@@ -164,3 +164,30 @@ def test_errors_are_reported_not_swallowed():
     with pytest.raises(ScorerError) as e:
         LatticeScorer(model, abi.ScoringConfig(40, 6, 1, 5))   # beams above 32 are refused, not truncated
     assert e.value.code == abi.NOT_IMPLEMENTED
+
+
+# The default build picks the compiled-in Jumandic program and, for layer size 128, the tcgen05 level kernel.  The
+# kernels every OTHER model gets (table-driven feature program, FFMA level kernel) are held to the same golden
+# vectors: the switches are read when a handle is created.
+@pytest.mark.parametrize("name", ["default", "beam20", "beam3_ties", "dyn_default", "ref_codegen_fixture"])
+def test_table_driven_program_matches_reference_and_oracle(name, monkeypatch):
+    monkeypatch.setenv("JPP_B200_NO_STATIC", "1")
+    d, model, cfg, batch = load_golden(name)
+    res, cnt = gpu_score(model, cfg, batch)
+    rep = parity.compare_with_expected(d, batch, res, rnn=False)
+    assert rep == {"patterns": 0, "beam_links": 0, "beam_totals": 0, "conn_scores": 0}, rep
+    ora, stats = oracle_lib.oracle_score(model, cfg, batch)
+    assert res.node_beam.tobytes() == ora.node_beam.tobytes()
+    assert np.array_equal(res.node_patterns, ora.node_patterns)
+    assert res.node_t0_score.tobytes() == ora.node_t0_score.tobytes()
+    assert cnt["gathers"] == stats.gathers
+
+
+def test_ffma_level_kernel_for_layer_size_128(rnn_dir, monkeypatch):
+    monkeypatch.setenv("JPP_B200_RNN_TC", "0")
+    monkeypatch.setenv("JPP_B200_NO_STATIC", "1")
+    d, model, cfg, batch = load_golden("rnn_h128", rnn_dir)
+    res, _ = gpu_score(model, cfg, batch)
+    rep = parity.compare_with_expected(d, batch, res, rnn=True, rnn_rtol=1e-4)
+    n = rep.pop("final_path_elements")
+    assert n > 0 and all(v == 0 for v in rep.values()), rep
