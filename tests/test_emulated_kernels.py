@@ -118,3 +118,23 @@ def test_compiled_in_t0_program_equals_the_table_driven_one(emul, name, monkeypa
     assert np.array_equal(tables.node_t0_score.view(np.uint32), static.node_t0_score.view(np.uint32))
     rep = parity.compare_with_expected(d, batch, static, rnn=False)
     assert rep == {"patterns": 0, "beam_links": 0, "beam_totals": 0, "conn_scores": 0}, rep
+
+
+def test_a_different_feature_program_is_not_taken_for_the_compiled_in_one(emul, monkeypatch):
+    """matches_static_t0 must refuse a program that differs from the generated header in one table entry
+    (such a model runs the table-driven kernels)."""
+    import dataclasses
+    d, model, cfg, batch = load_golden("default")
+    ngrams = model.ngrams.copy()
+    uni = [i for i in range(len(ngrams)) if ngrams[i][0] == 1]
+    ngrams[uni[3]][2], ngrams[uni[4]][2] = ngrams[uni[4]][2], ngrams[uni[3]][2]     # two unigram features swap their patterns
+    other = dataclasses.replace(model, ngrams=ngrams)
+    run_emul(emul, other, cfg, batch)                                                 # table-driven: fine
+    monkeypatch.setenv("JPP_B200_EMUL_STATIC_T0", "1")
+    res = abi.ScoreResult.allocate(batch.num_nodes, cfg.beam_size, other.num_scorers, other.num_stored_patterns,
+                                   batch.num_sentences, batch.num_boundaries)
+    w = oracle_lib.weights_for(other)
+    ms, cs, bs, rs = other.as_struct(), cfg.as_struct(), batch.as_struct(), res.as_struct()
+    err = C.create_string_buffer(512)
+    rc = emul.jpp_b200_emul_score_batch(C.byref(ms), C.byref(cs), C.byref(bs), C.byref(rs), C.c_void_p(w.ctypes.data), err, 512)
+    assert rc != 0 and b"not the compiled-in one" in err.value
