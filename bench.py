@@ -678,7 +678,7 @@ def main() -> None:
     ap.add_argument("--stage-chunk", type=int, default=2048)
     ap.add_argument("--cache", default=os.environ.get("JPP_B200_CACHE", "/tmp/jpp_b200_cache"))
     ap.add_argument("--cpu-sample-per-core", type=int, default=1500)
-    ap.add_argument("--parity-sample", type=int, default=2000)
+    ap.add_argument("--parity-sample", type=int, default=10000)
     ap.add_argument("--no-gather-probe", action="store_true")
     ap.add_argument("--no-numa-bind", action="store_true")
     ap.add_argument("--window", type=int, default=131072,
